@@ -1,0 +1,123 @@
+/* mocap_b200.h -- C-ABI of the B200-native MocapV2 capture hot path (libmocap_b200.so, sm_100a).
+ *
+ * The reference (RashmikaDushan/MocapV2) has no FFI: its "operator interface" for this path is the set of
+ * module-level Python functions in lib/ImageOperations.py and lib/Helpers.py.  Each entry point below is
+ * what a ctypes binding of one of those functions binds (see INTEGRATION.md for the stub); the reference
+ * interface it replaces is cited as file:line of /root/reference.
+ *
+ * Conventions: every *_dev pointer is device memory owned by the caller (torch tensors in the Python host
+ * layer); `stream` is a cudaStream_t passed as void*; all calls are asynchronous on that stream, allocate
+ * nothing, keep no global state and are re-entrant.  Return value: MOCAP_OK or a negative status; per-frame /
+ * per-frame-set problems (capacity overflows) are reported in the flags arrays, not in the return value.
+ */
+#ifndef MOCAP_B200_H
+#define MOCAP_B200_H
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define MOCAP_OK 0
+#define MOCAP_ERR_INVALID (-1)     /* bad argument (null pointer, non-positive size, unsupported shape) */
+#define MOCAP_ERR_WORKSPACE (-2)   /* workspace smaller than mocap_*_workspace_bytes() */
+#define MOCAP_ERR_CUDA (-3)        /* a CUDA runtime call failed (cudaGetLastError() is preserved) */
+#define MOCAP_ERR_UNSUPPORTED (-4) /* shape outside the compiled limits (see mocap_limits) */
+
+/* per-frame flags written to out_flags[] of mocap_detect_batch */
+#define MOCAP_FLAG_RUN_OVERFLOW 1      /* more foreground runs than max_runs: frame outputs invalid */
+#define MOCAP_FLAG_BLOB_OVERFLOW 2     /* more kept centroids than max_blobs: list truncated */
+#define MOCAP_FLAG_CONTOUR_OVERFLOW 4  /* more contours than max_contours: frame outputs invalid */
+#define MOCAP_FLAG_TILE_OVERFLOW 8     /* more foreground tiles than the workspace holds */
+#define MOCAP_FLAG_DEPTH_OVERFLOW 16   /* contour tree deeper than 8: order resolved by the slow path */
+#define MOCAP_FLAG_TRACE_OVERFLOW 32   /* a border longer than the step budget: frame outputs invalid */
+
+/* per-frame-set flags written by mocap_correspond_batch */
+#define MOCAP_CFLAG_GROUP_CAP 1        /* a root had more candidate groups than max_groups: mean over the first max_groups */
+#define MOCAP_CFLAG_CAND_CAP 2         /* a (root, camera) pair had more in-cutoff candidates than MOCAP_MAX_CAND */
+#define MOCAP_CFLAG_TIE 4              /* a distance within 1e-5 of the cutoff (Helpers.py:219), logged as a tie */
+
+#define MOCAP_MAX_CAND 8               /* candidates kept per (root, camera), ascending distance */
+#define MOCAP_MAX_CAMS 16              /* views per triangulation / cameras per frame-set */
+#define MOCAP_CAM_STRIDE 40            /* doubles per camera record, see mocap_pack_camera layout below */
+
+/* Camera record layout (doubles): [0..11] P = K[R|t] row-major 3x4 (Helpers.py:58-62)
+ *                                 [12..20] R row-major, [21..23] t, [24..32] K row-major, [33..37] k1 k2 p1 p2 k3 */
+
+const char* mocap_status_string(int status);
+int mocap_abi_version(void);
+
+/* ---- undistortion table: cv.undistort(img, K0, dist0) of _find_dot (lib/ImageOperations.py:37-38) -------
+ * Built once per (K, dist, H, W).  Holds the 1/32-px fixed-point displacement map of
+ * cv::initUndistortRectifyMap (FP64, same operation order) plus the source-cell -> output-tile reach table. */
+size_t mocap_undistort_table_bytes(int H, int W);
+int mocap_undistort_table_build(const double* K9_host, const double* dist5_host, int H, int W,
+                                void* table_dev, size_t table_bytes, void* stream);
+
+/* ---- detection: _find_dot(img)[1] for a batch of frames (lib/ImageOperations.py:33-78) --------------------
+ * frames_dev: n_frames x H x W uint8 (row stride W, frame stride `frame_stride` bytes).
+ * out_xy[n][max_blobs][2] int32 centroids in the reference's output order, out_count[n] how many
+ * (0 = the reference's [[None, None]]), out_flags[n] MOCAP_FLAG_*.
+ * Optional (may be NULL) parity outputs:
+ *   out_bits[n][H][ceil(W/32)]   the filtered binary image (image_filter_gpu, :23-31), LSB = leftmost pixel
+ *   out_labels[n][H][W] int32    8-connected blob labels, 0 = background, k = k-th blob in raster order
+ *   out_blob_sums[n][max_blobs][3] int64  per-blob pixel m00, m10, m01;  out_blob_count[n]
+ *   out_contours[n][max_contours][8] double: a00, a10, a01 (exact integers), perimeter, is_hole,
+ *                                   parent (index in output order or -1), kept, start pixel index
+ *   out_contour_count[n]
+ */
+size_t mocap_detect_workspace_bytes(int n_frames, int H, int W, int max_blobs, int max_contours, int max_runs);
+int mocap_detect_batch(const uint8_t* frames_dev, int n_frames, int H, int W, int64_t frame_stride,
+                       const void* table_dev, int thresh, double min_area, double min_circ,
+                       int max_blobs, int max_contours, int max_runs,
+                       int32_t* out_xy, int32_t* out_count, int32_t* out_flags,
+                       uint32_t* out_bits, int32_t* out_labels, int64_t* out_blob_sums, int32_t* out_blob_count,
+                       double* out_contours, int32_t* out_contour_count,
+                       void* workspace, size_t workspace_bytes, void* stream);
+
+/* stage entry points of the same path (used by the parity tests and the bench's per-kernel timing) */
+int mocap_filter_batch(const uint8_t* frames_dev, int n_frames, int H, int W, int64_t frame_stride,
+                       const void* table_dev, int thresh, uint32_t* out_bits,
+                       void* workspace, size_t workspace_bytes, void* stream);
+
+/* ---- the reference's own GPU op: fast_cuda_blur(image, 5) (lib/CudaOperations.py:24-41) -------------------- */
+int mocap_blur5_batch(const uint8_t* frames_dev, int n_frames, int H, int W, uint8_t* out_dev, void* stream);
+/* cv.undistort alone (lib/ImageOperations.py:38), for stage parity */
+int mocap_undistort_batch(const uint8_t* frames_dev, int n_frames, int H, int W, const void* table_dev,
+                          uint8_t* out_dev, void* stream);
+
+/* ---- triangulation + reprojection error: triangulate_points / calculate_reprojection_errors ----------------
+ * (lib/Helpers.py:43-99 DLT on B = A^T A, smallest singular vector; :102-143 mean squared pixel residual
+ * through cv.projectPoints incl. distortion and its float32 roundings.)
+ * pts_dev [P][C][2]: float32 (fp64_mode 0) or float64 (fp64_mode 1).  valid_dev [P][C] uint8 or NULL (all valid).
+ * xyz_out [P][3], err_out [P] in the same dtype as pts; points with fewer than 2 valid views get NaN
+ * (the reference's [None, None, None], Helpers.py:55-56).  err_out may be NULL. */
+int mocap_triangulate_batch(const void* pts_dev, const uint8_t* valid_dev, const double* cams_dev, int C,
+                            int64_t P, int fp64_mode, void* xyz_out, void* err_out, void* stream);
+/* reprojection error of given object points (Helpers.py:102-143), same dtypes as above */
+int mocap_reproject_batch(const void* pts_dev, const uint8_t* valid_dev, const void* xyz_dev,
+                          const double* cams_dev, int C, int64_t P, int fp64_mode, void* err_out, void* stream);
+
+/* ---- epipolar correspondence + candidate groups + ranking ---------------------------------------------------
+ * find_point_correspondance_and_object_points (lib/Helpers.py:178-280) for S frame-sets.
+ * xy_dev [S][C][max_pts][2] int32 centroid lists (the [None, None] entry already dropped), count_dev [S][C].
+ * F_dev [C-1][9]: Fs[i-1] maps camera-0 points to epilines in camera i (Helpers.py:205-207).
+ * Outputs per frame-set: obj_out [S][max_pts][3] float64 object points sorted by mean reprojection error and
+ * cut to obj_count+1 (Helpers.py:274-279) with n_obj_out[S]; img_out [S][max_pts][C][2] the first (all-closest)
+ * group of every complete root in root order with n_valid_out[S]; err_out [S][max_pts] mean error per complete
+ * root (root order); cand_out [S][max_pts][C][MOCAP_MAX_CAND] int32 candidate indices (-1 padded) or NULL;
+ * flags_out [S] MOCAP_CFLAG_*. */
+size_t mocap_correspond_workspace_bytes(int S, int C, int max_pts, int max_groups);
+int mocap_correspond_batch(const int32_t* xy_dev, const int32_t* count_dev, int S, int C, int max_pts,
+                           const double* F_dev, const double* cams_dev, double cutoff, int obj_count,
+                           int max_groups, int fp64_mode,
+                           double* obj_out, int32_t* n_obj_out, int32_t* img_out, int32_t* n_valid_out,
+                           double* err_out, int32_t* cand_out, int32_t* flags_out,
+                           void* workspace, size_t workspace_bytes, void* stream);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* MOCAP_B200_H */

@@ -1,0 +1,72 @@
+"""ctypes binding of libmocap_b200.so -- the C-ABI declared in include/mocap_b200.h.
+
+This is the whole FFI surface: plain pointers and sizes, no torch types.  The library is built in-tree by
+``mocapv2_b200.build`` (nvcc, sm_100a).  There is no CPU implementation behind these symbols: if the shared
+library is missing or no CUDA device is present the package raises instead of degrading.
+"""
+from __future__ import annotations
+
+import ctypes as C
+import os
+
+HERE = os.path.dirname(os.path.abspath(__file__))
+DEFAULT_LIB = os.path.join(HERE, "libmocap_b200.so")
+
+ABI_VERSION = 1
+MAX_CAND = 8
+MAX_CAMS = 16
+CAM_STRIDE = 40
+
+OK = 0
+FLAG_RUN_OVERFLOW, FLAG_BLOB_OVERFLOW, FLAG_CONTOUR_OVERFLOW, FLAG_TILE_OVERFLOW, FLAG_DEPTH_OVERFLOW, FLAG_TRACE_OVERFLOW = 1, 2, 4, 8, 16, 32
+CFLAG_GROUP_CAP, CFLAG_CAND_CAP, CFLAG_TIE = 1, 2, 4
+
+_p = C.c_void_p
+_i = C.c_int
+_i64 = C.c_int64
+_sz = C.c_size_t
+_d = C.c_double
+
+# name -> (restype, argtypes); mirrors include/mocap_b200.h declaration by declaration
+SIGNATURES = {
+    "mocap_status_string": (C.c_char_p, [_i]),
+    "mocap_abi_version": (_i, []),
+    "mocap_undistort_table_bytes": (_sz, [_i, _i]),
+    "mocap_undistort_table_build": (_i, [_p, _p, _i, _i, _p, _sz, _p]),
+    "mocap_detect_workspace_bytes": (_sz, [_i, _i, _i, _i, _i, _i]),
+    "mocap_detect_batch": (_i, [_p, _i, _i, _i, _i64, _p, _i, _d, _d, _i, _i, _i,
+                                _p, _p, _p, _p, _p, _p, _p, _p, _p, _p, _sz, _p]),
+    "mocap_filter_batch": (_i, [_p, _i, _i, _i, _i64, _p, _i, _p, _p, _sz, _p]),
+    "mocap_blur5_batch": (_i, [_p, _i, _i, _i, _p, _p]),
+    "mocap_undistort_batch": (_i, [_p, _i, _i, _i, _p, _p, _p]),
+    "mocap_triangulate_batch": (_i, [_p, _p, _p, _i, _i64, _i, _p, _p, _p]),
+    "mocap_reproject_batch": (_i, [_p, _p, _p, _p, _i, _i64, _i, _p, _p]),
+    "mocap_correspond_workspace_bytes": (_sz, [_i, _i, _i, _i]),
+    "mocap_correspond_batch": (_i, [_p, _p, _i, _i, _i, _p, _p, _d, _i, _i, _i,
+                                    _p, _p, _p, _p, _p, _p, _p, _p, _sz, _p]),
+}
+
+
+class MocapError(RuntimeError):
+    pass
+
+
+def load(path: str | None = None) -> C.CDLL:
+    """dlopen the C-ABI library and attach the prototypes.  Raises if it is not there (no fallback)."""
+    path = path or os.environ.get("MOCAP_B200_LIB", DEFAULT_LIB)
+    if not os.path.exists(path):
+        raise MocapError(f"{path} not found: build it with `python -m mocapv2_b200.build` (nvcc, sm_100a); "
+                         "there is no CPU implementation of this path")
+    lib = C.CDLL(path)
+    for name, (res, args) in SIGNATURES.items():
+        fn = getattr(lib, name)          # AttributeError if the library does not export a declared symbol
+        fn.restype = res
+        fn.argtypes = args
+    if lib.mocap_abi_version() != ABI_VERSION:
+        raise MocapError(f"ABI mismatch: library {lib.mocap_abi_version()} != binding {ABI_VERSION}")
+    return lib
+
+
+def check(lib, status: int, what: str):
+    if status != OK:
+        raise MocapError(f"{what}: {lib.mocap_status_string(status).decode()} ({status})")

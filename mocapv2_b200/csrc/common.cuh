@@ -1,0 +1,83 @@
+// Shared device/host helpers for libmocap_b200 (sm_100a only).
+#pragma once
+#ifdef MOCAP_EMU
+// tests/emu builds this same source with g++ for the GPU-less CPU test-suite (never part of the product library)
+#include "cuda_emu.h"
+#define LAUNCH(kernel, grid, block, smem, stream, ...) \
+    emu::launch(dim3(grid), dim3(block), (size_t)(smem), [=]() { kernel(__VA_ARGS__); })
+#define DYN_SHARED(name) unsigned char* name = emu::dyn_smem()
+#else
+#include <cuda_runtime.h>
+#define LAUNCH(kernel, grid, block, smem, stream, ...) kernel<<<grid, block, smem, stream>>>(__VA_ARGS__)
+#define DYN_SHARED(name) extern __shared__ __align__(16) unsigned char name[]
+#endif
+#include <stdint.h>
+#include "../../include/mocap_b200.h"
+
+#define MOCAP_ABI_VERSION 1
+
+#define TILE 32              // output tile edge (pixels) == bits per packed word
+#define HALO_U 4             // undistorted pixels needed around an output tile (2 blur + 2 majority)
+#define REG_U (TILE + 2 * HALO_U)   // 40
+#define REG_B (TILE + 4)            // 36
+
+#define CUDA_TRY(expr)                                  \
+    do {                                                \
+        cudaError_t _e = (expr);                        \
+        if (_e != cudaSuccess) return MOCAP_ERR_CUDA;   \
+    } while (0)
+
+static inline int cdiv(int a, int b) { return (a + b - 1) / b; }
+static inline size_t align_up(size_t x, size_t a) { return (x + a - 1) / a * a; }
+
+// ---------------------------------------------------------------------------------------------------------
+// Undistortion table (built by mocap_undistort_table_build, consumed by the detection kernels)
+// ---------------------------------------------------------------------------------------------------------
+struct TableHeader {
+    uint32_t magic;
+    int32_t H, W;
+    int32_t TX, TY;          // output tiles (32x32) == source cells
+    int32_t overflow;        // a displacement did not fit the int16 fixed-point encoding
+    int32_t n_zero;          // pixels whose source lies fully outside the frame
+    int32_t pad;
+    uint64_t off_map;        // int32 [H][W]: low16 = iu - 32*x, high16 = iv - 32*y (1/32 px), 0x80008000 = outside
+    uint64_t off_cell;       // int32 [TY][TX][4]: output-tile rectangle (tx0,ty0,tx1,ty1) that samples this source cell
+    uint64_t off_tile;       // int32 [TY][TX][8]: source box sx0,sy0,sx1,sy1 and displacement bounds dxmin,dxmax,dymin,dymax
+    uint64_t total_bytes;
+};
+#define TABLE_MAGIC 0x4d43424bu
+#define MAP_OUTSIDE 0x80008000u
+
+struct TableView {
+    const int32_t* map;
+    const int32_t* cell;
+    const int32_t* tile;
+    int H, W, TX, TY;
+};
+
+// workspace slices of the filter stage (carved by api.cu)
+struct FilterWs {
+    uint32_t* active;    // [n][TY][TXW] bitmap of output tiles that can hold foreground
+    uint32_t* list;      // [n * TX * TY] work list: frame * (TX*TY) + tile
+    int* counters;       // [0] = list length, [1] = work cursor
+    uint32_t* bits;      // [n][H][TX] packed binary image (only active tiles and their neighbours are defined)
+    uint32_t* fg_tiles;  // [n][max_fg] tiles that hold at least one foreground pixel
+    int* n_fg;           // [n]
+};
+
+// ---------------------------------------------------------------------------------------------------------
+// Packed binary image access: word (y, x>>5), bit x&31 (LSB = leftmost pixel)
+// ---------------------------------------------------------------------------------------------------------
+struct BitImg {
+    const uint32_t* p;
+    int W, H, WPR;
+    __device__ __forceinline__ int get(int x, int y) const {
+        if ((unsigned)x >= (unsigned)W || (unsigned)y >= (unsigned)H) return 0;
+        return (p[(size_t)y * WPR + (x >> 5)] >> (x & 31)) & 1;
+    }
+};
+
+// 8-neighbour codes: 0=E 1=NE 2=N 3=NW 4=W 5=SW 6=S 7=SE (y grows downwards)
+// dx+1 = {2,2,1,0,0,0,1,2}, dy+1 = {1,0,0,0,1,2,2,2} packed two bits per direction
+__device__ __forceinline__ int dir_dx(int d) { return ((0x901A >> (2 * d)) & 3) - 1; }
+__device__ __forceinline__ int dir_dy(int d) { return ((0xA901 >> (2 * d)) & 3) - 1; }

@@ -1,0 +1,564 @@
+// Blob stage of _find_dot: packed binary image -> 8-connected blobs, contours, centroids.
+//
+// Replaces lib/ImageOperations.py:41-65 of the reference for a batch of frames:
+//     cv.findContours(RETR_TREE, CHAIN_APPROX_SIMPLE) -> contourArea / arcLength filter -> cv.moments centroid
+// One CTA per frame, working on the sparse foreground tiles left by filter_tiles:
+//   runs        horizontal foreground runs extracted from the 32-bit row words (ffs/popc), bucketed by row
+//   labelling   union-find over runs (8-connectivity, smaller raster index wins) -> blob = root run, whose
+//               first pixel is the blob's raster-first pixel = start of its outer border;
+//               per-blob pixel sums m00/m10/m01 accumulated with atomics (closed form per run)
+//   holes       every run's right edge starts a short Suzuki-Abe walk; the walk that returns to its own
+//               start without meeting a smaller west/east edge of the same border is a hole border start
+//   contours    one thread per border: border following with CHAIN_APPROX_SIMPLE vertices, Green sums
+//               a00/a10/a01 in int64, perimeter = sum of float32 sqrt per segment (exact in double)
+//   tree/order  parents from the nearest foreground pixel to the left (Suzuki Table 1), output order =
+//               pre-order with siblings in reverse raster order, then the reference's filter and centroid.
+#include "common.cuh"
+
+#define BLOB_THREADS 256
+#define MAX_DEPTH 8
+
+struct BlobWs {                 // per-frame slices of the workspace
+    int* rowptr;                // [H + 2]
+    int* rowfill;               // [H + 1]
+    uint32_t* run_xx;           // [max_runs] x0 | x1 << 16
+    uint16_t* run_y;            // [max_runs]
+    int* run_parent;            // [max_runs]
+    int* run_rank;              // [max_runs] blob rank of a root run (exclusive scan of root flags)
+    unsigned long long* run_sum;// [max_runs][3] pixel sums accumulated at the root run
+    // contours
+    int* c_start;               // [max_contours] start pixel index y*W+x
+    int* c_type;                // 0 outer, 1 hole
+    int* c_comp;                // blob rank owning the border
+    int* c_parent;              // contour index, -1 top level, <= -2: same parent as outer contour (-2 - v)
+    long long* c_a;             // [max_contours][3] a00 a10 a01
+    double* c_per;              // perimeter
+    int* c_n;                   // chain length
+    int* c_rank;                // output position
+    int* c_keep;
+    int* holes_of;              // [max_contours] number of holes per blob
+};
+
+__device__ __forceinline__ int uf_find(const int* parent, int x)
+{
+    int p = parent[x];
+    while (p != x) { x = p; p = parent[x]; }
+    return x;
+}
+__device__ __forceinline__ void uf_union(int* parent, int a, int b)
+{
+    for (;;) {
+        a = uf_find(parent, a);
+        b = uf_find(parent, b);
+        if (a == b) return;
+        if (a < b) { int t = a; a = b; b = t; }       // a > b: hang a under b
+        int old = atomicMin(&parent[a], b);
+        if (old == a) return;
+        a = old;                                      // somebody else re-parented a meanwhile
+    }
+}
+
+// Walker state for Suzuki-Abe border following started from the west (side 4) or east (side 0) edge of a pixel.
+struct Walk {
+    int x0, y0;      // start pixel
+    int x1, y1;      // its predecessor on the border
+    int x, y;        // current pixel
+    int s;           // direction from current pixel to the previous one
+    bool single;
+};
+
+__device__ __forceinline__ void walk_init(const BitImg& im, Walk& w, int x, int y, int side)
+{
+    w.x0 = x; w.y0 = y; w.x = x; w.y = y;
+    int s = side;
+    w.single = true;
+    for (int k = 0; k < 7; ++k) {
+        s = (s + 7) & 7;                                     // clockwise
+        if (im.get(x + dir_dx(s), y + dir_dy(s))) { w.single = false; break; }
+    }
+    w.s = s;
+    w.x1 = x + dir_dx(s); w.y1 = y + dir_dy(s);
+}
+
+// One step: counter-clockwise search from the previous pixel; returns the step direction, `zeros` = bitmask of
+// neighbour directions examined and found empty.  Advances the walker.  `done` when back at the start.
+__device__ __forceinline__ int walk_step(const BitImg& im, Walk& w, unsigned& zeros, bool& done)
+{
+    int d = w.s;
+    zeros = 0;
+    int nx = w.x, ny = w.y;
+    for (int k = 0; k < 8; ++k) {
+        d = (d + 1) & 7;
+        nx = w.x + dir_dx(d); ny = w.y + dir_dy(d);
+        if (im.get(nx, ny)) break;
+        zeros |= 1u << d;
+    }
+    done = (nx == w.x0 && ny == w.y0 && w.x == w.x1 && w.y == w.y1);
+    w.x = nx; w.y = ny;
+    w.s = (d + 4) & 7;
+    return d;
+}
+
+#define WALK_BUDGET (1 << 22)
+
+// key of a west/east edge: 2 * pixel index + (east ? 1 : 0)
+__device__ __forceinline__ long long edge_key(int x, int y, int W, int east) { return 2LL * ((long long)y * W + x) + east; }
+
+// Walk the border owning edge (x, y, side).  mode 0: stop as soon as a smaller west/east edge of the same border is
+// seen (returns 1 if the start edge is the border's smallest edge).  mode 1: full loop, *min_key = smallest edge key.
+__device__ int walk_min_edge(const BitImg& im, int x, int y, int side, int mode, long long* min_key, int* overflow)
+{
+    const int W = im.W;
+    long long key0 = edge_key(x, y, W, side == 0);
+    long long best = key0;
+    Walk w; walk_init(im, w, x, y, side);
+    if (w.single) { if (min_key) *min_key = edge_key(x, y, W, 0); return side == 4; }   // isolated pixel: its west edge is smaller
+    for (int step = 0; step < WALK_BUDGET; ++step) {
+        int cx = w.x, cy = w.y;
+        unsigned zeros; bool done;
+        walk_step(im, w, zeros, done);
+        if (zeros & (1u << 4)) { long long k = edge_key(cx, cy, W, 0); if (k < best) { best = k; if (!mode) return 0; } }
+        if (zeros & (1u << 0)) { long long k = edge_key(cx, cy, W, 1); if (k < best) { best = k; if (!mode) return 0; } }
+        if (done) { if (min_key) *min_key = best; return best == key0; }
+    }
+    *overflow = 1;
+    if (min_key) *min_key = best;
+    return 0;
+}
+
+// Full trace of a border from its start edge: Green sums over the CHAIN_APPROX_SIMPLE vertices, perimeter, length.
+__device__ void trace_contour(const BitImg& im, int x, int y, int side, long long* a, double* per, int* n_chain, int* overflow)
+{
+    Walk w; walk_init(im, w, x, y, side);
+    if (w.single) { a[0] = a[1] = a[2] = 0; *per = 0.0; *n_chain = 1; return; }
+    long long a00 = 0, a10 = 0, a01 = 0;
+    double perim = 0.0;
+    int n = 0;
+    int prev_dir = w.s ^ 4;             // direction of the closing step (predecessor -> start)
+    bool have_v = false;
+    int vx = 0, vy = 0, fx = 0, fy = 0; // previous vertex, first vertex
+    for (int step = 0; step < WALK_BUDGET; ++step) {
+        int cx = w.x, cy = w.y;
+        unsigned zeros; bool done;
+        int d = walk_step(im, w, zeros, done);
+        ++n;
+        if (d != prev_dir) {            // direction change: (cx, cy) is a vertex
+            if (have_v) {
+                long long dxy = (long long)vx * cy - (long long)cx * vy;
+                a00 += dxy; a10 += dxy * (vx + cx); a01 += dxy * (vy + cy);
+                float ddx = (float)(cx - vx), ddy = (float)(cy - vy);
+                perim += (double)__fsqrt_rn(__fadd_rn(__fmul_rn(ddx, ddx), __fmul_rn(ddy, ddy)));
+            } else { fx = cx; fy = cy; have_v = true; }
+            vx = cx; vy = cy;
+        }
+        prev_dir = d;
+        if (done) {
+            if (have_v) {               // closing segment last vertex -> first vertex
+                long long dxy = (long long)vx * fy - (long long)fx * vy;
+                a00 += dxy; a10 += dxy * (vx + fx); a01 += dxy * (vy + fy);
+                float ddx = (float)(fx - vx), ddy = (float)(fy - vy);
+                float q = __fadd_rn(__fmul_rn(ddx, ddx), __fmul_rn(ddy, ddy));
+                if (q > 0.f) perim += (double)__fsqrt_rn(q);
+            }
+            a[0] = a00; a[1] = a10; a[2] = a01; *per = perim; *n_chain = n;
+            return;
+        }
+    }
+    *overflow = 1;
+    a[0] = a[1] = a[2] = 0; *per = 0.0; *n_chain = n;
+}
+
+// block-wide exclusive scan helper over an int array in global memory (in place), returns total in *total_s (shared)
+__device__ void block_exclusive_scan(int* data, int n, int* sh /*[BLOB_THREADS + 1]*/)
+{
+    const int tid = threadIdx.x, nt = blockDim.x;
+    int chunk = (n + nt - 1) / nt;
+    int b = tid * chunk, e = min(b + chunk, n);
+    int s = 0;
+    for (int k = b; k < e; ++k) s += data[k];
+    sh[tid] = s;
+    __syncthreads();
+    if (tid == 0) {
+        int acc = 0;
+        for (int k = 0; k < nt; ++k) { int v = sh[k]; sh[k] = acc; acc += v; }
+        sh[nt] = acc;
+    }
+    __syncthreads();
+    int acc = sh[tid];
+    for (int k = b; k < e; ++k) { int v = data[k]; data[k] = acc; acc += v; }
+    __syncthreads();
+}
+
+struct BlobParams {
+    int H, W, TX;
+    int max_fg, max_runs, max_blobs, max_contours;
+    double min_area, min_circ;
+};
+
+__global__ void __launch_bounds__(BLOB_THREADS) blobs_kernel(
+    const uint32_t* __restrict__ bits_all, const uint32_t* __restrict__ fg_tiles_all, const int* __restrict__ n_fg_all,
+    BlobParams P, char* __restrict__ ws_base, size_t ws_stride,
+    int32_t* __restrict__ out_xy, int32_t* __restrict__ out_count, int32_t* __restrict__ out_flags,
+    int64_t* __restrict__ out_blob_sums, int32_t* __restrict__ out_blob_count,
+    double* __restrict__ out_contours, int32_t* __restrict__ out_contour_count,
+    int32_t* __restrict__ out_labels)
+{
+    const int f = blockIdx.x, tid = threadIdx.x, nt = blockDim.x;
+    const int H = P.H, W = P.W, TX = P.TX;
+    __shared__ int sh[BLOB_THREADS + 1];
+    __shared__ int s_nruns, s_nblobs, s_nholes, s_flag, s_ncont;
+
+    // carve the per-frame workspace
+    char* p = ws_base + (size_t)f * ws_stride;
+    BlobWs w;
+    auto take = [&](size_t bytes) { char* r = p; p += (bytes + 15) & ~(size_t)15; return r; };
+    w.rowptr = (int*)take((size_t)(H + 2) * 4);
+    w.rowfill = (int*)take((size_t)(H + 2) * 4);
+    w.run_xx = (uint32_t*)take((size_t)P.max_runs * 4);
+    w.run_y = (uint16_t*)take((size_t)P.max_runs * 2);
+    w.run_parent = (int*)take((size_t)P.max_runs * 4);
+    w.run_rank = (int*)take((size_t)(P.max_runs + 1) * 4);
+    w.run_sum = (unsigned long long*)take((size_t)P.max_runs * 24);
+    w.c_start = (int*)take((size_t)P.max_contours * 4);
+    w.c_type = (int*)take((size_t)P.max_contours * 4);
+    w.c_comp = (int*)take((size_t)P.max_contours * 4);
+    w.c_parent = (int*)take((size_t)P.max_contours * 4);
+    w.c_a = (long long*)take((size_t)P.max_contours * 24);
+    w.c_per = (double*)take((size_t)P.max_contours * 8);
+    w.c_n = (int*)take((size_t)P.max_contours * 4);
+    w.c_rank = (int*)take((size_t)P.max_contours * 4);
+    w.c_keep = (int*)take((size_t)P.max_contours * 4);
+    w.holes_of = (int*)take((size_t)P.max_contours * 4);
+
+    const uint32_t* bits = bits_all + (size_t)f * H * TX;
+    const uint32_t* fg_tiles = fg_tiles_all + (size_t)f * P.max_fg;
+    BitImg im; im.p = bits; im.W = W; im.H = H; im.WPR = TX;
+    int n_t = min(n_fg_all[f], P.max_fg);
+
+    if (tid == 0) { s_flag = 0; s_nholes = 0; }
+    for (int y = tid; y < H + 2; y += nt) w.rowptr[y] = 0;
+    __syncthreads();
+
+    // ---- runs per row --------------------------------------------------------------------------------------
+    for (int it = tid; it < n_t * TILE; it += nt) {
+        int t = fg_tiles[it >> 5], r = it & 31;
+        int ty = t / TX, tx = t - ty * TX, y = ty * TILE + r;
+        if (y >= H) continue;
+        uint32_t v = bits[(size_t)y * TX + tx];
+        int n = __popc(v & ~(v << 1));
+        if (n) atomicAdd(&w.rowptr[y], n);
+    }
+    __syncthreads();
+    block_exclusive_scan(w.rowptr, H + 1, sh);
+    int n_runs = w.rowptr[H];
+    if (n_runs > P.max_runs) {
+        if (tid == 0) {
+            out_flags[f] |= MOCAP_FLAG_RUN_OVERFLOW;
+            out_count[f] = 0;
+            if (out_blob_count) out_blob_count[f] = 0;
+            if (out_contour_count) out_contour_count[f] = 0;
+        }
+        return;
+    }
+    for (int y = tid; y < H + 1; y += nt) w.rowfill[y] = w.rowptr[y];
+    __syncthreads();
+    for (int it = tid; it < n_t * TILE; it += nt) {
+        int t = fg_tiles[it >> 5], r = it & 31;
+        int ty = t / TX, tx = t - ty * TX, y = ty * TILE + r;
+        if (y >= H) continue;
+        uint32_t v = bits[(size_t)y * TX + tx];
+        int n = __popc(v & ~(v << 1));
+        if (!n) continue;
+        int slot = atomicAdd(&w.rowfill[y], n);
+        while (v) {
+            int a = __ffs(v) - 1;
+            uint32_t sh_v = v >> a;
+            int len = (sh_v == 0xffffffffu) ? 32 : (__ffs(~sh_v) - 1);
+            uint32_t mask = (len >= 32) ? 0xffffffffu : (((1u << len) - 1u) << a);
+            v &= ~mask;
+            int x0 = tx * TILE + a, x1 = x0 + len - 1;
+            w.run_xx[slot] = (uint32_t)x0 | ((uint32_t)x1 << 16);
+            w.run_y[slot] = (uint16_t)y;
+            ++slot;
+        }
+    }
+    __syncthreads();
+    // sort the (few) runs of every row by x0
+    for (int y = tid; y < H; y += nt) {
+        int b = w.rowptr[y], e = w.rowptr[y + 1];
+        for (int i = b + 1; i < e; ++i) {
+            uint32_t v = w.run_xx[i];
+            int k = i - 1;
+            while (k >= b && (w.run_xx[k] & 0xffff) > (v & 0xffff)) { w.run_xx[k + 1] = w.run_xx[k]; --k; }
+            w.run_xx[k + 1] = v;
+        }
+    }
+    for (int r = tid; r < n_runs; r += nt) {
+        w.run_parent[r] = r;
+        w.run_sum[3 * r] = 0; w.run_sum[3 * r + 1] = 0; w.run_sum[3 * r + 2] = 0;
+    }
+    __syncthreads();
+
+    // ---- labelling: union-find over runs (8-connectivity) -------------------------------------------------------
+    for (int r = tid; r < n_runs; r += nt) {
+        int y = w.run_y[r];
+        uint32_t xx = w.run_xx[r];
+        int x0 = xx & 0xffff, x1 = xx >> 16;
+        if (r > w.rowptr[y] && (int)(w.run_xx[r - 1] >> 16) + 1 == x0) uf_union(w.run_parent, r, r - 1);
+        if (y > 0) {
+            for (int k = w.rowptr[y - 1]; k < w.rowptr[y]; ++k) {
+                uint32_t kk = w.run_xx[k];
+                int k0 = kk & 0xffff, k1 = kk >> 16;
+                if (k0 > x1 + 1) break;
+                if (k1 >= x0 - 1) uf_union(w.run_parent, r, k);
+            }
+        }
+    }
+    __syncthreads();
+    for (int r = tid; r < n_runs; r += nt) {
+        int root = uf_find(w.run_parent, r);
+        w.run_parent[r] = root;          // races only write the same final value or an ancestor -> still valid
+    }
+    __syncthreads();
+    for (int r = tid; r < n_runs; r += nt) {
+        int root = uf_find(w.run_parent, r);
+        w.run_parent[r] = root;
+        uint32_t xx = w.run_xx[r];
+        unsigned long long x0 = xx & 0xffff, x1 = xx >> 16, len = x1 - x0 + 1, y = w.run_y[r];
+        atomicAdd(&w.run_sum[3 * root], len);
+        atomicAdd(&w.run_sum[3 * root + 1], (x0 + x1) * len / 2);
+        atomicAdd(&w.run_sum[3 * root + 2], y * len);
+        w.run_rank[r] = (root == r) ? 1 : 0;
+    }
+    if (tid == 0) w.run_rank[n_runs] = 0;
+    __syncthreads();
+    block_exclusive_scan(w.run_rank, n_runs + 1, sh);
+    const int n_blobs = w.run_rank[n_runs];
+    if (tid == 0) { s_nblobs = n_blobs; }
+    if (out_blob_count && tid == 0) out_blob_count[f] = n_blobs;
+    if (n_blobs > P.max_contours) {
+        if (tid == 0) {
+            out_flags[f] |= MOCAP_FLAG_CONTOUR_OVERFLOW;
+            out_count[f] = 0;
+            if (out_contour_count) out_contour_count[f] = 0;
+        }
+        return;
+    }
+    // blob records + outer contours (index = blob rank)
+    for (int r = tid; r < n_runs; r += nt) {
+        if (w.run_parent[r] != r) continue;
+        int k = w.run_rank[r];
+        if (out_blob_sums && k < P.max_blobs)
+            for (int q = 0; q < 3; ++q) out_blob_sums[((size_t)f * P.max_blobs + k) * 3 + q] = (int64_t)w.run_sum[3 * r + q];
+        w.c_start[k] = (int)w.run_y[r] * W + (int)(w.run_xx[r] & 0xffff);
+        w.c_type[k] = 0;
+        w.c_comp[k] = k;
+        w.holes_of[k] = 0;
+    }
+    if (out_labels) {
+        int32_t* lab = out_labels + (size_t)f * H * W;
+        for (int r = tid; r < n_runs; r += nt) {
+            int k = w.run_rank[w.run_parent[r]] + 1;
+            uint32_t xx = w.run_xx[r];
+            int y = w.run_y[r];
+            for (int x = xx & 0xffff; x <= (int)(xx >> 16); ++x) lab[(size_t)y * W + x] = k;
+        }
+    }
+    __syncthreads();
+
+    // ---- hole borders: canonical east edges ---------------------------------------------------------------------
+    for (int r = tid; r < n_runs; r += nt) {
+        int y = w.run_y[r];
+        uint32_t xx = w.run_xx[r];
+        int x1 = xx >> 16;
+        if (r + 1 < w.rowptr[y + 1] && (int)(w.run_xx[r + 1] & 0xffff) == x1 + 1) continue;   // run continues in the next word
+        int ovf = 0;
+        if (walk_min_edge(im, x1, y, 0, 0, nullptr, &ovf)) {
+            int k = n_blobs + atomicAdd(&s_nholes, 1);
+            if (k < P.max_contours) {
+                int comp = w.run_rank[w.run_parent[r]];
+                w.c_start[k] = y * W + x1;
+                w.c_type[k] = 1;
+                w.c_comp[k] = comp;
+                atomicAdd(&w.holes_of[comp], 1);
+            }
+        }
+        if (ovf) atomicOr(&s_flag, MOCAP_FLAG_TRACE_OVERFLOW);
+    }
+    __syncthreads();
+    int n_cont = n_blobs + s_nholes;
+    if (n_cont > P.max_contours || (s_flag & MOCAP_FLAG_TRACE_OVERFLOW)) {
+        if (tid == 0) {
+            out_flags[f] |= (n_cont > P.max_contours ? MOCAP_FLAG_CONTOUR_OVERFLOW : 0) | s_flag;
+            out_count[f] = 0;
+            if (out_contour_count) out_contour_count[f] = 0;
+        }
+        return;
+    }
+
+    // ---- trace every border -------------------------------------------------------------------------------------
+    for (int c = tid; c < n_cont; c += nt) {
+        int st = w.c_start[c];
+        int ovf = 0;
+        trace_contour(im, st % W, st / W, w.c_type[c] ? 0 : 4, &w.c_a[3 * c], &w.c_per[c], &w.c_n[c], &ovf);
+        if (ovf) atomicOr(&s_flag, MOCAP_FLAG_TRACE_OVERFLOW);
+    }
+    // ---- parents ------------------------------------------------------------------------------------------------
+    for (int c = tid; c < n_cont; c += nt) {
+        if (w.c_type[c]) { w.c_parent[c] = w.c_comp[c]; continue; }
+        // outer border: nearest foreground pixel to the left of the blob's first pixel, on the same row
+        int st = w.c_start[c], y = st / W, x0 = st - y * W;
+        // locate the root run: binary search not needed, rows hold few runs
+        int b = w.rowptr[y], e = w.rowptr[y + 1], r = b;
+        while (r < e && (int)(w.run_xx[r] & 0xffff) != x0) ++r;
+        if (r == b) { w.c_parent[c] = -1; continue; }
+        int q = r - 1;                                    // run ending left of us
+        int other = w.run_rank[w.run_parent[q]];          // blob owning it
+        if (w.holes_of[other] == 0) { w.c_parent[c] = -2 - other; continue; }
+        long long mk; int ovf = 0;
+        walk_min_edge(im, (int)(w.run_xx[q] >> 16), y, 0, 1, &mk, &ovf);
+        if (ovf) atomicOr(&s_flag, MOCAP_FLAG_TRACE_OVERFLOW);
+        if ((mk & 1) == 0) { w.c_parent[c] = -2 - other; continue; }     // smallest edge is a west edge: outer border of `other`
+        int hole_start = (int)(mk >> 1), par = -1;
+        for (int h = n_blobs; h < n_cont; ++h) if (w.c_start[h] == hole_start) { par = h; break; }
+        w.c_parent[c] = par;
+    }
+    __syncthreads();
+    for (int c = tid; c < n_blobs; c += nt) {             // resolve "same parent as the blob on my left"
+        int v = w.c_parent[c], guard = 0;
+        while (v <= -2 && guard++ < n_blobs) v = w.c_parent[-2 - v];
+        w.c_rank[c] = v;                                  // park the resolved parent
+    }
+    __syncthreads();
+    for (int c = tid; c < n_blobs; c += nt) w.c_parent[c] = w.c_rank[c];
+    __syncthreads();
+
+    // ---- output order: pre-order, siblings by descending start pixel ------------------------------------------------
+    // ancestor chain of start keys, root first; u precedes v iff at the first difference u's key is larger,
+    // or u's chain is a proper prefix of v's.
+    bool deep = false;
+    for (int c = tid; c < n_cont; c += nt) {
+        int chain_c[MAX_DEPTH], dc = 0;
+        for (int v = c; v >= 0; v = w.c_parent[v]) { if (dc == MAX_DEPTH) { deep = true; break; } chain_c[dc++] = w.c_start[v]; }
+        int before = 0;
+        for (int u = 0; u < n_cont && !deep; ++u) {
+            if (u == c) continue;
+            int chain_u[MAX_DEPTH], du = 0;
+            for (int v = u; v >= 0; v = w.c_parent[v]) { if (du == MAX_DEPTH) { deep = true; break; } chain_u[du++] = w.c_start[v]; }
+            if (deep) break;
+            // compare from the root end
+            int iu = du - 1, ic = dc - 1, res = 0;    // res: 1 = u first, -1 = c first
+            while (iu >= 0 && ic >= 0) {
+                if (chain_u[iu] != chain_c[ic]) { res = chain_u[iu] > chain_c[ic] ? 1 : -1; break; }
+                --iu; --ic;
+            }
+            if (res == 0) res = (iu < 0) ? 1 : -1;    // the shorter chain is the ancestor
+            before += res > 0;
+        }
+        w.c_rank[c] = before;
+    }
+    if (deep) atomicOr(&s_flag, MOCAP_FLAG_DEPTH_OVERFLOW);
+    __syncthreads();
+    if (s_flag & MOCAP_FLAG_DEPTH_OVERFLOW) {
+        // slow, fully general path: one thread walks the tree
+        if (tid == 0) {
+            int pos = 0, cur = -1;                 // cur = node whose children we enumerate; -1 = top level
+            // iterative DFS without a stack: c_keep temporarily stores "largest child key already emitted"
+            for (int c = 0; c < n_cont; ++c) w.c_keep[c] = 0x7fffffff;
+            int top_limit = 0x7fffffff;
+            while (true) {
+                int limit = cur < 0 ? top_limit : w.c_keep[cur];
+                int best = -1;
+                for (int c = 0; c < n_cont; ++c)
+                    if (w.c_parent[c] == cur && w.c_start[c] < limit && (best < 0 || w.c_start[c] > w.c_start[best])) best = c;
+                if (best >= 0) {
+                    if (cur < 0) top_limit = w.c_start[best]; else w.c_keep[cur] = w.c_start[best];
+                    w.c_rank[best] = pos++;
+                    cur = best;
+                } else {
+                    if (cur < 0) break;
+                    cur = w.c_parent[cur];
+                }
+            }
+        }
+        __syncthreads();
+    }
+
+    // ---- the reference's filter and centroid (ImageOperations.py:43-65) -------------------------------------------------
+    for (int c = tid; c < n_cont; c += nt) {
+        long long a00 = w.c_a[3 * c];
+        double area = (double)(a00 < 0 ? -a00 : a00) * 0.5;
+        double per = w.c_per[c];
+        int keep = 0;
+        if (per != 0.0) {
+            double circ = __ddiv_rn(__dmul_rn(12.566370614359172, area), __dmul_rn(per, per));
+            keep = (circ > P.min_circ && area > P.min_area) ? 1 : 0;
+        }
+        if (a00 == 0) keep = 0;                          // moments["m00"] == 0 -> no centroid
+        w.c_keep[c] = keep;
+    }
+    __syncthreads();
+    if (tid == 0) s_ncont = 0;
+    __syncthreads();
+    for (int c = tid; c < n_cont; c += nt) {
+        int rank = w.c_rank[c];
+        long long a00 = w.c_a[3 * c], a10 = w.c_a[3 * c + 1], a01 = w.c_a[3 * c + 2];
+        if (out_contours && rank < P.max_contours) {
+            double* o = out_contours + ((size_t)f * P.max_contours + rank) * 8;
+            int par = w.c_parent[c];
+            o[0] = (double)a00; o[1] = (double)a10; o[2] = (double)a01; o[3] = w.c_per[c];
+            o[4] = (double)w.c_type[c]; o[5] = (double)(par >= 0 ? w.c_rank[par] : -1);
+            o[6] = (double)w.c_keep[c]; o[7] = (double)w.c_start[c];
+        }
+        if (!w.c_keep[c]) continue;
+        int pos = 0;
+        for (int u = 0; u < n_cont; ++u) pos += (w.c_keep[u] && w.c_rank[u] < rank);
+        atomicAdd(&s_ncont, 1);
+        if (pos < P.max_blobs) {
+            double sgn = a00 > 0 ? 1.0 : -1.0;
+            double m00 = __dmul_rn((double)a00, sgn * 0.5);
+            double m10 = __dmul_rn((double)a10, sgn * 0.16666666666666666);
+            double m01 = __dmul_rn((double)a01, sgn * 0.16666666666666666);
+            out_xy[((size_t)f * P.max_blobs + pos) * 2 + 0] = (int32_t)__ddiv_rn(m10, m00);   // int(): toward zero
+            out_xy[((size_t)f * P.max_blobs + pos) * 2 + 1] = (int32_t)__ddiv_rn(m01, m00);
+        }
+    }
+    __syncthreads();
+    if (tid == 0) {
+        int kept = s_ncont;
+        int fl = s_flag;
+        if (kept > P.max_blobs) { fl |= MOCAP_FLAG_BLOB_OVERFLOW; kept = P.max_blobs; }
+        out_count[f] = kept;
+        out_flags[f] |= fl;
+        if (out_contour_count) out_contour_count[f] = n_cont;
+    }
+}
+
+size_t blob_ws_stride(int H, int max_runs, int max_contours)
+{
+    size_t b = 0;
+    auto add = [&](size_t bytes) { b += (bytes + 15) & ~(size_t)15; };
+    add((size_t)(H + 2) * 4); add((size_t)(H + 2) * 4);
+    add((size_t)max_runs * 4); add((size_t)max_runs * 2); add((size_t)max_runs * 4); add((size_t)(max_runs + 1) * 4);
+    add((size_t)max_runs * 24);
+    for (int k = 0; k < 4; ++k) add((size_t)max_contours * 4);
+    add((size_t)max_contours * 24); add((size_t)max_contours * 8);
+    for (int k = 0; k < 4; ++k) add((size_t)max_contours * 4);
+    return (b + 255) & ~(size_t)255;
+}
+
+int launch_blobs(const uint32_t* bits, const uint32_t* fg_tiles, const int* n_fg, int n, int H, int W, int TX,
+                 int max_fg, int max_runs, int max_blobs, int max_contours, double min_area, double min_circ,
+                 char* ws, size_t ws_stride,
+                 int32_t* out_xy, int32_t* out_count, int32_t* out_flags,
+                 int64_t* out_blob_sums, int32_t* out_blob_count, double* out_contours, int32_t* out_contour_count,
+                 int32_t* out_labels, cudaStream_t s)
+{
+    BlobParams P;
+    P.H = H; P.W = W; P.TX = TX; P.max_fg = max_fg; P.max_runs = max_runs; P.max_blobs = max_blobs;
+    P.max_contours = max_contours; P.min_area = min_area; P.min_circ = min_circ;
+    LAUNCH(blobs_kernel, n, BLOB_THREADS, 0, s, bits, fg_tiles, n_fg, P, ws, ws_stride, out_xy, out_count, out_flags,
+                                            out_blob_sums, out_blob_count, out_contours, out_contour_count, out_labels);
+    CUDA_TRY(cudaGetLastError());
+    return MOCAP_OK;
+}

@@ -1,0 +1,617 @@
+// Detection front end: frames (u8, HBM) -> filtered binary image (bit-packed) for _find_dot.
+//
+// Replaces, for a batch of frames, lib/ImageOperations.py:38-40 of the reference:
+//     cv.undistort(img, K0, dist0) -> fast_cuda_blur(.,5) -> cv.threshold(.,216.75) -> cv.medianBlur(.,5)
+// with the exact integer semantics pinned in oracle/restate.py.
+//
+// Design (sparse, HBM-bound):
+//   scan_hot      streams every source byte once (16-byte loads) and marks the output tiles that a source
+//                 cell holding a pixel > thresh can influence.  A filtered pixel can only be set if some
+//                 source tap within reach is > thresh (bilinear weights sum to 1, box mean <= max), so
+//                 unmarked tiles are exactly zero and are never touched again.
+//   compact       turns the per-frame active-tile bitmaps into a work list.
+//   filter_tiles  one warp per active 32x32 tile: exact hot bounding box of the tile's source window,
+//                 fixed-point remap + 5x5 floor-mean threshold + 5x5 majority only inside that box.
+#include "common.cuh"
+
+// ---------------------------------------------------------------------------------------------------------
+// table build
+// ---------------------------------------------------------------------------------------------------------
+struct MapParams {
+    double ir[9];
+    double fx, fy, cx, cy, k1, k2, p1, p2, k3;
+};
+
+// FP64 map of cv::initUndistortRectifyMap(K, dist, I, K), same operation order as oracle.restate
+// (no FMA contraction: every product and sum is rounded separately).
+__global__ void build_map_kernel(MapParams mp, int H, int W, int32_t* __restrict__ map, TableHeader* hdr)
+{
+    int j = blockIdx.x * blockDim.x + threadIdx.x;
+    int i = blockIdx.y * blockDim.y + threadIdx.y;
+    if (i >= H || j >= W) return;
+    double di = (double)i, dj = (double)j;
+    double _x = __dadd_rn(__dadd_rn(__dmul_rn(di, mp.ir[1]), mp.ir[2]), __dmul_rn(dj, mp.ir[0]));
+    double _y = __dadd_rn(__dadd_rn(__dmul_rn(di, mp.ir[4]), mp.ir[5]), __dmul_rn(dj, mp.ir[3]));
+    double _w = __dadd_rn(__dadd_rn(__dmul_rn(di, mp.ir[7]), mp.ir[8]), __dmul_rn(dj, mp.ir[6]));
+    double w = __ddiv_rn(1.0, _w);
+    double x = __dmul_rn(_x, w), y = __dmul_rn(_y, w);
+    double x2 = __dmul_rn(x, x), y2 = __dmul_rn(y, y);
+    double r2 = __dadd_rn(x2, y2);
+    double _2xy = __dmul_rn(__dmul_rn(2.0, x), y);
+    double kr = __dadd_rn(1.0, __dmul_rn(__dadd_rn(__dmul_rn(__dadd_rn(__dmul_rn(mp.k3, r2), mp.k2), r2), mp.k1), r2));
+    double xd = __dadd_rn(__dadd_rn(__dmul_rn(x, kr), __dmul_rn(mp.p1, _2xy)),
+                          __dmul_rn(mp.p2, __dadd_rn(r2, __dmul_rn(2.0, x2))));
+    double yd = __dadd_rn(__dadd_rn(__dmul_rn(y, kr), __dmul_rn(mp.p1, __dadd_rn(r2, __dmul_rn(2.0, y2)))),
+                          __dmul_rn(mp.p2, _2xy));
+    double u = __dadd_rn(__dmul_rn(mp.fx, xd), mp.cx);
+    double v = __dadd_rn(__dmul_rn(mp.fy, yd), mp.cy);
+    double u32 = __dmul_rn(u, 32.0), v32 = __dmul_rn(v, 32.0);
+    uint32_t enc = MAP_OUTSIDE;
+    if (fabs(u32) < 1.0e9 && fabs(v32) < 1.0e9) {          // also rejects NaN
+        long long iu = __double2ll_rn(u32), iv = __double2ll_rn(v32);   // rint (ties to even) like cvRound
+        long long sx = iu >> 5, sy = iv >> 5;
+        if (sx >= -1 && sx <= W - 1 && sy >= -1 && sy <= H - 1) {
+            long long du = iu - 32LL * j, dv = iv - 32LL * i;
+            if (du > -32768 && du < 32768 && dv > -32768 && dv < 32768)
+                enc = ((uint32_t)(du & 0xffff)) | ((uint32_t)(dv & 0xffff) << 16);
+            else
+                atomicAdd(&hdr->overflow, 1);
+        }
+    }
+    if (enc == MAP_OUTSIDE) atomicAdd(&hdr->n_zero, 1);
+    map[(size_t)i * W + j] = (int32_t)enc;
+}
+
+__global__ void init_tables_kernel(int32_t* cell, int32_t* tile, int n_tiles)
+{
+    int t = blockIdx.x * blockDim.x + threadIdx.x;
+    if (t >= n_tiles) return;
+    cell[4 * t + 0] = 0x7fffffff; cell[4 * t + 1] = 0x7fffffff; cell[4 * t + 2] = -1; cell[4 * t + 3] = -1;
+}
+
+// one CTA per output tile: source window + displacement bounds of its 40x40 undistorted region,
+// then scatter the tile index into the reach rectangle of every source cell the window overlaps.
+__global__ void build_tile_kernel(const int32_t* __restrict__ map, int H, int W, int TX, int TY,
+                                  int32_t* __restrict__ cell, int32_t* __restrict__ tile)
+{
+    int tx = blockIdx.x, ty = blockIdx.y;
+    int x0 = tx * TILE - HALO_U, y0 = ty * TILE - HALO_U;
+    __shared__ int s[8];
+    if (threadIdx.x < 8) s[threadIdx.x] = (threadIdx.x & 1) ? -0x7fffffff : 0x7fffffff;   // even: min, odd: max
+    __syncthreads();
+    int mn[4] = {0x7fffffff, 0x7fffffff, 0x7fffffff, 0x7fffffff};
+    int mx[4] = {-0x7fffffff, -0x7fffffff, -0x7fffffff, -0x7fffffff};
+    for (int idx = threadIdx.x; idx < REG_U * REG_U; idx += blockDim.x) {
+        int i = y0 + idx / REG_U, j = x0 + idx % REG_U;
+        if (i < 0 || j < 0 || i >= H || j >= W) continue;
+        uint32_t m = (uint32_t)map[(size_t)i * W + j];
+        if (m == MAP_OUTSIDE) continue;
+        int du = (int16_t)(m & 0xffff), dv = (int16_t)(m >> 16);
+        int ddx = du >> 5, ddy = dv >> 5;          // integer displacement (floor)
+        int sx = j + ddx, sy = i + ddy;
+        mn[0] = min(mn[0], sx); mx[0] = max(mx[0], sx + 1);
+        mn[1] = min(mn[1], sy); mx[1] = max(mx[1], sy + 1);
+        mn[2] = min(mn[2], ddx); mx[2] = max(mx[2], ddx);
+        mn[3] = min(mn[3], ddy); mx[3] = max(mx[3], ddy);
+    }
+    for (int k = 0; k < 4; ++k) { atomicMin(&s[2 * k], mn[k]); atomicMax(&s[2 * k + 1], mx[k]); }
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        int32_t* t = tile + 8 * (ty * TX + tx);
+        int sx0 = max(s[0], 0), sx1 = min(s[1], W - 1), sy0 = max(s[2], 0), sy1 = min(s[3], H - 1);
+        if (s[0] == 0x7fffffff) { sx0 = 0; sx1 = -1; sy0 = 0; sy1 = -1; }
+        t[0] = sx0; t[1] = sy0; t[2] = sx1; t[3] = sy1;
+        t[4] = s[4]; t[5] = s[5]; t[6] = s[6]; t[7] = s[7];
+        for (int cy = sy0 >> 5; cy <= (sy1 >> 5); ++cy)
+            for (int cx = sx0 >> 5; cx <= (sx1 >> 5); ++cx) {
+                int32_t* c = cell + 4 * (cy * TX + cx);
+                atomicMin(&c[0], tx); atomicMin(&c[1], ty); atomicMax(&c[2], tx); atomicMax(&c[3], ty);
+            }
+    }
+}
+
+static void invert3x3(const double* A, double* out)
+{
+    // closed-form adjugate inverse (what cv::invert does for 3x3): cofactors times 1/det
+    double d = A[0] * (A[4] * A[8] - A[5] * A[7]) - A[1] * (A[3] * A[8] - A[5] * A[6]) + A[2] * (A[3] * A[7] - A[4] * A[6]);
+    d = 1.0 / d;
+    out[0] = (A[4] * A[8] - A[5] * A[7]) * d;
+    out[1] = (A[2] * A[7] - A[1] * A[8]) * d;
+    out[2] = (A[1] * A[5] - A[2] * A[4]) * d;
+    out[3] = (A[5] * A[6] - A[3] * A[8]) * d;
+    out[4] = (A[0] * A[8] - A[2] * A[6]) * d;
+    out[5] = (A[2] * A[3] - A[0] * A[5]) * d;
+    out[6] = (A[3] * A[7] - A[4] * A[6]) * d;
+    out[7] = (A[1] * A[6] - A[0] * A[7]) * d;
+    out[8] = (A[0] * A[4] - A[1] * A[3]) * d;
+}
+
+static void table_layout(int H, int W, TableHeader* h)
+{
+    h->magic = TABLE_MAGIC;
+    h->H = H; h->W = W;
+    h->TX = cdiv(W, TILE); h->TY = cdiv(H, TILE);
+    h->overflow = 0; h->n_zero = 0; h->pad = 0;
+    size_t off = align_up(sizeof(TableHeader), 256);
+    h->off_map = off; off += align_up((size_t)H * W * 4, 256);
+    h->off_cell = off; off += align_up((size_t)h->TX * h->TY * 16, 256);
+    h->off_tile = off; off += align_up((size_t)h->TX * h->TY * 32, 256);
+    h->total_bytes = off;
+}
+
+extern "C" size_t mocap_undistort_table_bytes(int H, int W)
+{
+    if (H <= 0 || W <= 0) return 0;
+    TableHeader h; table_layout(H, W, &h);
+    return (size_t)h.total_bytes;
+}
+
+extern "C" int mocap_undistort_table_build(const double* K9, const double* dist5, int H, int W,
+                                           void* table_dev, size_t table_bytes, void* stream)
+{
+    if (!K9 || !dist5 || !table_dev || H <= 0 || W <= 0) return MOCAP_ERR_INVALID;
+    if (H > 16384 || W > 16384) return MOCAP_ERR_UNSUPPORTED;
+    TableHeader h; table_layout(H, W, &h);
+    if (table_bytes < h.total_bytes) return MOCAP_ERR_WORKSPACE;
+    cudaStream_t s = (cudaStream_t)stream;
+    MapParams mp;
+    invert3x3(K9, mp.ir);
+    mp.fx = K9[0]; mp.fy = K9[4]; mp.cx = K9[2]; mp.cy = K9[5];
+    mp.k1 = dist5[0]; mp.k2 = dist5[1]; mp.p1 = dist5[2]; mp.p2 = dist5[3]; mp.k3 = dist5[4];
+    char* base = (char*)table_dev;
+    CUDA_TRY(cudaMemcpyAsync(base, &h, sizeof(h), cudaMemcpyHostToDevice, s));
+    int32_t* map = (int32_t*)(base + h.off_map);
+    int32_t* cell = (int32_t*)(base + h.off_cell);
+    int32_t* tile = (int32_t*)(base + h.off_tile);
+    dim3 blk(32, 8), grd(cdiv(W, 32), cdiv(H, 8));
+    LAUNCH(build_map_kernel, grd, blk, 0, s, mp, H, W, map, (TableHeader*)base);
+    int nt = h.TX * h.TY;
+    LAUNCH(init_tables_kernel, cdiv(nt, 256), 256, 0, s, cell, tile, nt);
+    LAUNCH(build_tile_kernel, dim3(h.TX, h.TY), 256, 0, s, map, H, W, h.TX, h.TY, cell, tile);
+    CUDA_TRY(cudaGetLastError());
+    TableHeader back;
+    CUDA_TRY(cudaMemcpyAsync(&back, base, sizeof(back), cudaMemcpyDeviceToHost, s));
+    CUDA_TRY(cudaStreamSynchronize(s));
+    if (back.overflow) return MOCAP_ERR_UNSUPPORTED;   // displacement beyond +-1023 px
+    return MOCAP_OK;
+}
+
+int table_view(const void* table_dev, int H, int W, TableView* tv)
+{
+    // layout is a pure function of (H, W); the header on the device is only read by kernels
+    TableHeader h; table_layout(H, W, &h);
+    const char* base = (const char*)table_dev;
+    tv->map = (const int32_t*)(base + h.off_map);
+    tv->cell = (const int32_t*)(base + h.off_cell);
+    tv->tile = (const int32_t*)(base + h.off_tile);
+    tv->H = H; tv->W = W; tv->TX = h.TX; tv->TY = h.TY;
+    return MOCAP_OK;
+}
+
+// ---------------------------------------------------------------------------------------------------------
+// hot-pixel test: byte > thresh, four bytes at a time.  T = thresh + 1.
+//   T in 129..255: bit7(b) & bit7((b & 0x7f) + (256 - T));   T in 1..128: bit7(b) | bit7((b & 0x7f) + (128 - T))
+// ---------------------------------------------------------------------------------------------------------
+struct HotTest { uint32_t add; int mode; };   // mode 0: and, 1: or, 2: never, 3: always
+static HotTest make_hot_test(int thresh)
+{
+    HotTest h; int T = thresh + 1;
+    if (T >= 256) { h.mode = 2; h.add = 0; }
+    else if (T <= 0) { h.mode = 3; h.add = 0; }
+    else if (T > 128) { h.mode = 0; h.add = 0x01010101u * (uint32_t)(256 - T); }
+    else { h.mode = 1; h.add = 0x01010101u * (uint32_t)(128 - T); }
+    return h;
+}
+template <int MODE>
+__device__ __forceinline__ uint32_t hot4(uint32_t w, uint32_t add)
+{
+    uint32_t t = (w & 0x7f7f7f7fu) + add;
+    if (MODE == 0) return w & t;        // caller masks with 0x80808080
+    if (MODE == 1) return w | t;
+    if (MODE == 2) return 0u;
+    return 0x80808080u;
+}
+
+__device__ __forceinline__ uint4 ldg_stream16(const void* p)
+{
+#ifdef MOCAP_EMU
+    return *(const uint4*)p;
+#else
+    uint4 r;
+    asm volatile("ld.global.nc.L1::no_allocate.L2::128B.v4.u32 {%0,%1,%2,%3}, [%4];"
+                 : "=r"(r.x), "=r"(r.y), "=r"(r.z), "=r"(r.w) : "l"(p));
+    return r;
+#endif
+}
+
+__device__ __forceinline__ void mark_cell(const TableView& tv, uint32_t* __restrict__ active, int f, int cy, int cx, int TXW)
+{
+    const int32_t* c = tv.cell + 4 * (cy * tv.TX + cx);
+    int tx0 = c[0], ty0 = c[1], tx1 = c[2], ty1 = c[3];
+    if (tx1 < tx0) return;
+    for (int ty = ty0; ty <= ty1; ++ty) {
+        uint32_t* row = active + ((size_t)f * tv.TY + ty) * TXW;
+        for (int wq = tx0 >> 5; wq <= (tx1 >> 5); ++wq) {
+            int lo = max(tx0, wq * 32) - wq * 32, hi = min(tx1, wq * 32 + 31) - wq * 32;
+            uint32_t m = (hi == 31 ? 0xffffffffu : ((1u << (hi + 1)) - 1u)) & ~((1u << lo) - 1u);
+            if ((row[wq] & m) != m) atomicOr(&row[wq], m);
+        }
+    }
+}
+
+// Streams all source bytes.  One warp per 128x32-pixel block (4 source cells): lane = (row & 3, 16-byte segment).
+template <int MODE>
+__global__ void __launch_bounds__(256) scan_hot_vec_kernel(const uint8_t* __restrict__ frames, int n_frames, int64_t fstride,
+                                                           TableView tv, uint32_t* __restrict__ active, int TXW, uint32_t add)
+{
+    const int lane = threadIdx.x & 31;
+    const long long warp = ((long long)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+    const long long nwarps = ((long long)gridDim.x * blockDim.x) >> 5;
+    const int H = tv.H, W = tv.W;
+    const int CXB = (tv.TX + 3) >> 2;
+    const long long per_frame = (long long)tv.TY * CXB;
+    const long long total = per_frame * n_frames;
+    const int seg = lane & 7, r0 = lane >> 3;
+    for (long long it = warp; it < total; it += nwarps) {
+        int f = (int)(it / per_frame);
+        int rem = (int)(it - (long long)f * per_frame);
+        int cy = rem / CXB, cxb = rem - cy * CXB;
+        int x = cxb * 128 + seg * 16;
+        const uint8_t* base = frames + (size_t)f * fstride + (size_t)(cy * 32 + r0) * W + x;
+        bool colok = x < W;
+        uint32_t acc = 0;
+        uint4 v[8];
+#pragma unroll
+        for (int k = 0; k < 8; ++k) {
+            int row = cy * 32 + k * 4 + r0;
+            if (colok && row < H) v[k] = ldg_stream16(base + (size_t)(k * 4) * W);
+            else v[k] = make_uint4(0, 0, 0, 0);
+        }
+#pragma unroll
+        for (int k = 0; k < 8; ++k)
+            acc |= hot4<MODE>(v[k].x, add) | hot4<MODE>(v[k].y, add) | hot4<MODE>(v[k].z, add) | hot4<MODE>(v[k].w, add);
+        bool hot = (acc & 0x80808080u) != 0;
+        unsigned m = __ballot_sync(0xffffffffu, hot);
+        if (lane < 4) {
+            int cx = cxb * 4 + lane;
+            if (cx < tv.TX && (m & (0x03030303u << (2 * lane)))) mark_cell(tv, active, f, cy, cx, TXW);
+        }
+    }
+}
+
+// Generic (any W / alignment) variant: one warp per source cell, byte loads.
+__global__ void scan_hot_scalar_kernel(const uint8_t* __restrict__ frames, int n_frames, int64_t fstride,
+                                       TableView tv, uint32_t* __restrict__ active, int TXW, int thresh)
+{
+    const int lane = threadIdx.x & 31;
+    const long long warp = ((long long)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+    const long long nwarps = ((long long)gridDim.x * blockDim.x) >> 5;
+    const int H = tv.H, W = tv.W;
+    const long long per_frame = (long long)tv.TY * tv.TX;
+    const long long total = per_frame * n_frames;
+    for (long long it = warp; it < total; it += nwarps) {
+        int f = (int)(it / per_frame);
+        int rem = (int)(it - (long long)f * per_frame);
+        int cy = rem / tv.TX, cx = rem - cy * tv.TX;
+        int x = cx * 32 + lane;
+        bool hot = false;
+        if (x < W) {
+            const uint8_t* base = frames + (size_t)f * fstride + x;
+            for (int r = 0; r < 32; ++r) {
+                int y = cy * 32 + r;
+                if (y < H && (int)base[(size_t)y * W] > thresh) hot = true;
+            }
+        }
+        if (__any_sync(0xffffffffu, hot) && lane == 0) mark_cell(tv, active, f, cy, cx, TXW);
+    }
+}
+
+__global__ void compact_tiles_kernel(const uint32_t* __restrict__ active, long long n_words, int TX, int TY, int TXW,
+                                     uint32_t* __restrict__ list, int* __restrict__ count)
+{
+    long long idx = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    if (idx >= n_words) return;
+    uint32_t w = active[idx];
+    if (!w) return;
+    int f = (int)(idx / ((long long)TY * TXW));
+    int rem = (int)(idx - (long long)f * TY * TXW);
+    int ty = rem / TXW, wq = rem - ty * TXW;
+    int base = atomicAdd(count, __popc(w));
+    while (w) {
+        int b = __ffs(w) - 1;
+        w &= w - 1;
+        list[base++] = (uint32_t)f * (uint32_t)(TX * TY) + (uint32_t)(ty * TX + wq * 32 + b);
+    }
+}
+
+// ---------------------------------------------------------------------------------------------------------
+// filter_tiles: one warp per active tile
+// ---------------------------------------------------------------------------------------------------------
+__device__ __forceinline__ int fdiv20(int idx, int inv) { return (int)(((unsigned)idx * (unsigned)inv) >> 20); }
+__device__ __forceinline__ int finv20(int w) { return (1 << 20) / w + 1; }
+
+__device__ __forceinline__ int remap_px(const uint8_t* __restrict__ fr, int W, int H, int i, int j, uint32_t m)
+{
+    if (m == MAP_OUTSIDE) return 0;
+    int iu = 32 * j + (int)(int16_t)(m & 0xffff);
+    int iv = 32 * i + (int)(int16_t)(m >> 16);
+    int sx = iu >> 5, sy = iv >> 5, fx = iu & 31, fy = iv & 31;
+    const uint8_t* p = fr + (ptrdiff_t)sy * W + sx;
+    bool x0ok = (unsigned)sx < (unsigned)W, x1ok = (unsigned)(sx + 1) < (unsigned)W;
+    bool y0ok = (unsigned)sy < (unsigned)H, y1ok = (unsigned)(sy + 1) < (unsigned)H;
+    int p00 = (x0ok && y0ok) ? p[0] : 0;
+    int p01 = (x1ok && y0ok) ? p[1] : 0;
+    int p10 = (x0ok && y1ok) ? p[W] : 0;
+    int p11 = (x1ok && y1ok) ? p[W + 1] : 0;
+    int r0 = (32 - fx) * p00 + fx * p01;
+    int r1 = (32 - fx) * p10 + fx * p11;
+    return ((32 - fy) * r0 + fy * r1 + 512) >> 10;
+}
+
+#define FT_WARPS 8
+struct __align__(16) WarpScratch {
+    uint8_t U[REG_U * REG_U];        // undistorted pixels, origin (x0-4, y0-4)
+    uint16_t HS[REG_U * REG_B];      // horizontal 5-sums of U: rows = U rows, cols = B cols; reused for majority sums
+    uint8_t B[REG_B * REG_B];        // thresholded box mean, origin (x0-2, y0-2)
+};
+
+__global__ void __launch_bounds__(FT_WARPS * 32) filter_tiles_kernel(
+    const uint8_t* __restrict__ frames, int64_t fstride, TableView tv, int thresh,
+    const uint32_t* __restrict__ list, const int* __restrict__ n_list, int* __restrict__ cursor,
+    const uint32_t* __restrict__ active, int TXW,
+    uint32_t* __restrict__ bits, uint32_t* __restrict__ fg_tiles, int* __restrict__ n_fg, int max_fg, int* __restrict__ flags)
+{
+    __shared__ WarpScratch scratch[FT_WARPS];
+    const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
+    WarpScratch& S = scratch[wid];
+    const int H = tv.H, W = tv.W, TX = tv.TX, TY = tv.TY;
+    const int T = thresh + 1;
+    const int total = *n_list;
+    for (;;) {
+        int item = 0;
+        if (lane == 0) item = atomicAdd(cursor, 1);
+        item = __shfl_sync(0xffffffffu, item, 0);
+        if (item >= total) break;
+        uint32_t code = list[item];
+        int f = (int)(code / (uint32_t)(TX * TY)), t = (int)(code - (uint32_t)f * (uint32_t)(TX * TY));
+        int ty = t / TX, tx = t - ty * TX;
+        int x0 = tx * TILE, y0 = ty * TILE;
+        const uint8_t* fr = frames + (size_t)f * fstride;
+        uint32_t* brow = bits + ((size_t)f * H + y0) * TX + tx;
+        const int32_t* tt = tv.tile + 8 * t;
+        int sx0 = tt[0], sy0 = tt[1], sx1 = tt[2], sy1 = tt[3];
+        uint32_t myword = 0;
+
+        // ---- 1. exact hot bounding box of the source window -------------------------------------------
+        int hx0 = 0x7fffffff, hx1 = -1, hy0 = 0x7fffffff, hy1 = -1;
+        if (sx1 >= sx0) {
+            int bw = sx1 - sx0 + 1, n = bw * (sy1 - sy0 + 1), inv = finv20(bw);
+            const bool big = bw > 64 || n > 4096;          // fdiv20 is exact only while idx * bw < 2^20
+            for (int idx = lane; idx < n; idx += 32) {
+                int r = big ? idx / bw : fdiv20(idx, inv), c = idx - r * bw;
+                int v = fr[(size_t)(sy0 + r) * W + sx0 + c];
+                if (v >= T) {
+                    hx0 = min(hx0, sx0 + c); hx1 = max(hx1, sx0 + c);
+                    hy0 = min(hy0, sy0 + r); hy1 = max(hy1, sy0 + r);
+                }
+            }
+        }
+        hx0 = __reduce_min_sync(0xffffffffu, hx0); hx1 = __reduce_max_sync(0xffffffffu, hx1);
+        hy0 = __reduce_min_sync(0xffffffffu, hy0); hy1 = __reduce_max_sync(0xffffffffu, hy1);
+        bool any = hx1 >= 0;
+        int MX0 = 0, MX1 = -1, MY0 = 0, MY1 = -1;
+        if (any) {
+            // undistorted pixels that can be > thresh: j in [hx0-1-dxmax, hx1-dxmin], same for rows
+            int ux0 = hx0 - 1 - tt[5], ux1 = hx1 - tt[4], uy0 = hy0 - 1 - tt[7], uy1 = hy1 - tt[6];
+            // box-mean threshold can fire within +-2 of those, the majority within +-4
+            MX0 = max(max(ux0 - 4, x0), 0); MX1 = min(min(ux1 + 4, x0 + TILE - 1), W - 1);
+            MY0 = max(max(uy0 - 4, y0), 0); MY1 = min(min(uy1 + 4, y0 + TILE - 1), H - 1);
+            any = MX1 >= MX0 && MY1 >= MY0;
+            if (any) {
+                // B compute box (where the threshold can fire), clipped to the majority's read set
+                int BX0 = max(max(ux0 - 2, MX0 - 2), 0), BX1 = min(min(ux1 + 2, MX1 + 2), W - 1);
+                int BY0 = max(max(uy0 - 2, MY0 - 2), 0), BY1 = min(min(uy1 + 2, MY1 + 2), H - 1);
+                // B read set of the majority (replicated border = clamped coordinates)
+                int RX0 = max(MX0 - 2, 0), RX1 = min(MX1 + 2, W - 1), RY0 = max(MY0 - 2, 0), RY1 = min(MY1 + 2, H - 1);
+                if (BX1 >= BX0 && BY1 >= BY0) {
+                    // ---- 2. U on the B box dilated by 2 (zero outside the frame) ------------------------
+                    int UX0 = BX0 - 2, UX1 = BX1 + 2, UY0 = BY0 - 2, UY1 = BY1 + 2;
+                    {
+                        int bw = UX1 - UX0 + 1, n = bw * (UY1 - UY0 + 1), inv = finv20(bw);
+                        for (int idx = lane; idx < n; idx += 32) {
+                            int r = fdiv20(idx, inv), c = idx - r * bw;
+                            int i = UY0 + r, j = UX0 + c;
+                            int u = 0;
+                            if ((unsigned)i < (unsigned)H && (unsigned)j < (unsigned)W)
+                                u = remap_px(fr, W, H, i, j, (uint32_t)tv.map[(size_t)i * W + j]);
+                            S.U[(i - (y0 - HALO_U)) * REG_U + (j - (x0 - HALO_U))] = (uint8_t)u;
+                        }
+                    }
+                    __syncwarp();
+                    // ---- 3. horizontal 5-sums of U for rows UY0..UY1, cols BX0..BX1 --------------------
+                    {
+                        int bw = BX1 - BX0 + 1, n = bw * (UY1 - UY0 + 1), inv = finv20(bw);
+                        for (int idx = lane; idx < n; idx += 32) {
+                            int r = fdiv20(idx, inv), c = idx - r * bw;
+                            int ur = UY0 + r - (y0 - HALO_U), uc = BX0 + c - 2 - (x0 - HALO_U);
+                            const uint8_t* u = &S.U[ur * REG_U + uc];
+                            S.HS[ur * REG_B + (BX0 + c - (x0 - 2))] = (uint16_t)(u[0] + u[1] + u[2] + u[3] + u[4]);
+                        }
+                    }
+                    __syncwarp();
+                }
+                // ---- 4. B on the read set: threshold inside the compute box, 0 elsewhere ----------------
+                {
+                    int bw = RX1 - RX0 + 1, n = bw * (RY1 - RY0 + 1), inv = finv20(bw);
+                    for (int idx = lane; idx < n; idx += 32) {
+                        int r = fdiv20(idx, inv), c = idx - r * bw;
+                        int i = RY0 + r, j = RX0 + c;
+                        int b = 0;
+                        if (i >= BY0 && i <= BY1 && j >= BX0 && j <= BX1) {
+                            int ur = i - 2 - (y0 - HALO_U), bc = j - (x0 - 2);
+                            const uint16_t* h = &S.HS[ur * REG_B + bc];
+                            int s = h[0] + h[REG_B] + h[2 * REG_B] + h[3 * REG_B] + h[4 * REG_B];
+                            int cnt = (min(i + 2, H - 1) - max(i - 2, 0) + 1) * (min(j + 2, W - 1) - max(j - 2, 0) + 1);
+                            b = s >= T * cnt;
+                        }
+                        S.B[(i - (y0 - 2)) * REG_B + (j - (x0 - 2))] = (uint8_t)b;
+                    }
+                }
+                __syncwarp();
+                // ---- 5. majority: horizontal 5-sums (clamped columns) into HS, then vertical -------------
+                {
+                    int bw = MX1 - MX0 + 1, n = bw * (RY1 - RY0 + 1), inv = finv20(bw);
+                    for (int idx = lane; idx < n; idx += 32) {
+                        int r = fdiv20(idx, inv), c = idx - r * bw;
+                        int i = RY0 + r, j = MX0 + c;
+                        const uint8_t* b = &S.B[(i - (y0 - 2)) * REG_B - (x0 - 2)];
+                        int s = b[max(j - 2, 0)] + b[max(j - 1, 0)] + b[j] + b[min(j + 1, W - 1)] + b[min(j + 2, W - 1)];
+                        S.HS[(i - (y0 - 2)) * REG_B + (j - x0)] = (uint16_t)s;
+                    }
+                }
+                __syncwarp();
+                {
+                    int j = x0 + lane;
+                    bool colin = j >= MX0 && j <= MX1;
+                    for (int i = MY0; i <= MY1; ++i) {
+                        int s = 0;
+                        if (colin) {
+                            const uint16_t* h = &S.HS[-(y0 - 2) * REG_B + lane];
+                            s = h[max(i - 2, 0) * REG_B] + h[max(i - 1, 0) * REG_B] + h[i * REG_B] +
+                                h[min(i + 1, H - 1) * REG_B] + h[min(i + 2, H - 1) * REG_B];
+                        }
+                        unsigned wv = __ballot_sync(0xffffffffu, s >= 13);
+                        if (lane == i - y0) myword = wv;
+                    }
+                }
+                __syncwarp();
+            }
+        }
+        // ---- 6. write the tile's 32 words ---------------------------------------------------------------
+        if (y0 + lane < H) brow[(size_t)lane * TX] = myword;
+        unsigned nz = __ballot_sync(0xffffffffu, myword != 0);
+        if (nz) {
+            if (lane == 0) {
+                int slot = atomicAdd(&n_fg[f], 1);
+                if (slot < max_fg) fg_tiles[(size_t)f * max_fg + slot] = (uint32_t)t;
+                else atomicOr(&flags[f], MOCAP_FLAG_TILE_OVERFLOW);
+            }
+            // neighbours that no warp owns must read as background for the border walkers
+            if (lane < 8) {
+                int k = lane + (lane >= 4);
+                int nx = tx + k % 3 - 1, ny = ty + k / 3 - 1;
+                bool zero = nx >= 0 && ny >= 0 && nx < TX && ny < TY &&
+                            !((active[((size_t)f * TY + ny) * TXW + (nx >> 5)] >> (nx & 31)) & 1);
+                if (zero) {
+                    uint32_t* nb = bits + ((size_t)f * H + ny * TILE) * TX + nx;
+                    for (int r = 0; r < TILE && ny * TILE + r < H; ++r) nb[(size_t)r * TX] = 0;
+                }
+            }
+        }
+    }
+}
+
+// dense copy-out of the packed binary image (parity / debug output): inactive tiles read as zero
+__global__ void materialize_bits_kernel(const uint32_t* __restrict__ bits, const uint32_t* __restrict__ active,
+                                        int n_frames, int H, int TX, int TY, int TXW, int W, uint32_t* __restrict__ out)
+{
+    long long idx = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    long long total = (long long)n_frames * H * TX;
+    if (idx >= total) return;
+    int tx = (int)(idx % TX);
+    long long r = idx / TX;
+    int y = (int)(r % H), f = (int)(r / H);
+    bool act = (active[((size_t)f * TY + (y >> 5)) * TXW + (tx >> 5)] >> (tx & 31)) & 1;
+    uint32_t w = act ? bits[idx] : 0u;
+    int rem = W - tx * 32;
+    if (rem < 32) w &= (1u << rem) - 1u;
+    out[idx] = w;
+}
+
+// ---------------------------------------------------------------------------------------------------------
+// host-side launcher shared by mocap_filter_batch and mocap_detect_batch
+// ---------------------------------------------------------------------------------------------------------
+int launch_filter(const uint8_t* frames, int n, int H, int W, int64_t fstride, const TableView& tv, int thresh,
+                  const FilterWs& ws, int max_fg, int* flags, cudaStream_t s)
+{
+    const int TX = tv.TX, TY = tv.TY, TXW = cdiv(TX, 32);
+    size_t act_bytes = (size_t)n * TY * TXW * 4;
+    CUDA_TRY(cudaMemsetAsync(ws.active, 0, act_bytes, s));
+    CUDA_TRY(cudaMemsetAsync(ws.counters, 0, 2 * sizeof(int), s));
+    CUDA_TRY(cudaMemsetAsync(ws.n_fg, 0, (size_t)n * sizeof(int), s));
+    int dev = 0, sms = 148;
+    cudaGetDevice(&dev);
+    cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
+    HotTest ht = make_hot_test(thresh);
+    bool vec = (W % 16 == 0) && (fstride % 16 == 0) && (((uintptr_t)frames) % 16 == 0);
+    if (vec) {
+        int grid = sms * 8;
+        switch (ht.mode) {
+            case 0: LAUNCH(scan_hot_vec_kernel<0>, grid, 256, 0, s, frames, n, fstride, tv, ws.active, TXW, ht.add); break;
+            case 1: LAUNCH(scan_hot_vec_kernel<1>, grid, 256, 0, s, frames, n, fstride, tv, ws.active, TXW, ht.add); break;
+            case 2: LAUNCH(scan_hot_vec_kernel<2>, grid, 256, 0, s, frames, n, fstride, tv, ws.active, TXW, ht.add); break;
+            default: LAUNCH(scan_hot_vec_kernel<3>, grid, 256, 0, s, frames, n, fstride, tv, ws.active, TXW, ht.add); break;
+        }
+    } else {
+        LAUNCH(scan_hot_scalar_kernel, sms * 8, 256, 0, s, frames, n, fstride, tv, ws.active, TXW, thresh);
+    }
+    long long n_words = (long long)n * TY * TXW;
+    LAUNCH(compact_tiles_kernel, (unsigned)((n_words + 255) / 256), 256, 0, s, ws.active, n_words, TX, TY, TXW, ws.list, ws.counters);
+    LAUNCH(filter_tiles_kernel, sms * 4, FT_WARPS * 32, 0, s, frames, fstride, tv, thresh, ws.list, ws.counters, ws.counters + 1,
+                                                          ws.active, TXW, ws.bits, ws.fg_tiles, ws.n_fg, max_fg, flags);
+    CUDA_TRY(cudaGetLastError());
+    return MOCAP_OK;
+}
+
+int launch_materialize_bits(const FilterWs& ws, int n, int H, int W, const TableView& tv, uint32_t* out, cudaStream_t s)
+{
+    long long total = (long long)n * H * tv.TX;
+    LAUNCH(materialize_bits_kernel, (unsigned)((total + 255) / 256), 256, 0, s, ws.bits, ws.active, n, H, tv.TX, tv.TY,
+           cdiv(tv.TX, 32), W, out);
+    CUDA_TRY(cudaGetLastError());
+    return MOCAP_OK;
+}
+
+// ---------------------------------------------------------------------------------------------------------
+// stage kernels for parity tests: the reference's own blur (CudaOperations.py:5-41) and cv.undistort alone
+// ---------------------------------------------------------------------------------------------------------
+__global__ void blur5_kernel(const uint8_t* __restrict__ in, int n, int H, int W, uint8_t* __restrict__ out)
+{
+    int x = blockIdx.x * blockDim.x + threadIdx.x, y = blockIdx.y * blockDim.y + threadIdx.y, f = blockIdx.z;
+    if (x >= W || y >= H) return;
+    const uint8_t* fr = in + (size_t)f * H * W;
+    int s = 0, c = 0;
+    for (int dy = -2; dy <= 2; ++dy)
+        for (int dx = -2; dx <= 2; ++dx) {
+            int yy = y + dy, xx = x + dx;
+            if ((unsigned)yy < (unsigned)H && (unsigned)xx < (unsigned)W) { s += fr[(size_t)yy * W + xx]; ++c; }
+        }
+    out[(size_t)f * H * W + (size_t)y * W + x] = (uint8_t)(s / c);
+}
+
+extern "C" int mocap_blur5_batch(const uint8_t* frames_dev, int n, int H, int W, uint8_t* out_dev, void* stream)
+{
+    if (!frames_dev || !out_dev || n <= 0 || H <= 0 || W <= 0 || n > 65535) return MOCAP_ERR_INVALID;
+    LAUNCH(blur5_kernel, dim3(cdiv(W, 32), cdiv(H, 8), n), dim3(32, 8), 0, (cudaStream_t)stream, frames_dev, n, H, W, out_dev);
+    CUDA_TRY(cudaGetLastError());
+    return MOCAP_OK;
+}
+
+__global__ void undistort_kernel(const uint8_t* __restrict__ in, int n, int H, int W, const int32_t* __restrict__ map,
+                                 uint8_t* __restrict__ out)
+{
+    int x = blockIdx.x * blockDim.x + threadIdx.x, y = blockIdx.y * blockDim.y + threadIdx.y, f = blockIdx.z;
+    if (x >= W || y >= H) return;
+    out[(size_t)f * H * W + (size_t)y * W + x] =
+        (uint8_t)remap_px(in + (size_t)f * H * W, W, H, y, x, (uint32_t)map[(size_t)y * W + x]);
+}
+
+extern "C" int mocap_undistort_batch(const uint8_t* frames_dev, int n, int H, int W, const void* table_dev,
+                                     uint8_t* out_dev, void* stream)
+{
+    if (!frames_dev || !out_dev || !table_dev || n <= 0 || H <= 0 || W <= 0 || n > 65535) return MOCAP_ERR_INVALID;
+    TableView tv; table_view(table_dev, H, W, &tv);
+    LAUNCH(undistort_kernel, dim3(cdiv(W, 32), cdiv(H, 8), n), dim3(32, 8), 0, (cudaStream_t)stream, frames_dev, n, H, W, tv.map, out_dev);
+    CUDA_TRY(cudaGetLastError());
+    return MOCAP_OK;
+}

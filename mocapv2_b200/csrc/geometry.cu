@@ -1,0 +1,456 @@
+// Geometry stage: DLT triangulation, reprojection error, epipolar correspondence + group ranking.
+//
+// Replaces, for batches, lib/Helpers.py of the reference:
+//   triangulate_point / DLT            :43-84   rows y*P2-P1, P0-x*P2; B = A^T A; singular vector of the smallest
+//                                               singular value of B (scipy.linalg.svd) -> X = v[:3]/v[3]
+//   calculate_reprojection_error       :102-143 cv.projectPoints(float32(X)) incl. distortion, float32 (u,v),
+//                                               mean of squared x/y residuals (px^2)
+//   find_point_correspondance_and_object_points :178-280
+// B is a symmetric 4x4, so its SVD is its eigen-decomposition: a register-resident cyclic Jacobi solve, one
+// point (or candidate group) per thread, FP32 main mode and FP64 check mode (template parameter).  No tensor
+// cores: these are tiny independent solves, not dense contractions.
+#include "common.cuh"
+
+#define CAM_P 0
+#define CAM_R 12
+#define CAM_T 21
+#define CAM_K 24
+#define CAM_D 33
+
+template <typename T> struct Num;
+template <> struct Num<float> {
+    static __device__ __forceinline__ float sqrt_(float x) { return sqrtf(x); }
+    static __device__ __forceinline__ float abs_(float x) { return fabsf(x); }
+    static __device__ __forceinline__ float tiny() { return 1e-30f; }
+    static constexpr int sweeps = 8;
+};
+template <> struct Num<double> {
+    static __device__ __forceinline__ double sqrt_(double x) { return sqrt(x); }
+    static __device__ __forceinline__ double abs_(double x) { return fabs(x); }
+    static __device__ __forceinline__ double tiny() { return 1e-280; }
+    static constexpr int sweeps = 12;
+};
+
+// Smallest-eigenvalue eigenvector of a symmetric PSD 4x4 (upper triangle a[10]: 00 01 02 03 11 12 13 22 23 33).
+template <typename T>
+__device__ __forceinline__ void jacobi_min_eigvec(T b00, T b01, T b02, T b03, T b11, T b12, T b13, T b22, T b23, T b33, T v[4])
+{
+    T A[4][4] = {{b00, b01, b02, b03}, {b01, b11, b12, b13}, {b02, b12, b22, b23}, {b03, b13, b23, b33}};
+    T V[4][4] = {{1, 0, 0, 0}, {0, 1, 0, 0}, {0, 0, 1, 0}, {0, 0, 0, 1}};
+#pragma unroll 1
+    for (int sweep = 0; sweep < Num<T>::sweeps; ++sweep) {
+        T off = Num<T>::abs_(A[0][1]) + Num<T>::abs_(A[0][2]) + Num<T>::abs_(A[0][3]) +
+                Num<T>::abs_(A[1][2]) + Num<T>::abs_(A[1][3]) + Num<T>::abs_(A[2][3]);
+        if (off == (T)0) break;
+#pragma unroll
+        for (int p = 0; p < 3; ++p) {
+#pragma unroll
+            for (int q = p + 1; q < 4; ++q) {
+                T apq = A[p][q];
+                if (apq != (T)0) {
+                    T theta = (A[q][q] - A[p][p]) / ((T)2 * apq);
+                    T at = Num<T>::abs_(theta);
+                    T t;
+                    if (at > (T)1e15) t = (T)0.5 / theta;                       // avoid theta^2 overflow
+                    else { t = (T)1 / (at + Num<T>::sqrt_(theta * theta + (T)1)); if (theta < (T)0) t = -t; }
+                    T c = (T)1 / Num<T>::sqrt_(t * t + (T)1), s = t * c;
+                    T tau = s / ((T)1 + c);
+                    A[p][p] -= t * apq; A[q][q] += t * apq; A[p][q] = (T)0; A[q][p] = (T)0;
+#pragma unroll
+                    for (int r = 0; r < 4; ++r) {
+                        if (r != p && r != q) {
+                            T arp = A[r][p], arq = A[r][q];
+                            A[r][p] = arp - s * (arq + tau * arp); A[p][r] = A[r][p];
+                            A[r][q] = arq + s * (arp - tau * arq); A[q][r] = A[r][q];
+                        }
+                        T vrp = V[r][p], vrq = V[r][q];
+                        V[r][p] = vrp - s * (vrq + tau * vrp);
+                        V[r][q] = vrq + s * (vrp - tau * vrq);
+                    }
+                }
+            }
+        }
+    }
+    int k = 0;
+    T best = Num<T>::abs_(A[0][0]);
+#pragma unroll
+    for (int i = 1; i < 4; ++i) { T e = Num<T>::abs_(A[i][i]); if (e < best) { best = e; k = i; } }
+#pragma unroll
+    for (int r = 0; r < 4; ++r) v[r] = (k == 0) ? V[r][0] : (k == 1) ? V[r][1] : (k == 2) ? V[r][2] : V[r][3];
+}
+
+template <typename T>
+struct Accum {                          // B = A^T A accumulated view by view
+    T b[10];
+    __device__ __forceinline__ void clear() {
+#pragma unroll
+        for (int i = 0; i < 10; ++i) b[i] = (T)0;
+    }
+    __device__ __forceinline__ void add_row(const T r[4]) {
+        b[0] += r[0] * r[0]; b[1] += r[0] * r[1]; b[2] += r[0] * r[2]; b[3] += r[0] * r[3];
+        b[4] += r[1] * r[1]; b[5] += r[1] * r[2]; b[6] += r[1] * r[3];
+        b[7] += r[2] * r[2]; b[8] += r[2] * r[3]; b[9] += r[3] * r[3];
+    }
+    __device__ __forceinline__ void add_view(const T* P, T x, T y) {   // P row-major 3x4
+        T r1[4], r2[4];
+#pragma unroll
+        for (int c = 0; c < 4; ++c) { r1[c] = y * P[8 + c] - P[4 + c]; r2[c] = P[c] - x * P[8 + c]; }
+        add_row(r1); add_row(r2);
+    }
+    __device__ __forceinline__ void solve(T X[3]) {
+        T v[4];
+        jacobi_min_eigvec<T>(b[0], b[1], b[2], b[3], b[4], b[5], b[6], b[7], b[8], b[9], v);
+        X[0] = v[0] / v[3]; X[1] = v[1] / v[3]; X[2] = v[2] / v[3];
+    }
+};
+
+// cv.projectPoints restated.  FP64: reproduces the float32 roundings of X and of (u, v).
+template <typename T>
+__device__ __forceinline__ void project(const T* cam_pose /*R,t*/, const T* cam_kd /*K,dist*/, const T X[3], T& u, T& v);
+
+template <>
+__device__ __forceinline__ void project<double>(const double* pose, const double* kd, const double X[3], double& u, double& v)
+{
+    double X0 = (double)(float)X[0], X1 = (double)(float)X[1], X2 = (double)(float)X[2];
+    const double* R = pose; const double* t = pose + 9;
+    // cv::projectPoints: Y = R X + t evaluated left to right, no contraction
+    double Yx = __dadd_rn(__dadd_rn(__dadd_rn(__dmul_rn(R[0], X0), __dmul_rn(R[1], X1)), __dmul_rn(R[2], X2)), t[0]);
+    double Yy = __dadd_rn(__dadd_rn(__dadd_rn(__dmul_rn(R[3], X0), __dmul_rn(R[4], X1)), __dmul_rn(R[5], X2)), t[1]);
+    double Yz = __dadd_rn(__dadd_rn(__dadd_rn(__dmul_rn(R[6], X0), __dmul_rn(R[7], X1)), __dmul_rn(R[8], X2)), t[2]);
+    double z = Yz != 0.0 ? __ddiv_rn(1.0, Yz) : 1.0;
+    double x = __dmul_rn(Yx, z), y = __dmul_rn(Yy, z);
+    double r2 = __dadd_rn(__dmul_rn(x, x), __dmul_rn(y, y));
+    double r4 = __dmul_rn(r2, r2), r6 = __dmul_rn(r4, r2);
+    double a1 = __dmul_rn(__dmul_rn(2.0, x), y);
+    double a2 = __dadd_rn(r2, __dmul_rn(__dmul_rn(2.0, x), x));
+    double a3 = __dadd_rn(r2, __dmul_rn(__dmul_rn(2.0, y), y));
+    const double* K = kd; const double* d = kd + 9;       // d: k1 k2 p1 p2 k3
+    double cdist = __dadd_rn(__dadd_rn(__dadd_rn(1.0, __dmul_rn(d[0], r2)), __dmul_rn(d[1], r4)), __dmul_rn(d[4], r6));
+    double xd = __dadd_rn(__dadd_rn(__dmul_rn(x, cdist), __dmul_rn(d[2], a1)), __dmul_rn(d[3], a2));
+    double yd = __dadd_rn(__dadd_rn(__dmul_rn(y, cdist), __dmul_rn(d[2], a3)), __dmul_rn(d[3], a1));
+    u = (double)(float)__dadd_rn(__dmul_rn(xd, K[0]), K[2]);
+    v = (double)(float)__dadd_rn(__dmul_rn(yd, K[4]), K[5]);
+}
+
+template <>
+__device__ __forceinline__ void project<float>(const float* pose, const float* kd, const float X[3], float& u, float& v)
+{
+    const float* R = pose; const float* t = pose + 9;
+    float Yx = R[0] * X[0] + R[1] * X[1] + R[2] * X[2] + t[0];
+    float Yy = R[3] * X[0] + R[4] * X[1] + R[5] * X[2] + t[1];
+    float Yz = R[6] * X[0] + R[7] * X[1] + R[8] * X[2] + t[2];
+    float z = Yz != 0.f ? 1.f / Yz : 1.f;
+    float x = Yx * z, y = Yy * z;
+    float r2 = x * x + y * y, r4 = r2 * r2, r6 = r4 * r2;
+    float a1 = 2.f * x * y, a2 = r2 + 2.f * x * x, a3 = r2 + 2.f * y * y;
+    const float* K = kd; const float* d = kd + 9;
+    float cdist = 1.f + d[0] * r2 + d[1] * r4 + d[4] * r6;
+    float xd = x * cdist + d[2] * a1 + d[3] * a2;
+    float yd = y * cdist + d[2] * a3 + d[3] * a1;
+    u = xd * K[0] + K[2];
+    v = yd * K[4] + K[5];
+}
+
+// camera records in shared memory, converted to T: per camera 38 values (P 12, R 9, t 3, K 9, dist 5)
+#define CAM_T_STRIDE 38
+template <typename T>
+__device__ __forceinline__ void load_cams(const double* __restrict__ cams, int C, T* sm)
+{
+    for (int i = threadIdx.x; i < C * CAM_T_STRIDE; i += blockDim.x) {
+        int c = i / CAM_T_STRIDE, k = i - c * CAM_T_STRIDE;
+        sm[i] = (T)cams[(size_t)c * MOCAP_CAM_STRIDE + k];
+    }
+    __syncthreads();
+}
+
+// P = K[rank] @ [R|t][cam] (the reference indexes intrinsics by position among the *remaining* views, Helpers.py:58-62)
+template <typename T>
+__device__ __forceinline__ void make_P(const T* camK, const T* camPose, T* P)
+{
+    const T* K = camK + CAM_K; const T* R = camPose + CAM_R; const T* t = camPose + CAM_T;
+#pragma unroll
+    for (int r = 0; r < 3; ++r) {
+#pragma unroll
+        for (int c = 0; c < 3; ++c) P[4 * r + c] = K[3 * r] * R[c] + K[3 * r + 1] * R[3 + c] + K[3 * r + 2] * R[6 + c];
+        P[4 * r + 3] = K[3 * r] * t[0] + K[3 * r + 1] * t[1] + K[3 * r + 2] * t[2];
+    }
+}
+
+template <typename T, bool TRIANGULATE>
+__global__ void __launch_bounds__(128) triangulate_kernel(const T* __restrict__ pts, const uint8_t* __restrict__ valid,
+                                                          const T* __restrict__ xyz_in, const double* __restrict__ cams,
+                                                          int C, long long n, T* __restrict__ xyz_out, T* __restrict__ err_out)
+{
+    DYN_SHARED(smraw);
+    T* sm = (T*)smraw;
+    load_cams<T>(cams, C, sm);
+    const T nan = (T)NAN;
+    for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (long long)gridDim.x * blockDim.x) {
+        const T* p = pts + (size_t)i * C * 2;
+        const uint8_t* vm = valid ? valid + (size_t)i * C : nullptr;
+        T X[3];
+        int nv = 0;
+        if (TRIANGULATE) {
+            Accum<T> acc; acc.clear();
+            for (int c = 0; c < C; ++c) {
+                if (vm && !vm[c]) continue;
+                T x = p[2 * c], y = p[2 * c + 1];
+                if (vm) { T P[12]; make_P<T>(sm + nv * CAM_T_STRIDE, sm + c * CAM_T_STRIDE, P); acc.add_view(P, x, y); }
+                else acc.add_view(sm + c * CAM_T_STRIDE + CAM_P, x, y);
+                ++nv;
+            }
+            if (nv <= 1) { X[0] = X[1] = X[2] = nan; }
+            else acc.solve(X);
+            xyz_out[(size_t)i * 3] = X[0]; xyz_out[(size_t)i * 3 + 1] = X[1]; xyz_out[(size_t)i * 3 + 2] = X[2];
+        } else {
+            X[0] = xyz_in[(size_t)i * 3]; X[1] = xyz_in[(size_t)i * 3 + 1]; X[2] = xyz_in[(size_t)i * 3 + 2];
+            for (int c = 0; c < C; ++c) nv += (!vm || vm[c]);
+        }
+        if (err_out) {
+            T e = nan;
+            if (nv > 1) {
+                T s = (T)0;
+                int rank = 0;
+                for (int c = 0; c < C; ++c) {
+                    if (vm && !vm[c]) continue;
+                    T u, v;
+                    project<T>(sm + c * CAM_T_STRIDE + CAM_R, sm + (vm ? rank : c) * CAM_T_STRIDE + CAM_K, X, u, v);
+                    T dx = p[2 * c] - u, dy = p[2 * c + 1] - v;
+                    s += dx * dx; s += dy * dy;
+                    ++rank;
+                }
+                e = s / (T)(2 * nv);
+            }
+            err_out[i] = e;
+        }
+    }
+}
+
+template <typename T>
+static int launch_tri(const void* pts, const uint8_t* valid, const void* xyz_in, const double* cams, int C, int64_t n,
+                      void* xyz_out, void* err_out, bool tri, cudaStream_t s)
+{
+    int dev = 0, sms = 148;
+    cudaGetDevice(&dev);
+    cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
+    long long blocks = (n + 127) / 128;
+    if (blocks > (long long)sms * 16) blocks = (long long)sms * 16;
+    if (blocks < 1) blocks = 1;
+    size_t smem = (size_t)C * CAM_T_STRIDE * sizeof(T);
+    auto k_tri = triangulate_kernel<T, true>;
+    auto k_rep = triangulate_kernel<T, false>;
+    const T* no_in = nullptr;
+    T* no_out = nullptr;
+    if (tri) LAUNCH(k_tri, (unsigned)blocks, 128, smem, s, (const T*)pts, valid, no_in, cams, C, n, (T*)xyz_out, (T*)err_out);
+    else LAUNCH(k_rep, (unsigned)blocks, 128, smem, s, (const T*)pts, valid, (const T*)xyz_in, cams, C, n, no_out, (T*)err_out);
+    CUDA_TRY(cudaGetLastError());
+    return MOCAP_OK;
+}
+
+extern "C" int mocap_triangulate_batch(const void* pts_dev, const uint8_t* valid_dev, const double* cams_dev, int C,
+                                       int64_t P, int fp64_mode, void* xyz_out, void* err_out, void* stream)
+{
+    if (!pts_dev || !cams_dev || !xyz_out || C < 1 || C > MOCAP_MAX_CAMS || P < 0) return MOCAP_ERR_INVALID;
+    if (P == 0) return MOCAP_OK;
+    if (fp64_mode) return launch_tri<double>(pts_dev, valid_dev, nullptr, cams_dev, C, P, xyz_out, err_out, true, (cudaStream_t)stream);
+    return launch_tri<float>(pts_dev, valid_dev, nullptr, cams_dev, C, P, xyz_out, err_out, true, (cudaStream_t)stream);
+}
+
+extern "C" int mocap_reproject_batch(const void* pts_dev, const uint8_t* valid_dev, const void* xyz_dev,
+                                     const double* cams_dev, int C, int64_t P, int fp64_mode, void* err_out, void* stream)
+{
+    if (!pts_dev || !cams_dev || !xyz_dev || !err_out || C < 1 || C > MOCAP_MAX_CAMS || P < 0) return MOCAP_ERR_INVALID;
+    if (P == 0) return MOCAP_OK;
+    if (fp64_mode) return launch_tri<double>(pts_dev, valid_dev, xyz_dev, cams_dev, C, P, nullptr, err_out, false, (cudaStream_t)stream);
+    return launch_tri<float>(pts_dev, valid_dev, xyz_dev, cams_dev, C, P, nullptr, err_out, false, (cudaStream_t)stream);
+}
+
+// ---------------------------------------------------------------------------------------------------------
+// correspondence: one CTA per frame-set
+// ---------------------------------------------------------------------------------------------------------
+#define CORR_THREADS 128
+
+struct CorrWs { int32_t* cand; int32_t* ncand; };
+
+template <typename T>
+__global__ void __launch_bounds__(CORR_THREADS) correspond_kernel(
+    const int32_t* __restrict__ xy, const int32_t* __restrict__ count, int C, int max_pts,
+    const double* __restrict__ Fs, const double* __restrict__ cams, double cutoff, int obj_count, int max_groups,
+    double* __restrict__ obj_out, int32_t* __restrict__ n_obj_out, int32_t* __restrict__ img_out, int32_t* __restrict__ n_valid_out,
+    double* __restrict__ err_out, int32_t* __restrict__ cand_out, int32_t* __restrict__ flags_out,
+    char* __restrict__ ws_base, size_t ws_stride)
+{
+    DYN_SHARED(smraw);
+    T* sm = (T*)smraw;
+    const int s = blockIdx.x, tid = threadIdx.x, lane = tid & 31, wid = tid >> 5, nw = blockDim.x >> 5;
+    load_cams<T>(cams, C, sm);
+    __shared__ int s_flags, s_nvalid;
+    if (tid == 0) { s_flags = 0; s_nvalid = 0; }
+    const int32_t* fxy = xy + (size_t)s * C * max_pts * 2;
+    const int32_t* fcount = count + (size_t)s * C;
+    char* wp = ws_base + (size_t)s * ws_stride;
+    double* rerr = (double*)wp;                                             // [max_pts] mean error per root
+    double* rX = rerr + max_pts;                                            // [max_pts][3] first group's point
+    int32_t* cand = (int32_t*)(rX + 3 * (size_t)max_pts);                   // [max_pts][C][MAX_CAND]
+    int32_t* ncand = cand + (size_t)max_pts * C * MOCAP_MAX_CAND;           // [max_pts][C]
+    int32_t* vidx = ncand + (size_t)max_pts * C;                            // [max_pts] slot among complete roots, -1 = incomplete
+    const int R = min(fcount[0], max_pts);
+    __syncthreads();
+
+    // ---- candidates per (root, camera): epiline (FP64 -> f32) and point-line distances (FP64) --------------------------
+    for (int it = tid; it < R * C; it += blockDim.x) {
+        int j = it / C, i = it - j * C;
+        int32_t* cl = cand + ((size_t)j * C + i) * MOCAP_MAX_CAND;
+        if (i == 0) { ncand[j * C] = 1; cl[0] = j; continue; }
+        const double* F = Fs + (size_t)(i - 1) * 9;
+        double x = (double)(float)fxy[2 * j], y = (double)(float)fxy[2 * j + 1];      // root is camera-0 point j
+        double a = __dadd_rn(__dadd_rn(__dmul_rn(F[0], x), __dmul_rn(F[1], y)), F[2]);
+        double b = __dadd_rn(__dadd_rn(__dmul_rn(F[3], x), __dmul_rn(F[4], y)), F[5]);
+        double c = __dadd_rn(__dadd_rn(__dmul_rn(F[6], x), __dmul_rn(F[7], y)), F[8]);
+        double nu = __dadd_rn(__dmul_rn(a, a), __dmul_rn(b, b));
+        nu = nu != 0.0 ? __ddiv_rn(1.0, sqrt(nu)) : 1.0;
+        a = (double)(float)__dmul_rn(a, nu); b = (double)(float)__dmul_rn(b, nu); c = (double)(float)__dmul_rn(c, nu);
+        double den = sqrt(__dadd_rn(__dmul_rn(a, a), __dmul_rn(b, b)));
+        const int32_t* pp = fxy + (size_t)i * max_pts * 2;
+        int np = min(fcount[i], max_pts), n = 0, fl = 0;
+        double dist[MOCAP_MAX_CAND];
+        for (int k = 0; k < np; ++k) {
+            double d = __ddiv_rn(fabs(__dadd_rn(__dadd_rn(__dmul_rn(a, (double)pp[2 * k]), __dmul_rn(b, (double)pp[2 * k + 1])), c)), den);
+            if (fabs(d - cutoff) < 1e-5) fl |= MOCAP_CFLAG_TIE;
+            if (!(d < cutoff)) continue;
+            int pos;                                           // keep the MOCAP_MAX_CAND smallest, stable on ties
+            if (n < MOCAP_MAX_CAND) { pos = n; ++n; }
+            else { fl |= MOCAP_CFLAG_CAND_CAP; if (!(d < dist[MOCAP_MAX_CAND - 1])) continue; pos = MOCAP_MAX_CAND - 1; }
+            while (pos > 0 && d < dist[pos - 1]) { dist[pos] = dist[pos - 1]; cl[pos] = cl[pos - 1]; --pos; }
+            dist[pos] = d; cl[pos] = k;
+        }
+        ncand[j * C + i] = n;
+        if (fl) atomicOr(&s_flags, fl);
+        if (cand_out) {
+            int32_t* co = cand_out + (((size_t)s * max_pts + j) * C + i) * MOCAP_MAX_CAND;
+            for (int k = 0; k < MOCAP_MAX_CAND; ++k) co[k] = k < n ? cl[k] : -1;
+        }
+    }
+    __syncthreads();
+
+    // ---- per root (one warp each): enumerate candidate groups, triangulate, mean reprojection error ----------------------
+    for (int j = wid; j < R; j += nw) {
+        long long ng = 1;
+        bool complete = C >= 2;
+        for (int i = 1; i < C; ++i) { int n = ncand[j * C + i]; if (n == 0) complete = false; ng *= n; if (ng > (1LL << 40)) ng = 1LL << 40; }
+        if (!complete) { if (lane == 0) vidx[j] = -1; continue; }
+        int ne = (int)min(ng, (long long)max_groups);
+        if (ng > max_groups && lane == 0) atomicOr(&s_flags, MOCAP_CFLAG_GROUP_CAP);
+        T esum = (T)0;
+        T X0[3] = {0, 0, 0};
+        for (int g = lane; g < ne; g += 32) {
+            // mixed radix: camera 1 varies fastest (Helpers.py:239-245 appends the newest camera as the outer loop)
+            Accum<T> acc; acc.clear();
+            T px[MOCAP_MAX_CAMS], py[MOCAP_MAX_CAMS];
+            int rem = g;
+            for (int i = 0; i < C; ++i) {
+                int k;
+                if (i == 0) k = j;
+                else { int n = ncand[j * C + i]; int q = rem / n; k = cand[((size_t)j * C + i) * MOCAP_MAX_CAND + (rem - q * n)]; rem = q; }
+                const int32_t* pt = fxy + ((size_t)i * max_pts + k) * 2;
+                px[i] = (T)pt[0]; py[i] = (T)pt[1];
+                acc.add_view(sm + i * CAM_T_STRIDE + CAM_P, px[i], py[i]);
+            }
+            T X[3];
+            acc.solve(X);
+            T sq = (T)0;
+            for (int i = 0; i < C; ++i) {
+                T u, v;
+                project<T>(sm + i * CAM_T_STRIDE + CAM_R, sm + i * CAM_T_STRIDE + CAM_K, X, u, v);
+                T dx = px[i] - u, dy = py[i] - v;
+                sq += dx * dx; sq += dy * dy;
+            }
+            esum += sq / (T)(2 * C);
+            if (g == 0) { X0[0] = X[0]; X0[1] = X[1]; X0[2] = X[2]; }
+        }
+        // fixed-order warp reduction (bit-identical on any GPU count)
+        for (int o = 16; o > 0; o >>= 1) esum += __shfl_down_sync(0xffffffffu, esum, o);
+        if (lane == 0) {
+            rerr[j] = (double)esum / (double)ne;
+            rX[3 * j] = (double)X0[0]; rX[3 * j + 1] = (double)X0[1]; rX[3 * j + 2] = (double)X0[2];
+            vidx[j] = 0;
+        }
+    }
+    __syncthreads();
+    // ---- compact complete roots in root order, rank by mean error -------------------------------------------------------------
+    if (tid == 0) {
+        int n = 0;
+        for (int j = 0; j < R; ++j) if (vidx[j] >= 0) vidx[j] = n++;
+        s_nvalid = n;
+    }
+    __syncthreads();
+    const int nvalid = s_nvalid;
+    for (int j = tid; j < R; j += blockDim.x) {
+        int v = vidx[j];
+        if (v < 0) continue;
+        double e = rerr[j];
+        int rank = 0;
+        for (int k = 0; k < R; ++k) {
+            if (vidx[k] < 0 || k == j) continue;
+            double ek = rerr[k];
+            rank += (ek < e) || (ek == e && k < j);
+        }
+        int n_obj = obj_count > nvalid ? nvalid : min(obj_count + 1, nvalid);
+        if (rank < n_obj) {
+            double* o = obj_out + ((size_t)s * max_pts + rank) * 3;
+            o[0] = rX[3 * j]; o[1] = rX[3 * j + 1]; o[2] = rX[3 * j + 2];
+        }
+        err_out[(size_t)s * max_pts + v] = e;
+        int32_t* io = img_out + ((size_t)s * max_pts + v) * C * 2;
+        for (int i = 0; i < C; ++i) {
+            int k = i == 0 ? j : cand[((size_t)j * C + i) * MOCAP_MAX_CAND];
+            io[2 * i] = fxy[((size_t)i * max_pts + k) * 2];
+            io[2 * i + 1] = fxy[((size_t)i * max_pts + k) * 2 + 1];
+        }
+    }
+    if (tid == 0) {
+        n_valid_out[s] = nvalid;
+        n_obj_out[s] = obj_count > nvalid ? nvalid : min(obj_count + 1, nvalid);
+        flags_out[s] = s_flags;
+    }
+}
+
+static size_t corr_ws_stride(int C, int max_pts)
+{
+    size_t b = ((size_t)max_pts * C * MOCAP_MAX_CAND + (size_t)max_pts * C + (size_t)max_pts) * 4 + (size_t)max_pts * 4 * 8;
+    return (b + 255) & ~(size_t)255;
+}
+
+extern "C" size_t mocap_correspond_workspace_bytes(int S, int C, int max_pts, int max_groups)
+{
+    (void)max_groups;
+    if (S <= 0 || C <= 0 || max_pts <= 0) return 0;
+    return corr_ws_stride(C, max_pts) * (size_t)S;
+}
+
+extern "C" int mocap_correspond_batch(const int32_t* xy_dev, const int32_t* count_dev, int S, int C, int max_pts,
+                                      const double* F_dev, const double* cams_dev, double cutoff, int obj_count,
+                                      int max_groups, int fp64_mode,
+                                      double* obj_out, int32_t* n_obj_out, int32_t* img_out, int32_t* n_valid_out,
+                                      double* err_out, int32_t* cand_out, int32_t* flags_out,
+                                      void* workspace, size_t workspace_bytes, void* stream)
+{
+    if (!xy_dev || !count_dev || !cams_dev || !obj_out || !n_obj_out || !img_out || !n_valid_out || !err_out || !flags_out || !workspace)
+        return MOCAP_ERR_INVALID;
+    if (S < 0 || C < 1 || C > MOCAP_MAX_CAMS || max_pts < 1 || max_groups < 1 || obj_count < 0) return MOCAP_ERR_INVALID;
+    if (C > 1 && !F_dev) return MOCAP_ERR_INVALID;
+    if (S == 0) return MOCAP_OK;
+    size_t stride = corr_ws_stride(C, max_pts);
+    if (workspace_bytes < stride * (size_t)S) return MOCAP_ERR_WORKSPACE;
+    cudaStream_t s = (cudaStream_t)stream;
+    if (fp64_mode)
+        LAUNCH(correspond_kernel<double>, S, CORR_THREADS, (size_t)C * CAM_T_STRIDE * sizeof(double), s, 
+            xy_dev, count_dev, C, max_pts, F_dev, cams_dev, cutoff, obj_count, max_groups, obj_out, n_obj_out, img_out,
+            n_valid_out, err_out, cand_out, flags_out, (char*)workspace, stride);
+    else
+        LAUNCH(correspond_kernel<float>, S, CORR_THREADS, (size_t)C * CAM_T_STRIDE * sizeof(float), s, 
+            xy_dev, count_dev, C, max_pts, F_dev, cams_dev, cutoff, obj_count, max_groups, obj_out, n_obj_out, img_out,
+            n_valid_out, err_out, cand_out, flags_out, (char*)workspace, stride);
+    CUDA_TRY(cudaGetLastError());
+    return MOCAP_OK;
+}

@@ -1,0 +1,322 @@
+"""Host side of the B200 capture path: device memory, streams and batching around the C-ABI.
+
+PyTorch is plumbing here (HBM allocations, the current CUDA stream, torch.distributed); every computation of the
+path happens inside libmocap_b200.so.  `CaptureEngine()` refuses to exist without a CUDA device and the built
+library -- there is no CPU path.  (`_test_lib`/`device` exist so that tests/ can drive the same host logic against
+the CPU emulation build of the kernel sources, tests/emu; the package itself never does that.)
+"""
+from __future__ import annotations
+
+import ctypes
+import threading
+from dataclasses import dataclass, field
+
+import numpy as np
+import torch
+
+from . import _cabi
+
+THRESH_U8 = 216          # cv.threshold(x, 255*0.85) on uint8  (lib/ImageOperations.py:29)
+MIN_AREA = 500.0         # area > 500                           (lib/ImageOperations.py:50)
+MIN_CIRC = 0.5           # circularity > 0.5                    (lib/ImageOperations.py:50)
+EPI_CUTOFF = 10.0        # distance_cutoff                      (lib/Helpers.py:219)
+
+
+def pack_cameras(camera_poses, camera_params) -> np.ndarray:
+    """[C, 40] float64 camera records for the C-ABI (layout in include/mocap_b200.h).
+
+    P = K @ [R|t] is formed here in FP64 exactly like lib/Helpers.py:58-62 does per call.
+    """
+    C = len(camera_poses)
+    if len(camera_params) < C:
+        raise IndexError("camera_params shorter than camera_poses")      # the reference raises IndexError here too
+    out = np.zeros((C, _cabi.CAM_STRIDE), dtype=np.float64)
+    for i, pose in enumerate(camera_poses):
+        R = np.asarray(pose["R"], dtype=np.float64).reshape(3, 3)
+        t = np.asarray(pose["t"], dtype=np.float64).reshape(3)
+        K = np.asarray(camera_params[i]["intrinsic_matrix"], dtype=np.float64).reshape(3, 3)
+        d = np.zeros(5)
+        dd = np.asarray(camera_params[i]["distortion_coef"], dtype=np.float64).ravel()
+        d[:min(5, dd.size)] = dd[:5]
+        P = K @ np.c_[R, t]
+        out[i, 0:12] = P.ravel()
+        out[i, 12:21] = R.ravel()
+        out[i, 21:24] = t
+        out[i, 24:33] = K.ravel()
+        out[i, 33:38] = d
+    return out
+
+
+@dataclass
+class DetectResult:
+    xy: torch.Tensor                 # [n, max_blobs, 2] int32, reference output order
+    count: torch.Tensor              # [n] int32 (0 == the reference's [[None, None]])
+    flags: torch.Tensor              # [n] int32 MOCAP_FLAG_*
+    extras: dict = field(default_factory=dict)
+
+    def points(self, i: int):
+        """Frame i as the reference returns it: [[x, y], ...] Python ints, or [[None, None]]."""
+        n = int(self.count[i])
+        if n == 0:
+            return [[None, None]]
+        return [[int(a), int(b)] for a, b in self.xy[i, :n].tolist()]
+
+
+@dataclass
+class CorrespondResult:
+    obj: torch.Tensor        # [S, max_pts, 3] float64, sorted by mean error, first n_obj valid
+    n_obj: torch.Tensor      # [S]
+    img: torch.Tensor        # [S, max_pts, C, 2] int32, first n_valid valid (root order)
+    n_valid: torch.Tensor    # [S]
+    err: torch.Tensor        # [S, max_pts] float64 mean error per complete root (root order)
+    flags: torch.Tensor      # [S]
+    cand: torch.Tensor | None = None
+
+
+class CaptureEngine:
+    def __init__(self, device=None, *, _test_lib: str | None = None):
+        if _test_lib is None:
+            if not torch.cuda.is_available():
+                raise _cabi.MocapError("mocapv2_b200 needs a CUDA device (B200, sm_100a); there is no CPU fallback")
+            self.device = torch.device(device if device is not None else f"cuda:{torch.cuda.current_device()}")
+            if self.device.type != "cuda":
+                raise _cabi.MocapError("mocapv2_b200 runs on CUDA devices only")
+            self.lib = _cabi.load()
+        else:                                   # tests/ only: CPU emulation build of the same kernel sources
+            self.device = torch.device("cpu")
+            self.lib = _cabi.load(_test_lib)
+        self._tables = {}
+        self._ws = None
+        self._lock = threading.Lock()           # _find_dot is called from one thread per camera (RealtimeTracking_FLIR.py:309)
+        self.launches = 0                       # kernels launched through this engine (bench bookkeeping)
+
+    # ---- plumbing ------------------------------------------------------------------------------------------------
+    def _stream(self):
+        if self.device.type == "cuda":
+            return ctypes.c_void_p(torch.cuda.current_stream(self.device).cuda_stream)
+        return ctypes.c_void_p(0)
+
+    def _check_dev(self, t: torch.Tensor, dtype, name):
+        if t.device != self.device or t.dtype != dtype or not t.is_contiguous():
+            raise ValueError(f"{name}: expected contiguous {dtype} tensor on {self.device}, got {t.dtype} on {t.device}")
+        return t
+
+    @staticmethod
+    def _ptr(t):
+        return ctypes.c_void_p(t.data_ptr()) if t is not None else ctypes.c_void_p(0)
+
+    def _workspace(self, nbytes: int) -> torch.Tensor:
+        if self._ws is None or self._ws.numel() < nbytes:
+            self._ws = None
+            self._ws = torch.empty(int(nbytes), dtype=torch.uint8, device=self.device)
+        return self._ws
+
+    def empty(self, shape, dtype):
+        return torch.empty(shape, dtype=dtype, device=self.device)
+
+    # ---- undistortion table ---------------------------------------------------------------------------------------------
+    def table(self, K, dist, H: int, W: int) -> torch.Tensor:
+        K = np.ascontiguousarray(np.asarray(K, dtype=np.float64).reshape(9))
+        d = np.zeros(5, dtype=np.float64)
+        dd = np.asarray(dist, dtype=np.float64).ravel()
+        d[:min(5, dd.size)] = dd[:5]
+        key = (K.tobytes(), d.tobytes(), H, W)
+        tab = self._tables.get(key)
+        if tab is None:
+            nbytes = self.lib.mocap_undistort_table_bytes(H, W)
+            if nbytes == 0:
+                raise _cabi.MocapError("unsupported frame size")
+            tab = torch.zeros(int(nbytes), dtype=torch.uint8, device=self.device)
+            with torch.cuda.device(self.device) if self.device.type == "cuda" else _nullctx():
+                st = self.lib.mocap_undistort_table_build(K.ctypes.data, d.ctypes.data, H, W, self._ptr(tab), nbytes, self._stream())
+            _cabi.check(self.lib, st, "mocap_undistort_table_build")
+            self.launches += 3
+            self._tables[key] = tab
+        return tab
+
+    # ---- detection ----------------------------------------------------------------------------------------------------------
+    def default_caps(self, H, W, max_blobs=None, max_contours=None, max_runs=None):
+        max_blobs = 256 if max_blobs is None else int(max_blobs)
+        max_contours = max(2 * max_blobs, 512) if max_contours is None else int(max_contours)
+        max_runs = 4 * H + 4096 if max_runs is None else int(max_runs)
+        return max_blobs, max_contours, max_runs
+
+    def detect(self, frames: torch.Tensor, K, dist, *, thresh=THRESH_U8, min_area=MIN_AREA, min_circ=MIN_CIRC,
+               max_blobs=None, max_contours=None, max_runs=None, outputs=(), out: DetectResult | None = None) -> DetectResult:
+        """_find_dot(img)[1] for a batch (lib/ImageOperations.py:33-78).  frames: [n, H, W] uint8 on the device.
+
+        outputs: any of "bits", "labels", "blob_sums", "contours" (parity outputs, see include/mocap_b200.h).
+        """
+        if frames.dim() != 3:
+            raise ValueError("frames must be [n, H, W]")
+        if frames.device != self.device or frames.dtype != torch.uint8:
+            raise ValueError(f"frames must be uint8 on {self.device}")
+        n, H, W = frames.shape
+        if frames.stride(2) != 1 or frames.stride(1) != W:
+            frames = frames.contiguous()
+        stride = frames.stride(0) if n > 1 else H * W
+        max_blobs, max_contours, max_runs = self.default_caps(H, W, max_blobs, max_contours, max_runs)
+        tab = self.table(K, dist, H, W)
+        if out is None:
+            out = DetectResult(self.empty((n, max_blobs, 2), torch.int32), self.empty((n,), torch.int32),
+                               self.empty((n,), torch.int32))
+        ex = out.extras
+        TX = (W + 31) // 32
+        if "bits" in outputs and "bits" not in ex:
+            ex["bits"] = self.empty((n, H, TX), torch.int32)
+        if "labels" in outputs and "labels" not in ex:
+            ex["labels"] = self.empty((n, H, W), torch.int32)
+        if "blob_sums" in outputs and "blob_sums" not in ex:
+            ex["blob_sums"] = torch.zeros((n, max_blobs, 3), dtype=torch.int64, device=self.device)
+            ex["blob_count"] = self.empty((n,), torch.int32)
+        if "contours" in outputs and "contours" not in ex:
+            ex["contours"] = torch.zeros((n, max_contours, 8), dtype=torch.float64, device=self.device)
+            ex["contour_count"] = self.empty((n,), torch.int32)
+        nbytes = self.lib.mocap_detect_workspace_bytes(n, H, W, max_blobs, max_contours, max_runs)
+        if nbytes == 0:
+            raise _cabi.MocapError("mocap_detect_workspace_bytes: unsupported shape")
+        with self._lock:
+            ws = self._workspace(nbytes)
+            st = self.lib.mocap_detect_batch(
+                self._ptr(frames), n, H, W, stride, self._ptr(tab), int(thresh), float(min_area), float(min_circ),
+                max_blobs, max_contours, max_runs, self._ptr(out.xy), self._ptr(out.count), self._ptr(out.flags),
+                self._ptr(ex.get("bits")), self._ptr(ex.get("labels")), self._ptr(ex.get("blob_sums")),
+                self._ptr(ex.get("blob_count")), self._ptr(ex.get("contours")), self._ptr(ex.get("contour_count")),
+                self._ptr(ws), nbytes, self._stream())
+            _cabi.check(self.lib, st, "mocap_detect_batch")
+            self.launches += 4 + (1 if "bits" in ex else 0)
+        return out
+
+    def filter(self, frames: torch.Tensor, K, dist, *, thresh=THRESH_U8) -> torch.Tensor:
+        """undistort -> image_filter_gpu (lib/ImageOperations.py:38-40, 23-31): packed binary image [n, H, ceil(W/32)]."""
+        n, H, W = frames.shape
+        frames = self._check_dev(frames.contiguous(), torch.uint8, "frames")
+        tab = self.table(K, dist, H, W)
+        bits = self.empty((n, H, (W + 31) // 32), torch.int32)
+        nbytes = self.lib.mocap_detect_workspace_bytes(n, H, W, 1, 1, 1)
+        with self._lock:
+            ws = self._workspace(nbytes)
+            st = self.lib.mocap_filter_batch(self._ptr(frames), n, H, W, H * W, self._ptr(tab), int(thresh), self._ptr(bits),
+                                             self._ptr(ws), nbytes, self._stream())
+            _cabi.check(self.lib, st, "mocap_filter_batch")
+            self.launches += 4
+        return bits
+
+    def blur5(self, frames: torch.Tensor) -> torch.Tensor:
+        """fast_cuda_blur(image, 5) (lib/CudaOperations.py:24-41) for a batch [n, H, W] uint8."""
+        frames = self._check_dev(frames.contiguous(), torch.uint8, "frames")
+        n, H, W = frames.shape
+        out = torch.empty_like(frames)
+        _cabi.check(self.lib, self.lib.mocap_blur5_batch(self._ptr(frames), n, H, W, self._ptr(out), self._stream()), "mocap_blur5_batch")
+        self.launches += 1
+        return out
+
+    def undistort(self, frames: torch.Tensor, K, dist) -> torch.Tensor:
+        """cv.undistort(img, K, dist) (lib/ImageOperations.py:38) for a batch [n, H, W] uint8."""
+        frames = self._check_dev(frames.contiguous(), torch.uint8, "frames")
+        n, H, W = frames.shape
+        tab = self.table(K, dist, H, W)
+        out = torch.empty_like(frames)
+        _cabi.check(self.lib, self.lib.mocap_undistort_batch(self._ptr(frames), n, H, W, self._ptr(tab), self._ptr(out), self._stream()),
+                    "mocap_undistort_batch")
+        self.launches += 1
+        return out
+
+    # ---- geometry -----------------------------------------------------------------------------------------------------------
+    def cameras(self, camera_poses, camera_params) -> torch.Tensor:
+        return torch.from_numpy(pack_cameras(camera_poses, camera_params)).to(self.device)
+
+    def triangulate(self, pts: torch.Tensor, cams: torch.Tensor, valid: torch.Tensor | None = None, *, want_err=True,
+                    xyz: torch.Tensor | None = None, err: torch.Tensor | None = None):
+        """triangulate_points + calculate_reprojection_errors (lib/Helpers.py:43-143) for pts [P, C, 2] (f32 or f64)."""
+        if pts.dtype not in (torch.float32, torch.float64):
+            raise ValueError("pts must be float32 (main mode) or float64 (check mode)")
+        pts = self._check_dev(pts, pts.dtype, "pts")
+        cams = self._check_dev(cams, torch.float64, "cams")
+        P, C, _ = pts.shape
+        if valid is not None:
+            valid = self._check_dev(valid, torch.uint8, "valid")
+        if xyz is None:
+            xyz = self.empty((P, 3), pts.dtype)
+        if err is None and want_err:
+            err = self.empty((P,), pts.dtype)
+        st = self.lib.mocap_triangulate_batch(self._ptr(pts), self._ptr(valid), self._ptr(cams), C, P,
+                                              1 if pts.dtype == torch.float64 else 0, self._ptr(xyz), self._ptr(err), self._stream())
+        _cabi.check(self.lib, st, "mocap_triangulate_batch")
+        self.launches += 1 if P else 0
+        return xyz, err
+
+    def reproject(self, pts: torch.Tensor, xyz: torch.Tensor, cams: torch.Tensor, valid: torch.Tensor | None = None):
+        """calculate_reprojection_errors (lib/Helpers.py:102-143) for given object points."""
+        pts = self._check_dev(pts, pts.dtype, "pts")
+        xyz = self._check_dev(xyz, pts.dtype, "xyz")
+        cams = self._check_dev(cams, torch.float64, "cams")
+        P, C, _ = pts.shape
+        if valid is not None:
+            valid = self._check_dev(valid, torch.uint8, "valid")
+        err = self.empty((P,), pts.dtype)
+        st = self.lib.mocap_reproject_batch(self._ptr(pts), self._ptr(valid), self._ptr(xyz), self._ptr(cams), C, P,
+                                            1 if pts.dtype == torch.float64 else 0, self._ptr(err), self._stream())
+        _cabi.check(self.lib, st, "mocap_reproject_batch")
+        self.launches += 1 if P else 0
+        return err
+
+    def correspond(self, xy: torch.Tensor, count: torch.Tensor, Fs: torch.Tensor, cams: torch.Tensor, *, obj_count=0,
+                   cutoff=EPI_CUTOFF, max_groups=4096, fp64=False, want_cand=False) -> CorrespondResult:
+        """find_point_correspondance_and_object_points (lib/Helpers.py:178-280) for S frame-sets.
+
+        xy [S, C, max_pts, 2] int32 centroid lists, count [S, C] int32, Fs [C-1, 3, 3] float64 (Fs[i-1]: camera 0 -> camera i).
+        """
+        xy = self._check_dev(xy, torch.int32, "xy")
+        count = self._check_dev(count, torch.int32, "count")
+        cams = self._check_dev(cams, torch.float64, "cams")
+        S, C, max_pts, _ = xy.shape
+        if C > 1:
+            Fs = self._check_dev(Fs, torch.float64, "Fs")
+            if Fs.shape[0] < C - 1:
+                raise IndexError("Fs shorter than camera count - 1")        # the reference raises IndexError (Helpers.py:206)
+        res = CorrespondResult(
+            obj=torch.zeros((S, max_pts, 3), dtype=torch.float64, device=self.device), n_obj=self.empty((S,), torch.int32),
+            img=torch.zeros((S, max_pts, C, 2), dtype=torch.int32, device=self.device), n_valid=self.empty((S,), torch.int32),
+            err=torch.zeros((S, max_pts), dtype=torch.float64, device=self.device), flags=self.empty((S,), torch.int32),
+            cand=self.empty((S, max_pts, C, _cabi.MAX_CAND), torch.int32) if want_cand else None)
+        if S == 0:
+            return res
+        nbytes = self.lib.mocap_correspond_workspace_bytes(S, C, max_pts, max_groups)
+        with self._lock:
+            ws = self._workspace(nbytes)
+            st = self.lib.mocap_correspond_batch(
+                self._ptr(xy), self._ptr(count), S, C, max_pts, self._ptr(Fs) if C > 1 else ctypes.c_void_p(0), self._ptr(cams),
+                float(cutoff), int(obj_count), int(max_groups), 1 if fp64 else 0,
+                self._ptr(res.obj), self._ptr(res.n_obj), self._ptr(res.img), self._ptr(res.n_valid), self._ptr(res.err),
+                self._ptr(res.cand), self._ptr(res.flags), self._ptr(ws), nbytes, self._stream())
+            _cabi.check(self.lib, st, "mocap_correspond_batch")
+            self.launches += 1
+        return res
+
+
+class _nullctx:
+    def __enter__(self):
+        return self
+
+    def __exit__(self, *a):
+        return False
+
+
+_default_engine = None
+_default_lock = threading.Lock()
+
+
+def default_engine() -> CaptureEngine:
+    """Process-wide engine on the current CUDA device (created on first use; raises without CUDA)."""
+    global _default_engine
+    with _default_lock:
+        if _default_engine is None:
+            _default_engine = CaptureEngine()
+        return _default_engine
+
+
+def set_default_engine(engine: CaptureEngine | None):
+    global _default_engine
+    with _default_lock:
+        _default_engine = engine
