@@ -82,6 +82,16 @@ int mocap_filter_batch(const uint8_t* frames_dev, int n_frames, int H, int W, in
                        const void* table_dev, int thresh, uint32_t* out_bits,
                        void* workspace, size_t workspace_bytes, void* stream);
 
+/* cv.findContours(RETR_TREE, CHAIN_APPROX_SIMPLE) -> area/circularity filter -> cv.moments centroid on a given packed
+ * binary image bits_dev [n][H][ceil(W/32)] (lib/ImageOperations.py:41-65); bits at x >= W must be zero.  Outputs as in
+ * mocap_detect_batch; workspace of mocap_detect_workspace_bytes(). */
+int mocap_blobs_batch(const uint32_t* bits_dev, int n_frames, int H, int W,
+                      double min_area, double min_circ, int max_blobs, int max_contours, int max_runs,
+                      int32_t* out_xy, int32_t* out_count, int32_t* out_flags,
+                      int32_t* out_labels, int64_t* out_blob_sums, int32_t* out_blob_count,
+                      double* out_contours, int32_t* out_contour_count,
+                      void* workspace, size_t workspace_bytes, void* stream);
+
 /* ---- the reference's own GPU op: fast_cuda_blur(image, 5) (lib/CudaOperations.py:24-41) -------------------- */
 int mocap_blur5_batch(const uint8_t* frames_dev, int n_frames, int H, int W, uint8_t* out_dev, void* stream);
 /* cv.undistort alone (lib/ImageOperations.py:38), for stage parity */

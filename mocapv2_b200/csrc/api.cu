@@ -8,6 +8,7 @@ int launch_filter(const uint8_t* frames, int n, int H, int W, int64_t fstride, c
                   const FilterWs& ws, int max_fg, int* flags, cudaStream_t s);
 int launch_materialize_bits(const FilterWs& ws, int n, int H, int W, const TableView& tv, uint32_t* out, cudaStream_t s);
 // detect_blobs.cu
+int launch_tiles_from_bits(const uint32_t* bits, int n, int H, int TX, int TY, uint32_t* fg_tiles, int* n_fg, int max_fg, cudaStream_t s);
 size_t blob_ws_stride(int H, int max_runs, int max_contours);
 int launch_blobs(const uint32_t* bits, const uint32_t* fg_tiles, const int* n_fg, int n, int H, int W, int TX,
                  int max_fg, int max_runs, int max_blobs, int max_contours, double min_area, double min_circ,
@@ -126,6 +127,32 @@ extern "C" int mocap_detect_batch(const uint8_t* frames_dev, int n_frames, int H
         if (st != MOCAP_OK) return st;
     }
     return launch_blobs(ws.bits, ws.fg_tiles, ws.n_fg, n_frames, H, W, L.TX, L.max_fg, max_runs, max_blobs, max_contours,
+                        min_area, min_circ, (char*)workspace + L.off_blob, L.blob_stride,
+                        out_xy, out_count, out_flags, out_blob_sums, out_blob_count, out_contours, out_contour_count,
+                        out_labels, s);
+}
+
+// findContours -> filter -> moments on a given packed binary image (lib/ImageOperations.py:41-65), stage parity entry
+extern "C" int mocap_blobs_batch(const uint32_t* bits_dev, int n_frames, int H, int W,
+                                 double min_area, double min_circ, int max_blobs, int max_contours, int max_runs,
+                                 int32_t* out_xy, int32_t* out_count, int32_t* out_flags,
+                                 int32_t* out_labels, int64_t* out_blob_sums, int32_t* out_blob_count,
+                                 double* out_contours, int32_t* out_contour_count,
+                                 void* workspace, size_t workspace_bytes, void* stream)
+{
+    if (!bits_dev || !out_xy || !out_count || !out_flags || !workspace) return MOCAP_ERR_INVALID;
+    if (max_blobs <= 0 || max_contours <= 0 || max_runs <= 0) return MOCAP_ERR_INVALID;
+    DetectLayout L;
+    int st = detect_layout(n_frames, H, W, max_contours, max_runs, true, &L);
+    if (st != MOCAP_OK) return st;
+    if (workspace_bytes < L.total) return MOCAP_ERR_WORKSPACE;
+    cudaStream_t s = (cudaStream_t)stream;
+    FilterWs ws = filter_ws((char*)workspace, L);
+    CUDA_TRY(cudaMemsetAsync(out_flags, 0, (size_t)n_frames * 4, s));
+    if (out_labels) CUDA_TRY(cudaMemsetAsync(out_labels, 0, (size_t)n_frames * H * W * 4, s));
+    st = launch_tiles_from_bits(bits_dev, n_frames, H, L.TX, L.TY, ws.fg_tiles, ws.n_fg, L.max_fg, s);
+    if (st != MOCAP_OK) return st;
+    return launch_blobs(bits_dev, ws.fg_tiles, ws.n_fg, n_frames, H, W, L.TX, L.max_fg, max_runs, max_blobs, max_contours,
                         min_area, min_circ, (char*)workspace + L.off_blob, L.blob_stride,
                         out_xy, out_count, out_flags, out_blob_sums, out_blob_count, out_contours, out_contour_count,
                         out_labels, s);

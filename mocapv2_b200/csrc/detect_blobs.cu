@@ -534,6 +534,31 @@ __global__ void __launch_bounds__(BLOB_THREADS) blobs_kernel(
     }
 }
 
+// foreground-tile list of a dense packed binary image (stage entry mocap_blobs_batch; the fused path gets it from filter_tiles)
+__global__ void tiles_from_bits_kernel(const uint32_t* __restrict__ bits, int n, int H, int TX, int TY,
+                                       uint32_t* __restrict__ fg_tiles, int* __restrict__ n_fg, int max_fg)
+{
+    long long idx = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    if (idx >= (long long)n * TX * TY) return;
+    int f = (int)(idx / (TX * TY)), t = (int)(idx - (long long)f * TX * TY);
+    int ty = t / TX, tx = t - ty * TX;
+    uint32_t any = 0;
+    for (int r = 0; r < TILE && ty * TILE + r < H; ++r) any |= bits[((size_t)f * H + ty * TILE + r) * TX + tx];
+    if (any) {
+        int slot = atomicAdd(&n_fg[f], 1);
+        if (slot < max_fg) fg_tiles[(size_t)f * max_fg + slot] = (uint32_t)t;
+    }
+}
+
+int launch_tiles_from_bits(const uint32_t* bits, int n, int H, int TX, int TY, uint32_t* fg_tiles, int* n_fg, int max_fg, cudaStream_t s)
+{
+    CUDA_TRY(cudaMemsetAsync(n_fg, 0, (size_t)n * sizeof(int), s));
+    long long total = (long long)n * TX * TY;
+    LAUNCH(tiles_from_bits_kernel, (unsigned)((total + 255) / 256), 256, 0, s, bits, n, H, TX, TY, fg_tiles, n_fg, max_fg);
+    CUDA_TRY(cudaGetLastError());
+    return MOCAP_OK;
+}
+
 size_t blob_ws_stride(int H, int max_runs, int max_contours)
 {
     size_t b = 0;

@@ -187,6 +187,38 @@ class CaptureEngine:
             self.launches += 4 + (1 if "bits" in ex else 0)
         return out
 
+    def blobs(self, bits: torch.Tensor, W: int, *, min_area=MIN_AREA, min_circ=MIN_CIRC, max_blobs=None, max_contours=None,
+              max_runs=None, outputs=()) -> DetectResult:
+        """findContours -> filter -> moments (lib/ImageOperations.py:41-65) on a packed binary image [n, H, ceil(W/32)] int32."""
+        bits = self._check_dev(bits, torch.int32, "bits")
+        n, H, TX = bits.shape
+        if TX != (W + 31) // 32:
+            raise ValueError("bits row length does not match W")
+        max_blobs, max_contours, max_runs = self.default_caps(H, W, max_blobs, max_contours, max_runs)
+        out = DetectResult(self.empty((n, max_blobs, 2), torch.int32), self.empty((n,), torch.int32), self.empty((n,), torch.int32))
+        ex = out.extras
+        if "labels" in outputs:
+            ex["labels"] = self.empty((n, H, W), torch.int32)
+        if "blob_sums" in outputs:
+            ex["blob_sums"] = torch.zeros((n, max_blobs, 3), dtype=torch.int64, device=self.device)
+            ex["blob_count"] = self.empty((n,), torch.int32)
+        if "contours" in outputs:
+            ex["contours"] = torch.zeros((n, max_contours, 8), dtype=torch.float64, device=self.device)
+            ex["contour_count"] = self.empty((n,), torch.int32)
+        nbytes = self.lib.mocap_detect_workspace_bytes(n, H, W, max_blobs, max_contours, max_runs)
+        if nbytes == 0:
+            raise _cabi.MocapError("mocap_detect_workspace_bytes: unsupported shape")
+        with self._lock:
+            ws = self._workspace(nbytes)
+            st = self.lib.mocap_blobs_batch(
+                self._ptr(bits), n, H, W, float(min_area), float(min_circ), max_blobs, max_contours, max_runs,
+                self._ptr(out.xy), self._ptr(out.count), self._ptr(out.flags), self._ptr(ex.get("labels")),
+                self._ptr(ex.get("blob_sums")), self._ptr(ex.get("blob_count")), self._ptr(ex.get("contours")),
+                self._ptr(ex.get("contour_count")), self._ptr(ws), nbytes, self._stream())
+            _cabi.check(self.lib, st, "mocap_blobs_batch")
+            self.launches += 2
+        return out
+
     def filter(self, frames: torch.Tensor, K, dist, *, thresh=THRESH_U8) -> torch.Tensor:
         """undistort -> image_filter_gpu (lib/ImageOperations.py:38-40, 23-31): packed binary image [n, H, ceil(W/32)]."""
         n, H, W = frames.shape
@@ -240,6 +272,8 @@ class CaptureEngine:
             xyz = self.empty((P, 3), pts.dtype)
         if err is None and want_err:
             err = self.empty((P,), pts.dtype)
+        if P == 0:                                  # triangulate_points([]) -> np.array([]) (Helpers.py:87-99)
+            return xyz, err
         st = self.lib.mocap_triangulate_batch(self._ptr(pts), self._ptr(valid), self._ptr(cams), C, P,
                                               1 if pts.dtype == torch.float64 else 0, self._ptr(xyz), self._ptr(err), self._stream())
         _cabi.check(self.lib, st, "mocap_triangulate_batch")
@@ -255,6 +289,8 @@ class CaptureEngine:
         if valid is not None:
             valid = self._check_dev(valid, torch.uint8, "valid")
         err = self.empty((P,), pts.dtype)
+        if P == 0:
+            return err
         st = self.lib.mocap_reproject_batch(self._ptr(pts), self._ptr(valid), self._ptr(xyz), self._ptr(cams), C, P,
                                             1 if pts.dtype == torch.float64 else 0, self._ptr(err), self._stream())
         _cabi.check(self.lib, st, "mocap_reproject_batch")

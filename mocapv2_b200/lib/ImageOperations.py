@@ -1,0 +1,83 @@
+"""B200 drop-in for the reference's lib/ImageOperations.py (frame -> blob centroids).
+
+Same names and conventions as the reference module:
+  _find_dot(img, print_location=False, return_filtered=False) -> (img, image_points)   lib/ImageOperations.py:33-78
+  image_filter_gpu(image, camera_number=0)                                             lib/ImageOperations.py:23-31
+  module globals `camera_params`, `intrinsics_json`, `cuda_lock` stay assignable.
+All arithmetic runs in libmocap_b200.so on the GPU (undistort + 5x5 floor-mean + threshold + 5x5 majority +
+contour-polygon centroids, bit-exact with the reference's cv2/numba path); without CUDA every call raises.
+"""
+import json
+import threading
+
+import numpy as np
+import torch
+
+from .. import engine as _engine
+
+cuda_lock = threading.Lock()           # kept for API compatibility (lib/ImageOperations.py:9); the engine serialises itself
+
+intrinsics_json = "./jsons/camera-params-in.json"      # lib/ImageOperations.py:11 (cwd-relative, like the reference)
+camera_params = None                   # the reference loads this at import; here on first use, still overridable
+
+ANNOTATE = True                        # draw the reference's display-only overlays when cv2 is importable
+
+
+def _params():
+    global camera_params
+    if camera_params is None:
+        with open(intrinsics_json) as f:
+            camera_params = json.load(f)
+    return camera_params
+
+
+def _to_device(img, eng):
+    a = np.ascontiguousarray(img)
+    if a.dtype != np.uint8 or a.ndim != 2:
+        raise ValueError("expected a single-channel uint8 image (H, W)")
+    return torch.from_numpy(a)[None].to(eng.device, non_blocking=False)
+
+
+def image_filter_gpu(image, camera_number=0):
+    """fast_cuda_blur(5) -> threshold(255*0.85) -> medianBlur(5): uint8 {0,255} image (lib/ImageOperations.py:23-31).
+
+    `camera_number` is ignored exactly like in the reference.  No undistortion here (identity map)."""
+    eng = _engine.default_engine()
+    fr = _to_device(image, eng)
+    H, W = fr.shape[1:]
+    bits = eng.filter(fr, np.eye(3), np.zeros(5))[0]
+    b = bits.cpu().numpy().view(np.uint8)
+    return (np.unpackbits(b, axis=1, bitorder="little")[:, :W] * 255).astype(np.uint8)
+
+
+def _find_dot(img, print_location=False, return_filtered=False):
+    """output: image with dot and dot coordinates -- (img, [[x, y], ...]) or (img, [[None, None]]).
+
+    Undistortion always uses camera 0's calibration, like lib/ImageOperations.py:36-38."""
+    eng = _engine.default_engine()
+    cp = _params()[0]
+    K = np.array(cp["intrinsic_matrix"], dtype=np.float64)
+    dist = np.array(cp["distortion_coef"], dtype=np.float64)
+    fr = _to_device(img, eng)
+    H, W = fr.shape[1:]
+    res = eng.detect(fr, K, dist, outputs=("bits",) if return_filtered else ())
+    n = int(res.count[0])                                     # device -> host read of the result
+    image_points = res.xy[0, :n].tolist() if n else []
+    if return_filtered:
+        b = res.extras["bits"][0].cpu().numpy().view(np.uint8)
+        out = (np.unpackbits(b, axis=1, bitorder="little")[:, :W] * 255).astype(np.uint8)
+    else:
+        out = eng.undistort(fr, K, dist)[0].cpu().numpy()
+    if ANNOTATE and image_points:
+        try:                                                  # display-only overlays (lib/ImageOperations.py:67-73)
+            import cv2 as cv
+            for i, (x, y) in enumerate(image_points):
+                label = f"({x}, {y})" if print_location else str(i)
+                org = (x - 240, y - 15) if print_location else (x - 20, y - 15)
+                cv.putText(out, label, org, cv.FONT_HERSHEY_SIMPLEX, 2, (0, 0, 255), 4)
+                cv.circle(out, (x, y), 2, (0, 255, 0), 8)
+        except ImportError:
+            pass
+    if len(image_points) == 0:
+        image_points = [[None, None]]
+    return out, image_points

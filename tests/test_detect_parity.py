@@ -1,0 +1,238 @@
+"""Detection parity: the CUDA path through the C-ABI against the oracle / the reference-generated fixtures.
+
+Every test takes the `engine` fixture: param "emu" runs the kernel sources through the CPU emulation build (GPU-less
+CI of the kernel logic), param "gpu" (marked gpu) runs libmocap_b200.so on the device.  Integer work: bit-exact.
+"""
+import json
+import os
+
+import numpy as np
+import pytest
+import torch
+
+from mocapv2_b200 import synth as S
+from oracle import restate as R
+from util import GOLDEN, K, D, check_blob_outputs, pack_bits, unpack_bits
+
+ALL = ("bits", "labels", "blob_sums", "contours")
+
+
+def dev(engine, a):
+    return torch.from_numpy(np.ascontiguousarray(a)).to(engine.device)
+
+
+def is_gpu(engine):
+    return engine.device.type == "cuda"
+
+
+def detect_and_check(engine, frames, **kw):
+    """frames (n,H,W) uint8 numpy: full detection, every stage output compared with the oracle."""
+    res = engine.detect(dev(engine, frames), K, D, outputs=ALL, **kw)
+    W = frames.shape[2]
+    bits = unpack_bits(res.extras["bits"], W)
+    for i, img in enumerate(frames):
+        und, binimg = R.filter_frame(img, K, D)
+        assert np.array_equal(bits[i] != 0, binimg != 0), "filtered binary image differs"
+        check_blob_outputs(res, i, binimg, kw.get("min_area", R.MIN_AREA), kw.get("min_circ", R.MIN_CIRC))
+    return res
+
+
+def test_stage_undistort_and_blur(engine):
+    """cv.undistort (ImageOperations.py:38) and fast_cuda_blur (CudaOperations.py:24-41) as stand-alone stages."""
+    z = np.load(os.path.join(GOLDEN, "shapes.npz"))
+    for key in (("frame_0", "frame_3") if not is_gpu(engine) else ("frame_0", "frame_1", "frame_2", "frame_3", "frame_4", "frame_5")):
+        img = z[key]
+        und = engine.undistort(dev(engine, img[None]), K, D)[0].cpu().numpy()
+        assert np.array_equal(und, R.undistort(img, K, D))
+        blur = engine.blur5(dev(engine, img[None]))[0].cpu().numpy()
+        assert np.array_equal(blur, R.blur5_floor(img))
+
+
+def test_filter_matches_reference_bits(engine):
+    """undistort -> blur -> threshold -> median: the packed binary image equals what cv2 produced in the reference run."""
+    z = np.load(os.path.join(GOLDEN, "c1_frames.npz"))
+    frames = z["frames"].reshape(-1, 480, 640)[: (6 if is_gpu(engine) else 2)]
+    bits = unpack_bits(engine.filter(dev(engine, frames), K, D), 640)
+    for i in range(len(frames)):
+        ref = np.unpackbits(z[f"bin_{i // 2}_{i % 2}"], axis=1)[:, :640]
+        assert np.array_equal(bits[i], ref)
+
+
+def test_detect_c1_golden(engine):
+    """C1: 2 cameras 640x480, shipped calibration: centroids equal the reference's _find_dot output."""
+    z = np.load(os.path.join(GOLDEN, "c1_frames.npz"))
+    meta = json.load(open(os.path.join(GOLDEN, "c1.json")))
+    nf = 3 if is_gpu(engine) else 1
+    frames = z["frames"][:nf].reshape(-1, 480, 640)
+    res = detect_and_check(engine, frames)
+    for f in range(nf):
+        for c in range(2):
+            assert res.points(2 * f + c) == meta["records"][f][c]["points"]
+            assert int(res.extras["blob_count"][2 * f + c]) == meta["records"][f][c]["n_blobs"]
+
+
+def test_detect_shapes_golden(engine):
+    """Rings, holes, nested and edge-touching blobs at odd frame sizes (scalar scan path): reference order and centroids."""
+    z = np.load(os.path.join(GOLDEN, "shapes.npz"))
+    meta = json.load(open(os.path.join(GOLDEN, "shapes.json")))
+    for i in ((0, 1, 3, 4, 5) if not is_gpu(engine) else range(6)):
+        img = z[f"frame_{i}"]
+        res = detect_and_check(engine, img[None])
+        assert res.points(0) == meta["records"][i]["points"]
+        gold = z[f"contours_{i}"]                       # [a00, m10, m01, m00, perimeter, parent, keep] from cv2
+        got = res.extras["contours"][0, : len(gold)].cpu().numpy()
+        assert np.array_equal(got[:, 0], gold[:, 0]) and np.array_equal(got[:, 3], gold[:, 4])
+        assert np.array_equal(got[:, 5], gold[:, 5]) and np.array_equal(got[:, 6], gold[:, 6])
+
+
+def test_detect_c2_video_golden(engine):
+    """C2: frames of the reference's videos/cam*.mp4 (host-decoded, grey): blob count, contour stats and centroid parity."""
+    z = np.load(os.path.join(GOLDEN, "c2_video.npz"))
+    meta = json.load(open(os.path.join(GOLDEN, "c2_video.json")))
+    idx = list(range(10)) if is_gpu(engine) else [0, 3]
+    res = detect_and_check(engine, z["frames"][idx])
+    for k, i in enumerate(idx):
+        assert res.points(k) == meta["records"][i]["points"]
+        gold = z[f"contours_{i}"]
+        assert int(res.extras["contour_count"][k]) == len(gold)
+        got = res.extras["contours"][k, : len(gold)].cpu().numpy()
+        assert np.array_equal(got[:, 0], gold[:, 0]) and np.array_equal(got[:, 3], gold[:, 4])
+
+
+def test_blobs_random_topologies(engine):
+    """cv.findContours / moments restatement on arbitrary binary images: nesting, 8-connectivity, holes, order."""
+    rng = np.random.default_rng(11)
+    cases = 24 if not is_gpu(engine) else 200
+    for it in range(cases):
+        H, W = int(rng.integers(1, 90)), int(rng.integers(1, 120))
+        n = 1 if not is_gpu(engine) else 4
+        p = rng.choice([0.05, 0.3, 0.5, 0.6, 0.7, 0.9])
+        b = ((rng.random((n, H, W)) < p) * 255).astype(np.uint8)
+        ma = float(rng.choice([0.0, 2.0, 10.0]))
+        res = engine.blobs(dev(engine, np.stack([pack_bits(x) for x in b])), W, min_area=ma, outputs=ALL[1:],
+                           max_blobs=4096, max_contours=8192, max_runs=H * W + 1)
+        for i in range(n):
+            check_blob_outputs(res, i, b[i], ma)
+
+
+def test_blobs_deep_nesting_uses_general_ordering(engine):
+    b = np.zeros((90, 90), np.uint8)
+    for k in range(0, 44, 2):
+        b[k:90 - k, k:90 - k] = 255 if (k // 2) % 2 == 0 else 0
+    b2 = np.zeros((100, 200), np.uint8)
+    b2[:90, :90] = b
+    b2[5:95, 105:195] = b
+    b2[40:50, 140:150] = 255
+    res = engine.blobs(dev(engine, pack_bits(b2)[None]), 200, min_area=0.0, outputs=ALL[1:])
+    assert int(res.flags[0]) == 16                     # MOCAP_FLAG_DEPTH_OVERFLOW: order resolved by the general path
+    check_blob_outputs(res, 0, b2, 0.0)
+
+
+@pytest.mark.parametrize("shape", [(1, 1), (5, 5), (7, 33), (40, 65), (64, 64), (33, 130)])
+def test_edge_frames_empty_full_tiny(engine, shape):
+    H, W = shape
+    rng = np.random.default_rng(H * 1000 + W)
+    frames = np.stack([np.zeros(shape, np.uint8), np.full(shape, 255, np.uint8),
+                       rng.integers(0, 256, shape).astype(np.uint8),
+                       (rng.random(shape) < 0.7).astype(np.uint8) * 255])
+    res = detect_and_check(engine, frames, min_area=0.0)
+    assert res.points(0) == [[None, None]]             # the reference's "nothing found" value
+
+
+def test_blobs_touching_the_frame_edges_and_thresholds(engine):
+    rng = np.random.default_rng(3)
+    H, W = 96, 160
+    img = rng.integers(0, 40, (H, W)).astype(np.uint8)
+    yy, xx = np.mgrid[0:H, 0:W]
+    for cx, cy, r in ((0, 0, 25), (159, 40, 22), (80, 95, 20), (70, 30, 18)):
+        img[(xx - cx) ** 2 + (yy - cy) ** 2 <= r * r] = 255
+    for thresh in (216, 100, 254):
+        res = engine.detect(dev(engine, img[None]), K, D, outputs=ALL, thresh=thresh, min_area=50.0)
+        und = R.undistort(img, K, D)
+        binimg = R.majority5(np.where(R.blur5_floor(und) > thresh, 255, 0).astype(np.uint8))
+        assert np.array_equal(unpack_bits(res.extras["bits"], W)[0] != 0, binimg != 0)
+        check_blob_outputs(res, 0, binimg, 50.0)
+    assert res.count[0] >= 0
+
+
+def test_capacity_flags(engine):
+    """Overflowing max_blobs truncates and flags; overflowing max_runs / max_contours flags the frame invalid."""
+    H, W = 64, 96
+    b = np.zeros((H, W), np.uint8)
+    for k in range(6):
+        b[10:30, 4 + 15 * k: 14 + 15 * k] = 255
+    bits = dev(engine, pack_bits(b)[None])
+    res = engine.blobs(bits, W, min_area=0.0, max_blobs=4, max_contours=64, max_runs=4096)
+    assert int(res.flags[0]) & 2 and int(res.count[0]) == 4
+    full = engine.blobs(bits, W, min_area=0.0, max_blobs=8, max_contours=64, max_runs=4096)
+    assert full.points(0)[:4] == res.points(0)
+    res = engine.blobs(bits, W, min_area=0.0, max_blobs=8, max_contours=3, max_runs=4096)
+    assert int(res.flags[0]) & 4 and int(res.count[0]) == 0
+    res = engine.blobs(bits, W, min_area=0.0, max_blobs=8, max_contours=64, max_runs=50)
+    assert int(res.flags[0]) & 1 and int(res.count[0]) == 0
+
+
+def test_batch_equals_frame_by_frame(engine):
+    """A batch gives exactly the per-frame results (no cross-frame state), also when reusing the workspace."""
+    z = np.load(os.path.join(GOLDEN, "shapes.npz"))
+    img = z["frame_3"]
+    rng = np.random.default_rng(9)
+    frames = np.stack([img, np.zeros_like(img), img[::-1].copy(), rng.integers(0, 256, img.shape).astype(np.uint8), img.T.copy()])
+    res = engine.detect(dev(engine, frames), K, D, min_area=0.0)
+    for i in range(len(frames)):
+        one = engine.detect(dev(engine, frames[i:i + 1]), K, D, min_area=0.0)
+        assert one.points(0) == res.points(i)
+
+
+# ---------------------------------------------------------------------------------------------------------------------------
+# GPU only: the BASELINE.json sizes
+# ---------------------------------------------------------------------------------------------------------------------------
+@pytest.mark.gpu
+@pytest.mark.parametrize("idx", [0, 1, 2, 3])
+def test_big_frames_reference_golden(gpu_engine, idx):
+    """C3 (1440x1080, 32 markers) and C4 (2048x2048, 128 markers) frames regenerated by seed: the reference's outputs."""
+    import hashlib
+    rec = json.load(open(os.path.join(GOLDEN, "big_frames.json")))[idx]
+    name, cam = rec["config"], rec["cam"]
+    rig = S.config_rig(name)
+    base = S.SEED0 + {"c3": 3000, "c4": 4000}[name]
+    X = S.config_markers(name, rig, np.random.default_rng(base))
+    uv = S.marker_pixels(rig, X)
+    frng = np.random.default_rng(base + cam * 10)
+    radii = frng.integers(14, 23, len(X))
+    img = S.render_frame(rig["H"], rig["W"], uv[cam], radii, frng)
+    assert hashlib.sha256(img.tobytes()).hexdigest() == rec["sha"]
+    res = detect_and_check(gpu_engine, img[None])
+    assert res.points(0) == rec["points"]
+    assert int(res.extras["blob_count"][0]) == rec["n_blobs"] and int(res.extras["contour_count"][0]) == rec["n_contours"]
+    bits = unpack_bits(res.extras["bits"], rig["W"])[0]
+    assert hashlib.sha256(np.packbits(bits != 0, axis=1).tobytes()).hexdigest() == rec["bin_sha"]
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("name,n", [("c3", 96), ("c4", 48)])
+def test_full_size_batches_against_oracle_sample(gpu_engine, name, n):
+    """Device-rendered batches at the BASELINE sizes: oracle on a sample of frames, batch invariance on all of them."""
+    eng = gpu_engine
+    rig = S.config_rig(name)
+    H, W = rig["H"], rig["W"]
+    M = {"c3": 32, "c4": 128}[name]
+    g = torch.Generator().manual_seed(77)
+    centres = torch.stack([torch.randint(40, W - 40, (n, M), generator=g), torch.randint(40, H - 40, (n, M), generator=g)], dim=-1)
+    ridx = torch.randint(0, 9, (n, M), generator=g)
+    frames = S.render_batch_torch(H, W, centres.to(eng.device), ridx.to(eng.device), 123, eng.device)
+    res = eng.detect(frames, K, D, outputs=ALL)
+    assert int(res.flags.max()) == 0
+    host = frames.cpu().numpy()
+    for i in (0, n // 2, n - 1):
+        und, binimg = R.filter_frame(host[i], K, D)
+        assert np.array_equal(unpack_bits(res.extras["bits"][i], W) != 0, binimg != 0)
+        check_blob_outputs(res, i, binimg)
+    # same frames in another batch order / batch size: identical per-frame outputs
+    perm = torch.randperm(n, generator=g).to(eng.device)
+    res2 = eng.detect(frames[perm].contiguous(), K, D)
+    assert torch.equal(res2.count, res.count[perm])
+    live = torch.arange(res.xy.shape[1], device=eng.device)[None, :, None] < res2.count[:, None, None]
+    assert torch.equal(res2.xy * live, res.xy[perm] * live)
+    # blobs overlap at random, so only a loose sanity bound on the count
+    assert int(res.count.min()) > M // 4
