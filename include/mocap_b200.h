@@ -69,13 +69,23 @@ int mocap_undistort_table_build(const double* K9_host, const double* dist5_host,
  *   out_contour_count[n]
  */
 size_t mocap_detect_workspace_bytes(int n_frames, int H, int W, int max_blobs, int max_contours, int max_runs);
+
+/* Optional per-stage device timing of mocap_detect_batch (bench.py's roofline line): a timer owns CUDA events that
+ * the call records around its kernels on `stream`; read it after the stream has been synchronised.  Stages:
+ * 0 scan (streams every source byte), 1 compact (work list), 2 filter (remap+blur+threshold+majority on hot tiles),
+ * 3 blobs (runs, borders, moments).  ms_out[MOCAP_N_STAGES], -1 for a stage that was not recorded. */
+#define MOCAP_N_STAGES 4
+void* mocap_stage_timer_create(void);
+void mocap_stage_timer_destroy(void* timer);
+int mocap_stage_timer_read(void* timer, float* ms_out);
+const char* mocap_stage_name(int stage);
 int mocap_detect_batch(const uint8_t* frames_dev, int n_frames, int H, int W, int64_t frame_stride,
                        const void* table_dev, int thresh, double min_area, double min_circ,
                        int max_blobs, int max_contours, int max_runs,
                        int32_t* out_xy, int32_t* out_count, int32_t* out_flags,
                        uint32_t* out_bits, int32_t* out_labels, int64_t* out_blob_sums, int32_t* out_blob_count,
                        double* out_contours, int32_t* out_contour_count,
-                       void* workspace, size_t workspace_bytes, void* stream);
+                       void* workspace, size_t workspace_bytes, void* stream, void* stage_timer_or_null);
 
 /* stage entry points of the same path (used by the parity tests and the bench's per-kernel timing) */
 int mocap_filter_batch(const uint8_t* frames_dev, int n_frames, int H, int W, int64_t frame_stride,

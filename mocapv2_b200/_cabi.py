@@ -16,6 +16,7 @@ ABI_VERSION = 1
 MAX_CAND = 8
 MAX_CAMS = 16
 CAM_STRIDE = 40
+N_STAGES = 4
 
 OK = 0
 FLAG_RUN_OVERFLOW, FLAG_BLOB_OVERFLOW, FLAG_CONTOUR_OVERFLOW, FLAG_TILE_OVERFLOW, FLAG_DEPTH_OVERFLOW, FLAG_TRACE_OVERFLOW = 1, 2, 4, 8, 16, 32
@@ -35,7 +36,11 @@ SIGNATURES = {
     "mocap_undistort_table_build": (_i, [_p, _p, _i, _i, _p, _sz, _p]),
     "mocap_detect_workspace_bytes": (_sz, [_i, _i, _i, _i, _i, _i]),
     "mocap_detect_batch": (_i, [_p, _i, _i, _i, _i64, _p, _i, _d, _d, _i, _i, _i,
-                                _p, _p, _p, _p, _p, _p, _p, _p, _p, _p, _sz, _p]),
+                                _p, _p, _p, _p, _p, _p, _p, _p, _p, _p, _sz, _p, _p]),
+    "mocap_stage_timer_create": (_p, []),
+    "mocap_stage_timer_destroy": (None, [_p]),
+    "mocap_stage_timer_read": (_i, [_p, _p]),
+    "mocap_stage_name": (C.c_char_p, [_i]),
     "mocap_filter_batch": (_i, [_p, _i, _i, _i, _i64, _p, _i, _p, _p, _sz, _p]),
     "mocap_blobs_batch": (_i, [_p, _i, _i, _i, _d, _d, _i, _i, _i, _p, _p, _p, _p, _p, _p, _p, _p, _p, _sz, _p]),
     "mocap_blur5_batch": (_i, [_p, _i, _i, _i, _p, _p]),

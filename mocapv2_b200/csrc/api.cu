@@ -5,7 +5,7 @@
 // detect_filter.cu
 int table_view(const void* table_dev, int H, int W, TableView* tv);
 int launch_filter(const uint8_t* frames, int n, int H, int W, int64_t fstride, const TableView& tv, int thresh,
-                  const FilterWs& ws, int max_fg, int* flags, cudaStream_t s);
+                  const FilterWs& ws, int max_fg, int* flags, cudaStream_t s, StageTimer* timer);
 int launch_materialize_bits(const FilterWs& ws, int n, int H, int W, const TableView& tv, uint32_t* out, cudaStream_t s);
 // detect_blobs.cu
 int launch_tiles_from_bits(const uint32_t* bits, int n, int H, int TX, int TY, uint32_t* fg_tiles, int* n_fg, int max_fg, cudaStream_t s);
@@ -31,8 +31,44 @@ extern "C" const char* mocap_status_string(int status)
 
 extern "C" int mocap_abi_version(void) { return MOCAP_ABI_VERSION; }
 
+extern "C" const char* mocap_stage_name(int stage)
+{
+    static const char* names[MOCAP_N_STAGES] = {"scan", "compact", "filter", "blobs"};
+    return (stage >= 0 && stage < MOCAP_N_STAGES) ? names[stage] : "?";
+}
+
+extern "C" void* mocap_stage_timer_create(void)
+{
+    StageTimer* t = new StageTimer();
+    for (int i = 0; i < 2 * MOCAP_N_STAGES; ++i)
+        if (cudaEventCreate(&t->ev[i]) != cudaSuccess) { delete t; return nullptr; }
+    for (int i = 0; i < MOCAP_N_STAGES; ++i) t->recorded[i] = 0;
+    return t;
+}
+
+extern "C" void mocap_stage_timer_destroy(void* timer)
+{
+    StageTimer* t = (StageTimer*)timer;
+    if (!t) return;
+    for (int i = 0; i < 2 * MOCAP_N_STAGES; ++i) cudaEventDestroy(t->ev[i]);
+    delete t;
+}
+
+extern "C" int mocap_stage_timer_read(void* timer, float* ms_out)
+{
+    StageTimer* t = (StageTimer*)timer;
+    if (!t || !ms_out) return MOCAP_ERR_INVALID;
+    for (int i = 0; i < MOCAP_N_STAGES; ++i) {
+        ms_out[i] = -1.0f;
+        if (!t->recorded[i]) continue;
+        CUDA_TRY(cudaEventSynchronize(t->ev[2 * i + 1]));
+        CUDA_TRY(cudaEventElapsedTime(&ms_out[i], t->ev[2 * i], t->ev[2 * i + 1]));
+    }
+    return MOCAP_OK;
+}
+
 struct DetectLayout {
-    size_t off_active, off_list, off_counters, off_bits, off_fg, off_nfg, off_flags, off_blob;
+    size_t off_active, off_list, off_counters, off_bits, off_fg, off_nfg, off_flags, off_cellbox, off_blob;
     size_t blob_stride, total;
     int TX, TY, TXW, max_fg;
 };
@@ -53,6 +89,7 @@ static int detect_layout(int n, int H, int W, int max_contours, int max_runs, bo
     L->off_fg = take((size_t)n * L->max_fg * 4);
     L->off_nfg = take((size_t)n * 4);
     L->off_flags = take((size_t)n * 4);
+    L->off_cellbox = take((size_t)n * L->TX * L->TY * 4);
     L->blob_stride = with_blobs ? blob_ws_stride(H, max_runs, max_contours) : 0;
     L->off_blob = take(L->blob_stride * (size_t)n);
     L->total = off;
@@ -68,6 +105,7 @@ static FilterWs filter_ws(char* base, const DetectLayout& L)
     ws.bits = (uint32_t*)(base + L.off_bits);
     ws.fg_tiles = (uint32_t*)(base + L.off_fg);
     ws.n_fg = (int*)(base + L.off_nfg);
+    ws.cellbox = (uint32_t*)(base + L.off_cellbox);
     return ws;
 }
 
@@ -95,7 +133,7 @@ extern "C" int mocap_filter_batch(const uint8_t* frames_dev, int n_frames, int H
     FilterWs ws = filter_ws((char*)workspace, L);
     int* flags = (int*)((char*)workspace + L.off_flags);
     CUDA_TRY(cudaMemsetAsync(flags, 0, (size_t)n_frames * 4, s));
-    st = launch_filter(frames_dev, n_frames, H, W, frame_stride, tv, thresh, ws, L.max_fg, flags, s);
+    st = launch_filter(frames_dev, n_frames, H, W, frame_stride, tv, thresh, ws, L.max_fg, flags, s, nullptr);
     if (st != MOCAP_OK) return st;
     return launch_materialize_bits(ws, n_frames, H, W, tv, out_bits, s);
 }
@@ -106,8 +144,9 @@ extern "C" int mocap_detect_batch(const uint8_t* frames_dev, int n_frames, int H
                                   int32_t* out_xy, int32_t* out_count, int32_t* out_flags,
                                   uint32_t* out_bits, int32_t* out_labels, int64_t* out_blob_sums, int32_t* out_blob_count,
                                   double* out_contours, int32_t* out_contour_count,
-                                  void* workspace, size_t workspace_bytes, void* stream)
+                                  void* workspace, size_t workspace_bytes, void* stream, void* stage_timer)
 {
+    StageTimer* timer = (StageTimer*)stage_timer;
     if (!frames_dev || !table_dev || !out_xy || !out_count || !out_flags || !workspace) return MOCAP_ERR_INVALID;
     if (max_blobs <= 0 || max_contours <= 0 || max_runs <= 0) return MOCAP_ERR_INVALID;
     if (frame_stride < (int64_t)H * W) return MOCAP_ERR_INVALID;
@@ -120,16 +159,19 @@ extern "C" int mocap_detect_batch(const uint8_t* frames_dev, int n_frames, int H
     FilterWs ws = filter_ws((char*)workspace, L);
     CUDA_TRY(cudaMemsetAsync(out_flags, 0, (size_t)n_frames * 4, s));
     if (out_labels) CUDA_TRY(cudaMemsetAsync(out_labels, 0, (size_t)n_frames * H * W * 4, s));
-    st = launch_filter(frames_dev, n_frames, H, W, frame_stride, tv, thresh, ws, L.max_fg, out_flags, s);
+    st = launch_filter(frames_dev, n_frames, H, W, frame_stride, tv, thresh, ws, L.max_fg, out_flags, s, timer);
     if (st != MOCAP_OK) return st;
     if (out_bits) {
         st = launch_materialize_bits(ws, n_frames, H, W, tv, out_bits, s);
         if (st != MOCAP_OK) return st;
     }
-    return launch_blobs(ws.bits, ws.fg_tiles, ws.n_fg, n_frames, H, W, L.TX, L.max_fg, max_runs, max_blobs, max_contours,
-                        min_area, min_circ, (char*)workspace + L.off_blob, L.blob_stride,
-                        out_xy, out_count, out_flags, out_blob_sums, out_blob_count, out_contours, out_contour_count,
-                        out_labels, s);
+    stage_begin(timer, 3, s);
+    st = launch_blobs(ws.bits, ws.fg_tiles, ws.n_fg, n_frames, H, W, L.TX, L.max_fg, max_runs, max_blobs, max_contours,
+                      min_area, min_circ, (char*)workspace + L.off_blob, L.blob_stride,
+                      out_xy, out_count, out_flags, out_blob_sums, out_blob_count, out_contours, out_contour_count,
+                      out_labels, s);
+    stage_end(timer, 3, s);
+    return st;
 }
 
 // findContours -> filter -> moments on a given packed binary image (lib/ImageOperations.py:41-65), stage parity entry

@@ -55,6 +55,14 @@ struct TableView {
     int H, W, TX, TY;
 };
 
+// per-stage CUDA events of one mocap_detect_batch call (mocap_stage_timer_*)
+struct StageTimer {
+    cudaEvent_t ev[2 * MOCAP_N_STAGES];
+    int recorded[MOCAP_N_STAGES];
+};
+static inline void stage_begin(StageTimer* t, int stage, cudaStream_t s) { if (t) { cudaEventRecord(t->ev[2 * stage], s); } }
+static inline void stage_end(StageTimer* t, int stage, cudaStream_t s) { if (t) { cudaEventRecord(t->ev[2 * stage + 1], s); t->recorded[stage] = 1; } }
+
 // workspace slices of the filter stage (carved by api.cu)
 struct FilterWs {
     uint32_t* active;    // [n][TY][TXW] bitmap of output tiles that can hold foreground
@@ -63,6 +71,7 @@ struct FilterWs {
     uint32_t* bits;      // [n][H][TX] packed binary image (only active tiles and their neighbours are defined)
     uint32_t* fg_tiles;  // [n][max_fg] tiles that hold at least one foreground pixel
     int* n_fg;           // [n]
+    uint32_t* cellbox;   // [n][TY][TX] hot bounding box of every 32x32 source cell (written by the scan pass)
 };
 
 // ---------------------------------------------------------------------------------------------------------

@@ -17,6 +17,7 @@
 
 #define BLOB_THREADS 256
 #define MAX_DEPTH 8
+#define RUN_DEAD 0xffffffffu   // run slot emptied by merging (x0 = 0xffff sorts after every live run)
 
 struct BlobWs {                 // per-frame slices of the workspace
     int* rowptr;                // [H + 2]
@@ -39,10 +40,15 @@ struct BlobWs {                 // per-frame slices of the workspace
     int* holes_of;              // [max_contours] number of holes per blob
 };
 
-__device__ __forceinline__ int uf_find(const int* parent, int x)
+__device__ __forceinline__ int uf_find(int* parent, int x)
 {
+    // path halving: a non-root's parent only ever moves to an ancestor, so the racy plain store is benign
     int p = parent[x];
-    while (p != x) { x = p; p = parent[x]; }
+    while (p != x) {
+        int g = parent[p];
+        if (g != p) parent[x] = g;
+        x = p; p = g;
+    }
     return x;
 }
 __device__ __forceinline__ void uf_union(int* parent, int a, int b)
@@ -127,10 +133,13 @@ __device__ int walk_min_edge(const BitImg& im, int x, int y, int side, int mode,
 }
 
 // Full trace of a border from its start edge: Green sums over the CHAIN_APPROX_SIMPLE vertices, perimeter, length.
-__device__ void trace_contour(const BitImg& im, int x, int y, int side, long long* a, double* per, int* n_chain, int* overflow)
+// key0 >= 0: also verify that the start edge is the border's smallest west/east edge (i.e. where cv.findContours starts
+// it); returns 0 as soon as a smaller one is met.  key0 < 0: no check.  Returns 1 for a completed trace.
+__device__ int trace_contour(const BitImg& im, int x, int y, int side, long long key0, long long* a, double* per, int* n_chain, int* overflow)
 {
+    const int W = im.W;
     Walk w; walk_init(im, w, x, y, side);
-    if (w.single) { a[0] = a[1] = a[2] = 0; *per = 0.0; *n_chain = 1; return; }
+    if (w.single) { a[0] = a[1] = a[2] = 0; *per = 0.0; *n_chain = 1; return key0 < 0 || side == 4; }
     long long a00 = 0, a10 = 0, a01 = 0;
     double perim = 0.0;
     int n = 0;
@@ -142,6 +151,10 @@ __device__ void trace_contour(const BitImg& im, int x, int y, int side, long lon
         unsigned zeros; bool done;
         int d = walk_step(im, w, zeros, done);
         ++n;
+        if (key0 >= 0) {
+            if ((zeros & (1u << 4)) && edge_key(cx, cy, W, 0) < key0) return 0;
+            if ((zeros & (1u << 0)) && edge_key(cx, cy, W, 1) < key0) return 0;
+        }
         if (d != prev_dir) {            // direction change: (cx, cy) is a vertex
             if (have_v) {
                 long long dxy = (long long)vx * cy - (long long)cx * vy;
@@ -161,11 +174,12 @@ __device__ void trace_contour(const BitImg& im, int x, int y, int side, long lon
                 if (q > 0.f) perim += (double)__fsqrt_rn(q);
             }
             a[0] = a00; a[1] = a10; a[2] = a01; *per = perim; *n_chain = n;
-            return;
+            return 1;
         }
     }
     *overflow = 1;
     a[0] = a[1] = a[2] = 0; *per = 0.0; *n_chain = n;
+    return 0;
 }
 
 // block-wide exclusive scan helper over an int array in global memory (in place), returns total in *total_s (shared)
@@ -250,7 +264,7 @@ __global__ void __launch_bounds__(BLOB_THREADS) blobs_kernel(
     }
     __syncthreads();
     block_exclusive_scan(w.rowptr, H + 1, sh);
-    int n_runs = w.rowptr[H];
+    const int n_runs = w.rowptr[H];
     if (n_runs > P.max_runs) {
         if (tid == 0) {
             out_flags[f] |= MOCAP_FLAG_RUN_OVERFLOW;
@@ -283,7 +297,8 @@ __global__ void __launch_bounds__(BLOB_THREADS) blobs_kernel(
         }
     }
     __syncthreads();
-    // sort the (few) runs of every row by x0
+    // sort the (few) runs of every row by x0 and merge runs split at a 32-bit word boundary; the slots freed by
+    // merging become DEAD runs parked at the end of the row (rowfill[y] = end of the row's live runs)
     for (int y = tid; y < H; y += nt) {
         int b = w.rowptr[y], e = w.rowptr[y + 1];
         for (int i = b + 1; i < e; ++i) {
@@ -292,21 +307,106 @@ __global__ void __launch_bounds__(BLOB_THREADS) blobs_kernel(
             while (k >= b && (w.run_xx[k] & 0xffff) > (v & 0xffff)) { w.run_xx[k + 1] = w.run_xx[k]; --k; }
             w.run_xx[k + 1] = v;
         }
+        int wpos = b;
+        for (int i = b; i < e; ++i) {
+            uint32_t v = w.run_xx[i];
+            if (wpos > b && (w.run_xx[wpos - 1] >> 16) + 1 == (v & 0xffff)) w.run_xx[wpos - 1] = (w.run_xx[wpos - 1] & 0xffff) | (v & 0xffff0000u);
+            else w.run_xx[wpos++] = v;
+        }
+        for (int i = wpos; i < e; ++i) w.run_xx[i] = RUN_DEAD;
+        w.rowfill[y] = wpos;
     }
+    __syncthreads();
+
+    int n_blobs = 0, n_cont = 0, n_arr = 0;        // n_arr: extent of the contour arrays (fast path keeps rejected candidates)
+    bool fast_done = false;
+    const bool need_labels = out_labels != nullptr || out_blob_sums != nullptr || out_blob_count != nullptr;
+
+    // ---- fast path (no label outputs wanted): border starts straight from the runs --------------------------------------
+    // An outer border starts at the first pixel of a run with no 8-neighbour in the row above (necessary condition); a
+    // hole border at the last pixel of a run whose gap to the next run is completely covered by one run of the row above.
+    // Every candidate is traced once; the trace is discarded as soon as it meets a smaller west/east edge of its border
+    // (then it is not where cv.findContours starts that border).  Frames with a hole border fall through to the general
+    // path, which needs the labels for the contour tree.
+    if (!need_labels) {
+        if (tid == 0) { s_ncont = 0; s_nholes = 0; }
+        __syncthreads();
+        for (int r = tid; r < n_runs; r += nt) {
+            uint32_t xx = w.run_xx[r];
+            if (xx == RUN_DEAD) continue;
+            int y = w.run_y[r], x0 = xx & 0xffff, x1 = xx >> 16;
+            int nx0 = (r + 1 < w.rowfill[y]) ? (int)(w.run_xx[r + 1] & 0xffff) : -1;
+            bool top = true, covered = false;
+            if (y > 0) {
+                int lim = nx0 >= 0 ? nx0 : x1 + 1;
+                for (int k = w.rowptr[y - 1]; k < w.rowfill[y - 1]; ++k) {
+                    uint32_t kk = w.run_xx[k];
+                    int k0 = kk & 0xffff, k1 = kk >> 16;
+                    if (k0 > lim) break;
+                    if (k1 >= x0 - 1 && k0 <= x1 + 1) top = false;
+                    if (nx0 >= 0 && k0 <= x1 + 1 && k1 >= nx0 - 1) covered = true;
+                }
+            }
+            if (top) {
+                int k = atomicAdd(&s_ncont, 1);
+                if (k < P.max_contours) { w.c_start[k] = y * W + x0; w.c_type[k] = 0; }
+            }
+            if (covered) {
+                int k = atomicAdd(&s_ncont, 1);
+                if (k < P.max_contours) { w.c_start[k] = y * W + x1; w.c_type[k] = 1; }
+            }
+        }
+        __syncthreads();
+        const int n_cand = s_ncont;
+        __syncthreads();
+        if (n_cand <= P.max_contours) {
+            for (int c = tid; c < n_cand; c += nt) {
+                int st = w.c_start[c], ty = w.c_type[c], ovf = 0;
+                int ok = trace_contour(im, st % W, st / W, ty ? 0 : 4, 2LL * st + ty, &w.c_a[3 * c], &w.c_per[c], &w.c_n[c], &ovf);
+                if (ovf) atomicOr(&s_flag, MOCAP_FLAG_TRACE_OVERFLOW);
+                w.c_keep[c] = ok;                      // parked: candidate is a real border start
+                if (ok && ty) atomicAdd(&s_nholes, 1);
+            }
+            __syncthreads();
+            if (s_nholes == 0 && !(s_flag & MOCAP_FLAG_TRACE_OVERFLOW)) {
+                // only top-level outer borders: output order = reverse raster order of the start pixels
+                for (int c = tid; c < n_cand; c += nt) {
+                    int rank = -1;
+                    if (w.c_keep[c]) {
+                        rank = 0;
+                        int st = w.c_start[c];
+                        for (int u = 0; u < n_cand; ++u) rank += (w.c_keep[u] && w.c_start[u] > st);
+                    }
+                    w.c_rank[c] = rank;
+                    w.c_parent[c] = -1;
+                }
+                if (tid == 0) { int nb = 0; for (int c = 0; c < n_cand; ++c) nb += w.c_keep[c] != 0; s_nblobs = nb; }
+                __syncthreads();
+                n_blobs = s_nblobs; n_cont = n_blobs; n_arr = n_cand;
+                fast_done = true;
+            }
+        }
+        if (!fast_done) {
+            __syncthreads();
+            if (tid == 0) { s_nholes = 0; s_flag &= ~MOCAP_FLAG_TRACE_OVERFLOW; }
+            __syncthreads();
+        }
+    }
+
+    if (!fast_done) {
+    // ---- general path: labelling by union-find over runs (8-connectivity) ------------------------------------------------
     for (int r = tid; r < n_runs; r += nt) {
         w.run_parent[r] = r;
         w.run_sum[3 * r] = 0; w.run_sum[3 * r + 1] = 0; w.run_sum[3 * r + 2] = 0;
     }
     __syncthreads();
-
-    // ---- labelling: union-find over runs (8-connectivity) -------------------------------------------------------
     for (int r = tid; r < n_runs; r += nt) {
-        int y = w.run_y[r];
         uint32_t xx = w.run_xx[r];
+        if (xx == RUN_DEAD) continue;
+        int y = w.run_y[r];
         int x0 = xx & 0xffff, x1 = xx >> 16;
-        if (r > w.rowptr[y] && (int)(w.run_xx[r - 1] >> 16) + 1 == x0) uf_union(w.run_parent, r, r - 1);
         if (y > 0) {
-            for (int k = w.rowptr[y - 1]; k < w.rowptr[y]; ++k) {
+            for (int k = w.rowptr[y - 1]; k < w.rowfill[y - 1]; ++k) {
                 uint32_t kk = w.run_xx[k];
                 int k0 = kk & 0xffff, k1 = kk >> 16;
                 if (k0 > x1 + 1) break;
@@ -321,20 +421,22 @@ __global__ void __launch_bounds__(BLOB_THREADS) blobs_kernel(
     }
     __syncthreads();
     for (int r = tid; r < n_runs; r += nt) {
+        uint32_t xx = w.run_xx[r];
+        bool live = xx != RUN_DEAD;
         int root = uf_find(w.run_parent, r);
         w.run_parent[r] = root;
-        uint32_t xx = w.run_xx[r];
-        unsigned long long x0 = xx & 0xffff, x1 = xx >> 16, len = x1 - x0 + 1, y = w.run_y[r];
-        atomicAdd(&w.run_sum[3 * root], len);
-        atomicAdd(&w.run_sum[3 * root + 1], (x0 + x1) * len / 2);
-        atomicAdd(&w.run_sum[3 * root + 2], y * len);
-        w.run_rank[r] = (root == r) ? 1 : 0;
+        if (live) {
+            unsigned long long x0 = xx & 0xffff, x1 = xx >> 16, len = x1 - x0 + 1, y = w.run_y[r];
+            atomicAdd(&w.run_sum[3 * root], len);
+            atomicAdd(&w.run_sum[3 * root + 1], (x0 + x1) * len / 2);
+            atomicAdd(&w.run_sum[3 * root + 2], y * len);
+        }
+        w.run_rank[r] = (live && root == r) ? 1 : 0;
     }
     if (tid == 0) w.run_rank[n_runs] = 0;
     __syncthreads();
     block_exclusive_scan(w.run_rank, n_runs + 1, sh);
-    const int n_blobs = w.run_rank[n_runs];
-    if (tid == 0) { s_nblobs = n_blobs; }
+    n_blobs = w.run_rank[n_runs];
     if (out_blob_count && tid == 0) out_blob_count[f] = n_blobs;
     if (n_blobs > P.max_contours) {
         if (tid == 0) {
@@ -346,7 +448,7 @@ __global__ void __launch_bounds__(BLOB_THREADS) blobs_kernel(
     }
     // blob records + outer contours (index = blob rank)
     for (int r = tid; r < n_runs; r += nt) {
-        if (w.run_parent[r] != r) continue;
+        if (w.run_xx[r] == RUN_DEAD || w.run_parent[r] != r) continue;
         int k = w.run_rank[r];
         if (out_blob_sums && k < P.max_blobs)
             for (int q = 0; q < 3; ++q) out_blob_sums[((size_t)f * P.max_blobs + k) * 3 + q] = (int64_t)w.run_sum[3 * r + q];
@@ -358,8 +460,9 @@ __global__ void __launch_bounds__(BLOB_THREADS) blobs_kernel(
     if (out_labels) {
         int32_t* lab = out_labels + (size_t)f * H * W;
         for (int r = tid; r < n_runs; r += nt) {
-            int k = w.run_rank[w.run_parent[r]] + 1;
             uint32_t xx = w.run_xx[r];
+            if (xx == RUN_DEAD) continue;
+            int k = w.run_rank[w.run_parent[r]] + 1;
             int y = w.run_y[r];
             for (int x = xx & 0xffff; x <= (int)(xx >> 16); ++x) lab[(size_t)y * W + x] = k;
         }
@@ -368,10 +471,10 @@ __global__ void __launch_bounds__(BLOB_THREADS) blobs_kernel(
 
     // ---- hole borders: canonical east edges ---------------------------------------------------------------------
     for (int r = tid; r < n_runs; r += nt) {
-        int y = w.run_y[r];
         uint32_t xx = w.run_xx[r];
+        if (xx == RUN_DEAD) continue;
+        int y = w.run_y[r];
         int x1 = xx >> 16;
-        if (r + 1 < w.rowptr[y + 1] && (int)(w.run_xx[r + 1] & 0xffff) == x1 + 1) continue;   // run continues in the next word
         int ovf = 0;
         if (walk_min_edge(im, x1, y, 0, 0, nullptr, &ovf)) {
             int k = n_blobs + atomicAdd(&s_nholes, 1);
@@ -386,7 +489,8 @@ __global__ void __launch_bounds__(BLOB_THREADS) blobs_kernel(
         if (ovf) atomicOr(&s_flag, MOCAP_FLAG_TRACE_OVERFLOW);
     }
     __syncthreads();
-    int n_cont = n_blobs + s_nholes;
+    n_cont = n_blobs + s_nholes;
+    n_arr = n_cont;
     if (n_cont > P.max_contours || (s_flag & MOCAP_FLAG_TRACE_OVERFLOW)) {
         if (tid == 0) {
             out_flags[f] |= (n_cont > P.max_contours ? MOCAP_FLAG_CONTOUR_OVERFLOW : 0) | s_flag;
@@ -400,7 +504,7 @@ __global__ void __launch_bounds__(BLOB_THREADS) blobs_kernel(
     for (int c = tid; c < n_cont; c += nt) {
         int st = w.c_start[c];
         int ovf = 0;
-        trace_contour(im, st % W, st / W, w.c_type[c] ? 0 : 4, &w.c_a[3 * c], &w.c_per[c], &w.c_n[c], &ovf);
+        trace_contour(im, st % W, st / W, w.c_type[c] ? 0 : 4, -1, &w.c_a[3 * c], &w.c_per[c], &w.c_n[c], &ovf);
         if (ovf) atomicOr(&s_flag, MOCAP_FLAG_TRACE_OVERFLOW);
     }
     // ---- parents ------------------------------------------------------------------------------------------------
@@ -409,7 +513,7 @@ __global__ void __launch_bounds__(BLOB_THREADS) blobs_kernel(
         // outer border: nearest foreground pixel to the left of the blob's first pixel, on the same row
         int st = w.c_start[c], y = st / W, x0 = st - y * W;
         // locate the root run: binary search not needed, rows hold few runs
-        int b = w.rowptr[y], e = w.rowptr[y + 1], r = b;
+        int b = w.rowptr[y], e = w.rowfill[y], r = b;
         while (r < e && (int)(w.run_xx[r] & 0xffff) != x0) ++r;
         if (r == b) { w.c_parent[c] = -1; continue; }
         int q = r - 1;                                    // run ending left of us
@@ -483,9 +587,11 @@ __global__ void __launch_bounds__(BLOB_THREADS) blobs_kernel(
         }
         __syncthreads();
     }
+    }   // general path
 
     // ---- the reference's filter and centroid (ImageOperations.py:43-65) -------------------------------------------------
-    for (int c = tid; c < n_cont; c += nt) {
+    for (int c = tid; c < n_arr; c += nt) {
+        if (w.c_rank[c] < 0) { w.c_keep[c] = 0; continue; }     // rejected fast-path candidate
         long long a00 = w.c_a[3 * c];
         double area = (double)(a00 < 0 ? -a00 : a00) * 0.5;
         double per = w.c_per[c];
@@ -500,8 +606,9 @@ __global__ void __launch_bounds__(BLOB_THREADS) blobs_kernel(
     __syncthreads();
     if (tid == 0) s_ncont = 0;
     __syncthreads();
-    for (int c = tid; c < n_cont; c += nt) {
+    for (int c = tid; c < n_arr; c += nt) {
         int rank = w.c_rank[c];
+        if (rank < 0) continue;
         long long a00 = w.c_a[3 * c], a10 = w.c_a[3 * c + 1], a01 = w.c_a[3 * c + 2];
         if (out_contours && rank < P.max_contours) {
             double* o = out_contours + ((size_t)f * P.max_contours + rank) * 8;
@@ -512,7 +619,7 @@ __global__ void __launch_bounds__(BLOB_THREADS) blobs_kernel(
         }
         if (!w.c_keep[c]) continue;
         int pos = 0;
-        for (int u = 0; u < n_cont; ++u) pos += (w.c_keep[u] && w.c_rank[u] < rank);
+        for (int u = 0; u < n_arr; ++u) pos += (w.c_keep[u] && w.c_rank[u] < rank);
         atomicAdd(&s_ncont, 1);
         if (pos < P.max_blobs) {
             double sgn = a00 > 0 ? 1.0 : -1.0;

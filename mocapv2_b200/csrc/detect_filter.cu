@@ -239,10 +239,28 @@ __device__ __forceinline__ void mark_cell(const TableView& tv, uint32_t* __restr
     }
 }
 
+// hot byte lanes of a 32-bit word (bit 7 of every byte of h) -> 4-bit mask, bit b = byte b
+__device__ __forceinline__ uint32_t hot_nibble(uint32_t h)
+{
+    h &= 0x80808080u;
+    return ((h >> 7) | (h >> 14) | (h >> 21) | (h >> 28)) & 0xfu;
+}
+
+// cell-local hot bounding box packed x0 | x1 << 8 | y0 << 16 | y1 << 24; CELL_EMPTY when the cell holds no pixel > thresh
+#define CELL_EMPTY 0xffffffffu
+__device__ __forceinline__ uint32_t pack_cellbox(uint32_t xmask, uint32_t ymask)
+{
+    if (!xmask) return CELL_EMPTY;
+    uint32_t x0 = __ffs(xmask) - 1, x1 = 31 - __clz(xmask), y0 = __ffs(ymask) - 1, y1 = 31 - __clz(ymask);
+    return x0 | (x1 << 8) | (y0 << 16) | (y1 << 24);
+}
+
 // Streams all source bytes.  One warp per 128x32-pixel block (4 source cells): lane = (row & 3, 16-byte segment).
+// Writes the hot bounding box of every cell (cellbox) and marks the output tiles a hot cell can reach (active).
 template <int MODE>
 __global__ void __launch_bounds__(256) scan_hot_vec_kernel(const uint8_t* __restrict__ frames, int n_frames, int64_t fstride,
-                                                           TableView tv, uint32_t* __restrict__ active, int TXW, uint32_t add)
+                                                           TableView tv, uint32_t* __restrict__ active, int TXW, uint32_t add,
+                                                           uint32_t* __restrict__ cellbox)
 {
     const int lane = threadIdx.x & 31;
     const long long warp = ((long long)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
@@ -272,16 +290,39 @@ __global__ void __launch_bounds__(256) scan_hot_vec_kernel(const uint8_t* __rest
             acc |= hot4<MODE>(v[k].x, add) | hot4<MODE>(v[k].y, add) | hot4<MODE>(v[k].z, add) | hot4<MODE>(v[k].w, add);
         bool hot = (acc & 0x80808080u) != 0;
         unsigned m = __ballot_sync(0xffffffffu, hot);
+        uint32_t box = CELL_EMPTY;
+        if (m) {                                            // warp-uniform: some cell of this block is hot
+            uint32_t colmask = 0, rowbits = 0;              // lane-local: hot columns (16 bits), hot rows (bit 4k + r0)
+#pragma unroll
+            for (int k = 0; k < 8; ++k) {
+                uint32_t c = hot_nibble(hot4<MODE>(v[k].x, add)) | (hot_nibble(hot4<MODE>(v[k].y, add)) << 4) |
+                             (hot_nibble(hot4<MODE>(v[k].z, add)) << 8) | (hot_nibble(hot4<MODE>(v[k].w, add)) << 12);
+                colmask |= c;
+                if (c) rowbits |= 1u << (4 * k + r0);
+            }
+            colmask <<= (seg & 1) * 16;
+#pragma unroll
+            for (int c = 0; c < 4; ++c) {
+                bool mine = (seg >> 1) == c;
+                uint32_t xm = __reduce_or_sync(0xffffffffu, mine ? colmask : 0u);
+                uint32_t ym = __reduce_or_sync(0xffffffffu, mine ? rowbits : 0u);
+                if (lane == c) box = pack_cellbox(xm, ym);
+            }
+        }
         if (lane < 4) {
             int cx = cxb * 4 + lane;
-            if (cx < tv.TX && (m & (0x03030303u << (2 * lane)))) mark_cell(tv, active, f, cy, cx, TXW);
+            if (cx < tv.TX) {
+                cellbox[((size_t)f * tv.TY + cy) * tv.TX + cx] = box;
+                if (box != CELL_EMPTY) mark_cell(tv, active, f, cy, cx, TXW);
+            }
         }
     }
 }
 
 // Generic (any W / alignment) variant: one warp per source cell, byte loads.
 __global__ void scan_hot_scalar_kernel(const uint8_t* __restrict__ frames, int n_frames, int64_t fstride,
-                                       TableView tv, uint32_t* __restrict__ active, int TXW, int thresh)
+                                       TableView tv, uint32_t* __restrict__ active, int TXW, int thresh,
+                                       uint32_t* __restrict__ cellbox)
 {
     const int lane = threadIdx.x & 31;
     const long long warp = ((long long)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
@@ -294,15 +335,20 @@ __global__ void scan_hot_scalar_kernel(const uint8_t* __restrict__ frames, int n
         int rem = (int)(it - (long long)f * per_frame);
         int cy = rem / tv.TX, cx = rem - cy * tv.TX;
         int x = cx * 32 + lane;
-        bool hot = false;
+        uint32_t rowbits = 0;
         if (x < W) {
             const uint8_t* base = frames + (size_t)f * fstride + x;
             for (int r = 0; r < 32; ++r) {
                 int y = cy * 32 + r;
-                if (y < H && (int)base[(size_t)y * W] > thresh) hot = true;
+                if (y < H && (int)base[(size_t)y * W] > thresh) rowbits |= 1u << r;
             }
         }
-        if (__any_sync(0xffffffffu, hot) && lane == 0) mark_cell(tv, active, f, cy, cx, TXW);
+        uint32_t xm = __ballot_sync(0xffffffffu, rowbits != 0);
+        uint32_t ym = __reduce_or_sync(0xffffffffu, rowbits);
+        if (lane == 0) {
+            cellbox[((size_t)f * tv.TY + cy) * tv.TX + cx] = pack_cellbox(xm, ym);
+            if (xm) mark_cell(tv, active, f, cy, cx, TXW);
+        }
     }
 }
 
@@ -358,7 +404,7 @@ struct __align__(16) WarpScratch {
 __global__ void __launch_bounds__(FT_WARPS * 32) filter_tiles_kernel(
     const uint8_t* __restrict__ frames, int64_t fstride, TableView tv, int thresh,
     const uint32_t* __restrict__ list, const int* __restrict__ n_list, int* __restrict__ cursor,
-    const uint32_t* __restrict__ active, int TXW,
+    const uint32_t* __restrict__ active, int TXW, const uint32_t* __restrict__ cellbox,
     uint32_t* __restrict__ bits, uint32_t* __restrict__ fg_tiles, int* __restrict__ n_fg, int max_fg, int* __restrict__ flags)
 {
     __shared__ WarpScratch scratch[FT_WARPS];
@@ -382,17 +428,19 @@ __global__ void __launch_bounds__(FT_WARPS * 32) filter_tiles_kernel(
         int sx0 = tt[0], sy0 = tt[1], sx1 = tt[2], sy1 = tt[3];
         uint32_t myword = 0;
 
-        // ---- 1. exact hot bounding box of the source window -------------------------------------------
+        // ---- 1. hot bounding box of the source window from the scan pass' cell boxes (no pixel is re-read) -------------
         int hx0 = 0x7fffffff, hx1 = -1, hy0 = 0x7fffffff, hy1 = -1;
         if (sx1 >= sx0) {
-            int bw = sx1 - sx0 + 1, n = bw * (sy1 - sy0 + 1), inv = finv20(bw);
-            const bool big = bw > 64 || n > 4096;          // fdiv20 is exact only while idx * bw < 2^20
-            for (int idx = lane; idx < n; idx += 32) {
-                int r = big ? idx / bw : fdiv20(idx, inv), c = idx - r * bw;
-                int v = fr[(size_t)(sy0 + r) * W + sx0 + c];
-                if (v >= T) {
-                    hx0 = min(hx0, sx0 + c); hx1 = max(hx1, sx0 + c);
-                    hy0 = min(hy0, sy0 + r); hy1 = max(hy1, sy0 + r);
+            int cx0 = sx0 >> 5, cy0 = sy0 >> 5, ncx = (sx1 >> 5) - cx0 + 1, ncy = (sy1 >> 5) - cy0 + 1;
+            for (int ci = lane; ci < ncx * ncy; ci += 32) {
+                int cy = cy0 + ci / ncx, cx = cx0 + ci % ncx;
+                uint32_t b = cellbox[((size_t)f * TY + cy) * TX + cx];
+                if (b != CELL_EMPTY) {
+                    int bx0 = max(cx * 32 + (int)(b & 0xff), sx0), bx1 = min(cx * 32 + (int)((b >> 8) & 0xff), sx1);
+                    int by0 = max(cy * 32 + (int)((b >> 16) & 0xff), sy0), by1 = min(cy * 32 + (int)(b >> 24), sy1);
+                    if (bx0 <= bx1 && by0 <= by1) {
+                        hx0 = min(hx0, bx0); hx1 = max(hx1, bx1); hy0 = min(hy0, by0); hy1 = max(hy1, by1);
+                    }
                 }
             }
         }
@@ -532,7 +580,7 @@ __global__ void materialize_bits_kernel(const uint32_t* __restrict__ bits, const
 // host-side launcher shared by mocap_filter_batch and mocap_detect_batch
 // ---------------------------------------------------------------------------------------------------------
 int launch_filter(const uint8_t* frames, int n, int H, int W, int64_t fstride, const TableView& tv, int thresh,
-                  const FilterWs& ws, int max_fg, int* flags, cudaStream_t s)
+                  const FilterWs& ws, int max_fg, int* flags, cudaStream_t s, StageTimer* timer)
 {
     const int TX = tv.TX, TY = tv.TY, TXW = cdiv(TX, 32);
     size_t act_bytes = (size_t)n * TY * TXW * 4;
@@ -544,21 +592,27 @@ int launch_filter(const uint8_t* frames, int n, int H, int W, int64_t fstride, c
     cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
     HotTest ht = make_hot_test(thresh);
     bool vec = (W % 16 == 0) && (fstride % 16 == 0) && (((uintptr_t)frames) % 16 == 0);
+    stage_begin(timer, 0, s);
     if (vec) {
         int grid = sms * 8;
         switch (ht.mode) {
-            case 0: LAUNCH(scan_hot_vec_kernel<0>, grid, 256, 0, s, frames, n, fstride, tv, ws.active, TXW, ht.add); break;
-            case 1: LAUNCH(scan_hot_vec_kernel<1>, grid, 256, 0, s, frames, n, fstride, tv, ws.active, TXW, ht.add); break;
-            case 2: LAUNCH(scan_hot_vec_kernel<2>, grid, 256, 0, s, frames, n, fstride, tv, ws.active, TXW, ht.add); break;
-            default: LAUNCH(scan_hot_vec_kernel<3>, grid, 256, 0, s, frames, n, fstride, tv, ws.active, TXW, ht.add); break;
+            case 0: LAUNCH(scan_hot_vec_kernel<0>, grid, 256, 0, s, frames, n, fstride, tv, ws.active, TXW, ht.add, ws.cellbox); break;
+            case 1: LAUNCH(scan_hot_vec_kernel<1>, grid, 256, 0, s, frames, n, fstride, tv, ws.active, TXW, ht.add, ws.cellbox); break;
+            case 2: LAUNCH(scan_hot_vec_kernel<2>, grid, 256, 0, s, frames, n, fstride, tv, ws.active, TXW, ht.add, ws.cellbox); break;
+            default: LAUNCH(scan_hot_vec_kernel<3>, grid, 256, 0, s, frames, n, fstride, tv, ws.active, TXW, ht.add, ws.cellbox); break;
         }
     } else {
-        LAUNCH(scan_hot_scalar_kernel, sms * 8, 256, 0, s, frames, n, fstride, tv, ws.active, TXW, thresh);
+        LAUNCH(scan_hot_scalar_kernel, sms * 8, 256, 0, s, frames, n, fstride, tv, ws.active, TXW, thresh, ws.cellbox);
     }
+    stage_end(timer, 0, s);
     long long n_words = (long long)n * TY * TXW;
+    stage_begin(timer, 1, s);
     LAUNCH(compact_tiles_kernel, (unsigned)((n_words + 255) / 256), 256, 0, s, ws.active, n_words, TX, TY, TXW, ws.list, ws.counters);
+    stage_end(timer, 1, s);
+    stage_begin(timer, 2, s);
     LAUNCH(filter_tiles_kernel, sms * 4, FT_WARPS * 32, 0, s, frames, fstride, tv, thresh, ws.list, ws.counters, ws.counters + 1,
-                                                          ws.active, TXW, ws.bits, ws.fg_tiles, ws.n_fg, max_fg, flags);
+                                                          ws.active, TXW, ws.cellbox, ws.bits, ws.fg_tiles, ws.n_fg, max_fg, flags);
+    stage_end(timer, 2, s);
     CUDA_TRY(cudaGetLastError());
     return MOCAP_OK;
 }

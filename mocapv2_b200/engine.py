@@ -142,7 +142,8 @@ class CaptureEngine:
         return max_blobs, max_contours, max_runs
 
     def detect(self, frames: torch.Tensor, K, dist, *, thresh=THRESH_U8, min_area=MIN_AREA, min_circ=MIN_CIRC,
-               max_blobs=None, max_contours=None, max_runs=None, outputs=(), out: DetectResult | None = None) -> DetectResult:
+               max_blobs=None, max_contours=None, max_runs=None, outputs=(), out: DetectResult | None = None,
+               timer=None) -> DetectResult:
         """_find_dot(img)[1] for a batch (lib/ImageOperations.py:33-78).  frames: [n, H, W] uint8 on the device.
 
         outputs: any of "bits", "labels", "blob_sums", "contours" (parity outputs, see include/mocap_b200.h).
@@ -182,7 +183,7 @@ class CaptureEngine:
                 max_blobs, max_contours, max_runs, self._ptr(out.xy), self._ptr(out.count), self._ptr(out.flags),
                 self._ptr(ex.get("bits")), self._ptr(ex.get("labels")), self._ptr(ex.get("blob_sums")),
                 self._ptr(ex.get("blob_count")), self._ptr(ex.get("contours")), self._ptr(ex.get("contour_count")),
-                self._ptr(ws), nbytes, self._stream())
+                self._ptr(ws), nbytes, self._stream(), ctypes.c_void_p(timer) if timer else ctypes.c_void_p(0))
             _cabi.check(self.lib, st, "mocap_detect_batch")
             self.launches += 4 + (1 if "bits" in ex else 0)
         return out
@@ -254,6 +255,20 @@ class CaptureEngine:
         self.launches += 1
         return out
 
+    # ---- per-stage timing (bench) ---------------------------------------------------------------------------------------------
+    def stage_timer(self):
+        t = self.lib.mocap_stage_timer_create()
+        if not t:
+            raise _cabi.MocapError("mocap_stage_timer_create failed")
+        return t
+
+    def stage_timer_read(self, timer, destroy=True):
+        ms = (ctypes.c_float * _cabi.N_STAGES)()
+        _cabi.check(self.lib, self.lib.mocap_stage_timer_read(ctypes.c_void_p(timer), ms), "mocap_stage_timer_read")
+        if destroy:
+            self.lib.mocap_stage_timer_destroy(ctypes.c_void_p(timer))
+        return {self.lib.mocap_stage_name(i).decode(): float(ms[i]) for i in range(_cabi.N_STAGES)}
+
     # ---- geometry -----------------------------------------------------------------------------------------------------------
     def cameras(self, camera_poses, camera_params) -> torch.Tensor:
         return torch.from_numpy(pack_cameras(camera_poses, camera_params)).to(self.device)
@@ -298,7 +313,7 @@ class CaptureEngine:
         return err
 
     def correspond(self, xy: torch.Tensor, count: torch.Tensor, Fs: torch.Tensor, cams: torch.Tensor, *, obj_count=0,
-                   cutoff=EPI_CUTOFF, max_groups=4096, fp64=False, want_cand=False) -> CorrespondResult:
+                   cutoff=EPI_CUTOFF, max_groups=4096, fp64=False, want_cand=False, out: CorrespondResult | None = None) -> CorrespondResult:
         """find_point_correspondance_and_object_points (lib/Helpers.py:178-280) for S frame-sets.
 
         xy [S, C, max_pts, 2] int32 centroid lists, count [S, C] int32, Fs [C-1, 3, 3] float64 (Fs[i-1]: camera 0 -> camera i).
@@ -311,7 +326,7 @@ class CaptureEngine:
             Fs = self._check_dev(Fs, torch.float64, "Fs")
             if Fs.shape[0] < C - 1:
                 raise IndexError("Fs shorter than camera count - 1")        # the reference raises IndexError (Helpers.py:206)
-        res = CorrespondResult(
+        res = out if out is not None else CorrespondResult(
             obj=torch.zeros((S, max_pts, 3), dtype=torch.float64, device=self.device), n_obj=self.empty((S,), torch.int32),
             img=torch.zeros((S, max_pts, C, 2), dtype=torch.int32, device=self.device), n_valid=self.empty((S,), torch.int32),
             err=torch.zeros((S, max_pts), dtype=torch.float64, device=self.device), flags=self.empty((S,), torch.int32),

@@ -1,6 +1,12 @@
 // Runtime of the CUDA-on-CPU shim (TEST INFRASTRUCTURE ONLY, see cuda_emu.h).
 #include "cuda_emu.h"
 
+#include <chrono>
+double emu_now_ms()
+{
+    return std::chrono::duration<double, std::milli>(std::chrono::steady_clock::now().time_since_epoch()).count();
+}
+
 namespace emu {
 Block g_block;
 std::vector<unsigned char> g_dyn_smem;

@@ -53,6 +53,14 @@ static inline cudaError_t cudaStreamSynchronize(cudaStream_t) { return 0; }
 static inline cudaError_t cudaGetDevice(int* d) { *d = 0; return 0; }
 static inline cudaError_t cudaDeviceGetAttribute(int* v, cudaDeviceAttr, int) { *v = 1; return 0; }
 
+typedef double* cudaEvent_t;
+double emu_now_ms();
+static inline cudaError_t cudaEventCreate(cudaEvent_t* e) { *e = new double(0.0); return 0; }
+static inline cudaError_t cudaEventDestroy(cudaEvent_t e) { delete e; return 0; }
+static inline cudaError_t cudaEventRecord(cudaEvent_t e, cudaStream_t) { *e = emu_now_ms(); return 0; }
+static inline cudaError_t cudaEventSynchronize(cudaEvent_t) { return 0; }
+static inline cudaError_t cudaEventElapsedTime(float* ms, cudaEvent_t a, cudaEvent_t b) { *ms = (float)(*b - *a); return 0; }
+
 namespace emu {
 struct WarpBox {
     std::unique_ptr<std::barrier<>> bar;
@@ -116,6 +124,14 @@ static inline int __reduce_max_sync(unsigned, int v)
     emu::exchange((unsigned long long)(long long)v, s, &n);
     int r = v;
     for (int i = 0; i < n; ++i) r = std::max(r, (int)(long long)s[i]);
+    return r;
+}
+static inline unsigned __reduce_or_sync(unsigned, unsigned v)
+{
+    unsigned long long s[32]; int n;
+    emu::exchange(v, s, &n);
+    unsigned r = 0;
+    for (int i = 0; i < n; ++i) r |= (unsigned)s[i];
     return r;
 }
 template <typename T>

@@ -34,7 +34,19 @@ def detect_and_check(engine, frames, **kw):
         und, binimg = R.filter_frame(img, K, D)
         assert np.array_equal(bits[i] != 0, binimg != 0), "filtered binary image differs"
         check_blob_outputs(res, i, binimg, kw.get("min_area", R.MIN_AREA), kw.get("min_circ", R.MIN_CIRC))
+    # the product call (no label outputs -> border starts straight from the runs) gives the same contours and centroids
+    lean = engine.detect(dev(engine, frames), K, D, outputs=("contours",), **kw)
+    same_contours(res, lean)
     return res
+
+
+def same_contours(full, lean):
+    assert torch.equal(full.count, lean.count) and torch.equal(full.extras["contour_count"], lean.extras["contour_count"])
+    for i in range(len(full.count)):
+        nc = int(full.extras["contour_count"][i])
+        assert torch.equal(full.extras["contours"][i, :nc], lean.extras["contours"][i, :nc])
+        assert full.points(i) == lean.points(i)
+        assert int(full.flags[i]) == int(lean.flags[i])
 
 
 def test_stage_undistort_and_blur(engine):
@@ -113,6 +125,9 @@ def test_blobs_random_topologies(engine):
                            max_blobs=4096, max_contours=8192, max_runs=H * W + 1)
         for i in range(n):
             check_blob_outputs(res, i, b[i], ma)
+        lean = engine.blobs(dev(engine, np.stack([pack_bits(x) for x in b])), W, min_area=ma, outputs=("contours",),
+                            max_blobs=4096, max_contours=8192, max_runs=H * W + 1)
+        same_contours(res, lean)
 
 
 def test_blobs_deep_nesting_uses_general_ordering(engine):

@@ -1,0 +1,67 @@
+"""The N>1 path: cameras sharded over ranks, one all-gather of centroid records, frame-sets sharded for geometry.
+world_size 2 over gloo on the CPU (kernel sources through the emulation build); outputs must be bit-identical to the
+1-rank run.  The GPU-box variant of the same check runs under torchrun in bench.py --check."""
+import os
+import sys
+
+import numpy as np
+import pytest
+import torch
+import torch.distributed as dist
+import torch.multiprocessing as mp
+
+from mocapv2_b200 import synth as S
+from util import GOLDEN
+
+REPO = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+
+
+def _frames():
+    z = np.load(os.path.join(GOLDEN, "c1_frames.npz"))
+    return z["frames"][:2]                                   # [FS=2, C=2, 480, 640]
+
+
+def _run(rank, world, port, out_dir):
+    sys.path.insert(0, REPO)
+    sys.path.insert(0, os.path.join(REPO, "tests", "emu"))
+    import build_emu
+    from mocapv2_b200.engine import CaptureEngine
+    from mocapv2_b200.pipeline import CapturePipeline
+    if world > 1:
+        dist.init_process_group("gloo", init_method=f"tcp://127.0.0.1:{port}", rank=rank, world_size=world)
+    eng = CaptureEngine(_test_lib=build_emu.build())
+    rig = S.config_rig("c1")
+    pipe = CapturePipeline(eng, rig, max_blobs=8, obj_count=4, max_groups=16, fp64=False)
+    frames = torch.from_numpy(_frames())
+    local = frames[:, pipe.cam_begin:pipe.cam_begin + pipe.cams_local].contiguous()
+    res = pipe.step(local)
+    torch.save({"b": res.fs_begin, "e": res.fs_end, "obj": res.corr.obj, "n_obj": res.corr.n_obj, "img": res.corr.img,
+                "n_valid": res.corr.n_valid, "err": res.corr.err, "count": res.det.count, "collectives": pipe.collectives},
+               os.path.join(out_dir, f"rank{rank}_of{world}.pt"))
+    if world > 1:
+        dist.barrier()
+        dist.destroy_process_group()
+
+
+def test_two_ranks_equal_one_rank(tmp_path):
+    sys.path.insert(0, os.path.join(REPO, "tests", "emu"))
+    import build_emu
+    build_emu.build()
+    out = str(tmp_path)
+    _run(0, 1, 0, out)
+    port = 29500 + os.getpid() % 2000
+    mp.spawn(_run, args=(2, port, out), nprocs=2, join=True)
+    one = torch.load(os.path.join(out, "rank0_of1.pt"))
+    assert int(one["n_valid"].sum()) > 0 and one["collectives"] == 0
+    for r in range(2):
+        two = torch.load(os.path.join(out, f"rank{r}_of2.pt"))
+        b, e = two["b"], two["e"]
+        assert (b, e) == (r, r + 1) and two["collectives"] == 1          # exactly one exchange per batch
+        assert torch.equal(two["n_valid"], one["n_valid"][b:e]) and torch.equal(two["n_obj"], one["n_obj"][b:e])
+        for s in range(e - b):
+            nv, no = int(two["n_valid"][s]), int(two["n_obj"][s])
+            assert torch.equal(two["img"][s, :nv], one["img"][b + s, :nv])
+            assert torch.equal(two["obj"][s, :no], one["obj"][b + s, :no])  # bit-identical, no cross-rank reductions
+            assert torch.equal(two["err"][s, :nv], one["err"][b + s, :nv])
+        # each rank detected only its own camera
+        assert torch.equal(two["count"], one["count"].view(2, 2)[:, r])
