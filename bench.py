@@ -40,7 +40,7 @@ def parse():
     ap.add_argument("--steps", type=int, default=10)
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
-    ap.add_argument("--frame-sets", type=int, default=16, help="frame-sets per GPU per step (F0)")
+    ap.add_argument("--frame-sets", type=int, default=64, help="frame-sets per GPU per step (F0)")
     ap.add_argument("--e2e-steps", type=int, default=3)
     ap.add_argument("--cpu-sample", type=int, default=1, help="frame-sets timed for cpu_baseline (0 = skip)")
     ap.add_argument("--no-e2e", action="store_true")
@@ -247,13 +247,13 @@ def run_b200(args):
             dist.barrier()
         torch.cuda.synchronize()
 
+    sampler = ClockSampler(local)
+    if rank == 0:
+        sampler.start()                     # nvidia-smi needs ~100 ms to deliver its first sample: start before the warm-up
     for _ in range(max(args.warmup, 3)):
         step()
     barrier()
     timers = [eng.stage_timer() for _ in range(args.steps)]
-    sampler = ClockSampler(local)
-    if rank == 0:
-        sampler.start()
     launches0 = eng.launches
     ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     barrier()

@@ -84,6 +84,24 @@ struct BitImg {
         if ((unsigned)x >= (unsigned)W || (unsigned)y >= (unsigned)H) return 0;
         return (p[(size_t)y * WPR + (x >> 5)] >> (x & 31)) & 1;
     }
+    // bits x-1, x, x+1 of row y (bit 0 = x-1); pixels outside the image read 0.  x must be inside the image.
+    __device__ __forceinline__ uint32_t row3(int x, int y) const {
+        if ((unsigned)y >= (unsigned)H) return 0u;
+        const uint32_t* r = p + (size_t)y * WPR;
+        int wi = x >> 5, b = x & 31;
+        uint32_t w = r[wi], out;
+        if (b == 0) out = ((w & 3u) << 1) | (wi > 0 ? r[wi - 1] >> 31 : 0u);
+        else if (b == 31) out = (w >> 30) | (wi + 1 < WPR ? (r[wi + 1] & 1u) << 2 : 0u);
+        else out = (w >> (b - 1)) & 7u;
+        if (x + 1 >= W) out &= 3u;
+        return out;
+    }
+    // 8-neighbour occupancy of (x, y), bit d = neighbour in direction d (0=E 1=NE 2=N 3=NW 4=W 5=SW 6=S 7=SE)
+    __device__ __forceinline__ uint32_t nbr8(int x, int y) const {
+        uint32_t up = row3(x, y - 1), mid = row3(x, y), dn = row3(x, y + 1);
+        return ((mid >> 2) & 1u) | (((up >> 2) & 1u) << 1) | (((up >> 1) & 1u) << 2) | ((up & 1u) << 3) |
+               ((mid & 1u) << 4) | ((dn & 1u) << 5) | (((dn >> 1) & 1u) << 6) | (((dn >> 2) & 1u) << 7);
+    }
 };
 
 // 8-neighbour codes: 0=E 1=NE 2=N 3=NW 4=W 5=SW 6=S 7=SE (y grows downwards)

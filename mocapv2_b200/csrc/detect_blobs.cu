@@ -76,12 +76,13 @@ struct Walk {
 __device__ __forceinline__ void walk_init(const BitImg& im, Walk& w, int x, int y, int side)
 {
     w.x0 = x; w.y0 = y; w.x = x; w.y = y;
-    int s = side;
-    w.single = true;
-    for (int k = 0; k < 7; ++k) {
-        s = (s + 7) & 7;                                     // clockwise
-        if (im.get(x + dir_dx(s), y + dir_dy(s))) { w.single = false; break; }
-    }
+    // clockwise search (side-1, side-2, ... side-7) for the border's predecessor of the start pixel
+    uint32_t m = im.nbr8(x, y);
+    uint32_t rev = __brev(m) >> 24;                               // bit i = m[7 - i]
+    uint32_t sh = (8 - side) & 7;
+    uint32_t r = (((rev | (rev << 8)) >> sh) & 0x7fu);            // bit j = m[(side - 1 - j) & 7], j = 0..6
+    w.single = r == 0;
+    int s = w.single ? (side + 1) & 7 : (side - 1 - (__ffs(r) - 1)) & 7;
     w.s = s;
     w.x1 = x + dir_dx(s); w.y1 = y + dir_dy(s);
 }
@@ -90,15 +91,14 @@ __device__ __forceinline__ void walk_init(const BitImg& im, Walk& w, int x, int 
 // neighbour directions examined and found empty.  Advances the walker.  `done` when back at the start.
 __device__ __forceinline__ int walk_step(const BitImg& im, Walk& w, unsigned& zeros, bool& done)
 {
-    int d = w.s;
-    zeros = 0;
-    int nx = w.x, ny = w.y;
-    for (int k = 0; k < 8; ++k) {
-        d = (d + 1) & 7;
-        nx = w.x + dir_dx(d); ny = w.y + dir_dy(d);
-        if (im.get(nx, ny)) break;
-        zeros |= 1u << d;
-    }
+    uint32_t m = im.nbr8(w.x, w.y);
+    int start = (w.s + 1) & 7;
+    uint32_t rot = ((m | (m << 8)) >> start) & 0xffu;             // bit k = m[(start + k) & 7]
+    int k = rot ? __ffs(rot) - 1 : 8;
+    int d = (start + k) & 7;
+    uint32_t z = ((1u << k) - 1u) << start;                       // the k empty directions passed over
+    zeros = (z | (z >> 8)) & 0xffu;
+    int nx = w.x + dir_dx(d), ny = w.y + dir_dy(d);
     done = (nx == w.x0 && ny == w.y0 && w.x == w.x1 && w.y == w.y1);
     w.x = nx; w.y = ny;
     w.s = (d + 4) & 7;
