@@ -32,6 +32,7 @@ MAX_BLOBS = 160
 MAX_GROUPS = 64            # candidate groups evaluated per root (cap policy, flagged per frame-set)
 MAX_CAND = 8               # MOCAP_MAX_CAND
 JITTER = 0.01              # metres, per frame-set
+SPREAD = 0.95              # half-extent (m) of the marker volume around the rig centre: fills the 2048x2048 views
 
 
 def parse():
@@ -54,7 +55,9 @@ def make_scene(n_frame_sets, seed=S.SEED0 + 4000):
     """Marker positions per frame-set and their integer pixel centres per camera: (rig, centres [FS, C, M, 2] int64)."""
     rig = S.config_rig(CONFIG)
     rng = np.random.default_rng(seed)
-    X0 = S.config_markers(CONFIG, rig, rng)
+    # markers spread over the whole commonly visible volume, >= 2r+12 px apart in every view where that is achievable
+    # (with 16 views and 128 markers some views inevitably show touching blobs; the detector handles them)
+    X0 = S.sample_markers(rig, N_MARKERS, rng, spread=SPREAD, min_sep_px=56.0, margin=40.0, tries=300)
     cen = np.empty((n_frame_sets, len(rig["poses"]), N_MARKERS, 2), dtype=np.int64)
     for s in range(n_frame_sets):
         X = X0 + rng.uniform(-JITTER, JITTER, X0.shape)

@@ -33,6 +33,8 @@ extern "C" {
 #define MOCAP_FLAG_TILE_OVERFLOW 8     /* more foreground tiles than the workspace holds */
 #define MOCAP_FLAG_DEPTH_OVERFLOW 16   /* contour tree deeper than 8: order resolved by the slow path */
 #define MOCAP_FLAG_TRACE_OVERFLOW 32   /* a border longer than the step budget: frame outputs invalid */
+#define MOCAP_FLAG_GENERAL_PATH 64     /* informational: the frame was finished by the general per-frame path (hole borders,
+                                          oversized blob groups, parity outputs requested), not by the per-cluster units; bits 8.. say why */
 
 /* per-frame-set flags written by mocap_correspond_batch */
 #define MOCAP_CFLAG_GROUP_CAP 1        /* a root had more candidate groups than max_groups: mean over the first max_groups */
@@ -72,8 +74,9 @@ size_t mocap_detect_workspace_bytes(int n_frames, int H, int W, int max_blobs, i
 
 /* Optional per-stage device timing of mocap_detect_batch (bench.py's roofline line): a timer owns CUDA events that
  * the call records around its kernels on `stream`; read it after the stream has been synchronised.  Stages:
- * 0 scan (streams every source byte), 1 compact (work list), 2 filter (remap+blur+threshold+majority on hot tiles),
- * 3 blobs (runs, borders, moments).  ms_out[MOCAP_N_STAGES], -1 for a stage that was not recorded. */
+ * 0 scan (streams every source byte), 1 group (hot cells -> clusters), 2 cluster (remap+blur+threshold+majority and
+ * border tracing per cluster, in shared memory), 3 finish (general path for the frames that need it + per-frame
+ * ordering).  ms_out[MOCAP_N_STAGES], -1 for a stage that was not recorded. */
 #define MOCAP_N_STAGES 4
 void* mocap_stage_timer_create(void);
 void mocap_stage_timer_destroy(void* timer);

@@ -20,6 +20,8 @@ N_STAGES = 4
 
 OK = 0
 FLAG_RUN_OVERFLOW, FLAG_BLOB_OVERFLOW, FLAG_CONTOUR_OVERFLOW, FLAG_TILE_OVERFLOW, FLAG_DEPTH_OVERFLOW, FLAG_TRACE_OVERFLOW = 1, 2, 4, 8, 16, 32
+FLAG_GENERAL_PATH = 64          # informational
+FLAG_ERRORS = 1 | 2 | 4 | 8 | 32
 CFLAG_GROUP_CAP, CFLAG_CAND_CAP, CFLAG_TIE = 1, 2, 4
 
 _p = C.c_void_p

@@ -4,8 +4,18 @@
 
 // detect_filter.cu
 int table_view(const void* table_dev, int H, int W, TableView* tv);
-int launch_filter(const uint8_t* frames, int n, int H, int W, int64_t fstride, const TableView& tv, int thresh,
-                  const FilterWs& ws, int max_fg, int* flags, cudaStream_t s, StageTimer* timer);
+int launch_scan(const uint8_t* frames, int n, int H, int W, int64_t fstride, const TableView& tv, int thresh,
+                const FilterWs& ws, cudaStream_t s, StageTimer* timer);
+int launch_tiles(const uint8_t* frames, int n, int H, int W, int64_t fstride, const TableView& tv, int thresh,
+                 const FilterWs& ws, int max_fg, int* flags, const int* need_general, cudaStream_t s);
+// detect_cluster.cu
+size_t cluster_ws_bytes(int n, int max_contours, int q_cap, size_t* offs);
+bool cluster_path_supported(int H, int W);
+int launch_cluster_path(const uint8_t* frames, int n, int H, int W, int64_t fstride, const TableView& tv, int thresh,
+                        const uint32_t* cellbox, char* ws_base, const size_t* offs, int q_cap,
+                        int max_contours, int max_blobs, double min_area, double min_circ,
+                        int32_t* out_xy, int32_t* out_count, int32_t* out_flags, double* out_contours, int32_t* out_contour_count,
+                        bool finalize_only, cudaStream_t s, StageTimer* timer);
 int launch_materialize_bits(const FilterWs& ws, int n, int H, int W, const TableView& tv, uint32_t* out, cudaStream_t s);
 // detect_blobs.cu
 int launch_tiles_from_bits(const uint32_t* bits, int n, int H, int TX, int TY, uint32_t* fg_tiles, int* n_fg, int max_fg, cudaStream_t s);
@@ -15,7 +25,7 @@ int launch_blobs(const uint32_t* bits, const uint32_t* fg_tiles, const int* n_fg
                  char* ws, size_t ws_stride,
                  int32_t* out_xy, int32_t* out_count, int32_t* out_flags,
                  int64_t* out_blob_sums, int32_t* out_blob_count, double* out_contours, int32_t* out_contour_count,
-                 int32_t* out_labels, cudaStream_t s);
+                 int32_t* out_labels, const int* need_general, cudaStream_t s);
 
 extern "C" const char* mocap_status_string(int status)
 {
@@ -33,7 +43,7 @@ extern "C" int mocap_abi_version(void) { return MOCAP_ABI_VERSION; }
 
 extern "C" const char* mocap_stage_name(int stage)
 {
-    static const char* names[MOCAP_N_STAGES] = {"scan", "compact", "filter", "blobs"};
+    static const char* names[MOCAP_N_STAGES] = {"scan", "group", "cluster", "finish"};
     return (stage >= 0 && stage < MOCAP_N_STAGES) ? names[stage] : "?";
 }
 
@@ -68,9 +78,10 @@ extern "C" int mocap_stage_timer_read(void* timer, float* ms_out)
 }
 
 struct DetectLayout {
-    size_t off_active, off_list, off_counters, off_bits, off_fg, off_nfg, off_flags, off_cellbox, off_blob;
+    size_t off_active, off_list, off_counters, off_bits, off_fg, off_nfg, off_flags, off_cellbox, off_blob, off_cluster;
     size_t blob_stride, total;
-    int TX, TY, TXW, max_fg;
+    size_t cl_offs[16];
+    int TX, TY, TXW, max_fg, q_cap;
 };
 
 static int detect_layout(int n, int H, int W, int max_contours, int max_runs, bool with_blobs, DetectLayout* L)
@@ -92,6 +103,8 @@ static int detect_layout(int n, int H, int W, int max_contours, int max_runs, bo
     L->off_cellbox = take((size_t)n * L->TX * L->TY * 4);
     L->blob_stride = with_blobs ? blob_ws_stride(H, max_runs, max_contours) : 0;
     L->off_blob = take(L->blob_stride * (size_t)n);
+    L->q_cap = n * 256 + 1024;                          // cluster work-queue entries per size class
+    L->off_cluster = take(cluster_ws_bytes(n, max_contours, L->q_cap, L->cl_offs));
     L->total = off;
     return MOCAP_OK;
 }
@@ -133,7 +146,9 @@ extern "C" int mocap_filter_batch(const uint8_t* frames_dev, int n_frames, int H
     FilterWs ws = filter_ws((char*)workspace, L);
     int* flags = (int*)((char*)workspace + L.off_flags);
     CUDA_TRY(cudaMemsetAsync(flags, 0, (size_t)n_frames * 4, s));
-    st = launch_filter(frames_dev, n_frames, H, W, frame_stride, tv, thresh, ws, L.max_fg, flags, s, nullptr);
+    st = launch_scan(frames_dev, n_frames, H, W, frame_stride, tv, thresh, ws, s, nullptr);
+    if (st != MOCAP_OK) return st;
+    st = launch_tiles(frames_dev, n_frames, H, W, frame_stride, tv, thresh, ws, L.max_fg, flags, nullptr, s);
     if (st != MOCAP_OK) return st;
     return launch_materialize_bits(ws, n_frames, H, W, tv, out_bits, s);
 }
@@ -159,17 +174,38 @@ extern "C" int mocap_detect_batch(const uint8_t* frames_dev, int n_frames, int H
     FilterWs ws = filter_ws((char*)workspace, L);
     CUDA_TRY(cudaMemsetAsync(out_flags, 0, (size_t)n_frames * 4, s));
     if (out_labels) CUDA_TRY(cudaMemsetAsync(out_labels, 0, (size_t)n_frames * H * W * 4, s));
-    st = launch_filter(frames_dev, n_frames, H, W, frame_stride, tv, thresh, ws, L.max_fg, out_flags, s, timer);
+    // Product path (no label / bit-image outputs wanted): scan -> groups of hot cells -> per-cluster units in shared memory
+    // -> per-frame ordering.  Frames it cannot finish locally, and every frame when the parity outputs are requested,
+    // take the general per-frame path (tiles -> packed image -> runs, labels, contour tree).
+    const bool extras = out_bits || out_labels || out_blob_sums || out_blob_count;
+    const bool use_cluster = !extras && cluster_path_supported(H, W);
+    char* cl_base = (char*)workspace + L.off_cluster;
+    int* need_general = (int*)(cl_base + L.cl_offs[0]);
+    st = launch_scan(frames_dev, n_frames, H, W, frame_stride, tv, thresh, ws, s, timer);
+    if (st != MOCAP_OK) return st;
+    CUDA_TRY(cudaMemsetAsync(need_general, use_cluster ? 0 : 1, (size_t)n_frames * 4, s));
+    if (use_cluster) {
+        st = launch_cluster_path(frames_dev, n_frames, H, W, frame_stride, tv, thresh, ws.cellbox, cl_base, L.cl_offs, L.q_cap,
+                                 max_contours, max_blobs, min_area, min_circ, out_xy, out_count, out_flags, out_contours,
+                                 out_contour_count, false, s, timer);
+        if (st != MOCAP_OK) return st;
+    }
+    stage_begin(timer, 3, s);
+    st = launch_tiles(frames_dev, n_frames, H, W, frame_stride, tv, thresh, ws, L.max_fg, out_flags, need_general, s);
     if (st != MOCAP_OK) return st;
     if (out_bits) {
         st = launch_materialize_bits(ws, n_frames, H, W, tv, out_bits, s);
         if (st != MOCAP_OK) return st;
     }
-    stage_begin(timer, 3, s);
     st = launch_blobs(ws.bits, ws.fg_tiles, ws.n_fg, n_frames, H, W, L.TX, L.max_fg, max_runs, max_blobs, max_contours,
                       min_area, min_circ, (char*)workspace + L.off_blob, L.blob_stride,
                       out_xy, out_count, out_flags, out_blob_sums, out_blob_count, out_contours, out_contour_count,
-                      out_labels, s);
+                      out_labels, need_general, s);
+    if (st != MOCAP_OK) return st;
+    if (use_cluster)
+        st = launch_cluster_path(frames_dev, n_frames, H, W, frame_stride, tv, thresh, ws.cellbox, cl_base, L.cl_offs, L.q_cap,
+                                 max_contours, max_blobs, min_area, min_circ, out_xy, out_count, out_flags, out_contours,
+                                 out_contour_count, true, s, timer);
     stage_end(timer, 3, s);
     return st;
 }
@@ -197,5 +233,5 @@ extern "C" int mocap_blobs_batch(const uint32_t* bits_dev, int n_frames, int H, 
     return launch_blobs(bits_dev, ws.fg_tiles, ws.n_fg, n_frames, H, W, L.TX, L.max_fg, max_runs, max_blobs, max_contours,
                         min_area, min_circ, (char*)workspace + L.off_blob, L.blob_stride,
                         out_xy, out_count, out_flags, out_blob_sums, out_blob_count, out_contours, out_contour_count,
-                        out_labels, s);
+                        out_labels, nullptr, s);
 }

@@ -43,6 +43,7 @@ struct TableHeader {
     uint64_t off_map;        // int32 [H][W]: low16 = iu - 32*x, high16 = iv - 32*y (1/32 px), 0x80008000 = outside
     uint64_t off_cell;       // int32 [TY][TX][4]: output-tile rectangle (tx0,ty0,tx1,ty1) that samples this source cell
     uint64_t off_tile;       // int32 [TY][TX][8]: source box sx0,sy0,sx1,sy1 and displacement bounds dxmin,dxmax,dymin,dymax
+    uint64_t off_cellinv;    // int32 [TY][TX][4]: bounds dxmin,dxmax,dymin,dymax of (source - output) over every output pixel that can sample the cell
     uint64_t total_bytes;
 };
 #define TABLE_MAGIC 0x4d43424bu
@@ -52,6 +53,7 @@ struct TableView {
     const int32_t* map;
     const int32_t* cell;
     const int32_t* tile;
+    const int32_t* cellinv;
     int H, W, TX, TY;
 };
 

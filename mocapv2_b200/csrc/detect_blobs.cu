@@ -14,6 +14,7 @@
 //   tree/order  parents from the nearest foreground pixel to the left (Suzuki Table 1), output order =
 //               pre-order with siblings in reverse raster order, then the reference's filter and centroid.
 #include "common.cuh"
+#include "walk.cuh"
 
 #define BLOB_THREADS 256
 #define MAX_DEPTH 8
@@ -64,124 +65,6 @@ __device__ __forceinline__ void uf_union(int* parent, int a, int b)
     }
 }
 
-// Walker state for Suzuki-Abe border following started from the west (side 4) or east (side 0) edge of a pixel.
-struct Walk {
-    int x0, y0;      // start pixel
-    int x1, y1;      // its predecessor on the border
-    int x, y;        // current pixel
-    int s;           // direction from current pixel to the previous one
-    bool single;
-};
-
-__device__ __forceinline__ void walk_init(const BitImg& im, Walk& w, int x, int y, int side)
-{
-    w.x0 = x; w.y0 = y; w.x = x; w.y = y;
-    // clockwise search (side-1, side-2, ... side-7) for the border's predecessor of the start pixel
-    uint32_t m = im.nbr8(x, y);
-    uint32_t rev = __brev(m) >> 24;                               // bit i = m[7 - i]
-    uint32_t sh = (8 - side) & 7;
-    uint32_t r = (((rev | (rev << 8)) >> sh) & 0x7fu);            // bit j = m[(side - 1 - j) & 7], j = 0..6
-    w.single = r == 0;
-    int s = w.single ? (side + 1) & 7 : (side - 1 - (__ffs(r) - 1)) & 7;
-    w.s = s;
-    w.x1 = x + dir_dx(s); w.y1 = y + dir_dy(s);
-}
-
-// One step: counter-clockwise search from the previous pixel; returns the step direction, `zeros` = bitmask of
-// neighbour directions examined and found empty.  Advances the walker.  `done` when back at the start.
-__device__ __forceinline__ int walk_step(const BitImg& im, Walk& w, unsigned& zeros, bool& done)
-{
-    uint32_t m = im.nbr8(w.x, w.y);
-    int start = (w.s + 1) & 7;
-    uint32_t rot = ((m | (m << 8)) >> start) & 0xffu;             // bit k = m[(start + k) & 7]
-    int k = rot ? __ffs(rot) - 1 : 8;
-    int d = (start + k) & 7;
-    uint32_t z = ((1u << k) - 1u) << start;                       // the k empty directions passed over
-    zeros = (z | (z >> 8)) & 0xffu;
-    int nx = w.x + dir_dx(d), ny = w.y + dir_dy(d);
-    done = (nx == w.x0 && ny == w.y0 && w.x == w.x1 && w.y == w.y1);
-    w.x = nx; w.y = ny;
-    w.s = (d + 4) & 7;
-    return d;
-}
-
-#define WALK_BUDGET (1 << 22)
-
-// key of a west/east edge: 2 * pixel index + (east ? 1 : 0)
-__device__ __forceinline__ long long edge_key(int x, int y, int W, int east) { return 2LL * ((long long)y * W + x) + east; }
-
-// Walk the border owning edge (x, y, side).  mode 0: stop as soon as a smaller west/east edge of the same border is
-// seen (returns 1 if the start edge is the border's smallest edge).  mode 1: full loop, *min_key = smallest edge key.
-__device__ int walk_min_edge(const BitImg& im, int x, int y, int side, int mode, long long* min_key, int* overflow)
-{
-    const int W = im.W;
-    long long key0 = edge_key(x, y, W, side == 0);
-    long long best = key0;
-    Walk w; walk_init(im, w, x, y, side);
-    if (w.single) { if (min_key) *min_key = edge_key(x, y, W, 0); return side == 4; }   // isolated pixel: its west edge is smaller
-    for (int step = 0; step < WALK_BUDGET; ++step) {
-        int cx = w.x, cy = w.y;
-        unsigned zeros; bool done;
-        walk_step(im, w, zeros, done);
-        if (zeros & (1u << 4)) { long long k = edge_key(cx, cy, W, 0); if (k < best) { best = k; if (!mode) return 0; } }
-        if (zeros & (1u << 0)) { long long k = edge_key(cx, cy, W, 1); if (k < best) { best = k; if (!mode) return 0; } }
-        if (done) { if (min_key) *min_key = best; return best == key0; }
-    }
-    *overflow = 1;
-    if (min_key) *min_key = best;
-    return 0;
-}
-
-// Full trace of a border from its start edge: Green sums over the CHAIN_APPROX_SIMPLE vertices, perimeter, length.
-// key0 >= 0: also verify that the start edge is the border's smallest west/east edge (i.e. where cv.findContours starts
-// it); returns 0 as soon as a smaller one is met.  key0 < 0: no check.  Returns 1 for a completed trace.
-__device__ int trace_contour(const BitImg& im, int x, int y, int side, long long key0, long long* a, double* per, int* n_chain, int* overflow)
-{
-    const int W = im.W;
-    Walk w; walk_init(im, w, x, y, side);
-    if (w.single) { a[0] = a[1] = a[2] = 0; *per = 0.0; *n_chain = 1; return key0 < 0 || side == 4; }
-    long long a00 = 0, a10 = 0, a01 = 0;
-    double perim = 0.0;
-    int n = 0;
-    int prev_dir = w.s ^ 4;             // direction of the closing step (predecessor -> start)
-    bool have_v = false;
-    int vx = 0, vy = 0, fx = 0, fy = 0; // previous vertex, first vertex
-    for (int step = 0; step < WALK_BUDGET; ++step) {
-        int cx = w.x, cy = w.y;
-        unsigned zeros; bool done;
-        int d = walk_step(im, w, zeros, done);
-        ++n;
-        if (key0 >= 0) {
-            if ((zeros & (1u << 4)) && edge_key(cx, cy, W, 0) < key0) return 0;
-            if ((zeros & (1u << 0)) && edge_key(cx, cy, W, 1) < key0) return 0;
-        }
-        if (d != prev_dir) {            // direction change: (cx, cy) is a vertex
-            if (have_v) {
-                long long dxy = (long long)vx * cy - (long long)cx * vy;
-                a00 += dxy; a10 += dxy * (vx + cx); a01 += dxy * (vy + cy);
-                float ddx = (float)(cx - vx), ddy = (float)(cy - vy);
-                perim += (double)__fsqrt_rn(__fadd_rn(__fmul_rn(ddx, ddx), __fmul_rn(ddy, ddy)));
-            } else { fx = cx; fy = cy; have_v = true; }
-            vx = cx; vy = cy;
-        }
-        prev_dir = d;
-        if (done) {
-            if (have_v) {               // closing segment last vertex -> first vertex
-                long long dxy = (long long)vx * fy - (long long)fx * vy;
-                a00 += dxy; a10 += dxy * (vx + fx); a01 += dxy * (vy + fy);
-                float ddx = (float)(fx - vx), ddy = (float)(fy - vy);
-                float q = __fadd_rn(__fmul_rn(ddx, ddx), __fmul_rn(ddy, ddy));
-                if (q > 0.f) perim += (double)__fsqrt_rn(q);
-            }
-            a[0] = a00; a[1] = a10; a[2] = a01; *per = perim; *n_chain = n;
-            return 1;
-        }
-    }
-    *overflow = 1;
-    a[0] = a[1] = a[2] = 0; *per = 0.0; *n_chain = n;
-    return 0;
-}
-
 // block-wide exclusive scan helper over an int array in global memory (in place), returns total in *total_s (shared)
 __device__ void block_exclusive_scan(int* data, int n, int* sh /*[BLOB_THREADS + 1]*/)
 {
@@ -215,9 +98,10 @@ __global__ void __launch_bounds__(BLOB_THREADS) blobs_kernel(
     int32_t* __restrict__ out_xy, int32_t* __restrict__ out_count, int32_t* __restrict__ out_flags,
     int64_t* __restrict__ out_blob_sums, int32_t* __restrict__ out_blob_count,
     double* __restrict__ out_contours, int32_t* __restrict__ out_contour_count,
-    int32_t* __restrict__ out_labels)
+    int32_t* __restrict__ out_labels, const int* __restrict__ need_general)
 {
     const int f = blockIdx.x, tid = threadIdx.x, nt = blockDim.x;
+    if (need_general && !need_general[f]) return;           // frame fully handled by the cluster path
     const int H = P.H, W = P.W, TX = P.TX;
     __shared__ int sh[BLOB_THREADS + 1];
     __shared__ int s_nruns, s_nblobs, s_nholes, s_flag, s_ncont;
@@ -362,7 +246,7 @@ __global__ void __launch_bounds__(BLOB_THREADS) blobs_kernel(
         if (n_cand <= P.max_contours) {
             for (int c = tid; c < n_cand; c += nt) {
                 int st = w.c_start[c], ty = w.c_type[c], ovf = 0;
-                int ok = trace_contour(im, st % W, st / W, ty ? 0 : 4, 2LL * st + ty, &w.c_a[3 * c], &w.c_per[c], &w.c_n[c], &ovf);
+                int ok = trace_contour(im, st % W, st / W, ty ? 0 : 4, 2LL * st + ty, &w.c_a[3 * c], &w.c_per[c], &w.c_n[c], &ovf, 0, 0, W);
                 if (ovf) atomicOr(&s_flag, MOCAP_FLAG_TRACE_OVERFLOW);
                 w.c_keep[c] = ok;                      // parked: candidate is a real border start
                 if (ok && ty) atomicAdd(&s_nholes, 1);
@@ -504,7 +388,7 @@ __global__ void __launch_bounds__(BLOB_THREADS) blobs_kernel(
     for (int c = tid; c < n_cont; c += nt) {
         int st = w.c_start[c];
         int ovf = 0;
-        trace_contour(im, st % W, st / W, w.c_type[c] ? 0 : 4, -1, &w.c_a[3 * c], &w.c_per[c], &w.c_n[c], &ovf);
+        trace_contour(im, st % W, st / W, w.c_type[c] ? 0 : 4, -1, &w.c_a[3 * c], &w.c_per[c], &w.c_n[c], &ovf, 0, 0, W);
         if (ovf) atomicOr(&s_flag, MOCAP_FLAG_TRACE_OVERFLOW);
     }
     // ---- parents ------------------------------------------------------------------------------------------------
@@ -636,7 +520,7 @@ __global__ void __launch_bounds__(BLOB_THREADS) blobs_kernel(
         int fl = s_flag;
         if (kept > P.max_blobs) { fl |= MOCAP_FLAG_BLOB_OVERFLOW; kept = P.max_blobs; }
         out_count[f] = kept;
-        out_flags[f] |= fl;
+        out_flags[f] |= fl | (need_general ? (MOCAP_FLAG_GENERAL_PATH | (need_general[f] << 8)) : 0);   // bits 8.. = why (informational)
         if (out_contour_count) out_contour_count[f] = n_cont;
     }
 }
@@ -684,13 +568,13 @@ int launch_blobs(const uint32_t* bits, const uint32_t* fg_tiles, const int* n_fg
                  char* ws, size_t ws_stride,
                  int32_t* out_xy, int32_t* out_count, int32_t* out_flags,
                  int64_t* out_blob_sums, int32_t* out_blob_count, double* out_contours, int32_t* out_contour_count,
-                 int32_t* out_labels, cudaStream_t s)
+                 int32_t* out_labels, const int* need_general, cudaStream_t s)
 {
     BlobParams P;
     P.H = H; P.W = W; P.TX = TX; P.max_fg = max_fg; P.max_runs = max_runs; P.max_blobs = max_blobs;
     P.max_contours = max_contours; P.min_area = min_area; P.min_circ = min_circ;
     LAUNCH(blobs_kernel, n, BLOB_THREADS, 0, s, bits, fg_tiles, n_fg, P, ws, ws_stride, out_xy, out_count, out_flags,
-                                            out_blob_sums, out_blob_count, out_contours, out_contour_count, out_labels);
+                                            out_blob_sums, out_blob_count, out_contours, out_contour_count, out_labels, need_general);
     CUDA_TRY(cudaGetLastError());
     return MOCAP_OK;
 }

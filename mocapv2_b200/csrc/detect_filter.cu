@@ -13,6 +13,7 @@
 //   filter_tiles  one warp per active 32x32 tile: exact hot bounding box of the tile's source window,
 //                 fixed-point remap + 5x5 floor-mean threshold + 5x5 majority only inside that box.
 #include "common.cuh"
+#include "remap.cuh"
 
 // ---------------------------------------------------------------------------------------------------------
 // table build
@@ -62,17 +63,18 @@ __global__ void build_map_kernel(MapParams mp, int H, int W, int32_t* __restrict
     map[(size_t)i * W + j] = (int32_t)enc;
 }
 
-__global__ void init_tables_kernel(int32_t* cell, int32_t* tile, int n_tiles)
+__global__ void init_tables_kernel(int32_t* cell, int32_t* tile, int32_t* cellinv, int n_tiles)
 {
     int t = blockIdx.x * blockDim.x + threadIdx.x;
     if (t >= n_tiles) return;
     cell[4 * t + 0] = 0x7fffffff; cell[4 * t + 1] = 0x7fffffff; cell[4 * t + 2] = -1; cell[4 * t + 3] = -1;
+    cellinv[4 * t + 0] = 0x7fffffff; cellinv[4 * t + 1] = -0x7fffffff; cellinv[4 * t + 2] = 0x7fffffff; cellinv[4 * t + 3] = -0x7fffffff;
 }
 
 // one CTA per output tile: source window + displacement bounds of its 40x40 undistorted region,
 // then scatter the tile index into the reach rectangle of every source cell the window overlaps.
 __global__ void build_tile_kernel(const int32_t* __restrict__ map, int H, int W, int TX, int TY,
-                                  int32_t* __restrict__ cell, int32_t* __restrict__ tile)
+                                  int32_t* __restrict__ cell, int32_t* __restrict__ tile, int32_t* __restrict__ cellinv)
 {
     int tx = blockIdx.x, ty = blockIdx.y;
     int x0 = tx * TILE - HALO_U, y0 = ty * TILE - HALO_U;
@@ -106,6 +108,8 @@ __global__ void build_tile_kernel(const int32_t* __restrict__ map, int H, int W,
             for (int cx = sx0 >> 5; cx <= (sx1 >> 5); ++cx) {
                 int32_t* c = cell + 4 * (cy * TX + cx);
                 atomicMin(&c[0], tx); atomicMin(&c[1], ty); atomicMax(&c[2], tx); atomicMax(&c[3], ty);
+                int32_t* ci = cellinv + 4 * (cy * TX + cx);
+                atomicMin(&ci[0], s[4]); atomicMax(&ci[1], s[5]); atomicMin(&ci[2], s[6]); atomicMax(&ci[3], s[7]);
             }
     }
 }
@@ -136,6 +140,7 @@ static void table_layout(int H, int W, TableHeader* h)
     h->off_map = off; off += align_up((size_t)H * W * 4, 256);
     h->off_cell = off; off += align_up((size_t)h->TX * h->TY * 16, 256);
     h->off_tile = off; off += align_up((size_t)h->TX * h->TY * 32, 256);
+    h->off_cellinv = off; off += align_up((size_t)h->TX * h->TY * 16, 256);
     h->total_bytes = off;
 }
 
@@ -163,11 +168,12 @@ extern "C" int mocap_undistort_table_build(const double* K9, const double* dist5
     int32_t* map = (int32_t*)(base + h.off_map);
     int32_t* cell = (int32_t*)(base + h.off_cell);
     int32_t* tile = (int32_t*)(base + h.off_tile);
+    int32_t* cellinv = (int32_t*)(base + h.off_cellinv);
     dim3 blk(32, 8), grd(cdiv(W, 32), cdiv(H, 8));
     LAUNCH(build_map_kernel, grd, blk, 0, s, mp, H, W, map, (TableHeader*)base);
     int nt = h.TX * h.TY;
-    LAUNCH(init_tables_kernel, cdiv(nt, 256), 256, 0, s, cell, tile, nt);
-    LAUNCH(build_tile_kernel, dim3(h.TX, h.TY), 256, 0, s, map, H, W, h.TX, h.TY, cell, tile);
+    LAUNCH(init_tables_kernel, cdiv(nt, 256), 256, 0, s, cell, tile, cellinv, nt);
+    LAUNCH(build_tile_kernel, dim3(h.TX, h.TY), 256, 0, s, map, H, W, h.TX, h.TY, cell, tile, cellinv);
     CUDA_TRY(cudaGetLastError());
     TableHeader back;
     CUDA_TRY(cudaMemcpyAsync(&back, base, sizeof(back), cudaMemcpyDeviceToHost, s));
@@ -184,6 +190,7 @@ int table_view(const void* table_dev, int H, int W, TableView* tv)
     tv->map = (const int32_t*)(base + h.off_map);
     tv->cell = (const int32_t*)(base + h.off_cell);
     tv->tile = (const int32_t*)(base + h.off_tile);
+    tv->cellinv = (const int32_t*)(base + h.off_cellinv);
     tv->H = H; tv->W = W; tv->TX = h.TX; tv->TY = h.TY;
     return MOCAP_OK;
 }
@@ -353,13 +360,14 @@ __global__ void scan_hot_scalar_kernel(const uint8_t* __restrict__ frames, int n
 }
 
 __global__ void compact_tiles_kernel(const uint32_t* __restrict__ active, long long n_words, int TX, int TY, int TXW,
-                                     uint32_t* __restrict__ list, int* __restrict__ count)
+                                     uint32_t* __restrict__ list, int* __restrict__ count, const int* __restrict__ need_general)
 {
     long long idx = (long long)blockIdx.x * blockDim.x + threadIdx.x;
     if (idx >= n_words) return;
     uint32_t w = active[idx];
     if (!w) return;
     int f = (int)(idx / ((long long)TY * TXW));
+    if (need_general && !need_general[f]) return;          // frame fully handled by the cluster path
     int rem = (int)(idx - (long long)f * TY * TXW);
     int ty = rem / TXW, wq = rem - ty * TXW;
     int base = atomicAdd(count, __popc(w));
@@ -375,24 +383,6 @@ __global__ void compact_tiles_kernel(const uint32_t* __restrict__ active, long l
 // ---------------------------------------------------------------------------------------------------------
 __device__ __forceinline__ int fdiv20(int idx, int inv) { return (int)(((unsigned)idx * (unsigned)inv) >> 20); }
 __device__ __forceinline__ int finv20(int w) { return (1 << 20) / w + 1; }
-
-__device__ __forceinline__ int remap_px(const uint8_t* __restrict__ fr, int W, int H, int i, int j, uint32_t m)
-{
-    if (m == MAP_OUTSIDE) return 0;
-    int iu = 32 * j + (int)(int16_t)(m & 0xffff);
-    int iv = 32 * i + (int)(int16_t)(m >> 16);
-    int sx = iu >> 5, sy = iv >> 5, fx = iu & 31, fy = iv & 31;
-    const uint8_t* p = fr + (ptrdiff_t)sy * W + sx;
-    bool x0ok = (unsigned)sx < (unsigned)W, x1ok = (unsigned)(sx + 1) < (unsigned)W;
-    bool y0ok = (unsigned)sy < (unsigned)H, y1ok = (unsigned)(sy + 1) < (unsigned)H;
-    int p00 = (x0ok && y0ok) ? p[0] : 0;
-    int p01 = (x1ok && y0ok) ? p[1] : 0;
-    int p10 = (x0ok && y1ok) ? p[W] : 0;
-    int p11 = (x1ok && y1ok) ? p[W + 1] : 0;
-    int r0 = (32 - fx) * p00 + fx * p01;
-    int r1 = (32 - fx) * p10 + fx * p11;
-    return ((32 - fy) * r0 + fy * r1 + 512) >> 10;
-}
 
 #define FT_WARPS 8
 struct __align__(16) WarpScratch {
@@ -579,14 +569,12 @@ __global__ void materialize_bits_kernel(const uint32_t* __restrict__ bits, const
 // ---------------------------------------------------------------------------------------------------------
 // host-side launcher shared by mocap_filter_batch and mocap_detect_batch
 // ---------------------------------------------------------------------------------------------------------
-int launch_filter(const uint8_t* frames, int n, int H, int W, int64_t fstride, const TableView& tv, int thresh,
-                  const FilterWs& ws, int max_fg, int* flags, cudaStream_t s, StageTimer* timer)
+int launch_scan(const uint8_t* frames, int n, int H, int W, int64_t fstride, const TableView& tv, int thresh,
+                const FilterWs& ws, cudaStream_t s, StageTimer* timer)
 {
     const int TX = tv.TX, TY = tv.TY, TXW = cdiv(TX, 32);
     size_t act_bytes = (size_t)n * TY * TXW * 4;
     CUDA_TRY(cudaMemsetAsync(ws.active, 0, act_bytes, s));
-    CUDA_TRY(cudaMemsetAsync(ws.counters, 0, 2 * sizeof(int), s));
-    CUDA_TRY(cudaMemsetAsync(ws.n_fg, 0, (size_t)n * sizeof(int), s));
     int dev = 0, sms = 148;
     cudaGetDevice(&dev);
     cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
@@ -605,14 +593,24 @@ int launch_filter(const uint8_t* frames, int n, int H, int W, int64_t fstride, c
         LAUNCH(scan_hot_scalar_kernel, sms * 8, 256, 0, s, frames, n, fstride, tv, ws.active, TXW, thresh, ws.cellbox);
     }
     stage_end(timer, 0, s);
+    CUDA_TRY(cudaGetLastError());
+    return MOCAP_OK;
+}
+
+// general path, filter part: active tiles of the frames in need_general (all frames if null) -> packed binary image
+int launch_tiles(const uint8_t* frames, int n, int H, int W, int64_t fstride, const TableView& tv, int thresh,
+                 const FilterWs& ws, int max_fg, int* flags, const int* need_general, cudaStream_t s)
+{
+    const int TX = tv.TX, TY = tv.TY, TXW = cdiv(TX, 32);
+    CUDA_TRY(cudaMemsetAsync(ws.counters, 0, 2 * sizeof(int), s));
+    CUDA_TRY(cudaMemsetAsync(ws.n_fg, 0, (size_t)n * sizeof(int), s));
+    int dev = 0, sms = 148;
+    cudaGetDevice(&dev);
+    cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
     long long n_words = (long long)n * TY * TXW;
-    stage_begin(timer, 1, s);
-    LAUNCH(compact_tiles_kernel, (unsigned)((n_words + 255) / 256), 256, 0, s, ws.active, n_words, TX, TY, TXW, ws.list, ws.counters);
-    stage_end(timer, 1, s);
-    stage_begin(timer, 2, s);
+    LAUNCH(compact_tiles_kernel, (unsigned)((n_words + 255) / 256), 256, 0, s, ws.active, n_words, TX, TY, TXW, ws.list, ws.counters, need_general);
     LAUNCH(filter_tiles_kernel, sms * 4, FT_WARPS * 32, 0, s, frames, fstride, tv, thresh, ws.list, ws.counters, ws.counters + 1,
                                                           ws.active, TXW, ws.cellbox, ws.bits, ws.fg_tiles, ws.n_fg, max_fg, flags);
-    stage_end(timer, 2, s);
     CUDA_TRY(cudaGetLastError());
     return MOCAP_OK;
 }
