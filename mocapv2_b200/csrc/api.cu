@@ -9,10 +9,10 @@ int launch_scan(const uint8_t* frames, int n, int H, int W, int64_t fstride, con
 int launch_tiles(const uint8_t* frames, int n, int H, int W, int64_t fstride, const TableView& tv, int thresh,
                  const FilterWs& ws, int max_fg, int* flags, const int* need_general, cudaStream_t s);
 // detect_cluster.cu
-size_t cluster_ws_bytes(int n, int max_contours, int q_cap, size_t* offs);
+size_t cluster_ws_bytes(int n, int H, int W, int max_contours, size_t* offs);
 bool cluster_path_supported(int H, int W);
 int launch_cluster_path(const uint8_t* frames, int n, int H, int W, int64_t fstride, const TableView& tv, int thresh,
-                        const uint32_t* cellbox, char* ws_base, const size_t* offs, int q_cap,
+                        const uint32_t* cellbox, char* ws_base, const size_t* offs,
                         int max_contours, int max_blobs, double min_area, double min_circ,
                         int32_t* out_xy, int32_t* out_count, int32_t* out_flags, double* out_contours, int32_t* out_contour_count,
                         bool finalize_only, cudaStream_t s, StageTimer* timer);
@@ -81,7 +81,7 @@ struct DetectLayout {
     size_t off_active, off_list, off_counters, off_bits, off_fg, off_nfg, off_flags, off_cellbox, off_blob, off_cluster;
     size_t blob_stride, total;
     size_t cl_offs[16];
-    int TX, TY, TXW, max_fg, q_cap;
+    int TX, TY, TXW, max_fg;
 };
 
 static int detect_layout(int n, int H, int W, int max_contours, int max_runs, bool with_blobs, DetectLayout* L)
@@ -103,8 +103,7 @@ static int detect_layout(int n, int H, int W, int max_contours, int max_runs, bo
     L->off_cellbox = take((size_t)n * L->TX * L->TY * 4);
     L->blob_stride = with_blobs ? blob_ws_stride(H, max_runs, max_contours) : 0;
     L->off_blob = take(L->blob_stride * (size_t)n);
-    L->q_cap = n * 256 + 1024;                          // cluster work-queue entries per size class
-    L->off_cluster = take(cluster_ws_bytes(n, max_contours, L->q_cap, L->cl_offs));
+    L->off_cluster = take(cluster_ws_bytes(n, H, W, max_contours, L->cl_offs));
     L->total = off;
     return MOCAP_OK;
 }
@@ -185,7 +184,7 @@ extern "C" int mocap_detect_batch(const uint8_t* frames_dev, int n_frames, int H
     if (st != MOCAP_OK) return st;
     CUDA_TRY(cudaMemsetAsync(need_general, use_cluster ? 0 : 1, (size_t)n_frames * 4, s));
     if (use_cluster) {
-        st = launch_cluster_path(frames_dev, n_frames, H, W, frame_stride, tv, thresh, ws.cellbox, cl_base, L.cl_offs, L.q_cap,
+        st = launch_cluster_path(frames_dev, n_frames, H, W, frame_stride, tv, thresh, ws.cellbox, cl_base, L.cl_offs,
                                  max_contours, max_blobs, min_area, min_circ, out_xy, out_count, out_flags, out_contours,
                                  out_contour_count, false, s, timer);
         if (st != MOCAP_OK) return st;
@@ -203,7 +202,7 @@ extern "C" int mocap_detect_batch(const uint8_t* frames_dev, int n_frames, int H
                       out_labels, need_general, s);
     if (st != MOCAP_OK) return st;
     if (use_cluster)
-        st = launch_cluster_path(frames_dev, n_frames, H, W, frame_stride, tv, thresh, ws.cellbox, cl_base, L.cl_offs, L.q_cap,
+        st = launch_cluster_path(frames_dev, n_frames, H, W, frame_stride, tv, thresh, ws.cellbox, cl_base, L.cl_offs,
                                  max_contours, max_blobs, min_area, min_circ, out_xy, out_count, out_flags, out_contours,
                                  out_contour_count, true, s, timer);
     stage_end(timer, 3, s);

@@ -20,24 +20,27 @@
 #define HOT_MAX 1024            // hot cells per frame on the cluster path
 #define CELLS_MAX 8192          // TX*TY limit of the dense cell -> slot map held in shared memory
 #define ROOTS_MAX 512
-#define HUGE_MAX 512            // largest cluster box edge (third size class, staged through global scratch)
-#define HUGE_CTAS 48
+#define PIECE 64                // a cluster box is filtered in pieces of at most PIECE x PIECE output pixels
 #define CELL_EMPTY 0xffffffffu
 
+// counters[] slots
+#define CN_CLUSTERS 0
+#define CN_PIECES 1
+#define CN_PIECE_CUR 2
+#define CN_CANDS 3
+#define CN_ROWS 4               // words of bit-row storage handed out
+
 struct ClusterWs {
-    int* need_general;          // [n] frame takes the general path
-    int* q_count;               // [0] small queue length, [1] large queue length, [2] small cursor, [3] large cursor
-    int* q_small;               // [cap][4]: frame, x0 | y0 << 16, x1 | y1 << 16, member offset | count << 16  (box inclusive)
-    int* q_large;
-    int* q_huge;
-    int q_cap;
-    int q_caps[3];              // usable entries per size class (bounded by the bit-row storage)
+    int* need_general;          // [n] != 0: frame takes the general path (value = why)
+    int* counters;              // [16]
+    int* clusters;              // [cl_cap][8]: frame, x0 | y0 << 16, x1 | y1 << 16 (box, inclusive), rows word offset, words per row,
+                                //              member offset | count << 16, 0, 0
+    int* pieces;                // [pc_cap][2]: cluster, bx | by << 16
+    int cl_cap, pc_cap;
     short* memb;                // [n][HOT_MAX][4] output boxes of the hot cells, grouped by cluster
-    uint8_t* huge_scratch;      // [HUGE_CTAS][huge_scratch_stride]
-    size_t huge_stride;
-    uint32_t* rows_out;         // filtered bit rows of every cluster box: class 0 at item * 64 * 2 words, class 1 after them, ...
-    size_t rows_base[3];        // word offset of each size class in rows_out
-    int* cand_list;             // [cand_cap][6]: frame, x0 | y0 << 16, lx | ly << 16 | type << 31, rows word offset, mw | mh << 16, words per row
+    uint32_t* rows_out;         // filtered bit rows of every cluster box
+    unsigned rows_cap;          // words
+    int* cand_list;             // [cand_cap][2]: cluster, lx | ly << 16 | type << 31
     int cand_cap;
     int* rec_count;             // [n]
     int* rec_start;             // [n][max_contours] start pixel index y * W + x of an outer border
@@ -68,13 +71,15 @@ __device__ __forceinline__ void suf_union(int* parent, int a, int b)
     }
 }
 
+__device__ __forceinline__ int cdiv_dev(int a, int b) { return (a + b - 1) / b; }
+
 __device__ __forceinline__ bool boxes_touch(const int* a, const int* b)
 {
     return a[0] <= b[2] + 1 && b[0] <= a[2] + 1 && a[1] <= b[3] + 1 && b[1] <= a[3] + 1;
 }
 
 // ---------------------------------------------------------------------------------------------------------
-// per frame: hot cells -> groups with pairwise separated output boxes -> work queues
+// per frame: hot cells -> clusters (connected components of "output boxes touch") -> cluster table + filter pieces
 // ---------------------------------------------------------------------------------------------------------
 __global__ void __launch_bounds__(CL_THREADS) form_clusters_kernel(const uint32_t* __restrict__ cellbox, TableView tv, ClusterWs cw)
 {
@@ -160,7 +165,8 @@ __global__ void __launch_bounds__(CL_THREADS) form_clusters_kernel(const uint32_
         for (int i = 0; i < nr; ++i) { int r = roots[i]; int c = cbox[4 * r + 3]; cbox[4 * r + 3] = acc | (c << 16); acc += c; }
     }
     __syncthreads();
-    // one thread per cluster gathers its member boxes (a few hundred hot cells per frame at most) and emits the work item
+    // one thread per cluster gathers its member boxes (a few hundred hot cells per frame at most), reserves the bit rows
+    // of the cluster box and emits the filter pieces
     short* memb = cw.memb + (size_t)f * HOT_MAX * 4;
     for (int i = tid; i < nr; i += nt) {
         int r = roots[i];
@@ -174,140 +180,145 @@ __global__ void __launch_bounds__(CL_THREADS) form_clusters_kernel(const uint32_
             ++k;
         }
         int x0 = cbox[4 * r], y0 = cbox[4 * r + 1], x1 = cbox[4 * r + 2];
-        int ew = x1 - x0 + 1, eh = y1 - y0 + 1, e = max(ew, eh);
-        int* q; int* cnt;
-        if (e <= 64) { q = cw.q_small; cnt = &cw.q_count[0]; }
-        else if (e <= 128) { q = cw.q_large; cnt = &cw.q_count[1]; }
-        else if (e <= HUGE_MAX) { q = cw.q_huge; cnt = &cw.q_count[4]; }
-        else { s_bad = 1; continue; }
-        int slot = atomicAdd(cnt, 1);
-        if (slot >= cw.q_caps[e <= 64 ? 0 : (e <= 128 ? 1 : 2)]) { s_bad = 1; continue; }
-        q[4 * slot] = f; q[4 * slot + 1] = x0 | (y0 << 16); q[4 * slot + 2] = x1 | (y1 << 16); q[4 * slot + 3] = off | (k << 16);
+        int mw = x1 - x0 + 1, mh = y1 - y0 + 1;
+        int pbx = cdiv_dev(mw, PIECE), pby = cdiv_dev(mh, PIECE);
+        int wpr = pbx * (PIECE / 32);                                  // every piece owns whole words of the rows
+        unsigned words = (unsigned)(mh * wpr);
+        int cid = atomicAdd(&cw.counters[CN_CLUSTERS], 1);
+        if (cid >= cw.cl_cap) { s_bad = 1; continue; }
+        unsigned roff = atomicAdd((unsigned*)&cw.counters[CN_ROWS], words);
+        int* ce = cw.clusters + 8 * (size_t)cid;
+        ce[0] = f;
+        if (roff + words > cw.rows_cap) { ce[1] = 1; ce[2] = 0; ce[4] = 0; s_bad = 1; continue; }     // empty box: nothing downstream touches it
+        int p0 = atomicAdd(&cw.counters[CN_PIECES], pbx * pby);
+        if (p0 + pbx * pby > cw.pc_cap) { ce[1] = 1; ce[2] = 0; ce[4] = 0; s_bad = 1; continue; }
+        ce[1] = x0 | (y0 << 16); ce[2] = x1 | (y1 << 16); ce[3] = (int)roff; ce[4] = wpr; ce[5] = off | (k << 16); ce[6] = 0; ce[7] = 0;
+        for (int q = 0; q < pbx * pby; ++q) {
+            cw.pieces[2 * (size_t)(p0 + q)] = cid;
+            cw.pieces[2 * (size_t)(p0 + q) + 1] = (q % pbx) | ((q / pbx) << 16);
+        }
     }
     __syncthreads();
-    if (s_bad && tid == 0) cw.need_general[f] = 5;      // a group larger than the largest class (or a full queue): general path
+    if (s_bad && tid == 0) cw.need_general[f] = 5;      // out of cluster / piece / bit-row storage: general path
 }
 
 // ---------------------------------------------------------------------------------------------------------
-// per cluster: filter the output box in shared memory, find and trace the outer borders it owns
+// per piece: filter <= 64x64 output pixels of a cluster box in shared memory -> bit rows of the cluster (global)
 // ---------------------------------------------------------------------------------------------------------
-template <int MAXE>
-struct ClusterDims {
-    static constexpr int UW = MAXE + 8, BW = MAXE + 4, WPR = MAXE / 32;
-    static constexpr size_t U_BYTES = ((size_t)UW * UW + 15) & ~(size_t)15;       // undistorted pixels, origin (mx0 - 4, my0 - 4)
-    static constexpr size_t HS_BYTES = ((size_t)UW * BW * 2 + 15) & ~(size_t)15;  // horizontal 5-sums (U rows x B cols), reused for the majority
-    static constexpr size_t B_BYTES = ((size_t)BW * BW + 15) & ~(size_t)15;       // thresholded floor-mean, origin (mx0 - 2, my0 - 2)
-    static constexpr size_t ROWS_BYTES = (size_t)MAXE * WPR * 4;                  // filtered binary image of the box, bit x - mx0 of row y - my0
-    static constexpr size_t IMG_BYTES = U_BYTES + HS_BYTES + B_BYTES + ROWS_BYTES;
+struct PieceSmem {
+    static constexpr int UW = PIECE + 8, BW = PIECE + 4;
+    uint8_t U[UW * UW];            // undistorted pixels, origin (px0 - 4, py0 - 4); 0 outside the frame
+    uint16_t HS[UW * BW];          // horizontal 5-sums of U (U rows x B cols)
+    uint8_t B[BW * BW];            // thresholded floor-mean, origin (px0 - 2, py0 - 2)
+    uint8_t MH[BW * PIECE];        // horizontal 5-counts of B (B rows x output cols)
 };
 
-// GLOBAL = false: the box arrays live in shared memory (size classes 64 and 128); true: in a per-CTA global scratch (<= 512)
-template <int MAXE, bool GLOBAL>
-__global__ void __launch_bounds__(CL_THREADS) cluster_proc_kernel(const uint8_t* __restrict__ frames, int64_t fstride, TableView tv, int thresh,
-                                                                  ClusterWs cw, int which, int max_contours)
+__global__ void __launch_bounds__(CL_THREADS) piece_filter_kernel(const uint8_t* __restrict__ frames, int64_t fstride, TableView tv, int thresh,
+                                                                  ClusterWs cw)
 {
-    DYN_SHARED(smraw);
-    typedef ClusterDims<MAXE> DM;
-    constexpr int UW = DM::UW, BW = DM::BW, WPR = DM::WPR;
-    uint8_t* img = GLOBAL ? cw.huge_scratch + (size_t)blockIdx.x * cw.huge_stride : (uint8_t*)smraw;
-    uint8_t* U = img;
-    uint16_t* HS = (uint16_t*)(img + DM::U_BYTES);
-    uint8_t* B = img + DM::U_BYTES + DM::HS_BYTES;
-    uint32_t* rows = (uint32_t*)(img + DM::U_BYTES + DM::HS_BYTES + DM::B_BYTES);
-    __shared__ int s_item, s_skip;
+    __shared__ PieceSmem S;
+    constexpr int UW = PieceSmem::UW, BW = PieceSmem::BW;
+    __shared__ int s_item;
     const int tid = threadIdx.x, lane = tid & 31, wy = tid >> 5, NWARP = CL_THREADS / 32;
     const int H = tv.H, W = tv.W, T = thresh + 1;
-    const int* queue = which == 0 ? cw.q_small : (which == 1 ? cw.q_large : cw.q_huge);
-    const int i_len = which < 2 ? which : 4, i_cur = which < 2 ? 2 + which : 5;
-    const int total = min(cw.q_count[i_len], cw.q_caps[which]);
+    const int total = min(cw.counters[CN_PIECES], cw.pc_cap);
     for (;;) {
         __syncthreads();
-        if (tid == 0) {
-            int it = atomicAdd(&cw.q_count[i_cur], 1);
-            s_item = it;
-            s_skip = it < total ? cw.need_general[queue[4 * it]] : 0;      // frame already handed to the general path
-        }
+        if (tid == 0) s_item = atomicAdd(&cw.counters[CN_PIECE_CUR], 1);
         __syncthreads();
         const int item = s_item;
         if (item >= total) break;
-        if (s_skip) continue;
-        const int f = queue[4 * item];
-        const int mx0 = queue[4 * item + 1] & 0xffff, my0 = queue[4 * item + 1] >> 16;
-        const int mx1 = queue[4 * item + 2] & 0xffff, my1 = queue[4 * item + 2] >> 16;
-        const int m_off = queue[4 * item + 3] & 0xffff, m_cnt = queue[4 * item + 3] >> 16;
-        const int mw = mx1 - mx0 + 1, mh = my1 - my0 + 1;
+        const int* ce = cw.clusters + 8 * (size_t)cw.pieces[2 * (size_t)item];
+        const int bxy = cw.pieces[2 * (size_t)item + 1], bx = bxy & 0xffff, by = bxy >> 16;
+        const int f = ce[0];
+        const int cx0 = ce[1] & 0xffff, cy0 = ce[1] >> 16, cx1 = ce[2] & 0xffff, cy1 = ce[2] >> 16, wpr = ce[4];
+        const int px0 = cx0 + bx * PIECE, py0 = cy0 + by * PIECE;
+        const int px1 = min(px0 + PIECE - 1, cx1), py1 = min(py0 + PIECE - 1, cy1);
+        const int mw = px1 - px0 + 1, mh = py1 - py0 + 1;
         const int uw = mw + 8, uh = mh + 8, bw = mw + 4, bh = mh + 4;
         const uint8_t* fr = frames + (size_t)f * fstride;
-        // ---- 1. undistorted pixels of the box dilated by 4 (zero outside the frame) ----------------------------
+        // ---- 1. undistorted pixels of the piece dilated by 4 (zero outside the frame), then their horizontal 5-sums;
+        //         a warp owns whole rows, so only a warp-level sync separates the two ------------------------------------
         for (int r = wy; r < uh; r += NWARP) {
-            int i = my0 - 4 + r;
+            int i = py0 - 4 + r;
             bool rowin = (unsigned)i < (unsigned)H;
             for (int c = lane; c < uw; c += 32) {
-                int j = mx0 - 4 + c, u = 0;
+                int j = px0 - 4 + c, u = 0;
                 if (rowin && (unsigned)j < (unsigned)W) u = remap_px(fr, W, H, i, j, (uint32_t)tv.map[(size_t)i * W + j]);
-                U[r * UW + c] = (uint8_t)u;
+                S.U[r * UW + c] = (uint8_t)u;
+            }
+            __syncwarp();
+            for (int c = lane; c < bw; c += 32) {
+                const uint8_t* u = &S.U[r * UW + c];
+                S.HS[r * BW + c] = (uint16_t)(u[0] + u[1] + u[2] + u[3] + u[4]);
             }
         }
         __syncthreads();
-        // ---- 2. horizontal 5-sums -------------------------------------------------------------------------------
-        for (int r = wy; r < uh; r += NWARP)
-            for (int c = lane; c < bw; c += 32) {
-                const uint8_t* u = &U[r * UW + c];
-                HS[r * BW + c] = (uint16_t)(u[0] + u[1] + u[2] + u[3] + u[4]);
-            }
-        __syncthreads();
-        // ---- 3. floor-mean over the in-frame taps > thresh  <=>  sum >= T * count ------------------------------------
+        // ---- 2. floor-mean over the in-frame taps > thresh  <=>  sum >= T * count, then the horizontal 5-counts of the
+        //         majority (replicated frame border = clamped columns) ----------------------------------------------------------
         for (int r = wy; r < bh; r += NWARP) {
-            int i = my0 - 2 + r;
+            int i = py0 - 2 + r;
             int cnty = min(i + 2, H - 1) - max(i - 2, 0) + 1;
             bool rowin = (unsigned)i < (unsigned)H;
             for (int c = lane; c < bw; c += 32) {
-                int j = mx0 - 2 + c, b = 0;
+                int j = px0 - 2 + c, b = 0;
                 if (rowin && (unsigned)j < (unsigned)W) {
-                    const uint16_t* h = &HS[r * BW + c];
+                    const uint16_t* h = &S.HS[r * BW + c];
                     int s = h[0] + h[BW] + h[2 * BW] + h[3 * BW] + h[4 * BW];
                     int cnt = cnty * (min(j + 2, W - 1) - max(j - 2, 0) + 1);
                     b = s >= T * cnt;
                 }
-                B[r * BW + c] = (uint8_t)b;
+                S.B[r * BW + c] = (uint8_t)b;
             }
-        }
-        __syncthreads();
-        // ---- 4. 5x5 majority with replicated frame border: horizontal sums (clamped columns) into HS ----------------------
-        for (int r = wy; r < bh; r += NWARP) {
-            const uint8_t* b = &B[r * BW] - (mx0 - 2);                 // indexed by frame column
+            __syncwarp();
+            const uint8_t* b = &S.B[r * BW] - (px0 - 2);               // indexed by frame column
             for (int c = lane; c < mw; c += 32) {
-                int j = mx0 + c;
-                int s = b[max(j - 2, 0)] + b[max(j - 1, 0)] + b[j] + b[min(j + 1, W - 1)] + b[min(j + 2, W - 1)];
-                HS[r * BW + c] = (uint16_t)s;
+                int j = px0 + c;
+                S.MH[r * PIECE + c] = (uint8_t)(b[max(j - 2, 0)] + b[max(j - 1, 0)] + b[j] + b[min(j + 1, W - 1)] + b[min(j + 2, W - 1)]);
             }
         }
         __syncthreads();
-        //      vertical sums (clamped rows) -> bit rows via ballot
+        // ---- 3. vertical 5-counts (clamped rows) >= 13 -> bit rows of the cluster box ------------------------------------------
+        uint32_t* out = cw.rows_out + (unsigned)ce[3];
         for (int r = wy; r < mh; r += NWARP) {
-            int i = my0 + r;
-            int r0 = max(i - 2, 0) - (my0 - 2), r1 = max(i - 1, 0) - (my0 - 2), r2 = i - (my0 - 2);
-            int r3 = min(i + 1, H - 1) - (my0 - 2), r4 = min(i + 2, H - 1) - (my0 - 2);
-            for (int c0 = 0; c0 < MAXE; c0 += 32) {
+            int i = py0 + r;
+            int r0 = max(i - 2, 0) - (py0 - 2), r1 = max(i - 1, 0) - (py0 - 2), r2 = i - (py0 - 2);
+            int r3 = min(i + 1, H - 1) - (py0 - 2), r4 = min(i + 2, H - 1) - (py0 - 2);
+#pragma unroll
+            for (int c0 = 0; c0 < PIECE; c0 += 32) {
                 int c = c0 + lane, s = 0;
-                if (c < mw) s = HS[r0 * BW + c] + HS[r1 * BW + c] + HS[r2 * BW + c] + HS[r3 * BW + c] + HS[r4 * BW + c];
+                if (c < mw) s = S.MH[r0 * PIECE + c] + S.MH[r1 * PIECE + c] + S.MH[r2 * PIECE + c] + S.MH[r3 * PIECE + c] + S.MH[r4 * PIECE + c];
                 unsigned wv = __ballot_sync(0xffffffffu, s >= 13);
-                if (lane == 0) rows[r * WPR + (c0 >> 5)] = wv;
+                if (lane == 0) out[(size_t)(py0 - cy0 + r) * wpr + bx * (PIECE / 32) + (c0 >> 5)] = wv;
             }
         }
-        __syncthreads();
-        // ---- 5. export the bit rows; border-start candidates, one thread per row: a run with no 8-neighbour above starts
-        //         an outer border, a gap between two runs that is completely covered from above starts a hole border
-        //         (necessary conditions; the trace kernel verifies them).  Only candidates the cluster owns are kept:
-        //         start pixel inside one of its own cell boxes. ----------------------------------------------------------------
-        const size_t rows_off = cw.rows_base[which] + (size_t)item * MAXE * WPR;
-        for (int k = tid; k < mh * WPR; k += CL_THREADS) cw.rows_out[rows_off + k] = rows[k];
-        BitImg im; im.p = rows; im.W = mw; im.H = mh; im.WPR = WPR;
+    }
+}
+
+// ---------------------------------------------------------------------------------------------------------
+// per cluster row: border-start candidates.  A run with no 8-neighbour above starts an outer border, a gap between two
+// runs that is completely covered from above starts a hole border (necessary conditions; the trace verifies them).
+// Only candidates the cluster owns are kept: start pixel inside one of its own cell boxes.
+// ---------------------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(128) candidates_kernel(ClusterWs cw)
+{
+    const int lane = threadIdx.x & 31;
+    const int warp = (blockIdx.x * blockDim.x + threadIdx.x) >> 5, nwarps = (gridDim.x * blockDim.x) >> 5;
+    const int total = min(cw.counters[CN_CLUSTERS], cw.cl_cap);
+    for (int cid = warp; cid < total; cid += nwarps) {
+        const int* ce = cw.clusters + 8 * (size_t)cid;
+        const int f = ce[0];
+        const int cx0 = ce[1] & 0xffff, cy0 = ce[1] >> 16, cx1 = ce[2] & 0xffff, cy1 = ce[2] >> 16, wpr = ce[4];
+        const int mw = cx1 - cx0 + 1, mh = cy1 - cy0 + 1;
+        if (mw <= 0 || cw.need_general[f]) continue;
+        const int m_off = ce[5] & 0xffff, m_cnt = ce[5] >> 16;
         const short* memb = cw.memb + ((size_t)f * HOT_MAX + m_off) * 4;
-        for (int r = tid; r < mh; r += CL_THREADS) {
+        BitImg im; im.p = cw.rows_out + (unsigned)ce[3]; im.W = mw; im.H = mh; im.WPR = wpr;
+        for (int r = lane; r < mh; r += 32) {
+            const uint32_t* row = im.p + (size_t)r * wpr;
             int prev = 0, run_start = -1, last_end = -2;
             for (int x = 0; x <= mw; ++x) {
-                int cur = x < mw ? (int)((rows[r * WPR + (x >> 5)] >> (x & 31)) & 1u) : 0;
+                int cur = x < mw ? (int)((row[x >> 5] >> (x & 31)) & 1u) : 0;
                 int cx = -1, cty = 0;
                 if (cur && !prev) {
                     run_start = x;
@@ -326,33 +337,33 @@ __global__ void __launch_bounds__(CL_THREADS) cluster_proc_kernel(const uint8_t*
                 }
                 prev = cur;
                 if (cx < 0) continue;
-                int ax = cx + mx0, ay = r + my0;
+                int ax = cx + cx0, ay = r + cy0;
                 bool own = false;
                 for (int m = 0; m < m_cnt && !own; ++m)
                     own = ax >= memb[4 * m] && ax <= memb[4 * m + 2] && ay >= memb[4 * m + 1] && ay <= memb[4 * m + 3];
                 if (!own) continue;
-                int slot = atomicAdd(&cw.q_count[6], 1);
+                int slot = atomicAdd(&cw.counters[CN_CANDS], 1);
                 if (slot >= cw.cand_cap) { cw.need_general[f] = 7; continue; }
-                int* e = cw.cand_list + 6 * (size_t)slot;
-                e[0] = f; e[1] = mx0 | (my0 << 16); e[2] = cx | (r << 16) | (cty << 31);
-                e[3] = (int)rows_off; e[4] = mw | (mh << 16); e[5] = WPR;
+                cw.cand_list[2 * (size_t)slot] = cid;
+                cw.cand_list[2 * (size_t)slot + 1] = cx | (r << 16) | (cty << 31);
             }
         }
     }
 }
 
-// one thread per owned border-start candidate: Suzuki-Abe trace on the cluster's exported bit rows; a completed outer
-// border becomes a record of its frame, a completed hole border sends the frame to the general path (contour tree)
+// one thread per owned border-start candidate: Suzuki-Abe trace on the cluster's bit rows; a completed outer border
+// becomes a record of its frame, a completed hole border sends the frame to the general path (contour tree)
 __global__ void __launch_bounds__(128) trace_candidates_kernel(ClusterWs cw, int W, int max_contours)
 {
-    const int total = min(cw.q_count[6], cw.cand_cap);
+    const int total = min(cw.counters[CN_CANDS], cw.cand_cap);
     for (int c = blockIdx.x * blockDim.x + threadIdx.x; c < total; c += gridDim.x * blockDim.x) {
-        const int* e = cw.cand_list + 6 * (size_t)c;
-        const int f = e[0];
+        const int* ce = cw.clusters + 8 * (size_t)cw.cand_list[2 * (size_t)c];
+        const int code = cw.cand_list[2 * (size_t)c + 1];
+        const int f = ce[0];
         if (cw.need_general[f]) continue;
-        const int mx0 = e[1] & 0xffff, my0 = e[1] >> 16;
-        const int lx = e[2] & 0xffff, ly = (e[2] >> 16) & 0x7fff, ty = (e[2] >> 31) & 1;
-        BitImg im; im.p = cw.rows_out + (unsigned)e[3]; im.W = e[4] & 0xffff; im.H = e[4] >> 16; im.WPR = e[5];
+        const int mx0 = ce[1] & 0xffff, my0 = ce[1] >> 16, mx1 = ce[2] & 0xffff, my1 = ce[2] >> 16;
+        const int lx = code & 0xffff, ly = (code >> 16) & 0x7fff, ty = (code >> 31) & 1;
+        BitImg im; im.p = cw.rows_out + (unsigned)ce[3]; im.W = mx1 - mx0 + 1; im.H = my1 - my0 + 1; im.WPR = ce[4];
         long long st = (long long)(ly + my0) * W + (lx + mx0);
         long long a[3]; double per; int nch, ovf = 0;
         int ok = trace_contour(im, lx, ly, ty ? 0 : 4, 2 * st + ty, a, &per, &nch, &ovf, mx0, my0, W);
@@ -441,35 +452,26 @@ __global__ void __launch_bounds__(CL_THREADS) finalize_kernel(ClusterWs cw, int 
 // ---------------------------------------------------------------------------------------------------------
 // host side
 // ---------------------------------------------------------------------------------------------------------
-// queue capacities: every frame may contribute up to 192 small, 48 large and 4 huge clusters before it is sent to the general path
-static void cluster_caps(int n, int* caps) { caps[0] = n * 192 + 256; caps[1] = n * 48 + 64; caps[2] = n * 4 + 16; }
-static int cluster_cand_cap(int n) { return n * 512 + 1024; }
-static size_t cluster_rows_words(int n, int q_cap, size_t* base)
-{
-    (void)q_cap;
-    int caps[3]; cluster_caps(n, caps);
-    size_t b0 = 0, b1 = b0 + (size_t)caps[0] * 64 * 2, b2 = b1 + (size_t)caps[1] * 128 * 4, end = b2 + (size_t)caps[2] * HUGE_MAX * (HUGE_MAX / 32);
-    if (base) { base[0] = b0; base[1] = b1; base[2] = b2; }
-    return end;
-}
+static int cl_cap_of(int n) { return n * 256 + 1024; }
+static int pc_cap_of(int n) { return n * 512 + 2048; }
+static int cand_cap_of(int n) { return n * 512 + 1024; }
+static size_t rows_cap_of(int n, int H, int W) { size_t w = (size_t)n * ((size_t)H * W / 128 + 4096); return w > 0xf0000000ull ? 0xf0000000ull : w; }   // a quarter of the frame area per frame
 
-size_t cluster_ws_bytes(int n, int max_contours, int q_cap, size_t* offs /*[16]*/)
+size_t cluster_ws_bytes(int n, int H, int W, int max_contours, size_t* offs /*[16]*/)
 {
     size_t off = 0;
     auto take = [&](size_t bytes) { size_t r = off; off += align_up(bytes, 256); return r; };
     offs[0] = take((size_t)n * 4);                         // need_general
-    offs[1] = take(64);                                    // q_count
-    offs[2] = take((size_t)q_cap * 16);                    // q_small
-    offs[3] = take((size_t)q_cap * 16);                    // q_large
+    offs[1] = take(64);                                    // counters
+    offs[2] = take((size_t)cl_cap_of(n) * 32);             // clusters
+    offs[3] = take((size_t)pc_cap_of(n) * 8);              // pieces
     offs[4] = take((size_t)n * 4);                         // rec_count
     offs[5] = take((size_t)n * max_contours * 4);          // rec_start
     offs[6] = take((size_t)n * max_contours * 24);         // rec_a
     offs[7] = take((size_t)n * max_contours * 8);          // rec_per
-    offs[8] = take((size_t)q_cap * 16);                    // q_huge
-    offs[9] = take((size_t)n * HOT_MAX * 8);               // memb
-    offs[10] = take(align_up(ClusterDims<HUGE_MAX>::IMG_BYTES, 256) * HUGE_CTAS);   // huge scratch
-    offs[11] = take(cluster_rows_words(n, q_cap, nullptr) * 4);                      // rows_out
-    offs[12] = take((size_t)cluster_cand_cap(n) * 24);                               // cand_list
+    offs[8] = take((size_t)n * HOT_MAX * 8);               // memb
+    offs[9] = take(rows_cap_of(n, H, W) * 4);              // rows_out
+    offs[10] = take((size_t)cand_cap_of(n) * 8);           // cand_list
     return off;
 }
 
@@ -479,53 +481,42 @@ bool cluster_path_supported(int H, int W)
 }
 
 int launch_cluster_path(const uint8_t* frames, int n, int H, int W, int64_t fstride, const TableView& tv, int thresh,
-                        const uint32_t* cellbox, char* ws_base, const size_t* offs, int q_cap,
+                        const uint32_t* cellbox, char* ws_base, const size_t* offs,
                         int max_contours, int max_blobs, double min_area, double min_circ,
                         int32_t* out_xy, int32_t* out_count, int32_t* out_flags, double* out_contours, int32_t* out_contour_count,
                         bool finalize_only, cudaStream_t s, StageTimer* timer)
 {
     ClusterWs cw;
     cw.need_general = (int*)(ws_base + offs[0]);
-    cw.q_count = (int*)(ws_base + offs[1]);
-    cw.q_small = (int*)(ws_base + offs[2]);
-    cw.q_large = (int*)(ws_base + offs[3]);
-    cw.q_huge = (int*)(ws_base + offs[8]);
-    cw.q_cap = q_cap;
+    cw.counters = (int*)(ws_base + offs[1]);
+    cw.clusters = (int*)(ws_base + offs[2]);
+    cw.pieces = (int*)(ws_base + offs[3]);
+    cw.cl_cap = cl_cap_of(n); cw.pc_cap = pc_cap_of(n);
     cw.rec_count = (int*)(ws_base + offs[4]);
     cw.rec_start = (int*)(ws_base + offs[5]);
     cw.rec_a = (long long*)(ws_base + offs[6]);
     cw.rec_per = (double*)(ws_base + offs[7]);
-    cw.memb = (short*)(ws_base + offs[9]);
-    cw.huge_scratch = (uint8_t*)(ws_base + offs[10]);
-    cw.huge_stride = align_up(ClusterDims<HUGE_MAX>::IMG_BYTES, 256);
-    cw.rows_out = (uint32_t*)(ws_base + offs[11]);
-    cluster_rows_words(n, q_cap, cw.rows_base);
-    cw.cand_list = (int*)(ws_base + offs[12]);
-    cw.cand_cap = cluster_cand_cap(n);
-    cluster_caps(n, cw.q_caps);
+    cw.memb = (short*)(ws_base + offs[8]);
+    cw.rows_out = (uint32_t*)(ws_base + offs[9]);
+    cw.rows_cap = (unsigned)rows_cap_of(n, H, W);
+    cw.cand_list = (int*)(ws_base + offs[10]);
+    cw.cand_cap = cand_cap_of(n);
     if (finalize_only) {
         LAUNCH(finalize_kernel, n, CL_THREADS, (size_t)max_contours + 16, s, cw, max_contours, max_blobs, min_area, min_circ, out_xy, out_count, out_flags,
                out_contours, out_contour_count);
         CUDA_TRY(cudaGetLastError());
         return MOCAP_OK;
     }
-    CUDA_TRY(cudaMemsetAsync(cw.q_count, 0, 64, s));
+    CUDA_TRY(cudaMemsetAsync(cw.counters, 0, 64, s));
     CUDA_TRY(cudaMemsetAsync(cw.rec_count, 0, (size_t)n * 4, s));
     int dev = 0, sms = 148;
     cudaGetDevice(&dev);
     cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
     const int cells = tv.TX * tv.TY;
     size_t sm_form = (size_t)((cells + 7) & ~7) * 2 + (size_t)HOT_MAX * (2 + 4 + 16 + 8) + (size_t)ROOTS_MAX * 2 + 64;
-    size_t sm_small = ClusterDims<64>::IMG_BYTES;
-    size_t sm_large = ClusterDims<128>::IMG_BYTES;
-    size_t sm_huge = 16;
-    auto k_small = cluster_proc_kernel<64, false>;
-    auto k_large = cluster_proc_kernel<128, false>;
-    auto k_huge = cluster_proc_kernel<HUGE_MAX, true>;
 #ifndef MOCAP_EMU
     static bool attr_done = false;
     if (!attr_done) {
-        cudaFuncSetAttribute(k_large, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sm_large);
         cudaFuncSetAttribute(form_clusters_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 64 * 1024);
         attr_done = true;
     }
@@ -534,9 +525,8 @@ int launch_cluster_path(const uint8_t* frames, int n, int H, int W, int64_t fstr
     LAUNCH(form_clusters_kernel, n, CL_THREADS, sm_form, s, cellbox, tv, cw);
     stage_end(timer, 1, s);
     stage_begin(timer, 2, s);
-    LAUNCH(k_small, sms * 8, CL_THREADS, sm_small, s, frames, fstride, tv, thresh, cw, 0, max_contours);
-    LAUNCH(k_large, sms * 2, CL_THREADS, sm_large, s, frames, fstride, tv, thresh, cw, 1, max_contours);
-    LAUNCH(k_huge, HUGE_CTAS, CL_THREADS, sm_huge, s, frames, fstride, tv, thresh, cw, 2, max_contours);
+    LAUNCH(piece_filter_kernel, sms * 8, CL_THREADS, 0, s, frames, fstride, tv, thresh, cw);
+    LAUNCH(candidates_kernel, sms * 8, 128, 0, s, cw);
     LAUNCH(trace_candidates_kernel, sms * 4, 128, 0, s, cw, W, max_contours);
     stage_end(timer, 2, s);
     CUDA_TRY(cudaGetLastError());
