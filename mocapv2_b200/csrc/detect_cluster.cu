@@ -300,6 +300,19 @@ __global__ void __launch_bounds__(CL_THREADS) piece_filter_kernel(const uint8_t*
 // runs that is completely covered from above starts a hole border (necessary conditions; the trace verifies them).
 // Only candidates the cluster owns are kept: start pixel inside one of its own cell boxes.
 // ---------------------------------------------------------------------------------------------------------
+__device__ __forceinline__ void emit_candidate(const ClusterWs& cw, int cid, int f, const short* memb, int m_cnt, int cx, int r, int cty, int cx0, int cy0)
+{
+    int ax = cx + cx0, ay = r + cy0;
+    bool own = false;
+    for (int m = 0; m < m_cnt && !own; ++m)
+        own = ax >= memb[4 * m] && ax <= memb[4 * m + 2] && ay >= memb[4 * m + 1] && ay <= memb[4 * m + 3];
+    if (!own) return;
+    int slot = atomicAdd(&cw.counters[CN_CANDS], 1);
+    if (slot >= cw.cand_cap) { cw.need_general[f] = 7; return; }
+    cw.cand_list[2 * (size_t)slot] = cid;
+    cw.cand_list[2 * (size_t)slot + 1] = cx | (r << 16) | (cty << 31);
+}
+
 __global__ void __launch_bounds__(128) candidates_kernel(ClusterWs cw)
 {
     const int lane = threadIdx.x & 31;
@@ -316,36 +329,47 @@ __global__ void __launch_bounds__(128) candidates_kernel(ClusterWs cw)
         BitImg im; im.p = cw.rows_out + (unsigned)ce[3]; im.W = mw; im.H = mh; im.WPR = wpr;
         for (int r = lane; r < mh; r += 32) {
             const uint32_t* row = im.p + (size_t)r * wpr;
+            if (wpr == 2) {
+                // box at most 64 wide: the row and the row above are one 64-bit word each, runs and gaps come from bit scans
+                unsigned long long cur = (unsigned long long)row[0] | ((unsigned long long)row[1] << 32), up = 0ull;
+                if (r > 0) up = (unsigned long long)row[-2] | ((unsigned long long)row[-1] << 32);
+                int last_end = -2;
+                while (cur) {
+                    int s0 = __ffsll((long long)cur) - 1;
+                    unsigned long long t = cur >> s0;
+                    int len = (~t) ? __ffsll((long long)~t) - 1 : 64;
+                    unsigned long long runmask = (len >= 64 ? ~0ull : ((1ull << len) - 1ull)) << s0;
+                    cur &= ~runmask;
+                    int e0 = s0 + len - 1;
+                    unsigned long long dil = runmask | (runmask << 1) | (runmask >> 1);
+                    if (last_end >= 0 && r > 0) {
+                        unsigned long long gap = ((1ull << s0) - 1ull) & ~((2ull << last_end) - 1ull);      // bits last_end+1 .. s0-1
+                        if ((up & gap) == gap) emit_candidate(cw, cid, f, memb, m_cnt, last_end, r, 1, cx0, cy0);
+                    }
+                    if ((up & dil) == 0ull) emit_candidate(cw, cid, f, memb, m_cnt, s0, r, 0, cx0, cy0);
+                    last_end = e0;
+                }
+                continue;
+            }
             int prev = 0, run_start = -1, last_end = -2;
             for (int x = 0; x <= mw; ++x) {
                 int cur = x < mw ? (int)((row[x >> 5] >> (x & 31)) & 1u) : 0;
-                int cx = -1, cty = 0;
                 if (cur && !prev) {
                     run_start = x;
                     if (last_end >= 0 && r > 0) {
                         bool covered = true;
                         for (int g = last_end + 1; g < x; ++g) if (!im.get(g, r - 1)) { covered = false; break; }
-                        if (covered) { cx = last_end; cty = 1; }
+                        if (covered) emit_candidate(cw, cid, f, memb, m_cnt, last_end, r, 1, cx0, cy0);
                     }
                 }
                 if (!cur && prev) {
                     int xe = x - 1;
                     bool top = true;
                     if (r > 0) for (int g = run_start - 1; g <= xe + 1; ++g) if (im.get(g, r - 1)) { top = false; break; }
-                    if (top) { cx = run_start; cty = 0; }
+                    if (top) emit_candidate(cw, cid, f, memb, m_cnt, run_start, r, 0, cx0, cy0);
                     last_end = xe;
                 }
                 prev = cur;
-                if (cx < 0) continue;
-                int ax = cx + cx0, ay = r + cy0;
-                bool own = false;
-                for (int m = 0; m < m_cnt && !own; ++m)
-                    own = ax >= memb[4 * m] && ax <= memb[4 * m + 2] && ay >= memb[4 * m + 1] && ay <= memb[4 * m + 3];
-                if (!own) continue;
-                int slot = atomicAdd(&cw.counters[CN_CANDS], 1);
-                if (slot >= cw.cand_cap) { cw.need_general[f] = 7; continue; }
-                cw.cand_list[2 * (size_t)slot] = cid;
-                cw.cand_list[2 * (size_t)slot + 1] = cx | (r << 16) | (cty << 31);
             }
         }
     }

@@ -272,34 +272,38 @@ extern "C" int mocap_reproject_batch(const void* pts_dev, const uint8_t* valid_d
 
 struct CorrWs { int32_t* cand; int32_t* ncand; };
 
+#define CORR_RPC 8        // roots per CTA of the candidate / group kernel
+
+// Part 1, grid (S, ceil(max_pts / CORR_RPC)): candidates per (root, camera), candidate groups, triangulation and mean
+// reprojection error of the CTA's roots -> workspace.  Roots are independent until the ranking (Helpers.py:203-273).
 template <typename T>
 __global__ void __launch_bounds__(CORR_THREADS) correspond_kernel(
     const int32_t* __restrict__ xy, const int32_t* __restrict__ count, int C, int max_pts,
-    const double* __restrict__ Fs, const double* __restrict__ cams, double cutoff, int obj_count, int max_groups,
-    double* __restrict__ obj_out, int32_t* __restrict__ n_obj_out, int32_t* __restrict__ img_out, int32_t* __restrict__ n_valid_out,
-    double* __restrict__ err_out, int32_t* __restrict__ cand_out, int32_t* __restrict__ flags_out,
-    char* __restrict__ ws_base, size_t ws_stride)
+    const double* __restrict__ Fs, const double* __restrict__ cams, double cutoff, int max_groups,
+    int32_t* __restrict__ cand_out, int32_t* __restrict__ flags_out, char* __restrict__ ws_base, size_t ws_stride)
 {
     DYN_SHARED(smraw);
     T* sm = (T*)smraw;
     const int s = blockIdx.x, tid = threadIdx.x, lane = tid & 31, wid = tid >> 5, nw = blockDim.x >> 5;
-    load_cams<T>(cams, C, sm);
-    __shared__ int s_flags, s_nvalid;
-    if (tid == 0) { s_flags = 0; s_nvalid = 0; }
     const int32_t* fxy = xy + (size_t)s * C * max_pts * 2;
     const int32_t* fcount = count + (size_t)s * C;
+    const int R = min(fcount[0], max_pts);
+    const int j0 = blockIdx.y * CORR_RPC, j1 = min(j0 + CORR_RPC, R);
+    if (j0 >= R) return;
+    load_cams<T>(cams, C, sm);
+    __shared__ int s_flags;
+    if (tid == 0) s_flags = 0;
     char* wp = ws_base + (size_t)s * ws_stride;
     double* rerr = (double*)wp;                                             // [max_pts] mean error per root
     double* rX = rerr + max_pts;                                            // [max_pts][3] first group's point
     int32_t* cand = (int32_t*)(rX + 3 * (size_t)max_pts);                   // [max_pts][C][MAX_CAND]
     int32_t* ncand = cand + (size_t)max_pts * C * MOCAP_MAX_CAND;           // [max_pts][C]
-    int32_t* vidx = ncand + (size_t)max_pts * C;                            // [max_pts] slot among complete roots, -1 = incomplete
-    const int R = min(fcount[0], max_pts);
+    int32_t* vidx = ncand + (size_t)max_pts * C;                            // [max_pts] 0 = complete root, -1 = incomplete
     __syncthreads();
 
     // ---- candidates per (root, camera): epiline (FP64 -> f32) and point-line distances (FP64) --------------------------
-    for (int it = tid; it < R * C; it += blockDim.x) {
-        int j = it / C, i = it - j * C;
+    for (int it = tid; it < (j1 - j0) * C; it += blockDim.x) {
+        int j = j0 + it / C, i = it % C;
         int32_t* cl = cand + ((size_t)j * C + i) * MOCAP_MAX_CAND;
         if (i == 0) { ncand[j * C] = 1; cl[0] = j; continue; }
         const double* F = Fs + (size_t)(i - 1) * 9;
@@ -334,7 +338,7 @@ __global__ void __launch_bounds__(CORR_THREADS) correspond_kernel(
     __syncthreads();
 
     // ---- per root (one warp each): enumerate candidate groups, triangulate, mean reprojection error ----------------------
-    for (int j = wid; j < R; j += nw) {
+    for (int j = j0 + wid; j < j1; j += nw) {
         long long ng = 1;
         bool complete = C >= 2;
         for (int i = 1; i < C; ++i) { int n = ncand[j * C + i]; if (n == 0) complete = false; ng *= n; if (ng > (1LL << 40)) ng = 1LL << 40; }
@@ -377,7 +381,26 @@ __global__ void __launch_bounds__(CORR_THREADS) correspond_kernel(
         }
     }
     __syncthreads();
-    // ---- compact complete roots in root order, rank by mean error -------------------------------------------------------------
+    if (tid == 0 && s_flags) atomicOr(&flags_out[s], s_flags);
+}
+
+// Part 2, one CTA per frame-set: compact the complete roots in root order, rank them by mean error (Helpers.py:274-279)
+__global__ void __launch_bounds__(CORR_THREADS) correspond_rank_kernel(
+    const int32_t* __restrict__ xy, const int32_t* __restrict__ count, int C, int max_pts, int obj_count,
+    double* __restrict__ obj_out, int32_t* __restrict__ n_obj_out, int32_t* __restrict__ img_out, int32_t* __restrict__ n_valid_out,
+    double* __restrict__ err_out, char* __restrict__ ws_base, size_t ws_stride)
+{
+    const int s = blockIdx.x, tid = threadIdx.x;
+    const int32_t* fxy = xy + (size_t)s * C * max_pts * 2;
+    const int32_t* fcount = count + (size_t)s * C;
+    char* wp = ws_base + (size_t)s * ws_stride;
+    double* rerr = (double*)wp;
+    double* rX = rerr + max_pts;
+    int32_t* cand = (int32_t*)(rX + 3 * (size_t)max_pts);
+    int32_t* ncand = cand + (size_t)max_pts * C * MOCAP_MAX_CAND;
+    int32_t* vidx = ncand + (size_t)max_pts * C;
+    const int R = min(fcount[0], max_pts);
+    __shared__ int s_nvalid;
     if (tid == 0) {
         int n = 0;
         for (int j = 0; j < R; ++j) if (vidx[j] >= 0) vidx[j] = n++;
@@ -411,7 +434,6 @@ __global__ void __launch_bounds__(CORR_THREADS) correspond_kernel(
     if (tid == 0) {
         n_valid_out[s] = nvalid;
         n_obj_out[s] = obj_count > nvalid ? nvalid : min(obj_count + 1, nvalid);
-        flags_out[s] = s_flags;
     }
 }
 
@@ -443,14 +465,16 @@ extern "C" int mocap_correspond_batch(const int32_t* xy_dev, const int32_t* coun
     size_t stride = corr_ws_stride(C, max_pts);
     if (workspace_bytes < stride * (size_t)S) return MOCAP_ERR_WORKSPACE;
     cudaStream_t s = (cudaStream_t)stream;
+    CUDA_TRY(cudaMemsetAsync(flags_out, 0, (size_t)S * 4, s));
+    dim3 grid(S, cdiv(max_pts, CORR_RPC));
     if (fp64_mode)
-        LAUNCH(correspond_kernel<double>, S, CORR_THREADS, (size_t)C * CAM_T_STRIDE * sizeof(double), s, 
-            xy_dev, count_dev, C, max_pts, F_dev, cams_dev, cutoff, obj_count, max_groups, obj_out, n_obj_out, img_out,
-            n_valid_out, err_out, cand_out, flags_out, (char*)workspace, stride);
+        LAUNCH(correspond_kernel<double>, grid, CORR_THREADS, (size_t)C * CAM_T_STRIDE * sizeof(double), s,
+            xy_dev, count_dev, C, max_pts, F_dev, cams_dev, cutoff, max_groups, cand_out, flags_out, (char*)workspace, stride);
     else
-        LAUNCH(correspond_kernel<float>, S, CORR_THREADS, (size_t)C * CAM_T_STRIDE * sizeof(float), s, 
-            xy_dev, count_dev, C, max_pts, F_dev, cams_dev, cutoff, obj_count, max_groups, obj_out, n_obj_out, img_out,
-            n_valid_out, err_out, cand_out, flags_out, (char*)workspace, stride);
+        LAUNCH(correspond_kernel<float>, grid, CORR_THREADS, (size_t)C * CAM_T_STRIDE * sizeof(float), s,
+            xy_dev, count_dev, C, max_pts, F_dev, cams_dev, cutoff, max_groups, cand_out, flags_out, (char*)workspace, stride);
+    LAUNCH(correspond_rank_kernel, S, CORR_THREADS, 0, s, xy_dev, count_dev, C, max_pts, obj_count, obj_out, n_obj_out, img_out,
+           n_valid_out, err_out, (char*)workspace, stride);
     CUDA_TRY(cudaGetLastError());
     return MOCAP_OK;
 }

@@ -342,7 +342,7 @@ class CaptureEngine:
                 self._ptr(res.obj), self._ptr(res.n_obj), self._ptr(res.img), self._ptr(res.n_valid), self._ptr(res.err),
                 self._ptr(res.cand), self._ptr(res.flags), self._ptr(ws), nbytes, self._stream())
             _cabi.check(self.lib, st, "mocap_correspond_batch")
-            self.launches += 1
+            self.launches += 2
         return res
 
 
