@@ -21,6 +21,7 @@
 #define CELLS_MAX 8192          // TX*TY limit of the dense cell -> slot map held in shared memory
 #define ROOTS_MAX 512
 #define PIECE 64                // a cluster box is filtered in pieces of at most PIECE x PIECE output pixels
+#define CAND_PER_FRAME 512      // border-start candidates per frame on the cluster path
 #define CELL_EMPTY 0xffffffffu
 
 // counters[] slots
@@ -40,8 +41,9 @@ struct ClusterWs {
     short* memb;                // [n][HOT_MAX][4] output boxes of the hot cells, grouped by cluster
     uint32_t* rows_out;         // filtered bit rows of every cluster box
     unsigned rows_cap;          // words
-    int* cand_list;             // [cand_cap][2]: cluster, lx | ly << 16 | type << 31
-    int cand_cap;
+    int* cand_list;             // [n][CAND_PER_FRAME][2]: cluster, lx | ly << 16 | type << 31
+    int* cand_count;            // [n]
+    int n_frames;
     int* rec_count;             // [n]
     int* rec_start;             // [n][max_contours] start pixel index y * W + x of an outer border
     long long* rec_a;           // [n][max_contours][3] a00 a10 a01
@@ -205,13 +207,160 @@ __global__ void __launch_bounds__(CL_THREADS) form_clusters_kernel(const uint32_
 // ---------------------------------------------------------------------------------------------------------
 // per piece: filter <= 64x64 output pixels of a cluster box in shared memory -> bit rows of the cluster (global)
 // ---------------------------------------------------------------------------------------------------------
-struct PieceSmem {
+struct __align__(16) PieceSmem {
     static constexpr int UW = PIECE + 8, BW = PIECE + 4;
     uint8_t U[UW * UW];            // undistorted pixels, origin (px0 - 4, py0 - 4); 0 outside the frame
     uint16_t HS[UW * BW];          // horizontal 5-sums of U (U rows x B cols)
     uint8_t B[BW * BW];            // thresholded floor-mean, origin (px0 - 2, py0 - 2)
     uint8_t MH[BW * PIECE];        // horizontal 5-counts of B (B rows x output cols)
 };
+
+__device__ __forceinline__ uint32_t maj3(uint32_t a, uint32_t b, uint32_t c) { return (a & b) | (c & (a | b)); }
+
+// count of five 1-bit planes -> 3 bit planes (n0 + 2 n1 + 4 n2), 32 positions at a time
+__device__ __forceinline__ void count5(uint32_t a, uint32_t b, uint32_t c, uint32_t d, uint32_t e, uint32_t& n0, uint32_t& n1, uint32_t& n2)
+{
+    uint32_t s1 = a ^ b ^ c, c1 = maj3(a, b, c);
+    uint32_t s2 = s1 ^ d ^ e, c2 = maj3(s1, d, e);
+    n0 = s2; n1 = c1 ^ c2; n2 = c1 & c2;
+}
+
+// Stages 2 and 3 of a piece that has no frame border within reach (count = 25, no clamping), packed:
+//   A  horizontal 5-sums of U, four pixels per thread (two aligned 32-bit loads, sliding sum) -> HS (u16)
+//   B  vertical 5-sums of HS, eight pixels per thread (128-bit loads, packed 16-bit adds and compare) -> one byte of the
+//      thresholded bit row
+//   C  bit-sliced 5x5 majority: per B row the horizontal 5-counts as three bit planes, per output row the sum of five
+//      rows' planes (<= 25, five bit planes) and the test >= 13 -- 64 pixels per thread
+__device__ __forceinline__ void piece_threshold_majority_packed(PieceSmem& S, int mw, int mh, int T, uint32_t* __restrict__ out, int wpr)
+{
+    constexpr int UW = PieceSmem::UW, BW = PieceSmem::BW;
+    const int tid = threadIdx.x;
+    const int uh = mh + 8, bw = mw + 4, bh = mh + 4;
+    // ---- A ----
+    const int nq = (bw + 3) >> 2;
+    for (int t = tid; t < uh * nq; t += CL_THREADS) {
+        int r = t / nq, q = t - r * nq;
+        const uint32_t* up = (const uint32_t*)&S.U[r * UW + 4 * q];
+        uint32_t w0 = up[0], w1 = up[1];
+        uint32_t s0 = (w0 & 0xff) + ((w0 >> 8) & 0xff) + ((w0 >> 16) & 0xff) + (w0 >> 24) + (w1 & 0xff);
+        uint32_t s1 = s0 - (w0 & 0xff) + ((w1 >> 8) & 0xff);
+        uint32_t s2 = s1 - ((w0 >> 8) & 0xff) + ((w1 >> 16) & 0xff);
+        uint32_t s3 = s2 - ((w0 >> 16) & 0xff) + (w1 >> 24);
+        uint2 v; v.x = s0 | (s1 << 16); v.y = s2 | (s3 << 16);
+        *(uint2*)&S.HS[r * BW + 4 * q] = v;
+    }
+    __syncthreads();
+    // ---- B ----  bit rows of the thresholded mean: 16 bytes per row in S.B (72 bits used)
+    uint8_t* bbits = S.B;
+    const int no = (bw + 7) >> 3;
+    const uint32_t bias = (0x8000u - (uint32_t)(25 * T)) * 0x00010001u;          // bit 15 of (v + bias) set  <=>  v >= 25 T
+    for (int t = tid; t < bh * no; t += CL_THREADS) {
+        int r = t / no, o = t - r * no;
+        uint32_t a0 = 0, a1 = 0, a2 = 0, a3 = 0;
+#pragma unroll
+        for (int k = 0; k < 5; ++k) {
+            const uint2* hp = (const uint2*)&S.HS[(r + k) * BW + 8 * o];
+            uint2 lo = hp[0], hi = hp[1];
+            a0 += lo.x; a1 += lo.y; a2 += hi.x; a3 += hi.y;                       // packed u16 adds: sums <= 6375, no carry across halves
+        }
+        uint32_t m0 = (a0 + bias) & 0x80008000u, m1 = (a1 + bias) & 0x80008000u;
+        uint32_t m2 = (a2 + bias) & 0x80008000u, m3 = (a3 + bias) & 0x80008000u;
+        uint32_t y = (m0 >> 15) | (m1 >> 13) | (m2 >> 11) | (m3 >> 9);             // even bits 0..6 and 16..22
+        bbits[r * 16 + o] = (uint8_t)((y & 0x55u) | ((y >> 15) & 0xAAu));
+    }
+    __syncthreads();
+    // ---- C ----  horizontal 5-counts per B row as three 64-bit planes (two 32-bit halves each) in S.MH
+    uint32_t* planes = (uint32_t*)S.MH;                                           // [bh][3][2]
+    for (int r = tid; r < bh; r += CL_THREADS) {
+        const uint32_t* bp = (const uint32_t*)&bbits[r * 16];
+        uint32_t w0 = bp[0], w1 = bp[1], w2 = bp[2] & 0xffu;                      // bits 0..31, 32..63, 64..71
+#pragma unroll
+        for (int h = 0; h < 2; ++h) {
+            uint32_t lo = h ? w1 : w0, hi = h ? w2 : w1;
+            uint32_t x1 = __funnelshift_r(lo, hi, 1), x2 = __funnelshift_r(lo, hi, 2), x3 = __funnelshift_r(lo, hi, 3), x4 = __funnelshift_r(lo, hi, 4);
+            uint32_t n0, n1, n2;
+            count5(lo, x1, x2, x3, x4, n0, n1, n2);
+            planes[(r * 3 + 0) * 2 + h] = n0; planes[(r * 3 + 1) * 2 + h] = n1; planes[(r * 3 + 2) * 2 + h] = n2;
+        }
+    }
+    __syncthreads();
+    //          per output row: sum of five rows' counts (p + 2 q + 4 r with p, q, r = counts of the three planes) >= 13
+    for (int t = tid; t < mh * 2; t += CL_THREADS) {
+        int r = t >> 1, h = t & 1;
+        uint32_t p0, p1, p2, q0, q1, q2, r0, r1, r2;
+        const uint32_t* pl = planes + (size_t)r * 6 + h;
+        count5(pl[0], pl[6], pl[12], pl[18], pl[24], p0, p1, p2);
+        count5(pl[2], pl[8], pl[14], pl[20], pl[26], q0, q1, q2);
+        count5(pl[4], pl[10], pl[16], pl[22], pl[28], r0, r1, r2);
+        // total = p0 + 2 (p1 + q0) + 4 (p2 + q1 + r0) + 8 (q2 + r1) + 16 r2, rippled
+        uint32_t b0 = p0;
+        uint32_t b1 = p1 ^ q0, c1 = p1 & q0;
+        uint32_t s2 = p2 ^ q1 ^ r0, c2 = maj3(p2, q1, r0);
+        uint32_t b2 = s2 ^ c1, c2b = s2 & c1;
+        uint32_t s3 = q2 ^ r1 ^ c2, c3 = maj3(q2, r1, c2);
+        uint32_t b3 = s3 ^ c2b, c3b = s3 & c2b;
+        uint32_t b4 = r2 | c3 | c3b;                                              // total <= 25: bit 5 cannot be set
+        uint32_t ge13 = b4 | (b3 & b2 & (b1 | b0));
+        int rem = mw - 32 * h;                                                    // keep only the piece's own columns
+        if (rem < 32) ge13 &= rem > 0 ? ((1u << rem) - 1u) : 0u;
+        out[(size_t)r * wpr + h] = ge13;
+    }
+}
+
+// stages 2 and 3 of a piece: floor-mean of the in-frame taps > thresh (sum >= T * count), 5x5 majority with replicated
+// frame border (clamped coordinates), bit rows via ballot.  INTERIOR: the frame border is out of reach -> count = 25, no clamps.
+template <bool INTERIOR>
+__device__ __forceinline__ void piece_threshold_majority(PieceSmem& S, int px0, int py0, int mw, int mh, int W, int H, int T,
+                                                         uint32_t* __restrict__ out, int wpr)
+{
+    constexpr int BW = PieceSmem::BW;
+    const int tid = threadIdx.x, lane = tid & 31, wy = tid >> 5, NWARP = CL_THREADS / 32;
+    const int bw = mw + 4, bh = mh + 4;
+    for (int r = wy; r < bh; r += NWARP) {
+        int i = py0 - 2 + r;
+        int cnty = INTERIOR ? 5 : min(i + 2, H - 1) - max(i - 2, 0) + 1;
+        bool rowin = INTERIOR || (unsigned)i < (unsigned)H;
+        for (int c = lane; c < bw; c += 32) {
+            int j = px0 - 2 + c, b = 0;
+            if (rowin && (INTERIOR || (unsigned)j < (unsigned)W)) {
+                const uint16_t* h = &S.HS[r * BW + c];
+                int s = h[0] + h[BW] + h[2 * BW] + h[3 * BW] + h[4 * BW];
+                int cnt = INTERIOR ? 25 : cnty * (min(j + 2, W - 1) - max(j - 2, 0) + 1);
+                b = s >= T * cnt;
+            }
+            S.B[r * BW + c] = (uint8_t)b;
+        }
+        __syncwarp();
+        if (INTERIOR) {
+            for (int c = lane; c < mw; c += 32) {
+                const uint8_t* b = &S.B[r * BW + c];
+                S.MH[r * PIECE + c] = (uint8_t)(b[0] + b[1] + b[2] + b[3] + b[4]);
+            }
+        } else {
+            const uint8_t* b = &S.B[r * BW] - (px0 - 2);               // indexed by frame column
+            for (int c = lane; c < mw; c += 32) {
+                int j = px0 + c;
+                S.MH[r * PIECE + c] = (uint8_t)(b[max(j - 2, 0)] + b[max(j - 1, 0)] + b[j] + b[min(j + 1, W - 1)] + b[min(j + 2, W - 1)]);
+            }
+        }
+    }
+    __syncthreads();
+    for (int r = wy; r < mh; r += NWARP) {
+        int i = py0 + r;
+        int r0 = r, r1 = r + 1, r2 = r + 2, r3 = r + 3, r4 = r + 4;
+        if (!INTERIOR) {
+            r0 = max(i - 2, 0) - (py0 - 2); r1 = max(i - 1, 0) - (py0 - 2);
+            r3 = min(i + 1, H - 1) - (py0 - 2); r4 = min(i + 2, H - 1) - (py0 - 2);
+        }
+#pragma unroll
+        for (int c0 = 0; c0 < PIECE; c0 += 32) {
+            int c = c0 + lane, s = 0;
+            if (c < mw) s = S.MH[r0 * PIECE + c] + S.MH[r1 * PIECE + c] + S.MH[r2 * PIECE + c] + S.MH[r3 * PIECE + c] + S.MH[r4 * PIECE + c];
+            unsigned wv = __ballot_sync(0xffffffffu, s >= 13);
+            if (lane == 0) out[(size_t)r * wpr + (c0 >> 5)] = wv;
+        }
+    }
+}
 
 __global__ void __launch_bounds__(CL_THREADS) piece_filter_kernel(const uint8_t* __restrict__ frames, int64_t fstride, TableView tv, int thresh,
                                                                   ClusterWs cw)
@@ -222,12 +371,14 @@ __global__ void __launch_bounds__(CL_THREADS) piece_filter_kernel(const uint8_t*
     const int tid = threadIdx.x, lane = tid & 31, wy = tid >> 5, NWARP = CL_THREADS / 32;
     const int H = tv.H, W = tv.W, T = thresh + 1;
     const int total = min(cw.counters[CN_PIECES], cw.pc_cap);
+    int next = tid == 0 ? atomicAdd(&cw.counters[CN_PIECE_CUR], 1) : 0;
     for (;;) {
         __syncthreads();
-        if (tid == 0) s_item = atomicAdd(&cw.counters[CN_PIECE_CUR], 1);
+        if (tid == 0) s_item = next;
         __syncthreads();
         const int item = s_item;
         if (item >= total) break;
+        if (tid == 0) next = atomicAdd(&cw.counters[CN_PIECE_CUR], 1);     // fetched while this piece is processed
         const int* ce = cw.clusters + 8 * (size_t)cw.pieces[2 * (size_t)item];
         const int bxy = cw.pieces[2 * (size_t)item + 1], bx = bxy & 0xffff, by = bxy >> 16;
         const int f = ce[0];
@@ -237,61 +388,46 @@ __global__ void __launch_bounds__(CL_THREADS) piece_filter_kernel(const uint8_t*
         const int mw = px1 - px0 + 1, mh = py1 - py0 + 1;
         const int uw = mw + 8, uh = mh + 8, bw = mw + 4, bh = mh + 4;
         const uint8_t* fr = frames + (size_t)f * fstride;
-        // ---- 1. undistorted pixels of the piece dilated by 4 (zero outside the frame), then their horizontal 5-sums;
-        //         a warp owns whole rows, so only a warp-level sync separates the two ------------------------------------
-        for (int r = wy; r < uh; r += NWARP) {
-            int i = py0 - 4 + r;
-            bool rowin = (unsigned)i < (unsigned)H;
-            for (int c = lane; c < uw; c += 32) {
-                int j = px0 - 4 + c, u = 0;
-                if (rowin && (unsigned)j < (unsigned)W) u = remap_px(fr, W, H, i, j, (uint32_t)tv.map[(size_t)i * W + j]);
-                S.U[r * UW + c] = (uint8_t)u;
-            }
-            __syncwarp();
-            for (int c = lane; c < bw; c += 32) {
-                const uint8_t* u = &S.U[r * UW + c];
-                S.HS[r * BW + c] = (uint16_t)(u[0] + u[1] + u[2] + u[3] + u[4]);
-            }
-        }
-        __syncthreads();
-        // ---- 2. floor-mean over the in-frame taps > thresh  <=>  sum >= T * count, then the horizontal 5-counts of the
-        //         majority (replicated frame border = clamped columns) ----------------------------------------------------------
-        for (int r = wy; r < bh; r += NWARP) {
-            int i = py0 - 2 + r;
-            int cnty = min(i + 2, H - 1) - max(i - 2, 0) + 1;
-            bool rowin = (unsigned)i < (unsigned)H;
-            for (int c = lane; c < bw; c += 32) {
-                int j = px0 - 2 + c, b = 0;
-                if (rowin && (unsigned)j < (unsigned)W) {
-                    const uint16_t* h = &S.HS[r * BW + c];
-                    int s = h[0] + h[BW] + h[2 * BW] + h[3 * BW] + h[4 * BW];
-                    int cnt = cnty * (min(j + 2, W - 1) - max(j - 2, 0) + 1);
-                    b = s >= T * cnt;
-                }
-                S.B[r * BW + c] = (uint8_t)b;
-            }
-            __syncwarp();
-            const uint8_t* b = &S.B[r * BW] - (px0 - 2);               // indexed by frame column
-            for (int c = lane; c < mw; c += 32) {
-                int j = px0 + c;
-                S.MH[r * PIECE + c] = (uint8_t)(b[max(j - 2, 0)] + b[max(j - 1, 0)] + b[j] + b[min(j + 1, W - 1)] + b[min(j + 2, W - 1)]);
-            }
-        }
-        __syncthreads();
-        // ---- 3. vertical 5-counts (clamped rows) >= 13 -> bit rows of the cluster box ------------------------------------------
-        uint32_t* out = cw.rows_out + (unsigned)ce[3];
-        for (int r = wy; r < mh; r += NWARP) {
-            int i = py0 + r;
-            int r0 = max(i - 2, 0) - (py0 - 2), r1 = max(i - 1, 0) - (py0 - 2), r2 = i - (py0 - 2);
-            int r3 = min(i + 1, H - 1) - (py0 - 2), r4 = min(i + 2, H - 1) - (py0 - 2);
+        // no frame border within reach and a representable threshold: stages 2-3 run packed / bit-sliced
+        const bool packed = px0 >= 4 && py0 >= 4 && px1 + 4 < W && py1 + 4 < H && T >= 0 && T <= 256;
+        // ---- 1. undistorted pixels of the piece dilated by 4 (zero outside the frame), then their horizontal 5-sums.
+        //         A warp owns whole rows (only a warp-level sync between the two); it takes two rows x three 32-column
+        //         chunks at a time so that 6 map loads and then 24 tap loads are in flight per lane. ---------------------------
+        for (int r = 2 * wy; r < uh; r += 2 * NWARP) {
+            uint32_t m[2][3];
 #pragma unroll
-            for (int c0 = 0; c0 < PIECE; c0 += 32) {
-                int c = c0 + lane, s = 0;
-                if (c < mw) s = S.MH[r0 * PIECE + c] + S.MH[r1 * PIECE + c] + S.MH[r2 * PIECE + c] + S.MH[r3 * PIECE + c] + S.MH[r4 * PIECE + c];
-                unsigned wv = __ballot_sync(0xffffffffu, s >= 13);
-                if (lane == 0) out[(size_t)(py0 - cy0 + r) * wpr + bx * (PIECE / 32) + (c0 >> 5)] = wv;
+            for (int rr = 0; rr < 2; ++rr) {
+                int i = py0 - 4 + r + rr;
+                bool rowin = (r + rr < uh) && (unsigned)i < (unsigned)H;
+#pragma unroll
+                for (int k = 0; k < 3; ++k) {
+                    int c = lane + 32 * k, j = px0 - 4 + c;
+                    m[rr][k] = (rowin && c < uw && (unsigned)j < (unsigned)W) ? (uint32_t)tv.map[(size_t)i * W + j] : MAP_OUTSIDE;
+                }
             }
+            int u[2][3];
+#pragma unroll
+            for (int rr = 0; rr < 2; ++rr)
+#pragma unroll
+                for (int k = 0; k < 3; ++k)
+                    u[rr][k] = remap_px(fr, W, H, py0 - 4 + r + rr, px0 - 4 + lane + 32 * k, m[rr][k]);
+#pragma unroll
+            for (int rr = 0; rr < 2; ++rr)
+#pragma unroll
+                for (int k = 0; k < 3; ++k)
+                    if (r + rr < uh && lane + 32 * k < uw) S.U[(r + rr) * UW + lane + 32 * k] = (uint8_t)u[rr][k];
+            if (packed) continue;
+            __syncwarp();
+            for (int rr = 0; rr < 2 && r + rr < uh; ++rr)
+                for (int c = lane; c < bw; c += 32) {
+                    const uint8_t* up = &S.U[(r + rr) * UW + c];
+                    S.HS[(r + rr) * BW + c] = (uint16_t)(up[0] + up[1] + up[2] + up[3] + up[4]);
+                }
         }
+        __syncthreads();
+        uint32_t* out = cw.rows_out + (unsigned)ce[3] + (size_t)(py0 - cy0) * wpr + bx * (PIECE / 32);
+        if (packed) piece_threshold_majority_packed(S, mw, mh, T, out, wpr);
+        else piece_threshold_majority<false>(S, px0, py0, mw, mh, W, H, T, out, wpr);
     }
 }
 
@@ -307,10 +443,11 @@ __device__ __forceinline__ void emit_candidate(const ClusterWs& cw, int cid, int
     for (int m = 0; m < m_cnt && !own; ++m)
         own = ax >= memb[4 * m] && ax <= memb[4 * m + 2] && ay >= memb[4 * m + 1] && ay <= memb[4 * m + 3];
     if (!own) return;
-    int slot = atomicAdd(&cw.counters[CN_CANDS], 1);
-    if (slot >= cw.cand_cap) { cw.need_general[f] = 7; return; }
-    cw.cand_list[2 * (size_t)slot] = cid;
-    cw.cand_list[2 * (size_t)slot + 1] = cx | (r << 16) | (cty << 31);
+    int slot = atomicAdd(&cw.cand_count[f], 1);              // per-frame lists: no single hot counter
+    if (slot >= CAND_PER_FRAME) { cw.need_general[f] = 7; return; }
+    int* e = cw.cand_list + 2 * ((size_t)f * CAND_PER_FRAME + slot);
+    e[0] = cid;
+    e[1] = cx | (r << 16) | (cty << 31);
 }
 
 __global__ void __launch_bounds__(128) candidates_kernel(ClusterWs cw)
@@ -377,14 +514,14 @@ __global__ void __launch_bounds__(128) candidates_kernel(ClusterWs cw)
 
 // one thread per owned border-start candidate: Suzuki-Abe trace on the cluster's bit rows; a completed outer border
 // becomes a record of its frame, a completed hole border sends the frame to the general path (contour tree)
-__global__ void __launch_bounds__(128) trace_candidates_kernel(ClusterWs cw, int W, int max_contours)
+__global__ void __launch_bounds__(64) trace_candidates_kernel(ClusterWs cw, int W, int max_contours)
 {
-    const int total = min(cw.counters[CN_CANDS], cw.cand_cap);
+    const int total = cw.n_frames * CAND_PER_FRAME;
     for (int c = blockIdx.x * blockDim.x + threadIdx.x; c < total; c += gridDim.x * blockDim.x) {
+        const int f = c / CAND_PER_FRAME, cslot = c - f * CAND_PER_FRAME;
+        if (cslot >= cw.cand_count[f] || cw.need_general[f]) continue;
         const int* ce = cw.clusters + 8 * (size_t)cw.cand_list[2 * (size_t)c];
         const int code = cw.cand_list[2 * (size_t)c + 1];
-        const int f = ce[0];
-        if (cw.need_general[f]) continue;
         const int mx0 = ce[1] & 0xffff, my0 = ce[1] >> 16, mx1 = ce[2] & 0xffff, my1 = ce[2] >> 16;
         const int lx = code & 0xffff, ly = (code >> 16) & 0x7fff, ty = (code >> 31) & 1;
         BitImg im; im.p = cw.rows_out + (unsigned)ce[3]; im.W = mx1 - mx0 + 1; im.H = my1 - my0 + 1; im.WPR = ce[4];
@@ -478,7 +615,6 @@ __global__ void __launch_bounds__(CL_THREADS) finalize_kernel(ClusterWs cw, int 
 // ---------------------------------------------------------------------------------------------------------
 static int cl_cap_of(int n) { return n * 256 + 1024; }
 static int pc_cap_of(int n) { return n * 512 + 2048; }
-static int cand_cap_of(int n) { return n * 512 + 1024; }
 static size_t rows_cap_of(int n, int H, int W) { size_t w = (size_t)n * ((size_t)H * W / 128 + 4096); return w > 0xf0000000ull ? 0xf0000000ull : w; }   // a quarter of the frame area per frame
 
 size_t cluster_ws_bytes(int n, int H, int W, int max_contours, size_t* offs /*[16]*/)
@@ -495,7 +631,8 @@ size_t cluster_ws_bytes(int n, int H, int W, int max_contours, size_t* offs /*[1
     offs[7] = take((size_t)n * max_contours * 8);          // rec_per
     offs[8] = take((size_t)n * HOT_MAX * 8);               // memb
     offs[9] = take(rows_cap_of(n, H, W) * 4);              // rows_out
-    offs[10] = take((size_t)cand_cap_of(n) * 8);           // cand_list
+    offs[10] = take((size_t)n * CAND_PER_FRAME * 8);       // cand_list
+    offs[11] = take((size_t)n * 4);                        // cand_count
     return off;
 }
 
@@ -524,7 +661,8 @@ int launch_cluster_path(const uint8_t* frames, int n, int H, int W, int64_t fstr
     cw.rows_out = (uint32_t*)(ws_base + offs[9]);
     cw.rows_cap = (unsigned)rows_cap_of(n, H, W);
     cw.cand_list = (int*)(ws_base + offs[10]);
-    cw.cand_cap = cand_cap_of(n);
+    cw.cand_count = (int*)(ws_base + offs[11]);
+    cw.n_frames = n;
     if (finalize_only) {
         LAUNCH(finalize_kernel, n, CL_THREADS, (size_t)max_contours + 16, s, cw, max_contours, max_blobs, min_area, min_circ, out_xy, out_count, out_flags,
                out_contours, out_contour_count);
@@ -533,6 +671,7 @@ int launch_cluster_path(const uint8_t* frames, int n, int H, int W, int64_t fstr
     }
     CUDA_TRY(cudaMemsetAsync(cw.counters, 0, 64, s));
     CUDA_TRY(cudaMemsetAsync(cw.rec_count, 0, (size_t)n * 4, s));
+    CUDA_TRY(cudaMemsetAsync(cw.cand_count, 0, (size_t)n * 4, s));
     int dev = 0, sms = 148;
     cudaGetDevice(&dev);
     cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
@@ -551,7 +690,7 @@ int launch_cluster_path(const uint8_t* frames, int n, int H, int W, int64_t fstr
     stage_begin(timer, 2, s);
     LAUNCH(piece_filter_kernel, sms * 8, CL_THREADS, 0, s, frames, fstride, tv, thresh, cw);
     LAUNCH(candidates_kernel, sms * 8, 128, 0, s, cw);
-    LAUNCH(trace_candidates_kernel, sms * 4, 128, 0, s, cw, W, max_contours);
+    LAUNCH(trace_candidates_kernel, sms * 16, 64, 0, s, cw, W, max_contours);
     stage_end(timer, 2, s);
     CUDA_TRY(cudaGetLastError());
     return MOCAP_OK;
