@@ -21,6 +21,8 @@
 #define CELLS_MAX 8192          // TX*TY limit of the dense cell -> slot map held in shared memory
 #define ROOTS_MAX 512
 #define PIECE 64                // a cluster box is filtered in pieces of at most PIECE x PIECE output pixels
+#define WIN_W 96                // staged source window of a piece: up to 96 x 80 bytes
+#define WIN_H 80
 #define CAND_PER_FRAME 512      // border-start candidates per frame on the cluster path
 #define CELL_EMPTY 0xffffffffu
 
@@ -366,8 +368,11 @@ __global__ void __launch_bounds__(CL_THREADS) piece_filter_kernel(const uint8_t*
                                                                   ClusterWs cw)
 {
     __shared__ PieceSmem S;
+    __align__(16) __shared__ uint8_t win[WIN_W * WIN_H];           // staged source window
+    __shared__ int s_win[4];
     constexpr int UW = PieceSmem::UW, BW = PieceSmem::BW;
     __shared__ int s_item;
+    const bool vec_ok = (tv.W % 16 == 0) && (fstride % 16 == 0) && (((uintptr_t)frames) % 16 == 0);
     const int tid = threadIdx.x, lane = tid & 31, wy = tid >> 5, NWARP = CL_THREADS / 32;
     const int H = tv.H, W = tv.W, T = thresh + 1;
     const int total = min(cw.counters[CN_PIECES], cw.pc_cap);
@@ -390,9 +395,40 @@ __global__ void __launch_bounds__(CL_THREADS) piece_filter_kernel(const uint8_t*
         const uint8_t* fr = frames + (size_t)f * fstride;
         // no frame border within reach and a representable threshold: stages 2-3 run packed / bit-sliced
         const bool packed = px0 >= 4 && py0 >= 4 && px1 + 4 < W && py1 + 4 < H && T >= 0 && T <= 256;
+        // ---- 0. stage the source window of the piece in shared memory with 16-byte loads (zero outside the frame): the
+        //         bilinear taps then come from shared memory instead of four dependent global byte gathers per pixel.
+        //         Window = piece box +-4 shifted by the displacement bounds of the tiles it overlaps (undistortion table). ------
+        if (tid < 32) {
+            int tx0 = max((px0 - 4) >> 5, 0), tx1 = min((px1 + 4) >> 5, tv.TX - 1);
+            int ty0 = max((py0 - 4) >> 5, 0), ty1 = min((py1 + 4) >> 5, tv.TY - 1);
+            int ntx = tx1 - tx0 + 1, ntl = ntx * (ty1 - ty0 + 1);
+            int dx0 = 0x7fffffff, dx1 = -0x7fffffff, dy0 = 0x7fffffff, dy1 = -0x7fffffff;
+            for (int l = lane; l < ntl; l += 32) {
+                const int32_t* tt = tv.tile + 8 * ((ty0 + l / ntx) * tv.TX + tx0 + l % ntx);
+                if (tt[4] <= tt[5]) { dx0 = min(dx0, tt[4]); dx1 = max(dx1, tt[5]); dy0 = min(dy0, tt[6]); dy1 = max(dy1, tt[7]); }
+            }
+            dx0 = __reduce_min_sync(0xffffffffu, dx0); dx1 = __reduce_max_sync(0xffffffffu, dx1);
+            dy0 = __reduce_min_sync(0xffffffffu, dy0); dy1 = __reduce_max_sync(0xffffffffu, dy1);
+            if (lane == 0) {
+                int wx0 = (px0 - 4 + dx0) & ~15, wx1 = px1 + 4 + dx1 + 1, wy0 = py0 - 4 + dy0, wy1 = py1 + 4 + dy1 + 1;
+                bool ok = vec_ok && dx0 <= dx1 && wx1 - wx0 + 1 <= WIN_W && wy1 - wy0 + 1 <= WIN_H;
+                s_win[0] = wx0; s_win[1] = wy0; s_win[2] = ok ? wy1 - wy0 + 1 : 0; s_win[3] = ok;
+            }
+        }
+        __syncthreads();
+        const int wx0 = s_win[0], wy0 = s_win[1], wh = s_win[2];
+        const bool staged = s_win[3] != 0;
+        for (int idx = tid; idx < wh * (WIN_W / 16); idx += CL_THREADS) {
+            int row = idx / (WIN_W / 16), v = idx - row * (WIN_W / 16);
+            int gy = wy0 + row, gx = wx0 + 16 * v;
+            uint4 val = make_uint4(0, 0, 0, 0);
+            if ((unsigned)gy < (unsigned)H && gx >= 0 && gx + 16 <= W) val = *(const uint4*)(fr + (size_t)gy * W + gx);
+            *(uint4*)&win[row * WIN_W + 16 * v] = val;
+        }
+        __syncthreads();
         // ---- 1. undistorted pixels of the piece dilated by 4 (zero outside the frame), then their horizontal 5-sums.
         //         A warp owns whole rows (only a warp-level sync between the two); it takes two rows x three 32-column
-        //         chunks at a time so that 6 map loads and then 24 tap loads are in flight per lane. ---------------------------
+        //         chunks at a time so that the 6 map loads of a lane are in flight together. -----------------------------------
         for (int r = 2 * wy; r < uh; r += 2 * NWARP) {
             uint32_t m[2][3];
 #pragma unroll
@@ -406,11 +442,31 @@ __global__ void __launch_bounds__(CL_THREADS) piece_filter_kernel(const uint8_t*
                 }
             }
             int u[2][3];
+            if (staged) {
 #pragma unroll
-            for (int rr = 0; rr < 2; ++rr)
+                for (int rr = 0; rr < 2; ++rr)
 #pragma unroll
-                for (int k = 0; k < 3; ++k)
-                    u[rr][k] = remap_px(fr, W, H, py0 - 4 + r + rr, px0 - 4 + lane + 32 * k, m[rr][k]);
+                    for (int k = 0; k < 3; ++k) {
+                        uint32_t mm = m[rr][k];
+                        int val = 0;
+                        if (mm != MAP_OUTSIDE) {
+                            int iu = 32 * (px0 - 4 + lane + 32 * k) + (int)(int16_t)(mm & 0xffff);
+                            int iv = 32 * (py0 - 4 + r + rr) + (int)(int16_t)(mm >> 16);
+                            int fx = iu & 31, fy = iv & 31;
+                            const uint8_t* p = &win[((iv >> 5) - wy0) * WIN_W + ((iu >> 5) - wx0)];
+                            int r0 = (32 - fx) * p[0] + fx * p[1];
+                            int r1 = (32 - fx) * p[WIN_W] + fx * p[WIN_W + 1];
+                            val = ((32 - fy) * r0 + fy * r1 + 512) >> 10;
+                        }
+                        u[rr][k] = val;
+                    }
+            } else {
+#pragma unroll
+                for (int rr = 0; rr < 2; ++rr)
+#pragma unroll
+                    for (int k = 0; k < 3; ++k)
+                        u[rr][k] = remap_px(fr, W, H, py0 - 4 + r + rr, px0 - 4 + lane + 32 * k, m[rr][k]);
+            }
 #pragma unroll
             for (int rr = 0; rr < 2; ++rr)
 #pragma unroll
@@ -448,6 +504,31 @@ __device__ __forceinline__ void emit_candidate(const ClusterWs& cw, int cid, int
     int* e = cw.cand_list + 2 * ((size_t)f * CAND_PER_FRAME + slot);
     e[0] = cid;
     e[1] = cx | (r << 16) | (cty << 31);
+}
+
+// first bit >= x that differs from `inv` (inv = 0: first set bit, inv = ~0: first clear bit); wpr * 32 if none
+__device__ __forceinline__ int next_bit(const uint32_t* row, int wpr, int x, uint32_t inv)
+{
+    int wi = x >> 5;
+    uint32_t w = (row[wi] ^ inv) & (~0u << (x & 31));
+    while (!w && ++wi < wpr) w = row[wi] ^ inv;
+    return w ? wi * 32 + __ffs(w) - 1 : wpr * 32;
+}
+__device__ __forceinline__ uint32_t range_mask(int wi, int lo, int hi)          // bits of word wi inside [lo, hi]
+{
+    int a = max(lo - wi * 32, 0), b = min(hi - wi * 32, 31);
+    return (b == 31 ? ~0u : ((1u << (b + 1)) - 1u)) & (~0u << a);
+}
+__device__ __forceinline__ bool range_any(const uint32_t* row, int lo, int hi)
+{
+    for (int wi = lo >> 5; wi <= (hi >> 5); ++wi) if (row[wi] & range_mask(wi, lo, hi)) return true;
+    return false;
+}
+__device__ __forceinline__ bool range_all(const uint32_t* row, int lo, int hi)   // empty range: true
+{
+    if (lo > hi) return true;
+    for (int wi = lo >> 5; wi <= (hi >> 5); ++wi) { uint32_t m = range_mask(wi, lo, hi); if ((row[wi] & m) != m) return false; }
+    return true;
 }
 
 __global__ void __launch_bounds__(128) candidates_kernel(ClusterWs cw)
@@ -488,25 +569,19 @@ __global__ void __launch_bounds__(128) candidates_kernel(ClusterWs cw)
                 }
                 continue;
             }
-            int prev = 0, run_start = -1, last_end = -2;
-            for (int x = 0; x <= mw; ++x) {
-                int cur = x < mw ? (int)((row[x >> 5] >> (x & 31)) & 1u) : 0;
-                if (cur && !prev) {
-                    run_start = x;
-                    if (last_end >= 0 && r > 0) {
-                        bool covered = true;
-                        for (int g = last_end + 1; g < x; ++g) if (!im.get(g, r - 1)) { covered = false; break; }
-                        if (covered) emit_candidate(cw, cid, f, memb, m_cnt, last_end, r, 1, cx0, cy0);
-                    }
-                }
-                if (!cur && prev) {
-                    int xe = x - 1;
-                    bool top = true;
-                    if (r > 0) for (int g = run_start - 1; g <= xe + 1; ++g) if (im.get(g, r - 1)) { top = false; break; }
-                    if (top) emit_candidate(cw, cid, f, memb, m_cnt, run_start, r, 0, cx0, cy0);
-                    last_end = xe;
-                }
-                prev = cur;
+            // wider boxes: the same run / gap logic with word scans (bits at x >= mw are zero in every row)
+            const uint32_t* above = row - wpr;
+            int x = 0, last_end = -2;
+            while (x < mw) {
+                int s0 = next_bit(row, wpr, x, 0u);
+                if (s0 >= mw) break;
+                int e1 = min(next_bit(row, wpr, s0, ~0u), mw);              // first clear bit after the run
+                if (last_end >= 0 && r > 0 && range_all(above, last_end + 1, s0 - 1))
+                    emit_candidate(cw, cid, f, memb, m_cnt, last_end, r, 1, cx0, cy0);
+                if (r == 0 || !range_any(above, max(s0 - 1, 0), min(e1, mw - 1)))
+                    emit_candidate(cw, cid, f, memb, m_cnt, s0, r, 0, cx0, cy0);
+                last_end = e1 - 1;
+                x = e1;
             }
         }
     }
@@ -514,14 +589,16 @@ __global__ void __launch_bounds__(128) candidates_kernel(ClusterWs cw)
 
 // one thread per owned border-start candidate: Suzuki-Abe trace on the cluster's bit rows; a completed outer border
 // becomes a record of its frame, a completed hole border sends the frame to the general path (contour tree)
-__global__ void __launch_bounds__(64) trace_candidates_kernel(ClusterWs cw, int W, int max_contours)
+__global__ void __launch_bounds__(128) trace_candidates_kernel(ClusterWs cw, int W, int max_contours)
 {
-    const int total = cw.n_frames * CAND_PER_FRAME;
-    for (int c = blockIdx.x * blockDim.x + threadIdx.x; c < total; c += gridDim.x * blockDim.x) {
-        const int f = c / CAND_PER_FRAME, cslot = c - f * CAND_PER_FRAME;
-        if (cslot >= cw.cand_count[f] || cw.need_general[f]) continue;
-        const int* ce = cw.clusters + 8 * (size_t)cw.cand_list[2 * (size_t)c];
-        const int code = cw.cand_list[2 * (size_t)c + 1];
+    // one CTA per frame: all border starts of the batch are traced concurrently
+    const int f = blockIdx.x;
+    if (cw.need_general[f]) return;
+    const int n_cand = min(cw.cand_count[f], CAND_PER_FRAME);
+    for (int cslot = threadIdx.x; cslot < n_cand; cslot += blockDim.x) {
+        const size_t c = (size_t)f * CAND_PER_FRAME + cslot;
+        const int* ce = cw.clusters + 8 * (size_t)cw.cand_list[2 * c];
+        const int code = cw.cand_list[2 * c + 1];
         const int mx0 = ce[1] & 0xffff, my0 = ce[1] >> 16, mx1 = ce[2] & 0xffff, my1 = ce[2] >> 16;
         const int lx = code & 0xffff, ly = (code >> 16) & 0x7fff, ty = (code >> 31) & 1;
         BitImg im; im.p = cw.rows_out + (unsigned)ce[3]; im.W = mx1 - mx0 + 1; im.H = my1 - my0 + 1; im.WPR = ce[4];
@@ -690,7 +767,7 @@ int launch_cluster_path(const uint8_t* frames, int n, int H, int W, int64_t fstr
     stage_begin(timer, 2, s);
     LAUNCH(piece_filter_kernel, sms * 8, CL_THREADS, 0, s, frames, fstride, tv, thresh, cw);
     LAUNCH(candidates_kernel, sms * 8, 128, 0, s, cw);
-    LAUNCH(trace_candidates_kernel, sms * 16, 64, 0, s, cw, W, max_contours);
+    LAUNCH(trace_candidates_kernel, n, 128, 0, s, cw, W, max_contours);
     stage_end(timer, 2, s);
     CUDA_TRY(cudaGetLastError());
     return MOCAP_OK;
