@@ -373,11 +373,13 @@ def run_b200(args):
     except Exception:
         pass
     det_ms = sum(stage_avg.values())
-    roofline = {"bound": "hbm", "kernel": dom, "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
+    kernels = {"scan": "scan_hot_vec_kernel", "group": "form_clusters_kernel", "filter": "piece_filter_kernel",
+               "borders": "candidates_kernel + trace_candidates_kernel", "finish": "general path (compact/filter_tiles/blobs) + finalize_kernel"}
+    roofline = {"bound": "hbm", "kernel": kernels.get(dom, dom), "stage": dom, "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
                 "traffic": traffic, "peak_source": peak_src, "algorithmic_bytes_per_launch": alg_bytes,
                 "stage_ms": stage_avg, "detect_ms": det_ms,
                 "detect_pipeline": {"achieved": alg_bytes / (det_ms * 1e-3) / 1e9, "frac": alg_bytes / (det_ms * 1e-3) / 1e9 / peak,
-                                    "note": "all detection kernels of a step together (scan+compact+filter+blobs) against the same H*W bytes"}}
+                                    "note": "all detection kernels of a step together (scan+group+filter+borders+finish) against the same H*W bytes"}}
 
     # ---- CPU baseline on this host (N=1 only) -------------------------------------------------------------------------------------
     cpu = None

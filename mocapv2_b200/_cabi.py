@@ -16,7 +16,7 @@ ABI_VERSION = 1
 MAX_CAND = 8
 MAX_CAMS = 16
 CAM_STRIDE = 40
-N_STAGES = 4
+N_STAGES = 5
 
 OK = 0
 FLAG_RUN_OVERFLOW, FLAG_BLOB_OVERFLOW, FLAG_CONTOUR_OVERFLOW, FLAG_TILE_OVERFLOW, FLAG_DEPTH_OVERFLOW, FLAG_TRACE_OVERFLOW = 1, 2, 4, 8, 16, 32

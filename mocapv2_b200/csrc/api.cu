@@ -43,7 +43,7 @@ extern "C" int mocap_abi_version(void) { return MOCAP_ABI_VERSION; }
 
 extern "C" const char* mocap_stage_name(int stage)
 {
-    static const char* names[MOCAP_N_STAGES] = {"scan", "group", "cluster", "finish"};
+    static const char* names[MOCAP_N_STAGES] = {"scan", "group", "filter", "borders", "finish"};
     return (stage >= 0 && stage < MOCAP_N_STAGES) ? names[stage] : "?";
 }
 
@@ -189,7 +189,7 @@ extern "C" int mocap_detect_batch(const uint8_t* frames_dev, int n_frames, int H
                                  out_contour_count, false, s, timer);
         if (st != MOCAP_OK) return st;
     }
-    stage_begin(timer, 3, s);
+    stage_begin(timer, 4, s);
     st = launch_tiles(frames_dev, n_frames, H, W, frame_stride, tv, thresh, ws, L.max_fg, out_flags, need_general, s);
     if (st != MOCAP_OK) return st;
     if (out_bits) {
@@ -205,7 +205,7 @@ extern "C" int mocap_detect_batch(const uint8_t* frames_dev, int n_frames, int H
         st = launch_cluster_path(frames_dev, n_frames, H, W, frame_stride, tv, thresh, ws.cellbox, cl_base, L.cl_offs,
                                  max_contours, max_blobs, min_area, min_circ, out_xy, out_count, out_flags, out_contours,
                                  out_contour_count, true, s, timer);
-    stage_end(timer, 3, s);
+    stage_end(timer, 4, s);
     return st;
 }
 

@@ -426,61 +426,52 @@ __global__ void __launch_bounds__(CL_THREADS) piece_filter_kernel(const uint8_t*
             *(uint4*)&win[row * WIN_W + 16 * v] = val;
         }
         __syncthreads();
-        // ---- 1. undistorted pixels of the piece dilated by 4 (zero outside the frame), then their horizontal 5-sums.
-        //         A warp owns whole rows (only a warp-level sync between the two); it takes two rows x three 32-column
-        //         chunks at a time so that the 6 map loads of a lane are in flight together. -----------------------------------
-        for (int r = 2 * wy; r < uh; r += 2 * NWARP) {
-            uint32_t m[2][3];
+        // ---- 1. undistorted pixels of the piece dilated by 4 (zero outside the frame): the uw x uh box is walked as a flat
+        //         index (all lanes busy whatever the box width), four pixels per thread per pass so that the map loads of a
+        //         pass are in flight together. -----------------------------------------------------------------------------------
+        {
+            const int n_u = uw * uh;
+            const unsigned inv = (1u << 20) / (unsigned)uw + 1u;              // idx / uw == (idx * inv) >> 20 for idx * uw < 2^20
+            for (int base = tid; base < n_u; base += 4 * CL_THREADS) {
+                uint32_t m[4]; int ii[4], jj[4], rc[4];
 #pragma unroll
-            for (int rr = 0; rr < 2; ++rr) {
-                int i = py0 - 4 + r + rr;
-                bool rowin = (r + rr < uh) && (unsigned)i < (unsigned)H;
-#pragma unroll
-                for (int k = 0; k < 3; ++k) {
-                    int c = lane + 32 * k, j = px0 - 4 + c;
-                    m[rr][k] = (rowin && c < uw && (unsigned)j < (unsigned)W) ? (uint32_t)tv.map[(size_t)i * W + j] : MAP_OUTSIDE;
+                for (int k = 0; k < 4; ++k) {
+                    int idx = base + k * CL_THREADS;
+                    int r = (int)(((unsigned)idx * inv) >> 20), c = idx - r * uw;
+                    int i = py0 - 4 + r, j = px0 - 4 + c;
+                    ii[k] = i; jj[k] = j; rc[k] = r * UW + c;
+                    m[k] = (idx < n_u && (unsigned)i < (unsigned)H && (unsigned)j < (unsigned)W) ? (uint32_t)tv.map[(size_t)i * W + j] : MAP_OUTSIDE;
                 }
-            }
-            int u[2][3];
-            if (staged) {
 #pragma unroll
-                for (int rr = 0; rr < 2; ++rr)
-#pragma unroll
-                    for (int k = 0; k < 3; ++k) {
-                        uint32_t mm = m[rr][k];
-                        int val = 0;
+                for (int k = 0; k < 4; ++k) {
+                    int val = 0;
+                    uint32_t mm = m[k];
+                    if (staged) {
                         if (mm != MAP_OUTSIDE) {
-                            int iu = 32 * (px0 - 4 + lane + 32 * k) + (int)(int16_t)(mm & 0xffff);
-                            int iv = 32 * (py0 - 4 + r + rr) + (int)(int16_t)(mm >> 16);
+                            int iu = 32 * jj[k] + (int)(int16_t)(mm & 0xffff);
+                            int iv = 32 * ii[k] + (int)(int16_t)(mm >> 16);
                             int fx = iu & 31, fy = iv & 31;
                             const uint8_t* p = &win[((iv >> 5) - wy0) * WIN_W + ((iu >> 5) - wx0)];
                             int r0 = (32 - fx) * p[0] + fx * p[1];
                             int r1 = (32 - fx) * p[WIN_W] + fx * p[WIN_W + 1];
                             val = ((32 - fy) * r0 + fy * r1 + 512) >> 10;
                         }
-                        u[rr][k] = val;
+                    } else {
+                        val = remap_px(fr, W, H, ii[k], jj[k], mm);
                     }
-            } else {
-#pragma unroll
-                for (int rr = 0; rr < 2; ++rr)
-#pragma unroll
-                    for (int k = 0; k < 3; ++k)
-                        u[rr][k] = remap_px(fr, W, H, py0 - 4 + r + rr, px0 - 4 + lane + 32 * k, m[rr][k]);
-            }
-#pragma unroll
-            for (int rr = 0; rr < 2; ++rr)
-#pragma unroll
-                for (int k = 0; k < 3; ++k)
-                    if (r + rr < uh && lane + 32 * k < uw) S.U[(r + rr) * UW + lane + 32 * k] = (uint8_t)u[rr][k];
-            if (packed) continue;
-            __syncwarp();
-            for (int rr = 0; rr < 2 && r + rr < uh; ++rr)
-                for (int c = lane; c < bw; c += 32) {
-                    const uint8_t* up = &S.U[(r + rr) * UW + c];
-                    S.HS[(r + rr) * BW + c] = (uint16_t)(up[0] + up[1] + up[2] + up[3] + up[4]);
+                    if (base + k * CL_THREADS < n_u) S.U[rc[k]] = (uint8_t)val;
                 }
+            }
         }
         __syncthreads();
+        if (!packed) {
+            for (int r = wy; r < uh; r += NWARP)
+                for (int c = lane; c < bw; c += 32) {
+                    const uint8_t* up = &S.U[r * UW + c];
+                    S.HS[r * BW + c] = (uint16_t)(up[0] + up[1] + up[2] + up[3] + up[4]);
+                }
+            __syncthreads();
+        }
         uint32_t* out = cw.rows_out + (unsigned)ce[3] + (size_t)(py0 - cy0) * wpr + bx * (PIECE / 32);
         if (packed) piece_threshold_majority_packed(S, mw, mh, T, out, wpr);
         else piece_threshold_majority<false>(S, px0, py0, mw, mh, W, H, T, out, wpr);
@@ -766,9 +757,11 @@ int launch_cluster_path(const uint8_t* frames, int n, int H, int W, int64_t fstr
     stage_end(timer, 1, s);
     stage_begin(timer, 2, s);
     LAUNCH(piece_filter_kernel, sms * 8, CL_THREADS, 0, s, frames, fstride, tv, thresh, cw);
+    stage_end(timer, 2, s);
+    stage_begin(timer, 3, s);
     LAUNCH(candidates_kernel, sms * 8, 128, 0, s, cw);
     LAUNCH(trace_candidates_kernel, n, 128, 0, s, cw, W, max_contours);
-    stage_end(timer, 2, s);
+    stage_end(timer, 3, s);
     CUDA_TRY(cudaGetLastError());
     return MOCAP_OK;
 }
