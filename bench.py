@@ -265,7 +265,17 @@ def run_b200(args):
         det, corr = step(timers[k])
     ev1.record()
     barrier()
+    # nvidia-smi delivers a sample every ~50-100 ms and the timed region may be shorter than that: keep the same step loop
+    # running (untimed) for about a second more so that the clock record is taken under this very load
+    t_sus = time.perf_counter()
+    while time.perf_counter() - t_sus < 1.0:
+        for _ in range(5):
+            step()
+        torch.cuda.synchronize()
     clocks = sampler.stop() if rank == 0 else None
+    if clocks is not None:
+        clocks["window"] = "warm-up + timed region + 1 s of the same step loop (untimed)"
+    barrier()
     ms = torch.tensor([ev0.elapsed_time(ev1)], device=device, dtype=torch.float64)
     if world > 1:
         dist.all_reduce(ms, op=dist.ReduceOp.MAX)

@@ -50,6 +50,7 @@ struct ClusterWs {
     int* rec_start;             // [n][max_contours] start pixel index y * W + x of an outer border
     long long* rec_a;           // [n][max_contours][3] a00 a10 a01
     double* rec_per;            // [n][max_contours]
+    int* rec_info;              // [n][max_contours][4]: is_hole, start pixel of the parent outer border (holes), bbox x0 | y0 << 16, x1 | y1 << 16
 };
 
 __device__ __forceinline__ int suf_find(int* parent, int x)
@@ -578,13 +579,37 @@ __global__ void __launch_bounds__(128) candidates_kernel(ClusterWs cw)
     }
 }
 
-// one thread per owned border-start candidate: Suzuki-Abe trace on the cluster's bit rows; a completed outer border
-// becomes a record of its frame, a completed hole border sends the frame to the general path (contour tree)
+// Start pixel (frame index) of the outer border of the blob that owns the hole border starting at local pixel (lx, ly):
+// the west edge of the leftmost pixel of that pixel's run lies on another border of the same blob; if that border's
+// smallest edge is a west edge it is the blob's outer border, otherwise it is another hole of the blob further left and the
+// search continues from there.  -1 if it does not settle.
+__device__ long long hole_parent_start(const BitImg& im, int lx, int ly, int ox, int oy, int Wabs, int* overflow)
+{
+    for (int hop = 0; hop < 32; ++hop) {
+        int x = lx;
+        while (x > 0 && im.get(x - 1, ly)) --x;                    // leftmost pixel of the run
+        long long mk;
+        walk_min_edge(im, x, ly, 4, 1, &mk, overflow);             // smallest edge of the border through that west edge (local keys)
+        if (*overflow) return -1;
+        long long pix = mk >> 1;
+        int sx = (int)(pix % im.W), sy = (int)(pix / im.W);
+        if ((mk & 1) == 0) return (long long)(sy + oy) * Wabs + (sx + ox);
+        lx = sx; ly = sy;                                          // start pixel of another hole border of the same blob
+    }
+    return -1;
+}
+
+// One CTA per frame, one thread per owned border-start candidate: Suzuki-Abe trace on the cluster's bit rows.  A completed
+// border becomes a record of its frame; hole borders also record their blob's outer border (their parent in the contour
+// tree).  Afterwards the frame is checked for nesting (an outer border starting inside the bounding box of a hole border):
+// only then the contour tree is deeper than outer -> hole and the frame goes to the general path.
 __global__ void __launch_bounds__(128) trace_candidates_kernel(ClusterWs cw, int W, int max_contours)
 {
-    // one CTA per frame: all border starts of the batch are traced concurrently
     const int f = blockIdx.x;
     if (cw.need_general[f]) return;
+    __shared__ int s_holes;
+    if (threadIdx.x == 0) s_holes = 0;
+    __syncthreads();
     const int n_cand = min(cw.cand_count[f], CAND_PER_FRAME);
     for (int cslot = threadIdx.x; cslot < n_cand; cslot += blockDim.x) {
         const size_t c = (size_t)f * CAND_PER_FRAME + cslot;
@@ -594,16 +619,40 @@ __global__ void __launch_bounds__(128) trace_candidates_kernel(ClusterWs cw, int
         const int lx = code & 0xffff, ly = (code >> 16) & 0x7fff, ty = (code >> 31) & 1;
         BitImg im; im.p = cw.rows_out + (unsigned)ce[3]; im.W = mx1 - mx0 + 1; im.H = my1 - my0 + 1; im.WPR = ce[4];
         long long st = (long long)(ly + my0) * W + (lx + mx0);
-        long long a[3]; double per; int nch, ovf = 0;
-        int ok = trace_contour(im, lx, ly, ty ? 0 : 4, 2 * st + ty, a, &per, &nch, &ovf, mx0, my0, W);
-        if (ovf || (ok && ty)) { cw.need_general[f] = 8; continue; }           // hole border -> contour tree -> general path
+        long long a[3]; double per; int nch, ovf = 0, bbox[4];
+        int ok = trace_contour(im, lx, ly, ty ? 0 : 4, 2 * st + ty, a, &per, &nch, &ovf, mx0, my0, W, bbox);
+        if (ovf) { cw.need_general[f] = 8; continue; }
         if (!ok) continue;
+        long long parent = -1;
+        if (ty) {
+            parent = hole_parent_start(im, lx, ly, mx0, my0, W, &ovf);
+            if (parent < 0) { cw.need_general[f] = 8; continue; }
+            atomicAdd(&s_holes, 1);
+        }
         int slot = atomicAdd(&cw.rec_count[f], 1);
         if (slot < max_contours) {
-            cw.rec_start[(size_t)f * max_contours + slot] = (int)st;
-            long long* ra = cw.rec_a + ((size_t)f * max_contours + slot) * 3;
+            size_t k = (size_t)f * max_contours + slot;
+            cw.rec_start[k] = (int)st;
+            long long* ra = cw.rec_a + k * 3;
             ra[0] = a[0]; ra[1] = a[1]; ra[2] = a[2];
-            cw.rec_per[(size_t)f * max_contours + slot] = per;
+            cw.rec_per[k] = per;
+            int* ri = cw.rec_info + k * 4;
+            ri[0] = ty; ri[1] = (int)parent; ri[2] = bbox[0] | (bbox[1] << 16); ri[3] = bbox[2] | (bbox[3] << 16);
+        }
+    }
+    __syncthreads();
+    if (s_holes == 0) return;
+    // nesting check: an outer border whose start pixel lies inside the bounding box of a hole border
+    const int n = min(cw.rec_count[f], max_contours);
+    const int* start = cw.rec_start + (size_t)f * max_contours;
+    const int* info = cw.rec_info + (size_t)f * max_contours * 4;
+    for (int h = threadIdx.x; h < n; h += blockDim.x) {
+        if (!info[4 * h]) continue;
+        int x0 = info[4 * h + 2] & 0xffff, y0 = info[4 * h + 2] >> 16, x1 = info[4 * h + 3] & 0xffff, y1 = info[4 * h + 3] >> 16;
+        for (int o = 0; o < n; ++o) {
+            if (info[4 * o]) continue;
+            int ox = start[o] % W, oy = start[o] / W;
+            if (ox > x0 && ox < x1 && oy > y0 && oy < y1) { cw.need_general[f] = 9; break; }
         }
     }
 }
@@ -630,6 +679,7 @@ __global__ void __launch_bounds__(CL_THREADS) finalize_kernel(ClusterWs cw, int 
     const int* start = cw.rec_start + (size_t)f * max_contours;
     const long long* ra = cw.rec_a + (size_t)f * max_contours * 3;
     const double* rper = cw.rec_per + (size_t)f * max_contours;
+    const int* info = cw.rec_info + (size_t)f * max_contours * 4;
     for (int c = tid; c < n; c += CL_THREADS) {
         long long a00 = ra[3 * c];
         double area = (double)(a00 < 0 ? -a00 : a00) * 0.5, per = rper[c];
@@ -646,17 +696,31 @@ __global__ void __launch_bounds__(CL_THREADS) finalize_kernel(ClusterWs cw, int 
         long long a00 = ra[3 * c], a10 = ra[3 * c + 1], a01 = ra[3 * c + 2];
         double per = rper[c];
         int keep = keepv[c];
-        // all records are top-level outer borders: cv.findContours lists them in reverse raster order of their start pixel
-        int st = start[c], rank = 0, pos = 0;
+        // cv.findContours order for a two-level tree (top-level outer borders, each followed by its hole borders): outer
+        // borders in reverse raster order of their start pixel, the holes of a blob in reverse raster order of theirs
+        const int hole = info[4 * c], st = start[c];
+        const int top = hole ? info[4 * c + 1] : st;          // start pixel of the top-level border of my subtree
+        int rank = 0, pos = 0, parent_rank = -1;
         for (int u = 0; u < n; ++u) {
-            bool before = start[u] > st;
+            const int uh = info[4 * u], us = start[u], ut = uh ? info[4 * u + 1] : us;
+            bool before;
+            if (ut != top) before = ut > top;                 // another blob's subtree
+            else if (uh != hole) before = !uh;                // my blob: the outer border first
+            else before = us > st;                            // sibling holes
             rank += before;
             pos += before && keepv[u];
+        }
+        if (hole) {                                           // rank of my parent = number of subtrees that start later
+            parent_rank = 0;
+            for (int u = 0; u < n; ++u) {
+                const int uh = info[4 * u], us = start[u], ut = uh ? info[4 * u + 1] : us;
+                parent_rank += ut > top;
+            }
         }
         if (out_contours && rank < max_contours) {
             double* o = out_contours + ((size_t)f * max_contours + rank) * 8;
             o[0] = (double)a00; o[1] = (double)a10; o[2] = (double)a01; o[3] = per;
-            o[4] = 0.0; o[5] = -1.0; o[6] = (double)keep; o[7] = (double)st;
+            o[4] = (double)hole; o[5] = (double)parent_rank; o[6] = (double)keep; o[7] = (double)st;
         }
         if (!keep) continue;
         atomicAdd(&s_kept, 1);
@@ -701,6 +765,7 @@ size_t cluster_ws_bytes(int n, int H, int W, int max_contours, size_t* offs /*[1
     offs[9] = take(rows_cap_of(n, H, W) * 4);              // rows_out
     offs[10] = take((size_t)n * CAND_PER_FRAME * 8);       // cand_list
     offs[11] = take((size_t)n * 4);                        // cand_count
+    offs[12] = take((size_t)n * max_contours * 16);        // rec_info
     return off;
 }
 
@@ -730,6 +795,7 @@ int launch_cluster_path(const uint8_t* frames, int n, int H, int W, int64_t fstr
     cw.rows_cap = (unsigned)rows_cap_of(n, H, W);
     cw.cand_list = (int*)(ws_base + offs[10]);
     cw.cand_count = (int*)(ws_base + offs[11]);
+    cw.rec_info = (int*)(ws_base + offs[12]);
     cw.n_frames = n;
     if (finalize_only) {
         LAUNCH(finalize_kernel, n, CL_THREADS, (size_t)max_contours + 16, s, cw, max_contours, max_blobs, min_area, min_circ, out_xy, out_count, out_flags,

@@ -78,10 +78,11 @@ static __device__ int walk_min_edge(const BitImg& im, int x, int y, int side, in
 // (ox, oy, Wabs): the image `im` may be a window of the frame (cluster path): vertices and edge keys are taken in frame
 // coordinates (x + ox, y + oy) of a frame of width Wabs.
 static __device__ int trace_contour(const BitImg& im, int x, int y, int side, long long key0, long long* a, double* per, int* n_chain, int* overflow,
-                             int ox, int oy, int Wabs)
+                             int ox, int oy, int Wabs, int* bbox = nullptr)
 {
     const int W = Wabs;
     Walk w; walk_init(im, w, x, y, side);
+    if (bbox) { bbox[0] = bbox[2] = x + ox; bbox[1] = bbox[3] = y + oy; }
     if (w.single) { a[0] = a[1] = a[2] = 0; *per = 0.0; *n_chain = 1; return key0 < 0 || side == 4; }
     long long a00 = 0, a10 = 0, a01 = 0;
     double perim = 0.0;
@@ -106,6 +107,7 @@ static __device__ int trace_contour(const BitImg& im, int x, int y, int side, lo
                 perim += (double)__fsqrt_rn(__fadd_rn(__fmul_rn(ddx, ddx), __fmul_rn(ddy, ddy)));
             } else { fx = cx; fy = cy; have_v = true; }
             vx = cx; vy = cy;
+            if (bbox) { bbox[0] = min(bbox[0], cx); bbox[1] = min(bbox[1], cy); bbox[2] = max(bbox[2], cx); bbox[3] = max(bbox[3], cy); }
         }
         prev_dir = d;
         if (done) {
