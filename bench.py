@@ -358,6 +358,40 @@ def run_b200(args):
                       "match+triangulate -> D2H of object points/counts, host sync every step"}
         del host, stage_dev
 
+    # ---- geometry-only sweep (BASELINE config 5 shape): 8-view DLT + reprojection error, FP32 main mode, vs the FP32 pipe ------
+    geometry = None
+    if rank == 0:
+        rig5 = S.config_rig("c5")
+        cams5 = eng.cameras(rig5["poses"], rig5["camera_params"])
+        P5 = 4_000_000
+        g5 = torch.Generator(device=device).manual_seed(5)
+        X5 = torch.tensor(np.asarray(rig5["centre"]), device=device) + (torch.rand((P5, 3), generator=g5, device=device, dtype=torch.float64) - 0.5)
+        Pm = torch.tensor(cams5.cpu().numpy()[:, :12].reshape(8, 3, 4), device=device)
+        proj = torch.einsum("cij,pj->pci", Pm, torch.cat([X5, torch.ones((P5, 1), device=device, dtype=torch.float64)], dim=1))
+        pts5 = torch.floor(proj[..., :2] / proj[..., 2:3]).float().contiguous()
+        del proj, X5
+        xyz5 = torch.empty((P5, 3), device=device)
+        err5 = torch.empty((P5,), device=device)
+        for _ in range(3):
+            eng.triangulate(pts5, cams5, xyz=xyz5, err=err5)
+        ga, gb = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        torch.cuda.synchronize()
+        ga.record()
+        for _ in range(10):
+            eng.triangulate(pts5, cams5, xyz=xyz5, err=err5)
+        gb.record()
+        torch.cuda.synchronize()
+        tms = ga.elapsed_time(gb) / 10
+        flops = 140 * 8 + 1609                                     # F(N) = 140 N + 1609 per point
+        sm_mhz = (clocks or {}).get("sm_max_mhz") or 1965.0
+        peak32 = 148 * 128 * 2 * sm_mhz * 1e6 / 1e12
+        geometry = {"workload": "BASELINE config 5 shape: 8-view DLT triangulation + reprojection error, FP32", "points": P5, "views": 8,
+                    "ms": tms, "points_per_s": P5 / (tms * 1e-3), "flop_per_point": flops,
+                    "achieved_tflops": P5 * flops / (tms * 1e-3) / 1e12, "fp32_peak_tflops": peak32,
+                    "frac_of_fp32_pipe": P5 * flops / (tms * 1e-3) / 1e12 / peak32,
+                    "peak_source": "148 SMs x 128 FP32 lanes x 2 x clocks.max.sm (no tensor cores: tiny independent solves)"}
+        del pts5, xyz5, err5
+
     if rank != 0:
         if world > 1:
             dist.barrier()
@@ -411,10 +445,9 @@ def run_b200(args):
         "dtype": "u8 (detection, integer exact) / f32 (geometry)", "data": "synthetic",
         "config": workload_config(N, F0),
         "points_per_s": points_per_step * args.steps / (ms_total * 1e-3),
-        "dlt_solves_per_step_upper": None,
         "frame_sets_with_group_cap": float(n_pts[1].item()), "centroids_per_frame": float(n_pts[2].item()) / (n_local * N),
         "e2e": e2e, "gpu_launches": gpu_launches, "collectives_per_step": 1 if N > 1 else 0,
-        "clocks": clocks, "roofline": roofline, "cpu_baseline": cpu,
+        "clocks": clocks, "roofline": roofline, "cpu_baseline": cpu, "geometry": geometry,
     }
     print(json.dumps(line))
     if world > 1:

@@ -263,11 +263,10 @@ __device__ __forceinline__ uint32_t pack_cellbox(uint32_t xmask, uint32_t ymask)
 }
 
 // Streams all source bytes.  One warp per 128x32-pixel block (4 source cells): lane = (row & 3, 16-byte segment).
-// Writes the hot bounding box of every cell (cellbox) and marks the output tiles a hot cell can reach (active).
+// Writes the hot bounding box of every cell (cellbox); that is all later stages need to know about the frame.
 template <int MODE>
-__global__ void __launch_bounds__(256) scan_hot_vec_kernel(const uint8_t* __restrict__ frames, int n_frames, int64_t fstride,
-                                                           TableView tv, uint32_t* __restrict__ active, int TXW, uint32_t add,
-                                                           uint32_t* __restrict__ cellbox)
+__global__ void __launch_bounds__(256, 4) scan_hot_vec_kernel(const uint8_t* __restrict__ frames, int n_frames, int64_t fstride,
+                                                              TableView tv, uint32_t add, uint32_t* __restrict__ cellbox)
 {
     const int lane = threadIdx.x & 31;
     const long long warp = ((long long)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
@@ -318,18 +317,14 @@ __global__ void __launch_bounds__(256) scan_hot_vec_kernel(const uint8_t* __rest
         }
         if (lane < 4) {
             int cx = cxb * 4 + lane;
-            if (cx < tv.TX) {
-                cellbox[((size_t)f * tv.TY + cy) * tv.TX + cx] = box;
-                if (box != CELL_EMPTY) mark_cell(tv, active, f, cy, cx, TXW);
-            }
+            if (cx < tv.TX) cellbox[((size_t)f * tv.TY + cy) * tv.TX + cx] = box;
         }
     }
 }
 
 // Generic (any W / alignment) variant: one warp per source cell, byte loads.
 __global__ void scan_hot_scalar_kernel(const uint8_t* __restrict__ frames, int n_frames, int64_t fstride,
-                                       TableView tv, uint32_t* __restrict__ active, int TXW, int thresh,
-                                       uint32_t* __restrict__ cellbox)
+                                       TableView tv, int thresh, uint32_t* __restrict__ cellbox)
 {
     const int lane = threadIdx.x & 31;
     const long long warp = ((long long)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
@@ -352,11 +347,21 @@ __global__ void scan_hot_scalar_kernel(const uint8_t* __restrict__ frames, int n
         }
         uint32_t xm = __ballot_sync(0xffffffffu, rowbits != 0);
         uint32_t ym = __reduce_or_sync(0xffffffffu, rowbits);
-        if (lane == 0) {
-            cellbox[((size_t)f * tv.TY + cy) * tv.TX + cx] = pack_cellbox(xm, ym);
-            if (xm) mark_cell(tv, active, f, cy, cx, TXW);
-        }
+        if (lane == 0) cellbox[((size_t)f * tv.TY + cy) * tv.TX + cx] = pack_cellbox(xm, ym);
     }
+}
+
+// general path: the output tiles the hot cells of a flagged frame can reach (one thread per source cell)
+__global__ void mark_active_kernel(const uint32_t* __restrict__ cellbox, TableView tv, int n_frames, uint32_t* __restrict__ active, int TXW,
+                                   const int* __restrict__ need_general)
+{
+    const int cells = tv.TX * tv.TY;
+    long long idx = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    if (idx >= (long long)n_frames * cells) return;
+    int f = (int)(idx / cells), c = (int)(idx - (long long)f * cells);
+    if (need_general && !need_general[f]) return;
+    if (cellbox[idx] == CELL_EMPTY) return;
+    mark_cell(tv, active, f, c / tv.TX, c % tv.TX, TXW);
 }
 
 __global__ void compact_tiles_kernel(const uint32_t* __restrict__ active, long long n_words, int TX, int TY, int TXW,
@@ -572,9 +577,6 @@ __global__ void materialize_bits_kernel(const uint32_t* __restrict__ bits, const
 int launch_scan(const uint8_t* frames, int n, int H, int W, int64_t fstride, const TableView& tv, int thresh,
                 const FilterWs& ws, cudaStream_t s, StageTimer* timer)
 {
-    const int TX = tv.TX, TY = tv.TY, TXW = cdiv(TX, 32);
-    size_t act_bytes = (size_t)n * TY * TXW * 4;
-    CUDA_TRY(cudaMemsetAsync(ws.active, 0, act_bytes, s));
     int dev = 0, sms = 148;
     cudaGetDevice(&dev);
     cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
@@ -582,15 +584,15 @@ int launch_scan(const uint8_t* frames, int n, int H, int W, int64_t fstride, con
     bool vec = (W % 16 == 0) && (fstride % 16 == 0) && (((uintptr_t)frames) % 16 == 0);
     stage_begin(timer, 0, s);
     if (vec) {
-        int grid = sms * 8;
+        int grid = sms * 4;                      // persistent: exactly the resident CTAs (__launch_bounds__(256, 4)), one wave
         switch (ht.mode) {
-            case 0: LAUNCH(scan_hot_vec_kernel<0>, grid, 256, 0, s, frames, n, fstride, tv, ws.active, TXW, ht.add, ws.cellbox); break;
-            case 1: LAUNCH(scan_hot_vec_kernel<1>, grid, 256, 0, s, frames, n, fstride, tv, ws.active, TXW, ht.add, ws.cellbox); break;
-            case 2: LAUNCH(scan_hot_vec_kernel<2>, grid, 256, 0, s, frames, n, fstride, tv, ws.active, TXW, ht.add, ws.cellbox); break;
-            default: LAUNCH(scan_hot_vec_kernel<3>, grid, 256, 0, s, frames, n, fstride, tv, ws.active, TXW, ht.add, ws.cellbox); break;
+            case 0: LAUNCH(scan_hot_vec_kernel<0>, grid, 256, 0, s, frames, n, fstride, tv, ht.add, ws.cellbox); break;
+            case 1: LAUNCH(scan_hot_vec_kernel<1>, grid, 256, 0, s, frames, n, fstride, tv, ht.add, ws.cellbox); break;
+            case 2: LAUNCH(scan_hot_vec_kernel<2>, grid, 256, 0, s, frames, n, fstride, tv, ht.add, ws.cellbox); break;
+            default: LAUNCH(scan_hot_vec_kernel<3>, grid, 256, 0, s, frames, n, fstride, tv, ht.add, ws.cellbox); break;
         }
     } else {
-        LAUNCH(scan_hot_scalar_kernel, sms * 8, 256, 0, s, frames, n, fstride, tv, ws.active, TXW, thresh, ws.cellbox);
+        LAUNCH(scan_hot_scalar_kernel, sms * 8, 256, 0, s, frames, n, fstride, tv, thresh, ws.cellbox);
     }
     stage_end(timer, 0, s);
     CUDA_TRY(cudaGetLastError());
@@ -607,6 +609,9 @@ int launch_tiles(const uint8_t* frames, int n, int H, int W, int64_t fstride, co
     int dev = 0, sms = 148;
     cudaGetDevice(&dev);
     cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
+    CUDA_TRY(cudaMemsetAsync(ws.active, 0, (size_t)n * TY * TXW * 4, s));
+    long long n_cells = (long long)n * TX * TY;
+    LAUNCH(mark_active_kernel, (unsigned)((n_cells + 255) / 256), 256, 0, s, ws.cellbox, tv, n, ws.active, TXW, need_general);
     long long n_words = (long long)n * TY * TXW;
     LAUNCH(compact_tiles_kernel, (unsigned)((n_words + 255) / 256), 256, 0, s, ws.active, n_words, TX, TY, TXW, ws.list, ws.counters, need_general);
     LAUNCH(filter_tiles_kernel, sms * 4, FT_WARPS * 32, 0, s, frames, fstride, tv, thresh, ws.list, ws.counters, ws.counters + 1,

@@ -22,12 +22,18 @@ template <> struct Num<float> {
     static __device__ __forceinline__ float sqrt_(float x) { return sqrtf(x); }
     static __device__ __forceinline__ float abs_(float x) { return fabsf(x); }
     static __device__ __forceinline__ float tiny() { return 1e-30f; }
+    // Jacobi rotations are self-correcting: an angle that is off by a few ulp only leaves a slightly larger off-diagonal
+    // for the next sweep, so the FP32 main mode uses the SFU reciprocal / rsqrt (the FP64 check mode stays IEEE)
+    static __device__ __forceinline__ float rcp_(float x) { return __frcp_rn(x); }
+    static __device__ __forceinline__ float rsqrt_(float x) { return rsqrtf(x); }
     static constexpr int sweeps = 8;
 };
 template <> struct Num<double> {
     static __device__ __forceinline__ double sqrt_(double x) { return sqrt(x); }
     static __device__ __forceinline__ double abs_(double x) { return fabs(x); }
     static __device__ __forceinline__ double tiny() { return 1e-280; }
+    static __device__ __forceinline__ double rcp_(double x) { return 1.0 / x; }
+    static __device__ __forceinline__ double rsqrt_(double x) { return 1.0 / sqrt(x); }
     static constexpr int sweeps = 12;
 };
 
@@ -47,14 +53,20 @@ __device__ __forceinline__ void jacobi_min_eigvec(T b00, T b01, T b02, T b03, T 
 #pragma unroll
             for (int q = p + 1; q < 4; ++q) {
                 T apq = A[p][q];
+                // after the first sweeps an off-diagonal that no longer registers against either diagonal entry is dropped
+                // without a rotation (the classic Jacobi shortcut), so the last sweeps cost almost nothing
+                if (sweep >= 3 && apq != (T)0) {
+                    T g = (T)100 * Num<T>::abs_(apq), dp = Num<T>::abs_(A[p][p]), dq = Num<T>::abs_(A[q][q]);
+                    if (g + dp == dp && g + dq == dq) { A[p][q] = (T)0; A[q][p] = (T)0; apq = (T)0; }
+                }
                 if (apq != (T)0) {
-                    T theta = (A[q][q] - A[p][p]) / ((T)2 * apq);
+                    T theta = (A[q][q] - A[p][p]) * Num<T>::rcp_((T)2 * apq);
                     T at = Num<T>::abs_(theta);
                     T t;
-                    if (at > (T)1e15) t = (T)0.5 / theta;                       // avoid theta^2 overflow
-                    else { t = (T)1 / (at + Num<T>::sqrt_(theta * theta + (T)1)); if (theta < (T)0) t = -t; }
-                    T c = (T)1 / Num<T>::sqrt_(t * t + (T)1), s = t * c;
-                    T tau = s / ((T)1 + c);
+                    if (at > (T)1e15) t = (T)0.5 * Num<T>::rcp_(theta);         // avoid theta^2 overflow
+                    else { t = Num<T>::rcp_(at + Num<T>::sqrt_(theta * theta + (T)1)); if (theta < (T)0) t = -t; }
+                    T c = Num<T>::rsqrt_(t * t + (T)1), s = t * c;
+                    T tau = s * Num<T>::rcp_((T)1 + c);
                     A[p][p] -= t * apq; A[q][q] += t * apq; A[p][q] = (T)0; A[q][p] = (T)0;
 #pragma unroll
                     for (int r = 0; r < 4; ++r) {
