@@ -108,6 +108,8 @@ int mocap_blobs_batch(const uint32_t* bits_dev, int n_frames, int H, int W,
 
 /* ---- the reference's own GPU op: fast_cuda_blur(image, 5) (lib/CudaOperations.py:24-41) -------------------- */
 int mocap_blur5_batch(const uint8_t* frames_dev, int n_frames, int H, int W, uint8_t* out_dev, void* stream);
+/* image_filter_cpu (lib/ImageOperations.py:15-21): cv.medianBlur(image, 5) then cv.threshold(., thresh, 255, BINARY) -> u8 {0,255} */
+int mocap_median5_threshold_batch(const uint8_t* frames_dev, int n_frames, int H, int W, int thresh, uint8_t* out_dev, void* stream);
 /* cv.undistort alone (lib/ImageOperations.py:38), for stage parity */
 int mocap_undistort_batch(const uint8_t* frames_dev, int n_frames, int H, int W, const void* table_dev,
                           uint8_t* out_dev, void* stream);

@@ -46,6 +46,7 @@ SIGNATURES = {
     "mocap_filter_batch": (_i, [_p, _i, _i, _i, _i64, _p, _i, _p, _p, _sz, _p]),
     "mocap_blobs_batch": (_i, [_p, _i, _i, _i, _d, _d, _i, _i, _i, _p, _p, _p, _p, _p, _p, _p, _p, _p, _sz, _p]),
     "mocap_blur5_batch": (_i, [_p, _i, _i, _i, _p, _p]),
+    "mocap_median5_threshold_batch": (_i, [_p, _i, _i, _i, _i, _p, _p]),
     "mocap_undistort_batch": (_i, [_p, _i, _i, _i, _p, _p, _p]),
     "mocap_triangulate_batch": (_i, [_p, _p, _p, _i, _i64, _i, _p, _p, _p]),
     "mocap_reproject_batch": (_i, [_p, _p, _p, _p, _i, _i64, _i, _p, _p]),

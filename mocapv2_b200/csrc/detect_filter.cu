@@ -654,6 +654,39 @@ extern "C" int mocap_blur5_batch(const uint8_t* frames_dev, int n, int H, int W,
     return MOCAP_OK;
 }
 
+// cv.medianBlur(image, 5) on grey u8 (BORDER_REPLICATE) followed by cv.threshold(., thresh, 255, THRESH_BINARY):
+// image_filter_cpu of the reference (lib/ImageOperations.py:15-21; it has no callers there).  One pixel per thread:
+// the median is the value whose rank interval covers position 12 of the 25 window values.
+__global__ void median5_threshold_kernel(const uint8_t* __restrict__ in, int n, int H, int W, int thresh, uint8_t* __restrict__ out)
+{
+    int x = blockIdx.x * blockDim.x + threadIdx.x, y = blockIdx.y * blockDim.y + threadIdx.y, f = blockIdx.z;
+    if (x >= W || y >= H) return;
+    const uint8_t* fr = in + (size_t)f * H * W;
+    int v[25];
+#pragma unroll
+    for (int dy = -2; dy <= 2; ++dy)
+#pragma unroll
+        for (int dx = -2; dx <= 2; ++dx)
+            v[(dy + 2) * 5 + dx + 2] = fr[(size_t)min(max(y + dy, 0), H - 1) * W + min(max(x + dx, 0), W - 1)];
+    int med = 0;
+#pragma unroll
+    for (int a = 0; a < 25; ++a) {
+        int less = 0, leq = 0;
+#pragma unroll
+        for (int b = 0; b < 25; ++b) { less += v[b] < v[a]; leq += v[b] <= v[a]; }
+        if (less <= 12 && 12 < leq) med = v[a];
+    }
+    out[(size_t)f * H * W + (size_t)y * W + x] = med > thresh ? 255 : 0;
+}
+
+extern "C" int mocap_median5_threshold_batch(const uint8_t* frames_dev, int n, int H, int W, int thresh, uint8_t* out_dev, void* stream)
+{
+    if (!frames_dev || !out_dev || n <= 0 || H <= 0 || W <= 0 || n > 65535) return MOCAP_ERR_INVALID;
+    LAUNCH(median5_threshold_kernel, dim3(cdiv(W, 32), cdiv(H, 8), n), dim3(32, 8), 0, (cudaStream_t)stream, frames_dev, n, H, W, thresh, out_dev);
+    CUDA_TRY(cudaGetLastError());
+    return MOCAP_OK;
+}
+
 __global__ void undistort_kernel(const uint8_t* __restrict__ in, int n, int H, int W, const int32_t* __restrict__ map,
                                  uint8_t* __restrict__ out)
 {

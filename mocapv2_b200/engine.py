@@ -245,6 +245,16 @@ class CaptureEngine:
         self.launches += 1
         return out
 
+    def median5_threshold(self, frames: torch.Tensor, thresh=THRESH_U8) -> torch.Tensor:
+        """image_filter_cpu (lib/ImageOperations.py:15-21): cv.medianBlur(5) -> cv.threshold for a batch [n, H, W] uint8."""
+        frames = self._check_dev(frames.contiguous(), torch.uint8, "frames")
+        n, H, W = frames.shape
+        out = torch.empty_like(frames)
+        _cabi.check(self.lib, self.lib.mocap_median5_threshold_batch(self._ptr(frames), n, H, W, int(thresh), self._ptr(out), self._stream()),
+                    "mocap_median5_threshold_batch")
+        self.launches += 1
+        return out
+
     def undistort(self, frames: torch.Tensor, K, dist) -> torch.Tensor:
         """cv.undistort(img, K, dist) (lib/ImageOperations.py:38) for a batch [n, H, W] uint8."""
         frames = self._check_dev(frames.contiguous(), torch.uint8, "frames")

