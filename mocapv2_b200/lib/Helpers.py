@@ -4,6 +4,7 @@ Same names, arguments, return conventions and module globals as the reference:
   triangulate_point / triangulate_points                     lib/Helpers.py:43-99
   calculate_reprojection_error / calculate_reprojection_errors   lib/Helpers.py:102-143
   find_point_correspondance_and_object_points                lib/Helpers.py:178-280
+  bundle_adjustment, params_to_camera_poses                  lib/Helpers.py:145-176 (caller of the path)
   get_extrinsics, read_camera_params, read_fundamental_matrix lib/Helpers.py:282-291, 30-40, 22-28
   globals camera_params, camera_params_path, Fs (assignable: >2-camera rigs inject them, like with the reference)
 The arithmetic runs in libmocap_b200.so (sm_100a).  These list-in / ndarray-out calls handle one frame-set and are
@@ -131,6 +132,42 @@ def calculate_reprojection_errors(image_points, object_points, camera_poses):
         return np.array([])
     _, e, _ = _run_triangulate(groups, camera_poses, xyz=np.asarray(xyz, dtype=np.float64))
     return e
+
+
+def params_to_camera_poses(params, num_cameras=2):
+    """rotation vector + translation per camera after the first -> pose dicts (lib/Helpers.py:145-156)."""
+    from scipy.spatial.transform import Rotation
+    camera_poses = [{"R": np.eye(3), "t": np.array([0, 0, 0], dtype=np.float32)}]
+    for i in range(0, num_cameras - 1):
+        camera_poses.append({"R": Rotation.as_matrix(Rotation.from_rotvec(params[i * 6: i * 6 + 3])),
+                             "t": params[i * 6 + 3: i * 6 + 6]})
+    return camera_poses
+
+
+def bundle_adjustment(image_points, camera_poses):
+    """Refine the second camera's pose (lib/Helpers.py:158-176): scipy least_squares (TRF, 2-point finite differences)
+    over the mean squared reprojection errors, cast to float32 like the reference; the residual -- triangulate_points +
+    calculate_reprojection_errors on all points -- is the GPU path, in its FP64 check mode (finite differences need it).
+    Same quirks: two cameras hard-coded (:162, :174)."""
+    from scipy import optimize
+    from scipy.spatial.transform import Rotation
+    global precision
+    saved, precision = precision, "fp64"
+    try:
+        def residual_function(params):
+            poses = params_to_camera_poses(params, 2)
+            object_points = triangulate_points(image_points, poses)
+            errors = calculate_reprojection_errors(image_points, object_points, poses)
+            return errors.astype(np.float32)
+
+        init_params = np.array([])
+        for camera_pose in camera_poses[1:]:
+            init_params = np.concatenate([init_params, Rotation.from_matrix(camera_pose["R"]).as_rotvec(),
+                                          np.asarray(camera_pose["t"]).flatten()])
+        result = optimize.least_squares(residual_function, init_params, verbose=0, loss="linear", method="trf", ftol=1E-5, xtol=1E-15)
+    finally:
+        precision = saved
+    return params_to_camera_poses(result.x)
 
 
 def find_point_correspondance_and_object_points(image_points, camera_poses, obj_count=0, debug=False):

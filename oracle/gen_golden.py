@@ -56,6 +56,24 @@ print('EQUAL' if ok else 'DIFF')
     return out.stdout.strip().endswith("EQUAL")
 
 
+def kat_bundle_adjustment(Hh, ip):
+    """Second golden vector of the reference: jsons/before_ba_extrinsics.json --bundle_adjustment--> after_ba_extrinsics.json
+    (CalculateCameraPoses.py:243-254).  Stored: the input poses, the reference's result run here, and the shipped JSON."""
+    before = json.load(open("jsons/before_ba_extrinsics.json"))
+    after = json.load(open("jsons/after_ba_extrinsics.json"))
+    poses = [{"R": np.array(p["R"]), "t": np.array(p["t"])} for p in before]
+    Hh.camera_params = None
+    with quiet():
+        out = Hh.bundle_adjustment(ip, poses)
+    np.savez_compressed(os.path.join(OUT, "kat_bundle_adjustment.npz"), image_points=ip,
+                        R_before=np.stack([p["R"] for p in poses]), t_before=np.stack([p["t"] for p in poses]),
+                        R_ref=np.stack([np.asarray(p["R"], dtype=np.float64) for p in out]),
+                        t_ref=np.stack([np.asarray(p["t"], dtype=np.float64).ravel() for p in out]),
+                        R_json=np.stack([np.array(p["R"]) for p in after]), t_json=np.stack([np.array(p["t"]) for p in after]))
+    print("BA max |ref - json| R, t =", np.abs(np.asarray(out[1]["R"]) - np.array(after[1]["R"])).max(),
+          np.abs(np.asarray(out[1]["t"]).ravel() - np.array(after[1]["t"])).max())
+
+
 def main():
     import cv2
     os.makedirs(OUT, exist_ok=True)
@@ -108,6 +126,7 @@ def main():
                         dist=np.stack([np.array(c["distortion_coef"]) for c in cp]),
                         F=np.array(json.load(open("jsons/fundamentals.json"))))
     print("KAT max |ref - json| =", np.abs(tri - obj).max())
+    kat_bundle_adjustment(Hh, ip)
 
     # ---------------- C1: 2 cams 640x480, 4 markers, shipped calibration, reference as-is --------------
     rig = S.config_rig("c1")
