@@ -430,7 +430,36 @@ __global__ void __launch_bounds__(CL_THREADS) piece_filter_kernel(const uint8_t*
         // ---- 1. undistorted pixels of the piece dilated by 4 (zero outside the frame): the uw x uh box is walked as a flat
         //         index (all lanes busy whatever the box width), four pixels per thread per pass so that the map loads of a
         //         pass are in flight together. -----------------------------------------------------------------------------------
-        {
+        if (packed && staged) {
+            // fast path: the box lies inside the frame and its source window is staged; everything in piece-local
+            // coordinates (source column in the window = c + (du >> 5) + const, fraction = du & 31)
+            const int n_u = uw * uh;
+            const unsigned inv = (1u << 20) / (unsigned)uw + 1u;
+            const int32_t* mbase = tv.map + (size_t)(py0 - 4) * W + (px0 - 4);
+            const uint8_t* wbase = win + (py0 - 4 - wy0) * WIN_W + (px0 - 4 - wx0);
+            for (int base = tid; base < n_u; base += 4 * CL_THREADS) {
+                uint32_t m[4]; int rr[4], cc[4];
+#pragma unroll
+                for (int k = 0; k < 4; ++k) {
+                    int idx = min(base + k * CL_THREADS, n_u - 1);             // the surplus lanes redo the last pixel
+                    int r = (int)(((unsigned)idx * inv) >> 20), c = idx - r * uw;
+                    rr[k] = r; cc[k] = c;
+                    m[k] = (uint32_t)mbase[r * W + c];
+                }
+#pragma unroll
+                for (int k = 0; k < 4; ++k) {
+                    uint32_t mm = m[k];
+                    int du = (int)(int16_t)(mm & 0xffff), dv = (int)(int16_t)(mm >> 16);
+                    int fx = du & 31, fy = dv & 31;
+                    const uint8_t* p = wbase + (rr[k] + (dv >> 5)) * WIN_W + cc[k] + (du >> 5);
+                    if (mm == MAP_OUTSIDE) p = win;                            // any valid address; the value is discarded
+                    int r0 = (32 - fx) * p[0] + fx * p[1];
+                    int r1 = (32 - fx) * p[WIN_W] + fx * p[WIN_W + 1];
+                    int val = ((32 - fy) * r0 + fy * r1 + 512) >> 10;
+                    S.U[rr[k] * UW + cc[k]] = (uint8_t)(mm == MAP_OUTSIDE ? 0 : val);
+                }
+            }
+        } else {
             const int n_u = uw * uh;
             const unsigned inv = (1u << 20) / (unsigned)uw + 1u;              // idx / uw == (idx * inv) >> 20 for idx * uw < 2^20
             for (int base = tid; base < n_u; base += 4 * CL_THREADS) {
