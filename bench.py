@@ -418,7 +418,8 @@ def run_b200(args):
         pass
     det_ms = sum(stage_avg.values())
     kernels = {"scan": "scan_hot_vec_kernel", "group": "form_clusters_kernel", "filter": "piece_filter_kernel",
-               "borders": "candidates_kernel + trace_candidates_kernel", "finish": "general path (compact/filter_tiles/blobs) + finalize_kernel"}
+               "borders": "borders_finalize_kernel (border-start candidates, traces, filter/centroid/order)",
+               "finish": "general path for flagged frames (mark_active/compact_tiles/filter_tiles/blobs)"}
     roofline = {"bound": "hbm", "kernel": kernels.get(dom, dom), "stage": dom, "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
                 "traffic": traffic, "peak_source": peak_src, "algorithmic_bytes_per_launch": alg_bytes,
                 "stage_ms": stage_avg, "detect_ms": det_ms,

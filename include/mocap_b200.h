@@ -75,8 +75,8 @@ size_t mocap_detect_workspace_bytes(int n_frames, int H, int W, int max_blobs, i
 /* Optional per-stage device timing of mocap_detect_batch (bench.py's roofline line): a timer owns CUDA events that
  * the call records around its kernels on `stream`; read it after the stream has been synchronised.  Stages:
  * 0 scan (streams every source byte), 1 group (hot cells -> clusters -> 64x64 filter pieces), 2 filter (remap + floor-mean
- * threshold + majority per piece, in shared memory), 3 borders (border-start candidates + Suzuki-Abe traces), 4 finish
- * (general path for the frames that need it + per-frame filter / centroid / order).  ms_out[MOCAP_N_STAGES], -1 for a
+ * threshold + majority per piece, in shared memory), 3 borders (per frame: border-start candidates, Suzuki-Abe traces,
+ * filter / centroid / order), 4 finish (general path for the frames that need it).  ms_out[MOCAP_N_STAGES], -1 for a
  * stage that was not recorded. */
 #define MOCAP_N_STAGES 5
 void* mocap_stage_timer_create(void);

@@ -200,11 +200,6 @@ extern "C" int mocap_detect_batch(const uint8_t* frames_dev, int n_frames, int H
                       min_area, min_circ, (char*)workspace + L.off_blob, L.blob_stride,
                       out_xy, out_count, out_flags, out_blob_sums, out_blob_count, out_contours, out_contour_count,
                       out_labels, need_general, s);
-    if (st != MOCAP_OK) return st;
-    if (use_cluster)
-        st = launch_cluster_path(frames_dev, n_frames, H, W, frame_stride, tv, thresh, ws.cellbox, cl_base, L.cl_offs,
-                                 max_contours, max_blobs, min_area, min_circ, out_xy, out_count, out_flags, out_contours,
-                                 out_contour_count, true, s, timer);
     stage_end(timer, 4, s);
     return st;
 }

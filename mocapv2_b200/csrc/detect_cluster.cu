@@ -45,6 +45,7 @@ struct ClusterWs {
     unsigned rows_cap;          // words
     int* cand_list;             // [n][CAND_PER_FRAME][2]: cluster, lx | ly << 16 | type << 31
     int* cand_count;            // [n]
+    int* frame_clusters;        // [n][2]: first cluster id of the frame, number of clusters (contiguous ids)
     int n_frames;
     int* rec_count;             // [n]
     int* rec_start;             // [n][max_contours] start pixel index y * W + x of an outer border
@@ -99,6 +100,9 @@ __global__ void __launch_bounds__(CL_THREADS) form_clusters_kernel(const uint32_
     int* cbox = parent + HOT_MAX;
     short* box = (short*)(cbox + 4 * HOT_MAX);
     uint16_t* roots = (uint16_t*)(box + 4 * HOT_MAX);
+    int* r_words = (int*)(roots + ROOTS_MAX);           // per root: bit-row words, pieces, y1 of the box
+    int* r_pcs = r_words + ROOTS_MAX;
+    int* r_y1 = r_pcs + ROOTS_MAX;
     __shared__ int s_nhot, s_nroots, s_changed, s_bad;
     if (tid == 0) { s_nhot = 0; s_bad = 0; }
     for (int c = tid; c < cells; c += nt) idx_of[c] = 0xffff;
@@ -170,8 +174,9 @@ __global__ void __launch_bounds__(CL_THREADS) form_clusters_kernel(const uint32_
         for (int i = 0; i < nr; ++i) { int r = roots[i]; int c = cbox[4 * r + 3]; cbox[4 * r + 3] = acc | (c << 16); acc += c; }
     }
     __syncthreads();
-    // one thread per cluster gathers its member boxes (a few hundred hot cells per frame at most), reserves the bit rows
-    // of the cluster box and emits the filter pieces
+    // one thread per cluster gathers its member boxes (a few hundred hot cells per frame at most) and sizes its bit rows and
+    // filter pieces; the frame then reserves ONE contiguous block of cluster ids, bit-row words and pieces (three global
+    // atomics per frame instead of three per cluster)
     short* memb = cw.memb + (size_t)f * HOT_MAX * 4;
     for (int i = tid; i < nr; i += nt) {
         int r = roots[i];
@@ -184,27 +189,52 @@ __global__ void __launch_bounds__(CL_THREADS) form_clusters_kernel(const uint32_
             y1 = max(y1, (int)box[4 * h + 3]);
             ++k;
         }
-        int x0 = cbox[4 * r], y0 = cbox[4 * r + 1], x1 = cbox[4 * r + 2];
-        int mw = x1 - x0 + 1, mh = y1 - y0 + 1;
+        cbox[4 * r + 3] = off | (k << 16);
+        int mw = cbox[4 * r + 2] - cbox[4 * r] + 1, mh = y1 - cbox[4 * r + 1] + 1;
         int pbx = cdiv_dev(mw, PIECE), pby = cdiv_dev(mh, PIECE);
-        int wpr = pbx * (PIECE / 32);                                  // every piece owns whole words of the rows
-        unsigned words = (unsigned)(mh * wpr);
-        int cid = atomicAdd(&cw.counters[CN_CLUSTERS], 1);
-        if (cid >= cw.cl_cap) { s_bad = 1; continue; }
-        unsigned roff = atomicAdd((unsigned*)&cw.counters[CN_ROWS], words);
-        int* ce = cw.clusters + 8 * (size_t)cid;
-        ce[0] = f;
-        if (roff + words > cw.rows_cap) { ce[1] = 1; ce[2] = 0; ce[4] = 0; s_bad = 1; continue; }     // empty box: nothing downstream touches it
-        int p0 = atomicAdd(&cw.counters[CN_PIECES], pbx * pby);
-        if (p0 + pbx * pby > cw.pc_cap) { ce[1] = 1; ce[2] = 0; ce[4] = 0; s_bad = 1; continue; }
-        ce[1] = x0 | (y0 << 16); ce[2] = x1 | (y1 << 16); ce[3] = (int)roff; ce[4] = wpr; ce[5] = off | (k << 16); ce[6] = 0; ce[7] = 0;
-        for (int q = 0; q < pbx * pby; ++q) {
-            cw.pieces[2 * (size_t)(p0 + q)] = cid;
-            cw.pieces[2 * (size_t)(p0 + q) + 1] = (q % pbx) | ((q / pbx) << 16);
-        }
+        r_y1[i] = y1;
+        r_words[i] = mh * pbx * (PIECE / 32);           // every piece owns whole words of the rows
+        r_pcs[i] = pbx * pby;
     }
     __syncthreads();
-    if (s_bad && tid == 0) cw.need_general[f] = 5;      // out of cluster / piece / bit-row storage: general path
+    __shared__ int s_base[3];
+    if (tid == 0) {
+        unsigned tw = 0; int tp = 0;
+        for (int i = 0; i < nr; ++i) {                  // exclusive prefixes, in place
+            int w = r_words[i], pc = r_pcs[i];
+            r_words[i] = (int)tw; r_pcs[i] = tp;
+            tw += (unsigned)w; tp += pc;
+        }
+        int cid0 = atomicAdd(&cw.counters[CN_CLUSTERS], nr);
+        unsigned roff0 = atomicAdd((unsigned*)&cw.counters[CN_ROWS], tw);
+        int p00 = atomicAdd(&cw.counters[CN_PIECES], tp);
+        s_base[0] = cid0; s_base[1] = (int)roff0; s_base[2] = p00;
+        if (cid0 + nr > cw.cl_cap || roff0 + tw > cw.rows_cap || roff0 + tw < roff0 || p00 + tp > cw.pc_cap) s_bad = 1;
+    }
+    __syncthreads();
+    const int cid0 = s_base[0], p00 = s_base[2];
+    const unsigned roff0 = (unsigned)s_base[1];
+    const bool bad = s_bad != 0;
+    for (int i = tid; i < nr; i += nt) {
+        int cid = cid0 + i;
+        if (cid >= cw.cl_cap) continue;
+        int r = roots[i];
+        int x0 = cbox[4 * r], y0 = cbox[4 * r + 1], x1 = cbox[4 * r + 2], y1 = r_y1[i];
+        int pbx = cdiv_dev(x1 - x0 + 1, PIECE), pby = cdiv_dev(y1 - y0 + 1, PIECE);
+        int* ce = cw.clusters + 8 * (size_t)cid;
+        ce[0] = f;
+        if (bad) { ce[1] = 1; ce[2] = 0; ce[3] = 0; ce[4] = 0; ce[5] = 0; continue; }      // empty box: nothing downstream touches it
+        ce[1] = x0 | (y0 << 16); ce[2] = x1 | (y1 << 16); ce[3] = (int)(roff0 + (unsigned)r_words[i]); ce[4] = pbx * (PIECE / 32);
+        ce[5] = cbox[4 * r + 3]; ce[6] = 0; ce[7] = 0;
+        for (int q = 0; q < pbx * pby; ++q) {
+            cw.pieces[2 * (size_t)(p00 + r_pcs[i] + q)] = cid;
+            cw.pieces[2 * (size_t)(p00 + r_pcs[i] + q) + 1] = (q % pbx) | ((q / pbx) << 16);
+        }
+    }
+    if (tid == 0) {
+        cw.frame_clusters[2 * f] = cid0; cw.frame_clusters[2 * f + 1] = bad ? 0 : nr;
+        if (bad) cw.need_general[f] = 5;                // out of cluster / piece / bit-row storage: general path
+    }
 }
 
 // ---------------------------------------------------------------------------------------------------------
@@ -552,17 +582,15 @@ __device__ __forceinline__ bool range_all(const uint32_t* row, int lo, int hi)  
     return true;
 }
 
-__global__ void __launch_bounds__(128) candidates_kernel(ClusterWs cw)
+__device__ void frame_candidates(const ClusterWs& cw, int f)
 {
-    const int lane = threadIdx.x & 31;
-    const int warp = (blockIdx.x * blockDim.x + threadIdx.x) >> 5, nwarps = (gridDim.x * blockDim.x) >> 5;
-    const int total = min(cw.counters[CN_CLUSTERS], cw.cl_cap);
-    for (int cid = warp; cid < total; cid += nwarps) {
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5, nwarps = blockDim.x >> 5;
+    const int cid0 = cw.frame_clusters[2 * f], nr = cw.frame_clusters[2 * f + 1];
+    for (int cid = cid0 + warp; cid < cid0 + nr; cid += nwarps) {
         const int* ce = cw.clusters + 8 * (size_t)cid;
-        const int f = ce[0];
         const int cx0 = ce[1] & 0xffff, cy0 = ce[1] >> 16, cx1 = ce[2] & 0xffff, cy1 = ce[2] >> 16, wpr = ce[4];
         const int mw = cx1 - cx0 + 1, mh = cy1 - cy0 + 1;
-        if (mw <= 0 || cw.need_general[f]) continue;
+        if (mw <= 0) continue;
         const int m_off = ce[5] & 0xffff, m_cnt = ce[5] >> 16;
         const short* memb = cw.memb + ((size_t)f * HOT_MAX + m_off) * 4;
         BitImg im; im.p = cw.rows_out + (unsigned)ce[3]; im.W = mw; im.H = mh; im.WPR = wpr;
@@ -632,10 +660,8 @@ __device__ long long hole_parent_start(const BitImg& im, int lx, int ly, int ox,
 // border becomes a record of its frame; hole borders also record their blob's outer border (their parent in the contour
 // tree).  Afterwards the frame is checked for nesting (an outer border starting inside the bounding box of a hole border):
 // only then the contour tree is deeper than outer -> hole and the frame goes to the general path.
-__global__ void __launch_bounds__(128) trace_candidates_kernel(ClusterWs cw, int W, int max_contours)
+__device__ void frame_traces(const ClusterWs& cw, int f, int W, int max_contours)
 {
-    const int f = blockIdx.x;
-    if (cw.need_general[f]) return;
     __shared__ int s_holes;
     if (threadIdx.x == 0) s_holes = 0;
     __syncthreads();
@@ -649,7 +675,8 @@ __global__ void __launch_bounds__(128) trace_candidates_kernel(ClusterWs cw, int
         BitImg im; im.p = cw.rows_out + (unsigned)ce[3]; im.W = mx1 - mx0 + 1; im.H = my1 - my0 + 1; im.WPR = ce[4];
         long long st = (long long)(ly + my0) * W + (lx + mx0);
         long long a[3]; double per; int nch, ovf = 0, bbox[4];
-        int ok = trace_contour(im, lx, ly, ty ? 0 : 4, 2 * st + ty, a, &per, &nch, &ovf, mx0, my0, W, bbox);
+        int ok = im.WPR == 2 ? trace_contour64(im.p, im.H, lx, ly, ty ? 0 : 4, 2 * st + ty, a, &per, &nch, &ovf, mx0, my0, W, bbox)
+                             : trace_contour(im, lx, ly, ty ? 0 : 4, 2 * st + ty, a, &per, &nch, &ovf, mx0, my0, W, bbox);
         if (ovf) { cw.need_general[f] = 8; continue; }
         if (!ok) continue;
         long long parent = -1;
@@ -689,14 +716,12 @@ __global__ void __launch_bounds__(128) trace_candidates_kernel(ClusterWs cw, int
 // ---------------------------------------------------------------------------------------------------------
 // per frame: the reference's filter, centroid and output order on the frame's border records
 // ---------------------------------------------------------------------------------------------------------
-__global__ void __launch_bounds__(CL_THREADS) finalize_kernel(ClusterWs cw, int max_contours, int max_blobs, double min_area, double min_circ,
-                                                              int32_t* __restrict__ out_xy, int32_t* __restrict__ out_count, int32_t* __restrict__ out_flags,
-                                                              double* __restrict__ out_contours, int32_t* __restrict__ out_contour_count)
+__device__ void frame_finalize(const ClusterWs& cw, int f, uint8_t* keepv /*[max_contours], shared*/, int max_contours, int max_blobs,
+                               double min_area, double min_circ,
+                               int32_t* __restrict__ out_xy, int32_t* __restrict__ out_count, int32_t* __restrict__ out_flags,
+                               double* __restrict__ out_contours, int32_t* __restrict__ out_contour_count)
 {
-    DYN_SHARED(smraw);
-    uint8_t* keepv = (uint8_t*)smraw;                       // [max_contours]
-    const int f = blockIdx.x, tid = threadIdx.x;
-    if (cw.need_general[f]) return;                         // outputs come from the general path
+    const int tid = threadIdx.x;
     const int n = cw.rec_count[f];
     __shared__ int s_kept;
     if (tid == 0) s_kept = 0;
@@ -771,6 +796,24 @@ __global__ void __launch_bounds__(CL_THREADS) finalize_kernel(ClusterWs cw, int 
     }
 }
 
+// One CTA per frame: border-start candidates of the frame's clusters, their traces, the nesting check and -- unless the
+// frame was handed to the general path on the way -- the reference's filter / centroid / output order.
+__global__ void __launch_bounds__(CL_THREADS) borders_finalize_kernel(ClusterWs cw, int W, int max_contours, int max_blobs, double min_area, double min_circ,
+                                                                      int32_t* __restrict__ out_xy, int32_t* __restrict__ out_count, int32_t* __restrict__ out_flags,
+                                                                      double* __restrict__ out_contours, int32_t* __restrict__ out_contour_count)
+{
+    DYN_SHARED(smraw);
+    const int f = blockIdx.x;
+    if (cw.need_general[f]) return;
+    frame_candidates(cw, f);
+    __syncthreads();
+    if (cw.need_general[f]) return;                         // candidate list overflow
+    frame_traces(cw, f, W, max_contours);
+    __syncthreads();
+    if (cw.need_general[f]) return;                         // trace budget, unresolved hole parent or nested contour tree
+    frame_finalize(cw, f, (uint8_t*)smraw, max_contours, max_blobs, min_area, min_circ, out_xy, out_count, out_flags, out_contours, out_contour_count);
+}
+
 // ---------------------------------------------------------------------------------------------------------
 // host side
 // ---------------------------------------------------------------------------------------------------------
@@ -795,6 +838,7 @@ size_t cluster_ws_bytes(int n, int H, int W, int max_contours, size_t* offs /*[1
     offs[10] = take((size_t)n * CAND_PER_FRAME * 8);       // cand_list
     offs[11] = take((size_t)n * 4);                        // cand_count
     offs[12] = take((size_t)n * max_contours * 16);        // rec_info
+    offs[13] = take((size_t)n * 8);                        // frame_clusters
     return off;
 }
 
@@ -825,21 +869,18 @@ int launch_cluster_path(const uint8_t* frames, int n, int H, int W, int64_t fstr
     cw.cand_list = (int*)(ws_base + offs[10]);
     cw.cand_count = (int*)(ws_base + offs[11]);
     cw.rec_info = (int*)(ws_base + offs[12]);
+    cw.frame_clusters = (int*)(ws_base + offs[13]);
     cw.n_frames = n;
-    if (finalize_only) {
-        LAUNCH(finalize_kernel, n, CL_THREADS, (size_t)max_contours + 16, s, cw, max_contours, max_blobs, min_area, min_circ, out_xy, out_count, out_flags,
-               out_contours, out_contour_count);
-        CUDA_TRY(cudaGetLastError());
-        return MOCAP_OK;
-    }
+    (void)finalize_only;
     CUDA_TRY(cudaMemsetAsync(cw.counters, 0, 64, s));
     CUDA_TRY(cudaMemsetAsync(cw.rec_count, 0, (size_t)n * 4, s));
     CUDA_TRY(cudaMemsetAsync(cw.cand_count, 0, (size_t)n * 4, s));
+    CUDA_TRY(cudaMemsetAsync(cw.frame_clusters, 0, (size_t)n * 8, s));
     int dev = 0, sms = 148;
     cudaGetDevice(&dev);
     cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
     const int cells = tv.TX * tv.TY;
-    size_t sm_form = (size_t)((cells + 7) & ~7) * 2 + (size_t)HOT_MAX * (2 + 4 + 16 + 8) + (size_t)ROOTS_MAX * 2 + 64;
+    size_t sm_form = (size_t)((cells + 7) & ~7) * 2 + (size_t)HOT_MAX * (2 + 4 + 16 + 8) + (size_t)ROOTS_MAX * (2 + 12) + 64;
 #ifndef MOCAP_EMU
     static bool attr_done = false;
     if (!attr_done) {
@@ -854,8 +895,8 @@ int launch_cluster_path(const uint8_t* frames, int n, int H, int W, int64_t fstr
     LAUNCH(piece_filter_kernel, sms * 8, CL_THREADS, 0, s, frames, fstride, tv, thresh, cw);
     stage_end(timer, 2, s);
     stage_begin(timer, 3, s);
-    LAUNCH(candidates_kernel, sms * 8, 128, 0, s, cw);
-    LAUNCH(trace_candidates_kernel, n, 128, 0, s, cw, W, max_contours);
+    LAUNCH(borders_finalize_kernel, n, CL_THREADS, (size_t)max_contours + 16, s, cw, W, max_contours, max_blobs, min_area, min_circ,
+           out_xy, out_count, out_flags, out_contours, out_contour_count);
     stage_end(timer, 3, s);
     CUDA_TRY(cudaGetLastError());
     return MOCAP_OK;

@@ -127,3 +127,80 @@ static __device__ int trace_contour(const BitImg& im, int x, int y, int side, lo
     return 0;
 }
 
+
+// trace_contour for boxes at most 64 pixels wide (two 32-bit words per row): the three rows around the walker are kept
+// in registers as 64-bit words, so a step costs shifts and logic instead of up to six loads.  Same results.
+static __device__ int trace_contour64(const uint32_t* __restrict__ rows, int mh, int x, int y, int side, long long key0,
+                                      long long* a, double* per, int* n_chain, int* overflow, int ox, int oy, int Wabs, int* bbox)
+{
+    auto load = [&](int yy) -> unsigned long long {
+        return (unsigned)yy < (unsigned)mh ? ((unsigned long long)rows[2 * yy] | ((unsigned long long)rows[2 * yy + 1] << 32)) : 0ull;
+    };
+    auto nbr = [&](unsigned long long up, unsigned long long mid, unsigned long long dn, int xx) -> uint32_t {
+        uint32_t u, m, d;
+        if (xx) { u = (uint32_t)(up >> (xx - 1)) & 7u; m = (uint32_t)(mid >> (xx - 1)) & 7u; d = (uint32_t)(dn >> (xx - 1)) & 7u; }
+        else { u = ((uint32_t)up << 1) & 7u; m = ((uint32_t)mid << 1) & 7u; d = ((uint32_t)dn << 1) & 7u; }
+        return ((m >> 2) & 1u) | (((u >> 2) & 1u) << 1) | (((u >> 1) & 1u) << 2) | ((u & 1u) << 3) |
+               ((m & 1u) << 4) | ((d & 1u) << 5) | (((d >> 1) & 1u) << 6) | (((d >> 2) & 1u) << 7);
+    };
+    unsigned long long up = load(y - 1), mid = load(y), dn = load(y + 1);
+    if (bbox) { bbox[0] = bbox[2] = x + ox; bbox[1] = bbox[3] = y + oy; }
+    // start: clockwise search for the predecessor (see walk_init)
+    uint32_t m0 = nbr(up, mid, dn, x);
+    uint32_t rev = __brev(m0) >> 24, sh = (8 - side) & 7;
+    uint32_t r0 = (((rev | (rev << 8)) >> sh) & 0x7fu);
+    if (r0 == 0) { a[0] = a[1] = a[2] = 0; *per = 0.0; *n_chain = 1; return key0 < 0 || side == 4; }
+    int s = (side - 1 - (__ffs(r0) - 1)) & 7;
+    const int x0 = x, y0 = y, x1 = x + dir_dx(s), y1 = y + dir_dy(s);
+    long long a00 = 0, a10 = 0, a01 = 0;
+    double perim = 0.0;
+    int n = 0, prev_dir = s ^ 4;
+    bool have_v = false;
+    int vx = 0, vy = 0, fx = 0, fy = 0;
+    int wx = x, wy = y;
+    for (int step = 0; step < WALK_BUDGET; ++step) {
+        const int cx = wx + ox, cy = wy + oy;
+        uint32_t m = nbr(up, mid, dn, wx);
+        int start = (s + 1) & 7;
+        uint32_t rot = ((m | (m << 8)) >> start) & 0xffu;
+        int k = rot ? __ffs(rot) - 1 : 8;
+        int d = (start + k) & 7;
+        uint32_t z = ((1u << k) - 1u) << start;
+        uint32_t zeros = (z | (z >> 8)) & 0xffu;
+        int nx = wx + dir_dx(d), ny = wy + dir_dy(d);
+        bool done = (nx == x0 && ny == y0 && wx == x1 && wy == y1);
+        if (ny < wy) { dn = mid; mid = up; up = load(ny - 1); }
+        else if (ny > wy) { up = mid; mid = dn; dn = load(ny + 1); }
+        wx = nx; wy = ny; s = (d + 4) & 7;
+        ++n;
+        if (key0 >= 0) {
+            if ((zeros & (1u << 4)) && edge_key(cx, cy, Wabs, 0) < key0) return 0;
+            if ((zeros & (1u << 0)) && edge_key(cx, cy, Wabs, 1) < key0) return 0;
+        }
+        if (d != prev_dir) {
+            if (have_v) {
+                long long dxy = (long long)vx * cy - (long long)cx * vy;
+                a00 += dxy; a10 += dxy * (vx + cx); a01 += dxy * (vy + cy);
+                float ddx = (float)(cx - vx), ddy = (float)(cy - vy);
+                perim += (double)__fsqrt_rn(__fadd_rn(__fmul_rn(ddx, ddx), __fmul_rn(ddy, ddy)));
+            } else { fx = cx; fy = cy; have_v = true; }
+            vx = cx; vy = cy;
+            if (bbox) { bbox[0] = min(bbox[0], cx); bbox[1] = min(bbox[1], cy); bbox[2] = max(bbox[2], cx); bbox[3] = max(bbox[3], cy); }
+        }
+        prev_dir = d;
+        if (done) {
+            if (have_v) {
+                long long dxy = (long long)vx * fy - (long long)fx * vy;
+                a00 += dxy; a10 += dxy * (vx + fx); a01 += dxy * (vy + fy);
+                float ddx = (float)(fx - vx), ddy = (float)(fy - vy);
+                float q = __fadd_rn(__fmul_rn(ddx, ddx), __fmul_rn(ddy, ddy));
+                if (q > 0.f) perim += (double)__fsqrt_rn(q);
+            }
+            a[0] = a00; a[1] = a10; a[2] = a01; *per = perim; *n_chain = n;
+            return 1;
+        }
+    }
+    *overflow = 1;
+    a[0] = a[1] = a[2] = 0; *per = 0.0; *n_chain = n;
+    return 0;
+}
