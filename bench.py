@@ -264,6 +264,7 @@ def run_b200(args):
     for k in range(args.steps):
         det, corr = step(timers[k])
     ev1.record()
+    gpu_launches = eng.launches - launches0
     barrier()
     # nvidia-smi delivers a sample every ~50-100 ms and the timed region may be shorter than that: keep the same step loop
     # running (untimed) for about a second more so that the clock record is taken under this very load
@@ -280,7 +281,6 @@ def run_b200(args):
     if world > 1:
         dist.all_reduce(ms, op=dist.ReduceOp.MAX)
     ms_total = float(ms.item())
-    gpu_launches = eng.launches - launches0
     stage_ms = {}
     for t in timers:
         for k, v in eng.stage_timer_read(t).items():
@@ -418,7 +418,7 @@ def run_b200(args):
         pass
     det_ms = sum(stage_avg.values())
     kernels = {"scan": "scan_hot_vec_kernel", "group": "form_clusters_kernel", "filter": "piece_filter_kernel",
-               "borders": "borders_finalize_kernel (border-start candidates, traces, filter/centroid/order)",
+               "borders": "candidates_kernel + borders_finalize_kernel (traces, filter/centroid/order)",
                "finish": "general path for flagged frames (mark_active/compact_tiles/filter_tiles/blobs)"}
     roofline = {"bound": "hbm", "kernel": kernels.get(dom, dom), "stage": dom, "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
                 "traffic": traffic, "peak_source": peak_src, "algorithmic_bytes_per_launch": alg_bytes,

@@ -582,15 +582,17 @@ __device__ __forceinline__ bool range_all(const uint32_t* row, int lo, int hi)  
     return true;
 }
 
-__device__ void frame_candidates(const ClusterWs& cw, int f)
+__global__ void __launch_bounds__(128) candidates_kernel(ClusterWs cw)
 {
-    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5, nwarps = blockDim.x >> 5;
-    const int cid0 = cw.frame_clusters[2 * f], nr = cw.frame_clusters[2 * f + 1];
-    for (int cid = cid0 + warp; cid < cid0 + nr; cid += nwarps) {
+    const int lane = threadIdx.x & 31;
+    const int warp = (blockIdx.x * blockDim.x + threadIdx.x) >> 5, nwarps = (gridDim.x * blockDim.x) >> 5;
+    const int total = min(cw.counters[CN_CLUSTERS], cw.cl_cap);
+    for (int cid = warp; cid < total; cid += nwarps) {
         const int* ce = cw.clusters + 8 * (size_t)cid;
+        const int f = ce[0];
         const int cx0 = ce[1] & 0xffff, cy0 = ce[1] >> 16, cx1 = ce[2] & 0xffff, cy1 = ce[2] >> 16, wpr = ce[4];
         const int mw = cx1 - cx0 + 1, mh = cy1 - cy0 + 1;
-        if (mw <= 0) continue;
+        if (mw <= 0 || cw.need_general[f]) continue;
         const int m_off = ce[5] & 0xffff, m_cnt = ce[5] >> 16;
         const short* memb = cw.memb + ((size_t)f * HOT_MAX + m_off) * 4;
         BitImg im; im.p = cw.rows_out + (unsigned)ce[3]; im.W = mw; im.H = mh; im.WPR = wpr;
@@ -796,8 +798,8 @@ __device__ void frame_finalize(const ClusterWs& cw, int f, uint8_t* keepv /*[max
     }
 }
 
-// One CTA per frame: border-start candidates of the frame's clusters, their traces, the nesting check and -- unless the
-// frame was handed to the general path on the way -- the reference's filter / centroid / output order.
+// One CTA per frame: the traces of the frame's border-start candidates, the nesting check and -- unless the frame was
+// handed to the general path on the way -- the reference's filter / centroid / output order.
 __global__ void __launch_bounds__(CL_THREADS) borders_finalize_kernel(ClusterWs cw, int W, int max_contours, int max_blobs, double min_area, double min_circ,
                                                                       int32_t* __restrict__ out_xy, int32_t* __restrict__ out_count, int32_t* __restrict__ out_flags,
                                                                       double* __restrict__ out_contours, int32_t* __restrict__ out_contour_count)
@@ -805,9 +807,6 @@ __global__ void __launch_bounds__(CL_THREADS) borders_finalize_kernel(ClusterWs 
     DYN_SHARED(smraw);
     const int f = blockIdx.x;
     if (cw.need_general[f]) return;
-    frame_candidates(cw, f);
-    __syncthreads();
-    if (cw.need_general[f]) return;                         // candidate list overflow
     frame_traces(cw, f, W, max_contours);
     __syncthreads();
     if (cw.need_general[f]) return;                         // trace budget, unresolved hole parent or nested contour tree
@@ -895,6 +894,7 @@ int launch_cluster_path(const uint8_t* frames, int n, int H, int W, int64_t fstr
     LAUNCH(piece_filter_kernel, sms * 8, CL_THREADS, 0, s, frames, fstride, tv, thresh, cw);
     stage_end(timer, 2, s);
     stage_begin(timer, 3, s);
+    LAUNCH(candidates_kernel, sms * 8, 128, 0, s, cw);
     LAUNCH(borders_finalize_kernel, n, CL_THREADS, (size_t)max_contours + 16, s, cw, W, max_contours, max_blobs, min_area, min_circ,
            out_xy, out_count, out_flags, out_contours, out_contour_count);
     stage_end(timer, 3, s);

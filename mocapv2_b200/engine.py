@@ -185,8 +185,8 @@ class CaptureEngine:
                 self._ptr(ex.get("blob_count")), self._ptr(ex.get("contours")), self._ptr(ex.get("contour_count")),
                 self._ptr(ws), nbytes, self._stream(), ctypes.c_void_p(timer) if timer else ctypes.c_void_p(0))
             _cabi.check(self.lib, st, "mocap_detect_batch")
-            # scan, group, filter pieces, borders+finalize + the general path's mark / compact / tiles / blobs
-            self.launches += 8 + (1 if "bits" in ex else 0)
+            # scan, group, filter pieces, candidates, traces+finalize + the general path's mark / compact / tiles / blobs
+            self.launches += 9 + (1 if "bits" in ex else 0)
         return out
 
     def blobs(self, bits: torch.Tensor, W: int, *, min_area=MIN_AREA, min_circ=MIN_CIRC, max_blobs=None, max_contours=None,
