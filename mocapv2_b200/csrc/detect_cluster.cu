@@ -668,7 +668,23 @@ __device__ void frame_traces(const ClusterWs& cw, int f, int W, int max_contours
     if (threadIdx.x == 0) s_holes = 0;
     __syncthreads();
     const int n_cand = min(cw.cand_count[f], CAND_PER_FRAME);
+    // two dense work lists so that a warp runs ONE of the two trace loops: boxes up to 64 wide (rows cached in registers)
+    // first, the wider ones after them
+    __shared__ uint16_t s_order[CAND_PER_FRAME];
+    __shared__ int s_narrow, s_wide;
+    if (threadIdx.x == 0) { s_narrow = 0; s_wide = 0; }
+    __syncthreads();
     for (int cslot = threadIdx.x; cslot < n_cand; cslot += blockDim.x) {
+        const int* ce = cw.clusters + 8 * (size_t)cw.cand_list[2 * ((size_t)f * CAND_PER_FRAME + cslot)];
+        if (ce[4] == 2) s_order[atomicAdd(&s_narrow, 1)] = (uint16_t)cslot;
+        else s_order[CAND_PER_FRAME - 1 - atomicAdd(&s_wide, 1)] = (uint16_t)cslot;
+    }
+    __syncthreads();
+    const int n_narrow = s_narrow;
+    const int n_pad = (n_narrow + 31) & ~31;                    // the wide list starts on a warp boundary
+    for (int it = threadIdx.x; it < n_pad + (n_cand - n_narrow); it += blockDim.x) {
+        if (it >= n_narrow && it < n_pad) continue;
+        const int cslot = it < n_narrow ? s_order[it] : s_order[CAND_PER_FRAME - 1 - (it - n_pad)];
         const size_t c = (size_t)f * CAND_PER_FRAME + cslot;
         const int* ce = cw.clusters + 8 * (size_t)cw.cand_list[2 * c];
         const int code = cw.cand_list[2 * c + 1];
