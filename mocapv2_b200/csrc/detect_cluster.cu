@@ -245,7 +245,8 @@ struct __align__(16) PieceSmem {
     uint8_t U[UW * UW];            // undistorted pixels, origin (px0 - 4, py0 - 4); 0 outside the frame
     uint16_t HS[UW * BW];          // horizontal 5-sums of U (U rows x B cols)
     uint8_t B[BW * BW];            // thresholded floor-mean, origin (px0 - 2, py0 - 2)
-    uint8_t MH[BW * PIECE];        // horizontal 5-counts of B (B rows x output cols)
+    // the horizontal 5-counts of B (B rows x output cols, BW * PIECE bytes) reuse U, which is dead by then; the packed path
+    // keeps its bit planes in HS
 };
 
 __device__ __forceinline__ uint32_t maj3(uint32_t a, uint32_t b, uint32_t c) { return (a & b) | (c & (a | b)); }
@@ -271,8 +272,9 @@ __device__ __forceinline__ void piece_threshold_majority_packed(PieceSmem& S, in
     const int uh = mh + 8, bw = mw + 4, bh = mh + 4;
     // ---- A ----
     const int nq = (bw + 3) >> 2;
+    const unsigned inv_q = (1u << 20) / (unsigned)nq + 1u;                        // t / nq == (t * inv_q) >> 20 (t * nq < 2^20)
     for (int t = tid; t < uh * nq; t += CL_THREADS) {
-        int r = t / nq, q = t - r * nq;
+        int r = (int)(((unsigned)t * inv_q) >> 20), q = t - r * nq;
         const uint32_t* up = (const uint32_t*)&S.U[r * UW + 4 * q];
         uint32_t w0 = up[0], w1 = up[1];
         uint32_t s0 = (w0 & 0xff) + ((w0 >> 8) & 0xff) + ((w0 >> 16) & 0xff) + (w0 >> 24) + (w1 & 0xff);
@@ -287,8 +289,9 @@ __device__ __forceinline__ void piece_threshold_majority_packed(PieceSmem& S, in
     uint8_t* bbits = S.B;
     const int no = (bw + 7) >> 3;
     const uint32_t bias = (0x8000u - (uint32_t)(25 * T)) * 0x00010001u;          // bit 15 of (v + bias) set  <=>  v >= 25 T
+    const unsigned inv_o = (1u << 20) / (unsigned)no + 1u;
     for (int t = tid; t < bh * no; t += CL_THREADS) {
-        int r = t / no, o = t - r * no;
+        int r = (int)(((unsigned)t * inv_o) >> 20), o = t - r * no;
         uint32_t a0 = 0, a1 = 0, a2 = 0, a3 = 0;
 #pragma unroll
         for (int k = 0; k < 5; ++k) {
@@ -303,7 +306,7 @@ __device__ __forceinline__ void piece_threshold_majority_packed(PieceSmem& S, in
     }
     __syncthreads();
     // ---- C ----  horizontal 5-counts per B row as three 64-bit planes (two 32-bit halves each) in S.MH
-    uint32_t* planes = (uint32_t*)S.MH;                                           // [bh][3][2]
+    uint32_t* planes = (uint32_t*)S.HS;                                           // [bh][3][2]; HS is dead after stage B
     for (int r = tid; r < bh; r += CL_THREADS) {
         const uint32_t* bp = (const uint32_t*)&bbits[r * 16];
         uint32_t w0 = bp[0], w1 = bp[1], w2 = bp[2] & 0xffu;                      // bits 0..31, 32..63, 64..71
@@ -347,6 +350,7 @@ __device__ __forceinline__ void piece_threshold_majority(PieceSmem& S, int px0, 
                                                          uint32_t* __restrict__ out, int wpr)
 {
     constexpr int BW = PieceSmem::BW;
+    uint8_t* MH = S.U;                                             // U is dead once HS is complete
     const int tid = threadIdx.x, lane = tid & 31, wy = tid >> 5, NWARP = CL_THREADS / 32;
     const int bw = mw + 4, bh = mh + 4;
     for (int r = wy; r < bh; r += NWARP) {
@@ -367,13 +371,13 @@ __device__ __forceinline__ void piece_threshold_majority(PieceSmem& S, int px0, 
         if (INTERIOR) {
             for (int c = lane; c < mw; c += 32) {
                 const uint8_t* b = &S.B[r * BW + c];
-                S.MH[r * PIECE + c] = (uint8_t)(b[0] + b[1] + b[2] + b[3] + b[4]);
+                MH[r * PIECE + c] = (uint8_t)(b[0] + b[1] + b[2] + b[3] + b[4]);
             }
         } else {
             const uint8_t* b = &S.B[r * BW] - (px0 - 2);               // indexed by frame column
             for (int c = lane; c < mw; c += 32) {
                 int j = px0 + c;
-                S.MH[r * PIECE + c] = (uint8_t)(b[max(j - 2, 0)] + b[max(j - 1, 0)] + b[j] + b[min(j + 1, W - 1)] + b[min(j + 2, W - 1)]);
+                MH[r * PIECE + c] = (uint8_t)(b[max(j - 2, 0)] + b[max(j - 1, 0)] + b[j] + b[min(j + 1, W - 1)] + b[min(j + 2, W - 1)]);
             }
         }
     }
@@ -388,14 +392,14 @@ __device__ __forceinline__ void piece_threshold_majority(PieceSmem& S, int px0, 
 #pragma unroll
         for (int c0 = 0; c0 < PIECE; c0 += 32) {
             int c = c0 + lane, s = 0;
-            if (c < mw) s = S.MH[r0 * PIECE + c] + S.MH[r1 * PIECE + c] + S.MH[r2 * PIECE + c] + S.MH[r3 * PIECE + c] + S.MH[r4 * PIECE + c];
+            if (c < mw) s = MH[r0 * PIECE + c] + MH[r1 * PIECE + c] + MH[r2 * PIECE + c] + MH[r3 * PIECE + c] + MH[r4 * PIECE + c];
             unsigned wv = __ballot_sync(0xffffffffu, s >= 13);
             if (lane == 0) out[(size_t)r * wpr + (c0 >> 5)] = wv;
         }
     }
 }
 
-__global__ void __launch_bounds__(CL_THREADS) piece_filter_kernel(const uint8_t* __restrict__ frames, int64_t fstride, TableView tv, int thresh,
+__global__ void __launch_bounds__(CL_THREADS, 8) piece_filter_kernel(const uint8_t* __restrict__ frames, int64_t fstride, TableView tv, int thresh,
                                                                   ClusterWs cw)
 {
     __shared__ PieceSmem S;
