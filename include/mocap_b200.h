@@ -110,6 +110,9 @@ int mocap_blobs_batch(const uint32_t* bits_dev, int n_frames, int H, int W,
 int mocap_blur5_batch(const uint8_t* frames_dev, int n_frames, int H, int W, uint8_t* out_dev, void* stream);
 /* image_filter_cpu (lib/ImageOperations.py:15-21): cv.medianBlur(image, 5) then cv.threshold(., thresh, 255, BINARY) -> u8 {0,255} */
 int mocap_median5_threshold_batch(const uint8_t* frames_dev, int n_frames, int H, int W, int thresh, uint8_t* out_dev, void* stream);
+/* Bayer front step of the realtime loop: cv2.cvtColor(raw, COLOR_BAYER_GR2BGR) then cv2.cvtColor(., COLOR_BGR2GRAY)
+ * (RealtimeTracking_FLIR.py:103-104), fused: raw u8 [n][H][W] -> grey u8 [n][H][W].  H, W >= 3. */
+int mocap_bayer_gr2gray_batch(const uint8_t* raw_dev, int n_frames, int H, int W, uint8_t* out_dev, void* stream);
 /* cv.undistort alone (lib/ImageOperations.py:38), for stage parity */
 int mocap_undistort_batch(const uint8_t* frames_dev, int n_frames, int H, int W, const void* table_dev,
                           uint8_t* out_dev, void* stream);

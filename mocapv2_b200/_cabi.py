@@ -47,6 +47,7 @@ SIGNATURES = {
     "mocap_blobs_batch": (_i, [_p, _i, _i, _i, _d, _d, _i, _i, _i, _p, _p, _p, _p, _p, _p, _p, _p, _p, _sz, _p]),
     "mocap_blur5_batch": (_i, [_p, _i, _i, _i, _p, _p]),
     "mocap_median5_threshold_batch": (_i, [_p, _i, _i, _i, _i, _p, _p]),
+    "mocap_bayer_gr2gray_batch": (_i, [_p, _i, _i, _i, _p, _p]),
     "mocap_undistort_batch": (_i, [_p, _i, _i, _i, _p, _p, _p]),
     "mocap_triangulate_batch": (_i, [_p, _p, _p, _i, _i64, _i, _p, _p, _p]),
     "mocap_reproject_batch": (_i, [_p, _p, _p, _p, _i, _i64, _i, _p, _p]),

@@ -687,6 +687,37 @@ extern "C" int mocap_median5_threshold_batch(const uint8_t* frames_dev, int n, i
     return MOCAP_OK;
 }
 
+// Bayer front step of the realtime loop (RealtimeTracking_FLIR.py:103-104): cvtColor(BAYER_GR2BGR) -> cvtColor(BGR2GRAY),
+// fused: raw sensor bytes in, grey bytes out, no BGR intermediate.  Red on (odd row, even column), blue on (even row, odd
+// column); OpenCV's bilinear means ((a+b+1)>>1, (a+b+c+d+2)>>2), border rows / columns copy their inner neighbour;
+// grey = (9798 R + 19235 G + 3735 B + 16384) >> 15.  One thread per output pixel; neighbours come through L1.
+__global__ void bayer_gr2gray_kernel(const uint8_t* __restrict__ in, int n, int H, int W, uint8_t* __restrict__ out)
+{
+    int x = blockIdx.x * blockDim.x + threadIdx.x, y = blockIdx.y * blockDim.y + threadIdx.y, f = blockIdx.z;
+    if (x >= W || y >= H) return;
+    const uint8_t* fr = in + (size_t)f * H * W;
+    int yc = min(max(y, 1), H - 2), xc = min(max(x, 1), W - 2);
+    const uint8_t* p = fr + (size_t)yc * W + xc;
+    int c = p[0], l = p[-1], r = p[1], u = p[-W], d = p[W];
+    int ul = p[-W - 1], ur = p[-W + 1], dl = p[W - 1], dr = p[W + 1];
+    int cross = (u + d + l + r + 2) >> 2, diag = (ul + ur + dl + dr + 2) >> 2, hor = (l + r + 1) >> 1, ver = (u + d + 1) >> 1;
+    bool odd_row = yc & 1, odd_col = xc & 1;
+    int R, G, B;
+    if (odd_row && !odd_col) { R = c; G = cross; B = diag; }            // red site
+    else if (!odd_row && odd_col) { B = c; G = cross; R = diag; }       // blue site
+    else if (odd_row) { G = c; R = hor; B = ver; }                      // green on a red row
+    else { G = c; B = hor; R = ver; }                                   // green on a blue row
+    out[(size_t)f * H * W + (size_t)y * W + x] = (uint8_t)((R * 9798 + G * 19235 + B * 3735 + 16384) >> 15);
+}
+
+extern "C" int mocap_bayer_gr2gray_batch(const uint8_t* raw_dev, int n, int H, int W, uint8_t* out_dev, void* stream)
+{
+    if (!raw_dev || !out_dev || n <= 0 || H < 3 || W < 3 || n > 65535) return MOCAP_ERR_INVALID;
+    LAUNCH(bayer_gr2gray_kernel, dim3(cdiv(W, 64), cdiv(H, 4), n), dim3(64, 4), 0, (cudaStream_t)stream, raw_dev, n, H, W, out_dev);
+    CUDA_TRY(cudaGetLastError());
+    return MOCAP_OK;
+}
+
 __global__ void undistort_kernel(const uint8_t* __restrict__ in, int n, int H, int W, const int32_t* __restrict__ map,
                                  uint8_t* __restrict__ out)
 {

@@ -255,6 +255,16 @@ class CaptureEngine:
         self.launches += 1
         return out
 
+    def bayer_gr2gray(self, raw: torch.Tensor) -> torch.Tensor:
+        """cvtColor(BAYER_GR2BGR) -> cvtColor(BGR2GRAY) (RealtimeTracking_FLIR.py:103-104) for raw sensor frames [n, H, W] uint8."""
+        raw = self._check_dev(raw.contiguous(), torch.uint8, "raw")
+        n, H, W = raw.shape
+        out = torch.empty_like(raw)
+        _cabi.check(self.lib, self.lib.mocap_bayer_gr2gray_batch(self._ptr(raw), n, H, W, self._ptr(out), self._stream()),
+                    "mocap_bayer_gr2gray_batch")
+        self.launches += 1
+        return out
+
     def undistort(self, frames: torch.Tensor, K, dist) -> torch.Tensor:
         """cv.undistort(img, K, dist) (lib/ImageOperations.py:38) for a batch [n, H, W] uint8."""
         frames = self._check_dev(frames.contiguous(), torch.uint8, "frames")

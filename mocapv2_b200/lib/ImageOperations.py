@@ -38,6 +38,13 @@ def _to_device(img, eng):
     return torch.from_numpy(a)[None].to(eng.device, non_blocking=False)
 
 
+def bayer_gr_to_gray(image):
+    """The two cv2.cvtColor calls in front of _find_dot in the realtime loop (RealtimeTracking_FLIR.py:103-104), on the GPU:
+    raw BayerGR sensor frame (H, W) uint8 -> grey (H, W) uint8, bit-identical to OpenCV's."""
+    eng = _engine.default_engine()
+    return eng.bayer_gr2gray(_to_device(image, eng))[0].cpu().numpy()
+
+
 def image_filter_cpu(image, camera_number=0):
     """medianBlur(5) -> threshold(255*0.85): uint8 {0,255} image (lib/ImageOperations.py:15-21; no callers in the reference).
 

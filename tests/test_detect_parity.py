@@ -60,6 +60,16 @@ def test_stage_undistort_and_blur(engine):
         assert np.array_equal(blur, R.blur5_floor(img))
 
 
+@pytest.mark.parametrize("shape", [(3, 3), (7, 10), (33, 65), (120, 160)])
+def test_bayer_front_step(engine, shape):
+    """cvtColor(BAYER_GR2BGR) -> cvtColor(BGR2GRAY) in front of _find_dot (RealtimeTracking_FLIR.py:103-104), fused."""
+    rng = np.random.default_rng(shape[0])
+    raw = rng.integers(0, 256, (2,) + shape).astype(np.uint8)
+    got = engine.bayer_gr2gray(dev(engine, raw)).cpu().numpy()
+    for i in range(2):
+        assert np.array_equal(got[i], R.bayer_gr_to_gray(raw[i]))
+
+
 def test_filter_matches_reference_bits(engine):
     """undistort -> blur -> threshold -> median: the packed binary image equals what cv2 produced in the reference run."""
     z = np.load(os.path.join(GOLDEN, "c1_frames.npz"))

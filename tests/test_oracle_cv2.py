@@ -95,3 +95,13 @@ def test_dlt_matches_scipy_svd():
         _, _, Vh = linalg.svd(A.T @ A, full_matrices=False)
         ref = Vh[3, 0:3] / Vh[3, 3]
         assert np.allclose(R.triangulate_point(pts, Ps), ref, rtol=1e-9, atol=1e-12)
+
+
+@pytest.mark.parametrize("shape", [(3, 5), (4, 4), (20, 27), (21, 26), (480, 640)])
+def test_bayer_front_step(shape):
+    """RealtimeTracking_FLIR.py:103-104: cvtColor(BAYER_GR2BGR) then cvtColor(BGR2GRAY)."""
+    rng = np.random.default_rng(shape[1])
+    raw = rng.integers(0, 256, shape).astype(np.uint8)
+    bgr = cv2.cvtColor(raw, cv2.COLOR_BAYER_GR2BGR)
+    assert np.array_equal(R.bayer_gr_to_bgr(raw), bgr)
+    assert np.array_equal(R.bayer_gr_to_gray(raw), cv2.cvtColor(bgr, cv2.COLOR_BGR2GRAY))
