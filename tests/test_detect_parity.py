@@ -290,6 +290,22 @@ def test_big_frames_reference_golden(gpu_engine, idx):
 
 
 @pytest.mark.gpu
+def test_frame_larger_than_the_cluster_path_limit(gpu_engine):
+    """More than 8192 source cells (here 4100 x 3000, also not a multiple of 16 wide: scalar scan): every frame takes the
+    general path; same results as the oracle."""
+    rng = np.random.default_rng(8)
+    H, W = 3000, 4100
+    img = rng.integers(0, 40, (H, W)).astype(np.uint8)
+    yy, xx = np.mgrid[0:H, 0:W]
+    for _ in range(12):
+        cx, cy, r = int(rng.integers(50, W - 50)), int(rng.integers(50, H - 50)), int(rng.integers(14, 24))
+        img[(xx - cx) ** 2 + (yy - cy) ** 2 <= r * r] = 255
+    res = gpu_engine.detect(dev(gpu_engine, img[None]), K, D)
+    assert int(res.flags[0]) & 64 and int(res.flags[0]) & 63 == 0
+    assert res.points(0) == R.find_dot(img, K, D)
+
+
+@pytest.mark.gpu
 @pytest.mark.parametrize("name,n", [("c3", 96), ("c4", 48)])
 def test_full_size_batches_against_oracle_sample(gpu_engine, name, n):
     """Device-rendered batches at the BASELINE sizes: oracle on a sample of frames, batch invariance on all of them."""
