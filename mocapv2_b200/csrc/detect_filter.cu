@@ -269,17 +269,17 @@ __global__ void __launch_bounds__(256, 4) scan_hot_vec_kernel(const uint8_t* __r
                                                               TableView tv, uint32_t add, uint32_t* __restrict__ cellbox)
 {
     const int lane = threadIdx.x & 31;
-    const long long warp = ((long long)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
-    const long long nwarps = ((long long)gridDim.x * blockDim.x) >> 5;
+    const unsigned warp = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+    const unsigned nwarps = (gridDim.x * blockDim.x) >> 5;
     const int H = tv.H, W = tv.W;
-    const int CXB = (tv.TX + 3) >> 2;
-    const long long per_frame = (long long)tv.TY * CXB;
-    const long long total = per_frame * n_frames;
+    const unsigned CXB = (unsigned)(tv.TX + 3) >> 2;
+    const unsigned per_frame = (unsigned)tv.TY * CXB;
+    const unsigned total = per_frame * (unsigned)n_frames;         // < 2^31: the work-list codes of the library are 32-bit anyway
     const int seg = lane & 7, r0 = lane >> 3;
-    for (long long it = warp; it < total; it += nwarps) {
+    for (unsigned it = warp; it < total; it += nwarps) {
         int f = (int)(it / per_frame);
-        int rem = (int)(it - (long long)f * per_frame);
-        int cy = rem / CXB, cxb = rem - cy * CXB;
+        int rem = (int)(it - (unsigned)f * per_frame);
+        int cy = rem / (int)CXB, cxb = rem - cy * (int)CXB;
         int x = cxb * 128 + seg * 16;
         const uint8_t* base = frames + (size_t)f * fstride + (size_t)(cy * 32 + r0) * W + x;
         bool colok = x < W;
