@@ -404,7 +404,7 @@ __global__ void __launch_bounds__(CL_THREADS, 8) piece_filter_kernel(const uint8
 {
     __shared__ PieceSmem S;
     __align__(16) __shared__ uint8_t win[WIN_W * WIN_H];           // staged source window
-    __shared__ int s_win[4];
+    __shared__ int s_win[5];
     constexpr int UW = PieceSmem::UW, BW = PieceSmem::BW;
     __shared__ int s_item;
     const bool vec_ok = (tv.W % 16 == 0) && (fstride % 16 == 0) && (((uintptr_t)frames) % 16 == 0);
@@ -448,13 +448,16 @@ __global__ void __launch_bounds__(CL_THREADS, 8) piece_filter_kernel(const uint8
                 int wx0 = (px0 - 4 + dx0) & ~15, wx1 = px1 + 4 + dx1 + 1, wy0 = py0 - 4 + dy0, wy1 = py1 + 4 + dy1 + 1;
                 bool ok = vec_ok && dx0 <= dx1 && wx1 - wx0 + 1 <= WIN_W && wy1 - wy0 + 1 <= WIN_H;
                 s_win[0] = wx0; s_win[1] = wy0; s_win[2] = ok ? wy1 - wy0 + 1 : 0; s_win[3] = ok;
+                s_win[4] = ok ? (wx1 - wx0 + 16) >> 4 : 0;                  // 16-byte vectors per window row actually needed
             }
         }
         __syncthreads();
         const int wx0 = s_win[0], wy0 = s_win[1], wh = s_win[2];
         const bool staged = s_win[3] != 0;
-        for (int idx = tid; idx < wh * (WIN_W / 16); idx += CL_THREADS) {
-            int row = idx / (WIN_W / 16), v = idx - row * (WIN_W / 16);
+        const int nvec = s_win[4];
+        const unsigned inv_v = nvec ? (1u << 16) / (unsigned)nvec + 1u : 0u;        // idx / nvec for idx * nvec < 2^16
+        for (int idx = tid; idx < wh * nvec; idx += CL_THREADS) {
+            int row = (int)(((unsigned)idx * inv_v) >> 16), v = idx - row * nvec;
             int gy = wy0 + row, gx = wx0 + 16 * v;
             uint4 val = make_uint4(0, 0, 0, 0);
             if ((unsigned)gy < (unsigned)H && gx >= 0 && gx + 16 <= W) val = *(const uint4*)(fr + (size_t)gy * W + gx);
@@ -680,7 +683,7 @@ __device__ void frame_traces(const ClusterWs& cw, int f, int W, int max_contours
     __syncthreads();
     for (int cslot = threadIdx.x; cslot < n_cand; cslot += blockDim.x) {
         const int* ce = cw.clusters + 8 * (size_t)cw.cand_list[2 * ((size_t)f * CAND_PER_FRAME + cslot)];
-        if (ce[4] == 2) s_order[atomicAdd(&s_narrow, 1)] = (uint16_t)cslot;
+        if (ce[4] == 2 && (ce[2] >> 16) - (ce[1] >> 16) < 1024) s_order[atomicAdd(&s_narrow, 1)] = (uint16_t)cslot;
         else s_order[CAND_PER_FRAME - 1 - atomicAdd(&s_wide, 1)] = (uint16_t)cslot;
     }
     __syncthreads();
@@ -697,7 +700,7 @@ __device__ void frame_traces(const ClusterWs& cw, int f, int W, int max_contours
         BitImg im; im.p = cw.rows_out + (unsigned)ce[3]; im.W = mx1 - mx0 + 1; im.H = my1 - my0 + 1; im.WPR = ce[4];
         long long st = (long long)(ly + my0) * W + (lx + mx0);
         long long a[3]; double per; int nch, ovf = 0, bbox[4];
-        int ok = im.WPR == 2 ? trace_contour64(im.p, im.H, lx, ly, ty ? 0 : 4, 2 * st + ty, a, &per, &nch, &ovf, mx0, my0, W, bbox)
+        int ok = it < n_narrow ? trace_contour64(im.p, im.H, lx, ly, ty ? 0 : 4, 2 * st + ty, a, &per, &nch, &ovf, mx0, my0, W, bbox)
                              : trace_contour(im, lx, ly, ty ? 0 : 4, 2 * st + ty, a, &per, &nch, &ovf, mx0, my0, W, bbox);
         if (ovf) { cw.need_general[f] = 8; continue; }
         if (!ok) continue;

@@ -128,8 +128,14 @@ static __device__ int trace_contour(const BitImg& im, int x, int y, int side, lo
 }
 
 
-// trace_contour for boxes at most 64 pixels wide (two 32-bit words per row): the three rows around the walker are kept
-// in registers as 64-bit words, so a step costs shifts and logic instead of up to six loads.  Same results.
+// trace_contour for boxes at most 64 pixels wide and 1024 high (two 32-bit words per row).  Same results, cheaper steps:
+//  * the three rows around the walker live in registers as 64-bit words: a step is shifts and logic, one 8-byte load when
+//    the walker changes row;
+//  * Green sums over box-local vertex coordinates with 32-bit products (|dxy| < 2^16, factor < 2^11), translated at the end:
+//    a10 = a10' + 3 ox a00, a01 = a01' + 3 oy a00 (exact integer identity for a closed polygon);
+//  * perimeter: CHAIN_APPROX_SIMPLE segments are axis-parallel (length = an integer, exact in float32) or diagonal
+//    (length = float32 sqrt(2 k^2)); the double sum of such float32 values is exact in any order, so axis lengths are summed
+//    as integers, unit diagonals are counted, longer diagonals added one by one.
 static __device__ int trace_contour64(const uint32_t* __restrict__ rows, int mh, int x, int y, int side, long long key0,
                                       long long* a, double* per, int* n_chain, int* overflow, int ox, int oy, int Wabs, int* bbox)
 {
@@ -152,14 +158,19 @@ static __device__ int trace_contour64(const uint32_t* __restrict__ rows, int mh,
     if (r0 == 0) { a[0] = a[1] = a[2] = 0; *per = 0.0; *n_chain = 1; return key0 < 0 || side == 4; }
     int s = (side - 1 - (__ffs(r0) - 1)) & 7;
     const int x0 = x, y0 = y, x1 = x + dir_dx(s), y1 = y + dir_dy(s);
+    // edge keys in 32 bits: key = 2 * (row * Wabs + col) + east; the frame sizes the library accepts keep this below 2^31
+    const int kbase = 2 * (oy * Wabs + ox);
+    const int key0i = (int)key0;
     long long a00 = 0, a10 = 0, a01 = 0;
-    double perim = 0.0;
+    int axis_len = 0, n_diag1 = 0;
+    double perim_long = 0.0;
     int n = 0, prev_dir = s ^ 4;
     bool have_v = false;
-    int vx = 0, vy = 0, fx = 0, fy = 0;
+    int vx = 0, vy = 0, fx = 0, fy = 0;          // previous / first vertex, box-local
+    int bx0 = x, bx1 = x, by0 = y, by1 = y;
     int wx = x, wy = y;
     for (int step = 0; step < WALK_BUDGET; ++step) {
-        const int cx = wx + ox, cy = wy + oy;
+        const int cx = wx, cy = wy;
         uint32_t m = nbr(up, mid, dn, wx);
         int start = (s + 1) & 7;
         uint32_t rot = ((m | (m << 8)) >> start) & 0xffu;
@@ -173,30 +184,37 @@ static __device__ int trace_contour64(const uint32_t* __restrict__ rows, int mh,
         else if (ny > wy) { up = mid; mid = dn; dn = load(ny + 1); }
         wx = nx; wy = ny; s = (d + 4) & 7;
         ++n;
-        if (key0 >= 0) {
-            if ((zeros & (1u << 4)) && edge_key(cx, cy, Wabs, 0) < key0) return 0;
-            if ((zeros & (1u << 0)) && edge_key(cx, cy, Wabs, 1) < key0) return 0;
+        if (key0 >= 0 && (zeros & 0x11u)) {
+            int kk = kbase + 2 * (cy * Wabs + cx);
+            if ((zeros & (1u << 4)) && kk < key0i) return 0;
+            if ((zeros & (1u << 0)) && kk + 1 < key0i) return 0;
         }
         if (d != prev_dir) {
             if (have_v) {
-                long long dxy = (long long)vx * cy - (long long)cx * vy;
+                int dxy = vx * cy - cx * vy;
                 a00 += dxy; a10 += dxy * (vx + cx); a01 += dxy * (vy + cy);
-                float ddx = (float)(cx - vx), ddy = (float)(cy - vy);
-                perim += (double)__fsqrt_rn(__fadd_rn(__fmul_rn(ddx, ddx), __fmul_rn(ddy, ddy)));
+                int adx = abs(cx - vx), ady = abs(cy - vy);
+                if (adx == 0 || ady == 0) axis_len += adx + ady;
+                else if (adx == 1) ++n_diag1;
+                else perim_long += (double)__fsqrt_rn((float)(2 * adx * adx));
             } else { fx = cx; fy = cy; have_v = true; }
             vx = cx; vy = cy;
-            if (bbox) { bbox[0] = min(bbox[0], cx); bbox[1] = min(bbox[1], cy); bbox[2] = max(bbox[2], cx); bbox[3] = max(bbox[3], cy); }
+            bx0 = min(bx0, cx); bx1 = max(bx1, cx); by0 = min(by0, cy); by1 = max(by1, cy);
         }
         prev_dir = d;
         if (done) {
             if (have_v) {
-                long long dxy = (long long)vx * fy - (long long)fx * vy;
+                int dxy = vx * fy - fx * vy;
                 a00 += dxy; a10 += dxy * (vx + fx); a01 += dxy * (vy + fy);
-                float ddx = (float)(fx - vx), ddy = (float)(fy - vy);
-                float q = __fadd_rn(__fmul_rn(ddx, ddx), __fmul_rn(ddy, ddy));
-                if (q > 0.f) perim += (double)__fsqrt_rn(q);
+                int adx = abs(fx - vx), ady = abs(fy - vy);
+                if (adx == 0 || ady == 0) axis_len += adx + ady;
+                else if (adx == 1) ++n_diag1;
+                else perim_long += (double)__fsqrt_rn((float)(2 * adx * adx));
             }
-            a[0] = a00; a[1] = a10; a[2] = a01; *per = perim; *n_chain = n;
+            a[0] = a00; a[1] = a10 + 3LL * ox * a00; a[2] = a01 + 3LL * oy * a00;
+            *per = (double)axis_len + (double)n_diag1 * (double)__fsqrt_rn(2.0f) + perim_long;
+            *n_chain = n;
+            if (bbox) { bbox[0] = bx0 + ox; bbox[1] = by0 + oy; bbox[2] = bx1 + ox; bbox[3] = by1 + oy; }
             return 1;
         }
     }

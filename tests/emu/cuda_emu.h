@@ -216,6 +216,7 @@ static inline unsigned __vsetgtu4_emu(unsigned a, unsigned b)
     for (int k = 0; k < 4; ++k) if (((a >> (8 * k)) & 0xff) > ((b >> (8 * k)) & 0xff)) r |= 0xffu << (8 * k);
     return r;
 }
+using std::abs;
 using std::max;
 using std::min;
 static inline long long min(long long a, int b) { return a < b ? a : b; }
