@@ -322,6 +322,84 @@ __global__ void __launch_bounds__(256, 4) scan_hot_vec_kernel(const uint8_t* __r
     }
 }
 
+// 32 bytes per lane with one 256-bit load (sm_100: LDG.E.256) that also carries the L2 evict-first priority: the frames
+// are read exactly once per batch, so they should not push the undistortion map and the clusters' bit rows out of L2.
+struct uint8w { uint32_t w[8]; };
+__device__ __forceinline__ uint8w ldg_stream32(const void* p)
+{
+    uint8w r;
+#ifdef MOCAP_EMU
+    memcpy(&r, p, 32);
+#else
+    asm volatile("ld.global.nc.L1::no_allocate.L2::evict_first.v8.b32 {%0,%1,%2,%3,%4,%5,%6,%7}, [%8];"
+                 : "=r"(r.w[0]), "=r"(r.w[1]), "=r"(r.w[2]), "=r"(r.w[3]), "=r"(r.w[4]), "=r"(r.w[5]), "=r"(r.w[6]), "=r"(r.w[7]) : "l"(p));
+#endif
+    return r;
+}
+
+// Same as scan_hot_vec_kernel for rows that are 32-byte aligned: lane = (row & 7, 32-byte segment = one source cell)
+template <int MODE>
+__global__ void __launch_bounds__(256, 4) scan_hot_vec32_kernel(const uint8_t* __restrict__ frames, int n_frames, int64_t fstride,
+                                                                TableView tv, uint32_t add, uint32_t* __restrict__ cellbox)
+{
+    const int lane = threadIdx.x & 31;
+    const unsigned warp = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+    const unsigned nwarps = (gridDim.x * blockDim.x) >> 5;
+    const int H = tv.H, W = tv.W;
+    const unsigned CXB = (unsigned)(tv.TX + 3) >> 2;
+    const unsigned per_frame = (unsigned)tv.TY * CXB;
+    const unsigned total = per_frame * (unsigned)n_frames;
+    const int seg = lane & 3, r0 = lane >> 2;
+    for (unsigned it = warp; it < total; it += nwarps) {
+        int f = (int)(it / per_frame);
+        int rem = (int)(it - (unsigned)f * per_frame);
+        int cy = rem / (int)CXB, cxb = rem - cy * (int)CXB;
+        int x = cxb * 128 + seg * 32;
+        const uint8_t* base = frames + (size_t)f * fstride + (size_t)(cy * 32 + r0) * W + x;
+        bool colok = x < W;
+        uint32_t acc = 0;
+        uint8w v[4];
+#pragma unroll
+        for (int k = 0; k < 4; ++k) {
+            int row = cy * 32 + k * 8 + r0;
+            if (colok && row < H) v[k] = ldg_stream32(base + (size_t)(k * 8) * W);
+            else {
+#pragma unroll
+                for (int q = 0; q < 8; ++q) v[k].w[q] = 0;
+            }
+        }
+#pragma unroll
+        for (int k = 0; k < 4; ++k)
+#pragma unroll
+            for (int q = 0; q < 8; ++q) acc |= hot4<MODE>(v[k].w[q], add);
+        bool hot = (acc & 0x80808080u) != 0;
+        unsigned m = __ballot_sync(0xffffffffu, hot);
+        uint32_t box = CELL_EMPTY;
+        if (m) {                                            // warp-uniform: some cell of this block is hot
+            uint32_t colmask = 0, rowbits = 0;              // lane-local: hot columns of the cell (32 bits), hot rows (bit 8k + r0)
+#pragma unroll
+            for (int k = 0; k < 4; ++k) {
+                uint32_t c = 0;
+#pragma unroll
+                for (int q = 0; q < 8; ++q) c |= hot_nibble(hot4<MODE>(v[k].w[q], add)) << (4 * q);
+                colmask |= c;
+                if (c) rowbits |= 1u << (8 * k + r0);
+            }
+#pragma unroll
+            for (int c = 0; c < 4; ++c) {
+                bool mine = seg == c;
+                uint32_t xm = __reduce_or_sync(0xffffffffu, mine ? colmask : 0u);
+                uint32_t ym = __reduce_or_sync(0xffffffffu, mine ? rowbits : 0u);
+                if (lane == c) box = pack_cellbox(xm, ym);
+            }
+        }
+        if (lane < 4) {
+            int cx = cxb * 4 + lane;
+            if (cx < tv.TX) cellbox[((size_t)f * tv.TY + cy) * tv.TX + cx] = box;
+        }
+    }
+}
+
 // Generic (any W / alignment) variant: one warp per source cell, byte loads.
 __global__ void scan_hot_scalar_kernel(const uint8_t* __restrict__ frames, int n_frames, int64_t fstride,
                                        TableView tv, int thresh, uint32_t* __restrict__ cellbox)
@@ -582,9 +660,18 @@ int launch_scan(const uint8_t* frames, int n, int H, int W, int64_t fstride, con
     cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
     HotTest ht = make_hot_test(thresh);
     bool vec = (W % 16 == 0) && (fstride % 16 == 0) && (((uintptr_t)frames) % 16 == 0);
+    bool vec32 = (W % 32 == 0) && (fstride % 32 == 0) && (((uintptr_t)frames) % 32 == 0);
     stage_begin(timer, 0, s);
-    if (vec) {
+    if (vec32) {
         int grid = sms * 4;                      // persistent: exactly the resident CTAs (__launch_bounds__(256, 4)), one wave
+        switch (ht.mode) {
+            case 0: LAUNCH(scan_hot_vec32_kernel<0>, grid, 256, 0, s, frames, n, fstride, tv, ht.add, ws.cellbox); break;
+            case 1: LAUNCH(scan_hot_vec32_kernel<1>, grid, 256, 0, s, frames, n, fstride, tv, ht.add, ws.cellbox); break;
+            case 2: LAUNCH(scan_hot_vec32_kernel<2>, grid, 256, 0, s, frames, n, fstride, tv, ht.add, ws.cellbox); break;
+            default: LAUNCH(scan_hot_vec32_kernel<3>, grid, 256, 0, s, frames, n, fstride, tv, ht.add, ws.cellbox); break;
+        }
+    } else if (vec) {
+        int grid = sms * 4;
         switch (ht.mode) {
             case 0: LAUNCH(scan_hot_vec_kernel<0>, grid, 256, 0, s, frames, n, fstride, tv, ht.add, ws.cellbox); break;
             case 1: LAUNCH(scan_hot_vec_kernel<1>, grid, 256, 0, s, frames, n, fstride, tv, ht.add, ws.cellbox); break;
