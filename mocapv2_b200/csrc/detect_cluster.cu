@@ -675,23 +675,41 @@ __device__ void frame_traces(const ClusterWs& cw, int f, int W, int max_contours
     if (threadIdx.x == 0) s_holes = 0;
     __syncthreads();
     const int n_cand = min(cw.cand_count[f], CAND_PER_FRAME);
-    // two dense work lists so that a warp runs ONE of the two trace loops: boxes up to 64 wide (rows cached in registers)
-    // first, the wider ones after them
-    __shared__ uint16_t s_order[CAND_PER_FRAME];
-    __shared__ int s_narrow, s_wide;
-    if (threadIdx.x == 0) { s_narrow = 0; s_wide = 0; }
+    // Work order: a warp traces 32 borders in lockstep, so its time is its longest border.  The candidates are therefore
+    // counting-sorted by the size of their cluster box (a proxy for the border length), boxes up to 64 wide (rows cached in
+    // registers, trace_contour64) first and the wider ones (generic loop) after them, starting on a warp boundary.
+    __shared__ uint16_t s_order[CAND_PER_FRAME + 32];          // + the padding between the two lists
+    __shared__ int s_bucket[34];
+    if (threadIdx.x < 34) s_bucket[threadIdx.x] = 0;
     __syncthreads();
-    for (int cslot = threadIdx.x; cslot < n_cand; cslot += blockDim.x) {
-        const int* ce = cw.clusters + 8 * (size_t)cw.cand_list[2 * ((size_t)f * CAND_PER_FRAME + cslot)];
-        if (ce[4] == 2 && (ce[2] >> 16) - (ce[1] >> 16) < 1024) s_order[atomicAdd(&s_narrow, 1)] = (uint16_t)cslot;
-        else s_order[CAND_PER_FRAME - 1 - atomicAdd(&s_wide, 1)] = (uint16_t)cslot;
+    auto bucket_of = [&](const int* ce) -> int {
+        int mw = (ce[2] & 0xffff) - (ce[1] & 0xffff) + 1, mh = (ce[2] >> 16) - (ce[1] >> 16) + 1;
+        bool narrow = ce[4] == 2 && mh <= 1024;
+        int b = min((mw + mh) >> 4, 15);
+        return narrow ? b : 16 + b;
+    };
+    for (int cslot = threadIdx.x; cslot < n_cand; cslot += blockDim.x)
+        atomicAdd(&s_bucket[1 + bucket_of(cw.clusters + 8 * (size_t)cw.cand_list[2 * ((size_t)f * CAND_PER_FRAME + cslot)])], 1);
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        int acc = 0;
+        for (int b = 1; b <= 32; ++b) { int c = s_bucket[b]; s_bucket[b] = acc; acc += c; if (b == 16) { s_bucket[33] = acc; acc = (acc + 31) & ~31; } }
+        // s_bucket[1 + b] = start of bucket b; the wide buckets (16..31) start on a warp boundary; s_bucket[33] = #narrow
+        s_bucket[0] = acc;                                       // padded total
     }
     __syncthreads();
-    const int n_narrow = s_narrow;
-    const int n_pad = (n_narrow + 31) & ~31;                    // the wide list starts on a warp boundary
-    for (int it = threadIdx.x; it < n_pad + (n_cand - n_narrow); it += blockDim.x) {
-        if (it >= n_narrow && it < n_pad) continue;
-        const int cslot = it < n_narrow ? s_order[it] : s_order[CAND_PER_FRAME - 1 - (it - n_pad)];
+    const int n_narrow = s_bucket[33], n_pad = (n_narrow + 31) & ~31, n_total = s_bucket[0];
+    for (int i = threadIdx.x; i < CAND_PER_FRAME + 32; i += blockDim.x) s_order[i] = 0xffff;
+    __syncthreads();
+    for (int cslot = threadIdx.x; cslot < n_cand; cslot += blockDim.x) {
+        int b = bucket_of(cw.clusters + 8 * (size_t)cw.cand_list[2 * ((size_t)f * CAND_PER_FRAME + cslot)]);
+        int pos = atomicAdd(&s_bucket[1 + b], 1);
+        s_order[pos] = (uint16_t)cslot;                          // pos < n_cand + 31 <= CAND_PER_FRAME + 31
+    }
+    __syncthreads();
+    for (int it = threadIdx.x; it < n_total; it += blockDim.x) {
+        const int cslot = s_order[it];
+        if (cslot == 0xffff) continue;                           // padding between the two lists
         const size_t c = (size_t)f * CAND_PER_FRAME + cslot;
         const int* ce = cw.clusters + 8 * (size_t)cw.cand_list[2 * c];
         const int code = cw.cand_list[2 * c + 1];
@@ -700,7 +718,7 @@ __device__ void frame_traces(const ClusterWs& cw, int f, int W, int max_contours
         BitImg im; im.p = cw.rows_out + (unsigned)ce[3]; im.W = mx1 - mx0 + 1; im.H = my1 - my0 + 1; im.WPR = ce[4];
         long long st = (long long)(ly + my0) * W + (lx + mx0);
         long long a[3]; double per; int nch, ovf = 0, bbox[4];
-        int ok = it < n_narrow ? trace_contour64(im.p, im.H, lx, ly, ty ? 0 : 4, 2 * st + ty, a, &per, &nch, &ovf, mx0, my0, W, bbox)
+        int ok = it < n_pad ? trace_contour64(im.p, im.H, lx, ly, ty ? 0 : 4, 2 * st + ty, a, &per, &nch, &ovf, mx0, my0, W, bbox)
                              : trace_contour(im, lx, ly, ty ? 0 : 4, 2 * st + ty, a, &per, &nch, &ovf, mx0, my0, W, bbox);
         if (ovf) { cw.need_general[f] = 8; continue; }
         if (!ok) continue;
