@@ -290,6 +290,38 @@ def test_big_frames_reference_golden(gpu_engine, idx):
 
 
 @pytest.mark.gpu
+@pytest.mark.parametrize("n_blobs", [300, 560, 1500])
+def test_crowded_frames_overflow_into_the_general_path(gpu_engine, n_blobs):
+    """Hundreds of blobs per frame: more clusters / hot cells than the per-cluster path holds per frame (512 / 1024), so
+    the frame is handed to the general path; below the limits it stays on the cluster path.  Same answers either way."""
+    rng = np.random.default_rng(n_blobs)
+    H = W = 2048
+    img = rng.integers(0, 40, (H, W)).astype(np.uint8)
+    yy, xx = np.mgrid[0:H, 0:W]
+    side = int(np.ceil(np.sqrt(n_blobs)))
+    pitch = W // side
+    k = 0
+    for gy in range(side):
+        for gx in range(side):
+            if k >= n_blobs:
+                break
+            cx, cy = gx * pitch + pitch // 2 + int(rng.integers(-3, 4)), gy * pitch + pitch // 2 + int(rng.integers(-3, 4))
+            r = int(rng.integers(6, max(7, min(16, pitch // 2 - 4))))
+            sl = (slice(max(cy - r, 0), cy + r + 1), slice(max(cx - r, 0), cx + r + 1))
+            img[sl][(xx[sl] - cx) ** 2 + (yy[sl] - cy) ** 2 <= r * r] = 255
+            k += 1
+    res = gpu_engine.detect(dev(gpu_engine, img[None]), K, D, min_area=20.0, max_blobs=2048, max_contours=4096, outputs=("contours",))
+    _, binimg = R.filter_frame(img, K, D)
+    from util import oracle_contour_table
+    table, pts = oracle_contour_table(binimg, 20.0)
+    nc = int(res.extras["contour_count"][0])
+    assert nc == len(table) and np.array_equal(res.extras["contours"][0, :nc, :7].cpu().numpy(), table)
+    assert res.points(0) == pts and int(res.flags[0]) & 63 == 0
+    if n_blobs >= 560:
+        assert int(res.flags[0]) & 64                      # beyond the per-frame limits of the cluster path
+
+
+@pytest.mark.gpu
 def test_frame_larger_than_the_cluster_path_limit(gpu_engine):
     """More than 8192 source cells (here 4100 x 3000, also not a multiple of 16 wide: scalar scan): every frame takes the
     general path; same results as the oracle."""
