@@ -310,7 +310,8 @@ def test_crowded_frames_overflow_into_the_general_path(gpu_engine, n_blobs):
             sl = (slice(max(cy - r, 0), cy + r + 1), slice(max(cx - r, 0), cx + r + 1))
             img[sl][(xx[sl] - cx) ** 2 + (yy[sl] - cy) ** 2 <= r * r] = 255
             k += 1
-    res = gpu_engine.detect(dev(gpu_engine, img[None]), K, D, min_area=20.0, max_blobs=2048, max_contours=4096, outputs=("contours",))
+    res = gpu_engine.detect(dev(gpu_engine, img[None]), K, D, min_area=20.0, max_blobs=2048, max_contours=4096, max_runs=1 << 17,
+                            outputs=("contours",))
     _, binimg = R.filter_frame(img, K, D)
     from util import oracle_contour_table
     table, pts = oracle_contour_table(binimg, 20.0)
