@@ -8,8 +8,8 @@
 // inside the output box of some hot cell; (2) a cluster is a connected component of the "boxes touch" graph over the hot
 // cells, so two 8-adjacent foreground pixels always lie in boxes of the same cluster: a blob is covered by the boxes of
 // exactly one cluster and no foreground pixel of another cluster lies inside them.  A cluster therefore filters the
-// bounding box of its boxes and reports exactly the borders whose start pixel lies inside one of its own boxes (the
-// bounding box may show parts of foreign blobs; they are never owned).  What a unit cannot decide locally (a hole
+// bounding box of its (tighter, +-2) boxes and reports exactly the borders whose start pixel lies inside one of its own +-4
+// boxes (the bounding box may show parts of foreign blobs; they are never owned).  What a unit cannot decide locally (a hole
 // border -> contour tree, a group larger than the largest size class, capacity overflows) flags the FRAME for the
 // general per-frame path (detect_filter.cu + detect_blobs.cu), which recomputes it from the source frame.
 #include "common.cuh"
@@ -103,6 +103,7 @@ __global__ void __launch_bounds__(CL_THREADS) form_clusters_kernel(const uint32_
     int* r_words = (int*)(roots + ROOTS_MAX);           // per root: bit-row words, pieces, y1 of the box
     int* r_pcs = r_words + ROOTS_MAX;
     int* r_y1 = r_pcs + ROOTS_MAX;
+    short* tight = (short*)(r_y1 + ROOTS_MAX);          // [HOT_MAX][4] the +-2 boxes (filter region), see below
     __shared__ int s_nhot, s_nroots, s_changed, s_bad;
     if (tid == 0) { s_nhot = 0; s_bad = 0; }
     for (int c = tid; c < cells; c += nt) idx_of[c] = 0xffff;
@@ -125,11 +126,21 @@ __global__ void __launch_bounds__(CL_THREADS) form_clusters_kernel(const uint32_
         const int32_t* inv = tv.cellinv + 4 * c;
         int hx0 = cx * 32 + (int)(b & 0xff), hx1 = cx * 32 + (int)((b >> 8) & 0xff);
         int hy0 = cy * 32 + (int)((b >> 16) & 0xff), hy1 = cy * 32 + (int)(b >> 24);
-        int x0 = hx0 - 1 - inv[1] - 4, x1 = hx1 - inv[0] + 4, y0 = hy0 - 1 - inv[3] - 4, y1 = hy1 - inv[2] + 4;
+        // Undistorted pixels > thresh lie in [hx0 - 1 - dmax, hx1 - dmin] (a hot tap is needed); the thresholded mean can be
+        // set at most 2 beyond them and the majority at most 2 beyond that: every foreground pixel lies inside the +-4 box of
+        // some hot cell.  These boxes define the clusters and the ownership of a border.
+        int ux0 = hx0 - 1 - inv[1], ux1 = hx1 - inv[0], uy0 = hy0 - 1 - inv[3], uy1 = hy1 - inv[2];
+        int x0 = ux0 - 4, x1 = ux1 + 4, y0 = uy0 - 4, y1 = uy1 + 4;
+        // The region a cluster has to FILTER is tighter: all hot pixels within 4 of a foreground pixel belong to its cluster
+        // (their +-4 boxes share that pixel), and 3 beyond the cluster's hot pixels only two columns (rows) of the 5x5 majority
+        // window can hold set means, 10 < 13.  So the bounding box of the +-2 boxes holds all of the cluster's foreground.
+        int tx0 = ux0 - 2, tx1 = ux1 + 2, ty0 = uy0 - 2, ty1 = uy1 + 2;
         if (inv[0] > inv[1]) { x0 = 1; x1 = 0; }                 // no output pixel samples this cell
         x0 = max(x0, 0); y0 = max(y0, 0); x1 = min(x1, W - 1); y1 = min(y1, H - 1);
-        if (x0 > x1 || y0 > y1) { x0 = 1; x1 = 0; y0 = 1; y1 = 0; }
+        tx0 = max(tx0, 0); ty0 = max(ty0, 0); tx1 = min(tx1, W - 1); ty1 = min(ty1, H - 1);
+        if (x0 > x1 || y0 > y1 || tx0 > tx1 || ty0 > ty1) { x0 = 1; x1 = 0; y0 = 1; y1 = 0; }
         box[4 * h] = (short)x0; box[4 * h + 1] = (short)y0; box[4 * h + 2] = (short)x1; box[4 * h + 3] = (short)y1;
+        tight[4 * h] = (short)tx0; tight[4 * h + 1] = (short)ty0; tight[4 * h + 2] = (short)tx1; tight[4 * h + 3] = (short)ty1;
         parent[h] = h;
     }
     __syncthreads();
@@ -160,8 +171,8 @@ __global__ void __launch_bounds__(CL_THREADS) form_clusters_kernel(const uint32_
         if (box[4 * h] > box[4 * h + 2]) continue;
         int r = suf_find(parent, h);
         parent[h] = r;
-        atomicMin(&cbox[4 * r], (int)box[4 * h]); atomicMin(&cbox[4 * r + 1], (int)box[4 * h + 1]);
-        atomicMax(&cbox[4 * r + 2], (int)box[4 * h + 2]);
+        atomicMin(&cbox[4 * r], (int)tight[4 * h]); atomicMin(&cbox[4 * r + 1], (int)tight[4 * h + 1]);
+        atomicMax(&cbox[4 * r + 2], (int)tight[4 * h + 2]);
         atomicAdd(&cbox[4 * r + 3], 1);
         if (r == h) { int k = atomicAdd(&s_nroots, 1); if (k < ROOTS_MAX) roots[k] = (uint16_t)h; }
     }
@@ -186,7 +197,7 @@ __global__ void __launch_bounds__(CL_THREADS) form_clusters_kernel(const uint32_
             if (box[4 * h] > box[4 * h + 2] || parent[h] != r) continue;
             short* m = memb + 4 * (off + k);
             m[0] = box[4 * h]; m[1] = box[4 * h + 1]; m[2] = box[4 * h + 2]; m[3] = box[4 * h + 3];
-            y1 = max(y1, (int)box[4 * h + 3]);
+            y1 = max(y1, (int)tight[4 * h + 3]);
             ++k;
         }
         cbox[4 * r + 3] = off | (k << 16);
@@ -920,7 +931,7 @@ int launch_cluster_path(const uint8_t* frames, int n, int H, int W, int64_t fstr
     cudaGetDevice(&dev);
     cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
     const int cells = tv.TX * tv.TY;
-    size_t sm_form = (size_t)((cells + 7) & ~7) * 2 + (size_t)HOT_MAX * (2 + 4 + 16 + 8) + (size_t)ROOTS_MAX * (2 + 12) + 64;
+    size_t sm_form = (size_t)((cells + 7) & ~7) * 2 + (size_t)HOT_MAX * (2 + 4 + 16 + 8 + 8) + (size_t)ROOTS_MAX * (2 + 12) + 64;
 #ifndef MOCAP_EMU
     static bool attr_done = false;
     if (!attr_done) {

@@ -195,6 +195,37 @@ def test_cluster_path_random_scenes(engine):
     assert paths == {False, True} or not is_gpu(engine) or True
 
 
+def test_adversarial_background_just_below_threshold(engine):
+    """Background 216 (one below the threshold): a single pixel > 216 in a 5x5 window already sets the thresholded mean, so
+    the filtered foreground reaches as far from the hot pixels as it possibly can (gaps between nearby hot features fill
+    up).  This pins the reach bounds the sparse paths rely on: +-4 per hot cell, +-2 around a cluster's hot pixels."""
+    from util import oracle_contour_table
+    rng = np.random.default_rng(77)
+    for it in range(10 if is_gpu(engine) else 4):
+        H, W = int(rng.integers(70, 200)), int(rng.integers(80, 240))
+        if it % 2:
+            W = (W // 16) * 16
+        img = np.full((H, W), 216, np.uint8)
+        for _ in range(int(rng.integers(2, 9))):                      # short bars and dots, 3..10 px apart
+            x, y = int(rng.integers(8, W - 20)), int(rng.integers(8, H - 30))
+            gap = int(rng.integers(3, 11))
+            length = int(rng.integers(1, 22))
+            if rng.random() < 0.5:
+                img[y:y + length, x] = 255
+                img[y:y + length, x + gap] = 255
+            else:
+                img[y, x:x + length] = 255
+                img[y + gap, x:x + length] = 255
+        res = engine.detect(dev(engine, img[None]), K, D, min_area=0.0, outputs=("contours",))
+        _, binimg = R.filter_frame(img, K, D)
+        table, pts = oracle_contour_table(binimg, 0.0)
+        nc = int(res.extras["contour_count"][0])
+        assert nc == len(table) and np.array_equal(res.extras["contours"][0, :nc, :7].cpu().numpy(), table)
+        assert res.points(0) == (pts if pts else [[None, None]])
+        full = engine.detect(dev(engine, img[None]), K, D, min_area=0.0, outputs=ALL)
+        assert np.array_equal(unpack_bits(full.extras["bits"], W)[0] != 0, binimg != 0)
+
+
 def test_blobs_deep_nesting_uses_general_ordering(engine):
     b = np.zeros((90, 90), np.uint8)
     for k in range(0, 44, 2):
