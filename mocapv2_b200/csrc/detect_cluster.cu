@@ -276,11 +276,15 @@ __device__ __forceinline__ void count5(uint32_t a, uint32_t b, uint32_t c, uint3
 //      thresholded bit row
 //   C  bit-sliced 5x5 majority: per B row the horizontal 5-counts as three bit planes, per output row the sum of five
 //      rows' planes (<= 25, five bit planes) and the test >= 13 -- 64 pixels per thread
-__device__ __forceinline__ void piece_threshold_majority_packed(PieceSmem& S, int mw, int mh, int T, uint32_t* __restrict__ out, int wpr)
+// hl, hr, ht, hb (0 or 2): how far the thresholded-mean box extends beyond the piece on each side.  It stops at the
+// cluster box: outside of it the thresholded mean cannot be set by this cluster's hot pixels (it would lie more than 2 from
+// them), and whatever foreign hot pixels set there can only influence pixels that are not this cluster's foreground.
+__device__ __forceinline__ void piece_threshold_majority_packed(PieceSmem& S, int mw, int mh, int hl, int hr, int ht, int hb, int T,
+                                                                uint32_t* __restrict__ out, int wpr)
 {
     constexpr int UW = PieceSmem::UW, BW = PieceSmem::BW;
     const int tid = threadIdx.x;
-    const int uh = mh + 8, bw = mw + 4, bh = mh + 4;
+    const int bw = mw + hl + hr, bh = mh + ht + hb, uh = bh + 4;
     // ---- A ----
     const int nq = (bw + 3) >> 2;
     const unsigned inv_q = (1u << 20) / (unsigned)nq + 1u;                        // t / nq == (t * inv_q) >> 20 (t * nq < 2^20)
@@ -317,10 +321,20 @@ __device__ __forceinline__ void piece_threshold_majority_packed(PieceSmem& S, in
     }
     __syncthreads();
     // ---- C ----  horizontal 5-counts per B row as three 64-bit planes (two 32-bit halves each) in S.MH
-    uint32_t* planes = (uint32_t*)S.HS;                                           // [bh][3][2]; HS is dead after stage B
-    for (int r = tid; r < bh; r += CL_THREADS) {
-        const uint32_t* bp = (const uint32_t*)&bbits[r * 16];
-        uint32_t w0 = bp[0], w1 = bp[1], w2 = bp[2] & 0xffu;                      // bits 0..31, 32..63, 64..71
+    uint32_t* planes = (uint32_t*)S.HS;                                           // [mh + 4][3][2]; HS is dead after stage B
+    // plane row / bit position = offset from (piece - 2): the box rows and columns land at (2 - ht) / (2 - hl), what lies
+    // outside the box is zero
+    for (int r = tid; r < mh + 4; r += CL_THREADS) {
+        const int rb = r - (2 - ht);
+        uint32_t w0 = 0, w1 = 0, w2 = 0;
+        if (rb >= 0 && rb < bh) {
+            const uint32_t* bp = (const uint32_t*)&bbits[rb * 16];
+            w0 = bp[0]; w1 = bp[1]; w2 = bp[2] & 0xffu;                           // bits 0..31, 32..63, 64..71
+            if (bw < 32) { w0 &= (1u << bw) - 1u; w1 = 0; w2 = 0; }               // drop the surplus bits of the last byte
+            else if (bw < 64) { w1 &= bw == 32 ? 0u : (1u << (bw - 32)) - 1u; w2 = 0; }
+            else w2 &= bw == 64 ? 0u : (1u << (bw - 64)) - 1u;
+            if (hl == 0) { w2 = (w2 << 2) | (w1 >> 30); w1 = (w1 << 2) | (w0 >> 30); w0 <<= 2; }
+        }
 #pragma unroll
         for (int h = 0; h < 2; ++h) {
             uint32_t lo = h ? w1 : w0, hi = h ? w2 : w1;
@@ -437,16 +451,21 @@ __global__ void __launch_bounds__(CL_THREADS, 8) piece_filter_kernel(const uint8
         const int px0 = cx0 + bx * PIECE, py0 = cy0 + by * PIECE;
         const int px1 = min(px0 + PIECE - 1, cx1), py1 = min(py0 + PIECE - 1, cy1);
         const int mw = px1 - px0 + 1, mh = py1 - py0 + 1;
-        const int uw = mw + 8, uh = mh + 8, bw = mw + 4, bh = mh + 4;
         const uint8_t* fr = frames + (size_t)f * fstride;
-        // no frame border within reach and a representable threshold: stages 2-3 run packed / bit-sliced
-        const bool packed = px0 >= 4 && py0 >= 4 && px1 + 4 < W && py1 + 4 < H && T >= 0 && T <= 256;
+        // halo of the thresholded-mean box around the piece: 2, but never beyond the cluster box (see the packed stages)
+        const int hl = px0 - max(px0 - 2, cx0), hr = min(px1 + 2, cx1) - px1, ht = py0 - max(py0 - 2, cy0), hb = min(py1 + 2, cy1) - py1;
+        // no frame border within reach and a representable threshold: stages 2-3 run packed / bit-sliced on the tight boxes;
+        // otherwise the plain per-pixel code with the full +-4 halo and clamped coordinates
+        const bool packed = px0 - hl >= 2 && py0 - ht >= 2 && px1 + hr + 2 < W && py1 + hb + 2 < H && T >= 0 && T <= 256;
+        const int ux0 = packed ? px0 - hl - 2 : px0 - 4, uy0 = packed ? py0 - ht - 2 : py0 - 4;      // origin of the U box
+        const int ux1 = packed ? px1 + hr + 2 : px1 + 4, uy1 = packed ? py1 + hb + 2 : py1 + 4;
+        const int uw = ux1 - ux0 + 1, uh = uy1 - uy0 + 1, bw = mw + 4, bh = mh + 4;
         // ---- 0. stage the source window of the piece in shared memory with 16-byte loads (zero outside the frame): the
         //         bilinear taps then come from shared memory instead of four dependent global byte gathers per pixel.
         //         Window = piece box +-4 shifted by the displacement bounds of the tiles it overlaps (undistortion table). ------
         if (tid < 32) {
-            int tx0 = max((px0 - 4) >> 5, 0), tx1 = min((px1 + 4) >> 5, tv.TX - 1);
-            int ty0 = max((py0 - 4) >> 5, 0), ty1 = min((py1 + 4) >> 5, tv.TY - 1);
+            int tx0 = max(ux0 >> 5, 0), tx1 = min(ux1 >> 5, tv.TX - 1);
+            int ty0 = max(uy0 >> 5, 0), ty1 = min(uy1 >> 5, tv.TY - 1);
             int ntx = tx1 - tx0 + 1, ntl = ntx * (ty1 - ty0 + 1);
             int dx0 = 0x7fffffff, dx1 = -0x7fffffff, dy0 = 0x7fffffff, dy1 = -0x7fffffff;
             for (int l = lane; l < ntl; l += 32) {
@@ -456,7 +475,7 @@ __global__ void __launch_bounds__(CL_THREADS, 8) piece_filter_kernel(const uint8
             dx0 = __reduce_min_sync(0xffffffffu, dx0); dx1 = __reduce_max_sync(0xffffffffu, dx1);
             dy0 = __reduce_min_sync(0xffffffffu, dy0); dy1 = __reduce_max_sync(0xffffffffu, dy1);
             if (lane == 0) {
-                int wx0 = (px0 - 4 + dx0) & ~15, wx1 = px1 + 4 + dx1 + 1, wy0 = py0 - 4 + dy0, wy1 = py1 + 4 + dy1 + 1;
+                int wx0 = (ux0 + dx0) & ~15, wx1 = ux1 + dx1 + 1, wy0 = uy0 + dy0, wy1 = uy1 + dy1 + 1;
                 bool ok = vec_ok && dx0 <= dx1 && wx1 - wx0 + 1 <= WIN_W && wy1 - wy0 + 1 <= WIN_H;
                 s_win[0] = wx0; s_win[1] = wy0; s_win[2] = ok ? wy1 - wy0 + 1 : 0; s_win[3] = ok;
                 s_win[4] = ok ? (wx1 - wx0 + 16) >> 4 : 0;                  // 16-byte vectors per window row actually needed
@@ -483,8 +502,8 @@ __global__ void __launch_bounds__(CL_THREADS, 8) piece_filter_kernel(const uint8
             // coordinates (source column in the window = c + (du >> 5) + const, fraction = du & 31)
             const int n_u = uw * uh;
             const unsigned inv = (1u << 20) / (unsigned)uw + 1u;
-            const int32_t* mbase = tv.map + (size_t)(py0 - 4) * W + (px0 - 4);
-            const uint8_t* wbase = win + (py0 - 4 - wy0) * WIN_W + (px0 - 4 - wx0);
+            const int32_t* mbase = tv.map + (size_t)uy0 * W + ux0;
+            const uint8_t* wbase = win + (uy0 - wy0) * WIN_W + (ux0 - wx0);
             for (int base = tid; base < n_u; base += 4 * CL_THREADS) {
                 uint32_t m[4]; int rr[4], cc[4];
 #pragma unroll
@@ -516,7 +535,7 @@ __global__ void __launch_bounds__(CL_THREADS, 8) piece_filter_kernel(const uint8
                 for (int k = 0; k < 4; ++k) {
                     int idx = base + k * CL_THREADS;
                     int r = (int)(((unsigned)idx * inv) >> 20), c = idx - r * uw;
-                    int i = py0 - 4 + r, j = px0 - 4 + c;
+                    int i = uy0 + r, j = ux0 + c;
                     ii[k] = i; jj[k] = j; rc[k] = r * UW + c;
                     m[k] = (idx < n_u && (unsigned)i < (unsigned)H && (unsigned)j < (unsigned)W) ? (uint32_t)tv.map[(size_t)i * W + j] : MAP_OUTSIDE;
                 }
@@ -551,7 +570,7 @@ __global__ void __launch_bounds__(CL_THREADS, 8) piece_filter_kernel(const uint8
             __syncthreads();
         }
         uint32_t* out = cw.rows_out + (unsigned)ce[3] + (size_t)(py0 - cy0) * wpr + bx * (PIECE / 32);
-        if (packed) piece_threshold_majority_packed(S, mw, mh, T, out, wpr);
+        if (packed) piece_threshold_majority_packed(S, mw, mh, hl, hr, ht, hb, T, out, wpr);
         else piece_threshold_majority<false>(S, px0, py0, mw, mh, W, H, T, out, wpr);
     }
 }
