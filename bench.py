@@ -239,8 +239,7 @@ def run_b200(args):
     corr_out = [None]
 
     def step(timer=None):
-        det = eng.detect(frames.view(n_local, H, W), pipe.K0, pipe.dist0, max_blobs=MAX_BLOBS, out=pipe._det, timer=timer)
-        pipe._det = det
+        det = pipe.detect(frames, timer=timer)
         xy, count = pipe.exchange(det, FS)
         corr_out[0] = eng.correspond(xy, count, pipe.Fs, pipe.cams, obj_count=N_MARKERS, max_groups=MAX_GROUPS, out=corr_out[0])
         return det, corr_out[0]

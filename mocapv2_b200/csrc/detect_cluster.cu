@@ -965,7 +965,7 @@ int launch_cluster_path(const uint8_t* frames, int n, int H, int W, int64_t fstr
     LAUNCH(piece_filter_kernel, sms * 8, CL_THREADS, 0, s, frames, fstride, tv, thresh, cw);
     stage_end(timer, 2, s);
     stage_begin(timer, 3, s);
-    LAUNCH(candidates_kernel, sms * 8, 128, 0, s, cw);
+    LAUNCH(candidates_kernel, sms * 16, 128, 0, s, cw);
     LAUNCH(borders_finalize_kernel, n, CL_THREADS, (size_t)max_contours + 16, s, cw, W, max_contours, max_blobs, min_area, min_circ,
            out_xy, out_count, out_flags, out_contours, out_contour_count);
     stage_end(timer, 3, s);

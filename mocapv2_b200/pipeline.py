@@ -49,7 +49,7 @@ class CapturePipeline:
         self.cams = engine.cameras(rig["poses"], rig["camera_params"])
         self.Fs = torch.from_numpy(np.asarray(rig["Fs"], dtype=np.float64).reshape(-1, 3, 3).copy()).to(engine.device)
         self._det = None
-        self._rec = None
+        self._flat = None
         self._gath = None
         self.collectives = 0
 
@@ -59,14 +59,23 @@ class CapturePipeline:
         per = n_frame_sets // self.world
         return self.rank * per, (self.rank + 1) * per
 
-    def detect(self, frames: torch.Tensor) -> DetectResult:
+    def _buffers(self, n: int):
+        """Detection outputs of n frames as two views of ONE flat int32 buffer [xy (n*mb*2) | count (n)]: the exchange
+        all-gathers that buffer as it is, nothing is packed."""
+        if self._det is None or self._det.xy.shape[0] != n:
+            mb = self.max_blobs
+            self._flat = torch.zeros(n * (2 * mb + 1), dtype=torch.int32, device=self.eng.device)
+            self._det = DetectResult(self._flat[: n * mb * 2].view(n, mb, 2), self._flat[n * mb * 2:],
+                                     torch.zeros(n, dtype=torch.int32, device=self.eng.device))
+            self._gath = None
+        return self._det
+
+    def detect(self, frames: torch.Tensor, timer=None) -> DetectResult:
         """frames [FS, cams_local, H, W] uint8 on the device -> centroid lists of this rank's cameras."""
         FS, cl, H, W = frames.shape
         assert cl == self.cams_local and (H, W) == (self.H, self.W)
         flat = frames.view(FS * cl, H, W)
-        if self._det is not None and self._det.xy.shape[0] != FS * cl:
-            self._det = None
-        self._det = self.eng.detect(flat, self.K0, self.dist0, max_blobs=self.max_blobs, out=self._det)
+        self._det = self.eng.detect(flat, self.K0, self.dist0, max_blobs=self.max_blobs, out=self._buffers(FS * cl), timer=timer)
         return self._det
 
     def exchange(self, det: DetectResult, FS: int):
@@ -75,18 +84,18 @@ class CapturePipeline:
         b, e = self.frame_set_shard(FS)
         if self.world == 1:
             return det.xy.view(FS, cl, mb, 2), det.count.view(FS, cl)
-        R = 1 + 2 * mb
-        if self._rec is None or self._rec.shape[0] != FS * cl:
-            self._rec = torch.empty((FS * cl, R), dtype=torch.int32, device=self.eng.device)
-            self._gath = torch.empty((self.world, FS, cl, R), dtype=torch.int32, device=self.eng.device)
-        self._rec[:, 0] = det.count
-        self._rec[:, 1:] = det.xy.view(FS * cl, 2 * mb)
-        dist.all_gather_into_tensor(self._gath.view(-1), self._rec.view(-1), group=self.group)
+        n = FS * cl
+        if det is not self._det:                               # results that do not live in the pipeline's flat buffer
+            self._buffers(n)
+            self._det.xy.copy_(det.xy)
+            self._det.count.copy_(det.count)
+        if self._gath is None:
+            self._gath = torch.empty((self.world, self._flat.numel()), dtype=torch.int32, device=self.eng.device)
+        dist.all_gather_into_tensor(self._gath.view(-1), self._flat, group=self.group)
         self.collectives += 1
-        mine = self._gath[:, b:e].permute(1, 0, 2, 3).reshape(e - b, self.C, R)       # [F0, C, R], camera = rank * cl + local
-        count = mine[:, :, 0].contiguous()
-        xy = mine[:, :, 1:].reshape(e - b, self.C, mb, 2).contiguous()
-        return xy, count
+        xy = self._gath[:, : n * mb * 2].view(self.world, FS, cl, mb, 2)[:, b:e].permute(1, 0, 2, 3, 4).reshape(e - b, self.C, mb, 2)
+        count = self._gath[:, n * mb * 2:].view(self.world, FS, cl)[:, b:e].permute(1, 0, 2).reshape(e - b, self.C)
+        return xy.contiguous(), count.contiguous()                      # camera index = rank * cams_local + local
 
     def step(self, frames: torch.Tensor) -> StepResult:
         FS = frames.shape[0]
