@@ -108,10 +108,32 @@ __global__ void build_tile_kernel(const int32_t* __restrict__ map, int H, int W,
             for (int cx = sx0 >> 5; cx <= (sx1 >> 5); ++cx) {
                 int32_t* c = cell + 4 * (cy * TX + cx);
                 atomicMin(&c[0], tx); atomicMin(&c[1], ty); atomicMax(&c[2], tx); atomicMax(&c[3], ty);
-                int32_t* ci = cellinv + 4 * (cy * TX + cx);
-                atomicMin(&ci[0], s[4]); atomicMax(&ci[1], s[5]); atomicMin(&ci[2], s[6]); atomicMax(&ci[3], s[7]);
             }
     }
+}
+
+// Per 32x32 source cell: exact bounds of (source - output) integer displacement over every output pixel whose 2x2 tap
+// footprint touches the cell.  One thread per output pixel; pixels of a warp mostly hit the same cell, so the atomics are
+// few per address and this runs once per calibration.
+__global__ void build_cellinv_kernel(const int32_t* __restrict__ map, int H, int W, int TX, int32_t* __restrict__ cellinv)
+{
+    int j = blockIdx.x * blockDim.x + threadIdx.x, i = blockIdx.y * blockDim.y + threadIdx.y;
+    if (i >= H || j >= W) return;
+    uint32_t m = (uint32_t)map[(size_t)i * W + j];
+    if (m == MAP_OUTSIDE) return;
+    int ddx = (int)(int16_t)(m & 0xffff) >> 5, ddy = (int)(int16_t)(m >> 16) >> 5;
+    int sx = j + ddx, sy = i + ddy;
+    for (int ty = 0; ty < 2; ++ty)
+        for (int tx = 0; tx < 2; ++tx) {
+            int x = sx + tx, y = sy + ty;
+            if ((unsigned)x >= (unsigned)W || (unsigned)y >= (unsigned)H) continue;
+            if ((tx && ((x & 31) != 0)) || (ty && ((y & 31) != 0))) continue;      // same cell as the tap before it
+            int32_t* ci = cellinv + 4 * ((y >> 5) * TX + (x >> 5));
+            if (ci[0] > ddx) atomicMin(&ci[0], ddx);
+            if (ci[1] < ddx) atomicMax(&ci[1], ddx);
+            if (ci[2] > ddy) atomicMin(&ci[2], ddy);
+            if (ci[3] < ddy) atomicMax(&ci[3], ddy);
+        }
 }
 
 static void invert3x3(const double* A, double* out)
@@ -174,6 +196,7 @@ extern "C" int mocap_undistort_table_build(const double* K9, const double* dist5
     int nt = h.TX * h.TY;
     LAUNCH(init_tables_kernel, cdiv(nt, 256), 256, 0, s, cell, tile, cellinv, nt);
     LAUNCH(build_tile_kernel, dim3(h.TX, h.TY), 256, 0, s, map, H, W, h.TX, h.TY, cell, tile, cellinv);
+    LAUNCH(build_cellinv_kernel, grd, blk, 0, s, map, H, W, h.TX, cellinv);
     CUDA_TRY(cudaGetLastError());
     TableHeader back;
     CUDA_TRY(cudaMemcpyAsync(&back, base, sizeof(back), cudaMemcpyDeviceToHost, s));
