@@ -34,7 +34,10 @@ extern "C" {
 #define MOCAP_FLAG_DEPTH_OVERFLOW 16   /* contour tree deeper than 8: order resolved by the slow path */
 #define MOCAP_FLAG_TRACE_OVERFLOW 32   /* a border longer than the step budget: frame outputs invalid */
 #define MOCAP_FLAG_GENERAL_PATH 64     /* informational: the frame was finished by the general per-frame path (hole borders,
-                                          oversized blob groups, parity outputs requested), not by the per-cluster units; bits 8.. say why */
+                                          oversized blob groups, parity outputs requested), not by the per-cluster units; bits 8.. say why:
+                                          2 too many hot cells, 3 too many clusters, 5 cluster storage full, 7 too many border
+                                          starts, 8 border trace / hole parent outside the fast rules, 9 nested outer border,
+                                          10 lens displacement varies by more than 8 px inside a 32-px cell */
 
 /* per-frame-set flags written by mocap_correspond_batch */
 #define MOCAP_CFLAG_GROUP_CAP 1        /* a root had more candidate groups than max_groups: mean over the first max_groups */

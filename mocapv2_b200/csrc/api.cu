@@ -15,7 +15,7 @@ int launch_cluster_path(const uint8_t* frames, int n, int H, int W, int64_t fstr
                         const uint32_t* cellbox, char* ws_base, const size_t* offs,
                         int max_contours, int max_blobs, double min_area, double min_circ,
                         int32_t* out_xy, int32_t* out_count, int32_t* out_flags, double* out_contours, int32_t* out_contour_count,
-                        bool finalize_only, cudaStream_t s, StageTimer* timer);
+                        cudaStream_t s, StageTimer* timer);
 int launch_materialize_bits(const FilterWs& ws, int n, int H, int W, const TableView& tv, uint32_t* out, cudaStream_t s);
 // detect_blobs.cu
 int launch_tiles_from_bits(const uint32_t* bits, int n, int H, int TX, int TY, uint32_t* fg_tiles, int* n_fg, int max_fg, cudaStream_t s);
@@ -186,7 +186,7 @@ extern "C" int mocap_detect_batch(const uint8_t* frames_dev, int n_frames, int H
     if (use_cluster) {
         st = launch_cluster_path(frames_dev, n_frames, H, W, frame_stride, tv, thresh, ws.cellbox, cl_base, L.cl_offs,
                                  max_contours, max_blobs, min_area, min_circ, out_xy, out_count, out_flags, out_contours,
-                                 out_contour_count, false, s, timer);
+                                 out_contour_count, s, timer);
         if (st != MOCAP_OK) return st;
     }
     stage_begin(timer, 4, s);

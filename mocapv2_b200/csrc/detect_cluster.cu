@@ -104,7 +104,7 @@ __global__ void __launch_bounds__(CL_THREADS) form_clusters_kernel(const uint32_
     int* r_pcs = r_words + ROOTS_MAX;
     int* r_y1 = r_pcs + ROOTS_MAX;
     short* tight = (short*)(r_y1 + ROOTS_MAX);          // [HOT_MAX][4] the +-2 boxes (filter region), see below
-    __shared__ int s_nhot, s_nroots, s_changed, s_bad;
+    __shared__ int s_nhot, s_nroots, s_bad;
     if (tid == 0) { s_nhot = 0; s_bad = 0; }
     for (int c = tid; c < cells; c += nt) idx_of[c] = 0xffff;
     __syncthreads();
@@ -136,6 +136,10 @@ __global__ void __launch_bounds__(CL_THREADS) form_clusters_kernel(const uint32_
         // window can hold set means, 10 < 13.  So the bounding box of the +-2 boxes holds all of the cluster's foreground.
         int tx0 = ux0 - 2, tx1 = ux1 + 2, ty0 = uy0 - 2, ty1 = uy1 + 2;
         if (inv[0] > inv[1]) { x0 = 1; x1 = 0; }                 // no output pixel samples this cell
+        // Clusters are grown over 8-neighbour cells only: boxes of cells two apart must not be able to touch.  That holds while
+        // the displacement varies by at most 8 px inside a cell (margin <= 13 per side, hot pixels >= 33 apart); a lens that
+        // bends more than that goes to the general path.
+        else if (inv[1] - inv[0] > 8 || inv[3] - inv[2] > 8) s_bad = 1;
         x0 = max(x0, 0); y0 = max(y0, 0); x1 = min(x1, W - 1); y1 = min(y1, H - 1);
         tx0 = max(tx0, 0); ty0 = max(ty0, 0); tx1 = min(tx1, W - 1); ty1 = min(ty1, H - 1);
         if (x0 > x1 || y0 > y1 || tx0 > tx1 || ty0 > ty1) { x0 = 1; x1 = 0; y0 = 1; y1 = 0; }
@@ -144,6 +148,7 @@ __global__ void __launch_bounds__(CL_THREADS) form_clusters_kernel(const uint32_
         parent[h] = h;
     }
     __syncthreads();
+    if (s_bad) { if (tid == 0) cw.need_general[f] = 10; return; }
     // first grouping: hot 8-neighbour cells whose boxes touch
     for (int h = tid; h < n_hot; h += nt) {
         if (box[4 * h] > box[4 * h + 2]) continue;
@@ -162,7 +167,7 @@ __global__ void __launch_bounds__(CL_THREADS) form_clusters_kernel(const uint32_
     __syncthreads();
     // clusters = connected components of the "boxes touch" graph; members of a cluster are written contiguously
     for (int h = tid; h < n_hot; h += nt) {
-        cbox[4 * h] = 0x7fffffff; cbox[4 * h + 1] = 0x7fffffff; cbox[4 * h + 2] = -1; cbox[4 * h + 3] = 0;   // [3] doubles as member count, see below
+        cbox[4 * h] = 0x7fffffff; cbox[4 * h + 1] = 0x7fffffff; cbox[4 * h + 2] = -1; cbox[4 * h + 3] = 0;   // [3]: member count, then offset | count << 16
     }
     if (tid == 0) s_nroots = 0;
     __syncthreads();
@@ -921,7 +926,7 @@ int launch_cluster_path(const uint8_t* frames, int n, int H, int W, int64_t fstr
                         const uint32_t* cellbox, char* ws_base, const size_t* offs,
                         int max_contours, int max_blobs, double min_area, double min_circ,
                         int32_t* out_xy, int32_t* out_count, int32_t* out_flags, double* out_contours, int32_t* out_contour_count,
-                        bool finalize_only, cudaStream_t s, StageTimer* timer)
+                        cudaStream_t s, StageTimer* timer)
 {
     ClusterWs cw;
     cw.need_general = (int*)(ws_base + offs[0]);
@@ -941,7 +946,6 @@ int launch_cluster_path(const uint8_t* frames, int n, int H, int W, int64_t fstr
     cw.rec_info = (int*)(ws_base + offs[12]);
     cw.frame_clusters = (int*)(ws_base + offs[13]);
     cw.n_frames = n;
-    (void)finalize_only;
     CUDA_TRY(cudaMemsetAsync(cw.counters, 0, 64, s));
     CUDA_TRY(cudaMemsetAsync(cw.rec_count, 0, (size_t)n * 4, s));
     CUDA_TRY(cudaMemsetAsync(cw.cand_count, 0, (size_t)n * 4, s));

@@ -226,6 +226,28 @@ def test_adversarial_background_just_below_threshold(engine):
         assert np.array_equal(unpack_bits(full.extras["bits"], W)[0] != 0, binimg != 0)
 
 
+def test_strong_lens_goes_to_the_general_path(engine):
+    """A lens whose displacement changes by more than 8 px inside a 32-px cell breaks the cluster path's neighbour-cell
+    growth bound; such frames are flagged to the general path (reason 10) and must still match the oracle exactly."""
+    rng = np.random.default_rng(5)
+    H, W = 192, 256
+    Ks = np.array([[60.0, 0, W / 2], [0, 60.0, H / 2], [0, 0, 1]])
+    Ds = np.array([-0.35, 0.12, 0.0, 0.0, 0.0])
+    img = np.full((H, W), 20, np.uint8)
+    yy, xx = np.mgrid[:H, :W]
+    for _ in range(6):
+        cx, cy, r = rng.integers(30, W - 30), rng.integers(30, H - 30), rng.integers(6, 16)
+        img[(xx - cx) ** 2 + (yy - cy) ** 2 <= r * r] = 255
+    res = engine.detect(dev(engine, img[None]), Ks, Ds, min_area=20.0)
+    _, binimg = R.filter_frame(img, Ks, Ds)
+    from util import oracle_contour_table
+    _, pts = oracle_contour_table(binimg, 20.0)
+    assert pts, "scene should keep blobs"
+    assert res.points(0) == pts
+    fl = int(res.flags[0])
+    assert fl & 63 == 0 and fl & 64 and fl >> 8 == 10, fl
+
+
 def test_blobs_deep_nesting_uses_general_ordering(engine):
     b = np.zeros((90, 90), np.uint8)
     for k in range(0, 44, 2):
