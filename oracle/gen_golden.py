@@ -74,6 +74,37 @@ def kat_bundle_adjustment(Hh, ip):
           np.abs(np.asarray(out[1]["t"]).ravel() - np.array(after[1]["t"])).max())
 
 
+def kat_fundamentals():
+    """Golden vectors of poses_to_fundamental_matrix (CalculateCameraPoses.py:26-78).  That script cannot be imported (it
+    opens cameras' JSONs and imports the capture stack at import time), so the function's own source is compiled out of
+    the reference file with ast and RUN here; nothing of it is stored but its outputs."""
+    import ast
+    tree = ast.parse(open(os.path.join(REF, "CalculateCameraPoses.py")).read())
+    fn = [n for n in tree.body if isinstance(n, ast.FunctionDef) and n.name == "poses_to_fundamental_matrix"][0]
+    ns = {"np": np}
+    exec(compile(ast.Module(body=[fn], type_ignores=[]), "CalculateCameraPoses.py", "exec"), ns)
+    ref = ns["poses_to_fundamental_matrix"]
+    after = json.load(open(os.path.join(REF, "jsons/after_ba_extrinsics.json")))
+    cp = json.load(open(os.path.join(REF, "jsons/camera-params-in.json")))
+    rec = {}
+    poses = [{"R": np.array(p["R"]), "t": np.array(p["t"])} for p in after]
+    K = [np.array(c["intrinsic_matrix"]) for c in cp]
+    rec["shipped_R"] = np.stack([p["R"] for p in poses]); rec["shipped_t"] = np.stack([p["t"].ravel() for p in poses])
+    rec["shipped_K"] = np.stack(K[:2])
+    rec["shipped_F"] = ref(poses[0], poses[1], K[0], K[1])
+    rec["shipped_E"] = ref(poses[0], poses[1])
+    rig = S.config_rig("c3")
+    rp = rig["poses"]
+    rK = [np.array(c["intrinsic_matrix"], dtype=np.float64) for c in rig["camera_params"]]
+    rec["ring_R"] = np.stack([np.asarray(p["R"], dtype=np.float64) for p in rp])
+    rec["ring_t"] = np.stack([np.asarray(p["t"], dtype=np.float64).ravel() for p in rp])
+    rec["ring_K"] = np.stack(rK)
+    rec["ring_F"] = np.stack([ref({"R": rec["ring_R"][0], "t": rec["ring_t"][0]}, {"R": rec["ring_R"][i], "t": rec["ring_t"][i].reshape(3, 1)},
+                                  rK[0], rK[i]) for i in range(1, len(rp))])
+    np.savez_compressed(os.path.join(OUT, "kat_fundamentals.npz"), **rec)
+    print("fundamentals golden:", rec["shipped_F"].shape, rec["ring_F"].shape)
+
+
 def main():
     import cv2
     os.makedirs(OUT, exist_ok=True)
@@ -272,4 +303,8 @@ def main():
 
 
 if __name__ == "__main__":
-    main()
+    if sys.argv[1:] == ["fundamentals"]:
+        kat_fundamentals()
+    else:
+        main()
+        kat_fundamentals()
