@@ -164,7 +164,7 @@ def run_reference(args):
     frames = host_render(rig, cen, ridx, 1)
     from oracle import cv2_port
     if not cv2_port.available():
-        print(json.dumps({"impl": "reference", "unavailable": "opencv (cv2) is not importable on this host"}))
+        emit({"impl": "reference", "unavailable": "opencv (cv2) is not importable on this host"})
         return 0
     try:
         import cv2
@@ -196,7 +196,7 @@ def run_reference(args):
         "e2e": {"value": value, "unit": "frames/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
         "gpu_launches": 0,
     }
-    print(json.dumps(line))
+    emit(line)
     return 0
 
 
@@ -449,14 +449,29 @@ def run_b200(args):
         "e2e": e2e, "gpu_launches": gpu_launches, "collectives_per_step": 1 if N > 1 else 0,
         "clocks": clocks, "roofline": roofline, "cpu_baseline": cpu, "geometry": geometry,
     }
-    print(json.dumps(line))
+    emit(line)
     if world > 1:
         dist.barrier()
         dist.destroy_process_group()
     return 0
 
 
+RESULT_OUT = sys.stdout
+
+
+def emit(line: dict):
+    """The ONE JSON line of the contract, on the process's real stdout."""
+    RESULT_OUT.write(json.dumps(line) + "\n")
+    RESULT_OUT.flush()
+
+
 def main():
+    # Libraries write to fd 1 behind Python's back (NCCL prints its version line there at NCCL_DEBUG=WARN/VERSION): send fd 1
+    # to stderr for the whole run and keep a private handle on the real stdout for the result line.
+    global RESULT_OUT
+    sys.stdout.flush()
+    RESULT_OUT = os.fdopen(os.dup(1), "w")
+    os.dup2(2, 1)
     args = parse()
     if args.impl == "reference":
         return run_reference(args)

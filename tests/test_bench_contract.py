@@ -14,7 +14,8 @@ def test_reference_arm_json_line():
     out = subprocess.run([sys.executable, os.path.join(REPO, "bench.py"), "--impl", "reference", "--steps", "1", "--warmup", "0"],
                          capture_output=True, text=True, timeout=600, cwd=REPO)
     assert out.returncode == 0, out.stderr[-2000:]
-    line = json.loads(out.stdout.strip().splitlines()[-1])
+    assert len(out.stdout.strip().splitlines()) == 1, "stdout must hold the JSON line and nothing else"
+    line = json.loads(out.stdout.strip())
     assert line["impl"] == "reference" and line["unit"] == "frames/s" and line["higher_is_better"] is True
     assert line["value"] > 0 and line["steps"] == 1 and line["vs_baseline"] is None and line["data"] == "synthetic"
     assert line["cpu_baseline"]["kind"] == "port" and line["cpu_baseline"]["cores"] >= 1 and line["cpu_baseline"]["value"] == line["value"]
