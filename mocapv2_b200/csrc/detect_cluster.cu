@@ -21,8 +21,8 @@
 #define CELLS_MAX 8192          // TX*TY limit of the dense cell -> slot map held in shared memory
 #define ROOTS_MAX 512
 #define PIECE 64                // a cluster box is filtered in pieces of at most PIECE x PIECE output pixels
-#define WIN_W 96                // staged source window of a piece: up to 96 x 80 bytes
-#define WIN_H 80
+#define WIN_W 96                // staged source window of a piece: up to 96 x 79 bytes (sized so that 8 CTAs fit one SM)
+#define WIN_H 79
 #define CAND_PER_FRAME 512      // border-start candidates per frame on the cluster path
 #define CELL_EMPTY 0xffffffffu
 
@@ -38,7 +38,7 @@ struct ClusterWs {
     int* counters;              // [16]
     int* clusters;              // [cl_cap][8]: frame, x0 | y0 << 16, x1 | y1 << 16 (box, inclusive), rows word offset, words per row,
                                 //              member offset | count << 16, 0, 0
-    int* pieces;                // [pc_cap][2]: cluster, bx | by << 16
+    int* pieces;                // [pc_cap][8]: piece descriptors (make_piece_desc)
     int cl_cap, pc_cap;
     short* memb;                // [n][HOT_MAX][4] output boxes of the hot cells, grouped by cluster
     uint32_t* rows_out;         // filtered bit rows of every cluster box
@@ -82,6 +82,53 @@ __device__ __forceinline__ int cdiv_dev(int a, int b) { return (a + b - 1) / b; 
 __device__ __forceinline__ bool boxes_touch(const int* a, const int* b)
 {
     return a[0] <= b[2] + 1 && b[0] <= a[2] + 1 && a[1] <= b[3] + 1 && b[1] <= a[3] + 1;
+}
+
+// Descriptor of one filter piece (<= 64x64 output pixels of a cluster box), everything piece_filter_kernel needs in 32 bytes:
+//   [0] frame            [1] px0 | py0 << 16 (piece origin)
+//   [2] mw | mh << 8 | hl << 16 | hr << 18 | ht << 20 | hb << 22 | packed << 24 | window fits << 25
+//   [3] word offset of the piece's first bit-row word      [4] words per row | window rows << 16 | 16-byte vectors per row << 24
+//   [5] window origin x (s16) | y << 16
+// hl, hr, ht, hb (0 or 2): how far the thresholded-mean box extends beyond the piece; it stops at the cluster box.
+// packed: no frame border within reach of the piece, the tight boxes apply; else the +-4 box with clamped coordinates.
+// window = the source pixels the undistortion of the piece's U box can touch (displacement bounds of the tiles it overlaps).
+__device__ __forceinline__ void make_piece_desc(const TableView& tv, int f, int cx0, int cy0, int cx1, int cy1, int bx, int by,
+                                                unsigned cluster_rows, int wpr, int* __restrict__ d)
+{
+    const int W = tv.W, H = tv.H;
+    const int px0 = cx0 + bx * PIECE, py0 = cy0 + by * PIECE;
+    const int px1 = min(px0 + PIECE - 1, cx1), py1 = min(py0 + PIECE - 1, cy1);
+    const int mw = px1 - px0 + 1, mh = py1 - py0 + 1;
+    const int hl = px0 - max(px0 - 2, cx0), hr = min(px1 + 2, cx1) - px1, ht = py0 - max(py0 - 2, cy0), hb = min(py1 + 2, cy1) - py1;
+    const bool packed = px0 - hl >= 2 && py0 - ht >= 2 && px1 + hr + 2 < W && py1 + hb + 2 < H;
+    const int ux0 = packed ? px0 - hl - 2 : px0 - 4, uy0 = packed ? py0 - ht - 2 : py0 - 4;
+    const int ux1 = packed ? px1 + hr + 2 : px1 + 4, uy1 = packed ? py1 + hb + 2 : py1 + 4;
+    const int tx0 = max(ux0 >> 5, 0), tx1 = min(ux1 >> 5, tv.TX - 1), ty0 = max(uy0 >> 5, 0), ty1 = min(uy1 >> 5, tv.TY - 1);
+    int dx0 = 0x7fffffff, dx1 = -0x7fffffff, dy0 = 0x7fffffff, dy1 = -0x7fffffff;
+    for (int ty = ty0; ty <= ty1; ++ty)
+        for (int tx = tx0; tx <= tx1; ++tx) {
+            const int4 t = *(const int4*)(tv.tile + 8 * (ty * tv.TX + tx) + 4);
+            if (t.x <= t.y) { dx0 = min(dx0, t.x); dx1 = max(dx1, t.y); dy0 = min(dy0, t.z); dy1 = max(dy1, t.w); }
+        }
+    int wx0 = 0, wy0 = 0, wh = 0, nvec = 0;
+    bool fits = false;
+    if (dx0 <= dx1) {
+        wx0 = (ux0 + dx0) & ~15; wy0 = uy0 + dy0;
+        const int wx1 = ux1 + dx1 + 1, wy1 = uy1 + dy1 + 1;
+        fits = wx1 - wx0 + 1 <= WIN_W && wy1 - wy0 + 1 <= WIN_H && wx0 >= -32768 && wy0 >= -32768;
+        if (fits) { wh = wy1 - wy0 + 1; nvec = (wx1 - wx0 + 16) >> 4; }
+    }
+    if (!fits) { wx0 = 0; wy0 = 0; }
+    int4 lo, hi;
+    lo.x = f;
+    lo.y = px0 | (py0 << 16);
+    lo.z = mw | (mh << 8) | (hl << 16) | (hr << 18) | (ht << 20) | (hb << 22) | ((int)packed << 24) | ((int)fits << 25);
+    lo.w = (int)(cluster_rows + (unsigned)(py0 - cy0) * (unsigned)wpr + (unsigned)(bx * (PIECE / 32)));
+    hi.x = wpr | (wh << 16) | (nvec << 24);
+    hi.y = (wx0 & 0xffff) | (wy0 << 16);
+    hi.z = 0; hi.w = 0;
+    *(int4*)d = lo;
+    *(int4*)(d + 4) = hi;
 }
 
 // ---------------------------------------------------------------------------------------------------------
@@ -233,19 +280,23 @@ __global__ void __launch_bounds__(CL_THREADS) form_clusters_kernel(const uint32_
     const bool bad = s_bad != 0;
     for (int i = tid; i < nr; i += nt) {
         int cid = cid0 + i;
-        if (cid >= cw.cl_cap) continue;
         int r = roots[i];
         int x0 = cbox[4 * r], y0 = cbox[4 * r + 1], x1 = cbox[4 * r + 2], y1 = r_y1[i];
         int pbx = cdiv_dev(x1 - x0 + 1, PIECE), pby = cdiv_dev(y1 - y0 + 1, PIECE);
         int* ce = cw.clusters + 8 * (size_t)cid;
+        if (bad) {                                       // (a cluster id beyond the table implies bad)
+            if (cid < cw.cl_cap) { ce[0] = f; ce[1] = 1; ce[2] = 0; ce[3] = 0; ce[4] = 0; ce[5] = 0; }   // empty box: nothing downstream touches it
+            for (int q = 0; q < pbx * pby; ++q) {        // the pieces this frame reserved become empty ones
+                size_t pi = (size_t)p00 + (size_t)r_pcs[i] + (size_t)q;
+                if (pi < (size_t)cw.pc_cap) { *(int4*)(cw.pieces + 8 * pi) = make_int4(0, 0, 0, 0); *(int4*)(cw.pieces + 8 * pi + 4) = make_int4(0, 0, 0, 0); }
+            }
+            continue;
+        }
         ce[0] = f;
-        if (bad) { ce[1] = 1; ce[2] = 0; ce[3] = 0; ce[4] = 0; ce[5] = 0; continue; }      // empty box: nothing downstream touches it
         ce[1] = x0 | (y0 << 16); ce[2] = x1 | (y1 << 16); ce[3] = (int)(roff0 + (unsigned)r_words[i]); ce[4] = pbx * (PIECE / 32);
         ce[5] = cbox[4 * r + 3]; ce[6] = 0; ce[7] = 0;
-        for (int q = 0; q < pbx * pby; ++q) {
-            cw.pieces[2 * (size_t)(p00 + r_pcs[i] + q)] = cid;
-            cw.pieces[2 * (size_t)(p00 + r_pcs[i] + q) + 1] = (q % pbx) | ((q / pbx) << 16);
-        }
+        for (int q = 0; q < pbx * pby; ++q)
+            make_piece_desc(tv, f, x0, y0, x1, y1, q % pbx, q / pbx, (unsigned)ce[3], ce[4], cw.pieces + 8 * (size_t)(p00 + r_pcs[i] + q));
     }
     if (tid == 0) {
         cw.frame_clusters[2 * f] = cid0; cw.frame_clusters[2 * f + 1] = bad ? 0 : nr;
@@ -284,13 +335,14 @@ __device__ __forceinline__ void count5(uint32_t a, uint32_t b, uint32_t c, uint3
 // hl, hr, ht, hb (0 or 2): how far the thresholded-mean box extends beyond the piece on each side.  It stops at the
 // cluster box: outside of it the thresholded mean cannot be set by this cluster's hot pixels (it would lie more than 2 from
 // them), and whatever foreign hot pixels set there can only influence pixels that are not this cluster's foreground.
-__device__ __forceinline__ void piece_threshold_majority_packed(PieceSmem& S, int mw, int mh, int hl, int hr, int ht, int hb, int T,
-                                                                uint32_t* __restrict__ out, int wpr)
+struct PackedDims { int mw, mh, hl, hr, ht, hb; };
+
+// ---- A ----  horizontal 5-sums of U -> HS
+__device__ __forceinline__ void packed_stage_a(PieceSmem& S, const PackedDims& d)
 {
     constexpr int UW = PieceSmem::UW, BW = PieceSmem::BW;
     const int tid = threadIdx.x;
-    const int bw = mw + hl + hr, bh = mh + ht + hb, uh = bh + 4;
-    // ---- A ----
+    const int bw = d.mw + d.hl + d.hr, uh = d.mh + d.ht + d.hb + 4;
     const int nq = (bw + 3) >> 2;
     const unsigned inv_q = (1u << 20) / (unsigned)nq + 1u;                        // t / nq == (t * inv_q) >> 20 (t * nq < 2^20)
     for (int t = tid; t < uh * nq; t += CL_THREADS) {
@@ -304,8 +356,14 @@ __device__ __forceinline__ void piece_threshold_majority_packed(PieceSmem& S, in
         uint2 v; v.x = s0 | (s1 << 16); v.y = s2 | (s3 << 16);
         *(uint2*)&S.HS[r * BW + 4 * q] = v;
     }
-    __syncthreads();
-    // ---- B ----  bit rows of the thresholded mean: 16 bytes per row in S.B (72 bits used)
+}
+
+// ---- B ----  bit rows of the thresholded mean: 16 bytes per row in S.B (72 bits used)
+__device__ __forceinline__ void packed_stage_b(PieceSmem& S, const PackedDims& d, int T)
+{
+    constexpr int BW = PieceSmem::BW;
+    const int tid = threadIdx.x;
+    const int bw = d.mw + d.hl + d.hr, bh = d.mh + d.ht + d.hb;
     uint8_t* bbits = S.B;
     const int no = (bw + 7) >> 3;
     const uint32_t bias = (0x8000u - (uint32_t)(25 * T)) * 0x00010001u;          // bit 15 of (v + bias) set  <=>  v >= 25 T
@@ -324,13 +382,19 @@ __device__ __forceinline__ void piece_threshold_majority_packed(PieceSmem& S, in
         uint32_t y = (m0 >> 15) | (m1 >> 13) | (m2 >> 11) | (m3 >> 9);             // even bits 0..6 and 16..22
         bbits[r * 16 + o] = (uint8_t)((y & 0x55u) | ((y >> 15) & 0xAAu));
     }
-    __syncthreads();
-    // ---- C ----  horizontal 5-counts per B row as three 64-bit planes (two 32-bit halves each) in S.MH
-    uint32_t* planes = (uint32_t*)S.HS;                                           // [mh + 4][3][2]; HS is dead after stage B
+}
+
+// ---- C1 ----  horizontal 5-counts per B row as three 64-bit planes (two 32-bit halves each), kept in S.HS (dead after B)
+__device__ __forceinline__ void packed_stage_c1(PieceSmem& S, const PackedDims& d)
+{
+    const int tid = threadIdx.x;
+    const int bw = d.mw + d.hl + d.hr, bh = d.mh + d.ht + d.hb;
+    const uint8_t* bbits = S.B;
+    uint32_t* planes = (uint32_t*)S.HS;                                           // [mh + 4][3][2]
     // plane row / bit position = offset from (piece - 2): the box rows and columns land at (2 - ht) / (2 - hl), what lies
     // outside the box is zero
-    for (int r = tid; r < mh + 4; r += CL_THREADS) {
-        const int rb = r - (2 - ht);
+    for (int r = tid; r < d.mh + 4; r += CL_THREADS) {
+        const int rb = r - (2 - d.ht);
         uint32_t w0 = 0, w1 = 0, w2 = 0;
         if (rb >= 0 && rb < bh) {
             const uint32_t* bp = (const uint32_t*)&bbits[rb * 16];
@@ -338,7 +402,7 @@ __device__ __forceinline__ void piece_threshold_majority_packed(PieceSmem& S, in
             if (bw < 32) { w0 &= (1u << bw) - 1u; w1 = 0; w2 = 0; }               // drop the surplus bits of the last byte
             else if (bw < 64) { w1 &= bw == 32 ? 0u : (1u << (bw - 32)) - 1u; w2 = 0; }
             else w2 &= bw == 64 ? 0u : (1u << (bw - 64)) - 1u;
-            if (hl == 0) { w2 = (w2 << 2) | (w1 >> 30); w1 = (w1 << 2) | (w0 >> 30); w0 <<= 2; }
+            if (d.hl == 0) { w2 = (w2 << 2) | (w1 >> 30); w1 = (w1 << 2) | (w0 >> 30); w0 <<= 2; }
         }
 #pragma unroll
         for (int h = 0; h < 2; ++h) {
@@ -349,9 +413,14 @@ __device__ __forceinline__ void piece_threshold_majority_packed(PieceSmem& S, in
             planes[(r * 3 + 0) * 2 + h] = n0; planes[(r * 3 + 1) * 2 + h] = n1; planes[(r * 3 + 2) * 2 + h] = n2;
         }
     }
-    __syncthreads();
-    //          per output row: sum of five rows' counts (p + 2 q + 4 r with p, q, r = counts of the three planes) >= 13
-    for (int t = tid; t < mh * 2; t += CL_THREADS) {
+}
+
+// ---- C2 ----  per output row: sum of five rows' counts (p + 2 q + 4 r with p, q, r = counts of the three planes) >= 13
+__device__ __forceinline__ void packed_stage_c2(PieceSmem& S, const PackedDims& d, uint32_t* __restrict__ out, int wpr)
+{
+    const int tid = threadIdx.x;
+    const uint32_t* planes = (const uint32_t*)S.HS;
+    for (int t = tid; t < d.mh * 2; t += CL_THREADS) {
         int r = t >> 1, h = t & 1;
         uint32_t p0, p1, p2, q0, q1, q2, r0, r1, r2;
         const uint32_t* pl = planes + (size_t)r * 6 + h;
@@ -367,7 +436,7 @@ __device__ __forceinline__ void piece_threshold_majority_packed(PieceSmem& S, in
         uint32_t b3 = s3 ^ c2b, c3b = s3 & c2b;
         uint32_t b4 = r2 | c3 | c3b;                                              // total <= 25: bit 5 cannot be set
         uint32_t ge13 = b4 | (b3 & b2 & (b1 | b0));
-        int rem = mw - 32 * h;                                                    // keep only the piece's own columns
+        int rem = d.mw - 32 * h;                                                  // keep only the piece's own columns
         if (rem < 32) ge13 &= rem > 0 ? ((1u << rem) - 1u) : 0u;
         out[(size_t)r * wpr + h] = ge13;
     }
@@ -429,79 +498,88 @@ __device__ __forceinline__ void piece_threshold_majority(PieceSmem& S, int px0, 
     }
 }
 
+// 16 bytes global -> shared without a register round trip (lands asynchronously; piece_copy_wait before the data is used)
+__device__ __forceinline__ void piece_copy16(void* dst_smem, const void* src)
+{
+#ifdef MOCAP_EMU
+    *(uint4*)dst_smem = *(const uint4*)src;
+#else
+    unsigned d = (unsigned)__cvta_generic_to_shared(dst_smem);
+    asm volatile("cp.async.cg.shared.global [%0], [%1], 16;\n" :: "r"(d), "l"(src) : "memory");
+#endif
+}
+__device__ __forceinline__ void piece_copy_wait()
+{
+#ifndef MOCAP_EMU
+    asm volatile("cp.async.wait_all;\n" ::: "memory");
+#endif
+}
+
+// source window of a piece -> shared memory, 16 bytes per copy, zero outside the frame
+__device__ __forceinline__ void piece_issue_window(uint8_t* win, const int* d, const uint8_t* __restrict__ frames, int64_t fstride, int W, int H)
+{
+    const int wh = (d[4] >> 16) & 0xff, nvec = (d[4] >> 24) & 0xff;
+    const int wx0 = (int)(int16_t)(d[5] & 0xffff), wy0 = d[5] >> 16;
+    const uint8_t* fr = frames + (size_t)d[0] * fstride;
+    const unsigned inv_v = nvec ? (1u << 16) / (unsigned)nvec + 1u : 0u;            // idx / nvec for idx * nvec < 2^16
+    for (int idx = threadIdx.x; idx < wh * nvec; idx += CL_THREADS) {
+        int row = (int)(((unsigned)idx * inv_v) >> 16), v = idx - row * nvec;
+        int gy = wy0 + row, gx = wx0 + 16 * v;
+        uint8_t* dst = &win[row * WIN_W + 16 * v];
+        if ((unsigned)gy < (unsigned)H && gx >= 0 && gx + 16 <= W) piece_copy16(dst, fr + (size_t)gy * W + gx);
+        else *(uint4*)dst = make_uint4(0, 0, 0, 0);
+    }
+}
+
+// Persistent CTAs over the piece list.  The loop is software-pipelined over pieces: while the packed stages of piece i run,
+// warp 0 fetches the descriptor of piece i + 1 and every thread posts that piece's source window into `win` (free again once
+// the remap of piece i is done), so that neither the descriptor nor the window latency is waited for.
 __global__ void __launch_bounds__(CL_THREADS, 8) piece_filter_kernel(const uint8_t* __restrict__ frames, int64_t fstride, TableView tv, int thresh,
                                                                   ClusterWs cw)
 {
     __shared__ PieceSmem S;
     __align__(16) __shared__ uint8_t win[WIN_W * WIN_H];           // staged source window
-    __shared__ int s_win[5];
+    __align__(16) __shared__ int s_desc[2][8];
+    __shared__ int s_next;
     constexpr int UW = PieceSmem::UW, BW = PieceSmem::BW;
-    __shared__ int s_item;
     const bool vec_ok = (tv.W % 16 == 0) && (fstride % 16 == 0) && (((uintptr_t)frames) % 16 == 0);
     const int tid = threadIdx.x, lane = tid & 31, wy = tid >> 5, NWARP = CL_THREADS / 32;
     const int H = tv.H, W = tv.W, T = thresh + 1;
+    const bool t_ok = T >= 0 && T <= 256;                          // thresholds the packed stages can represent
+    const bool use_win = vec_ok && t_ok;                           // else: descriptors' windows are ignored, taps come from global memory
     const int total = min(cw.counters[CN_PIECES], cw.pc_cap);
-    int next = tid == 0 ? atomicAdd(&cw.counters[CN_PIECE_CUR], 1) : 0;
+    if (tid == 0) s_next = atomicAdd(&cw.counters[CN_PIECE_CUR], 1);
+    __syncthreads();
+    int item = s_next;
+    if (item >= total) return;
+    if (tid < 8) s_desc[0][tid] = cw.pieces[8 * (size_t)item + tid];
+    int next = tid == 0 ? atomicAdd(&cw.counters[CN_PIECE_CUR], 1) : 0;      // in flight while the first piece is processed
+    __syncthreads();
+    if (use_win) piece_issue_window(win, s_desc[0], frames, fstride, W, H);
+    int slot = 0;
     for (;;) {
-        __syncthreads();
-        if (tid == 0) s_item = next;
-        __syncthreads();
-        const int item = s_item;
-        if (item >= total) break;
-        if (tid == 0) next = atomicAdd(&cw.counters[CN_PIECE_CUR], 1);     // fetched while this piece is processed
-        const int* ce = cw.clusters + 8 * (size_t)cw.pieces[2 * (size_t)item];
-        const int bxy = cw.pieces[2 * (size_t)item + 1], bx = bxy & 0xffff, by = bxy >> 16;
-        const int f = ce[0];
-        const int cx0 = ce[1] & 0xffff, cy0 = ce[1] >> 16, cx1 = ce[2] & 0xffff, cy1 = ce[2] >> 16, wpr = ce[4];
-        const int px0 = cx0 + bx * PIECE, py0 = cy0 + by * PIECE;
-        const int px1 = min(px0 + PIECE - 1, cx1), py1 = min(py0 + PIECE - 1, cy1);
-        const int mw = px1 - px0 + 1, mh = py1 - py0 + 1;
+        const int* d = s_desc[slot];
+        const int f = d[0], px0 = d[1] & 0xffff, py0 = d[1] >> 16;
+        const int dims = d[2];
+        PackedDims pd;
+        pd.mw = dims & 0xff; pd.mh = (dims >> 8) & 0xff;
+        pd.hl = (dims >> 16) & 3; pd.hr = (dims >> 18) & 3; pd.ht = (dims >> 20) & 3; pd.hb = (dims >> 22) & 3;
+        const int mw = pd.mw, mh = pd.mh;
+        const bool packed = ((dims >> 24) & 1) && t_ok;
+        const bool staged = ((dims >> 25) & 1) && use_win;
+        const int wpr = d[4] & 0xffff;
+        const int wx0 = (int)(int16_t)(d[5] & 0xffff), wy0 = d[5] >> 16;
+        uint32_t* out = cw.rows_out + (unsigned)d[3];
+        const int px1 = px0 + mw - 1, py1 = py0 + mh - 1;
+        const int ux0 = packed ? px0 - pd.hl - 2 : px0 - 4, uy0 = packed ? py0 - pd.ht - 2 : py0 - 4;      // origin of the U box
+        const int ux1 = packed ? px1 + pd.hr + 2 : px1 + 4, uy1 = packed ? py1 + pd.hb + 2 : py1 + 4;
+        const int uw = ux1 - ux0 + 1, uh = uy1 - uy0 + 1, bw = mw + 4;
         const uint8_t* fr = frames + (size_t)f * fstride;
-        // halo of the thresholded-mean box around the piece: 2, but never beyond the cluster box (see the packed stages)
-        const int hl = px0 - max(px0 - 2, cx0), hr = min(px1 + 2, cx1) - px1, ht = py0 - max(py0 - 2, cy0), hb = min(py1 + 2, cy1) - py1;
-        // no frame border within reach and a representable threshold: stages 2-3 run packed / bit-sliced on the tight boxes;
-        // otherwise the plain per-pixel code with the full +-4 halo and clamped coordinates
-        const bool packed = px0 - hl >= 2 && py0 - ht >= 2 && px1 + hr + 2 < W && py1 + hb + 2 < H && T >= 0 && T <= 256;
-        const int ux0 = packed ? px0 - hl - 2 : px0 - 4, uy0 = packed ? py0 - ht - 2 : py0 - 4;      // origin of the U box
-        const int ux1 = packed ? px1 + hr + 2 : px1 + 4, uy1 = packed ? py1 + hb + 2 : py1 + 4;
-        const int uw = ux1 - ux0 + 1, uh = uy1 - uy0 + 1, bw = mw + 4, bh = mh + 4;
-        // ---- 0. stage the source window of the piece in shared memory with 16-byte loads (zero outside the frame): the
-        //         bilinear taps then come from shared memory instead of four dependent global byte gathers per pixel.
-        //         Window = piece box +-4 shifted by the displacement bounds of the tiles it overlaps (undistortion table). ------
-        if (tid < 32) {
-            int tx0 = max(ux0 >> 5, 0), tx1 = min(ux1 >> 5, tv.TX - 1);
-            int ty0 = max(uy0 >> 5, 0), ty1 = min(uy1 >> 5, tv.TY - 1);
-            int ntx = tx1 - tx0 + 1, ntl = ntx * (ty1 - ty0 + 1);
-            int dx0 = 0x7fffffff, dx1 = -0x7fffffff, dy0 = 0x7fffffff, dy1 = -0x7fffffff;
-            for (int l = lane; l < ntl; l += 32) {
-                const int32_t* tt = tv.tile + 8 * ((ty0 + l / ntx) * tv.TX + tx0 + l % ntx);
-                if (tt[4] <= tt[5]) { dx0 = min(dx0, tt[4]); dx1 = max(dx1, tt[5]); dy0 = min(dy0, tt[6]); dy1 = max(dy1, tt[7]); }
-            }
-            dx0 = __reduce_min_sync(0xffffffffu, dx0); dx1 = __reduce_max_sync(0xffffffffu, dx1);
-            dy0 = __reduce_min_sync(0xffffffffu, dy0); dy1 = __reduce_max_sync(0xffffffffu, dy1);
-            if (lane == 0) {
-                int wx0 = (ux0 + dx0) & ~15, wx1 = ux1 + dx1 + 1, wy0 = uy0 + dy0, wy1 = uy1 + dy1 + 1;
-                bool ok = vec_ok && dx0 <= dx1 && wx1 - wx0 + 1 <= WIN_W && wy1 - wy0 + 1 <= WIN_H;
-                s_win[0] = wx0; s_win[1] = wy0; s_win[2] = ok ? wy1 - wy0 + 1 : 0; s_win[3] = ok;
-                s_win[4] = ok ? (wx1 - wx0 + 16) >> 4 : 0;                  // 16-byte vectors per window row actually needed
-            }
-        }
-        __syncthreads();
-        const int wx0 = s_win[0], wy0 = s_win[1], wh = s_win[2];
-        const bool staged = s_win[3] != 0;
-        const int nvec = s_win[4];
-        const unsigned inv_v = nvec ? (1u << 16) / (unsigned)nvec + 1u : 0u;        // idx / nvec for idx * nvec < 2^16
-        for (int idx = tid; idx < wh * nvec; idx += CL_THREADS) {
-            int row = (int)(((unsigned)idx * inv_v) >> 16), v = idx - row * nvec;
-            int gy = wy0 + row, gx = wx0 + 16 * v;
-            uint4 val = make_uint4(0, 0, 0, 0);
-            if ((unsigned)gy < (unsigned)H && gx >= 0 && gx + 16 <= W) val = *(const uint4*)(fr + (size_t)gy * W + gx);
-            *(uint4*)&win[row * WIN_W + 16 * v] = val;
-        }
-        __syncthreads();
-        // ---- 1. undistorted pixels of the piece dilated by 4 (zero outside the frame): the uw x uh box is walked as a flat
-        //         index (all lanes busy whatever the box width), four pixels per thread per pass so that the map loads of a
-        //         pass are in flight together. -----------------------------------------------------------------------------------
+        piece_copy_wait();
+        __syncthreads();                                            // the window of this piece has landed
+        // ---- 1. undistorted pixels of the U box (zero outside the frame): the uw x uh box is walked as a flat index (all
+        //         lanes busy whatever the box width), four pixels per thread per pass so that the map loads of a pass are
+        //         in flight together; the bilinear taps come from the staged window. ----------------------------------------
         if (packed && staged) {
             // fast path: the box lies inside the frame and its source window is staged; everything in piece-local
             // coordinates (source column in the window = c + (du >> 5) + const, fraction = du & 31)
@@ -565,18 +643,46 @@ __global__ void __launch_bounds__(CL_THREADS, 8) piece_filter_kernel(const uint8
                 }
             }
         }
-        __syncthreads();
-        if (!packed) {
+        __syncthreads();                                            // U complete; the window is free again
+        // warp 0 starts fetching the next piece's descriptor (used two barriers further down)
+        int nx = 0, dn = 0;
+        if (wy == 0) {
+            nx = __shfl_sync(0xffffffffu, next, 0);
+            if (lane < 8 && nx < total) dn = cw.pieces[8 * (size_t)nx + lane];
+        }
+        if (packed) {
+            packed_stage_a(S, pd);
+            __syncthreads();
+            if (wy == 0 && lane < 8) s_desc[slot ^ 1][lane] = dn;
+            if (tid == 0) s_next = nx;
+            packed_stage_b(S, pd, T);
+            __syncthreads();
+            if (s_next < total) {
+                if (use_win) piece_issue_window(win, s_desc[slot ^ 1], frames, fstride, W, H);
+                if (tid == 0) next = atomicAdd(&cw.counters[CN_PIECE_CUR], 1);
+            }
+            packed_stage_c1(S, pd);
+            __syncthreads();
+            packed_stage_c2(S, pd, out, wpr);
+        } else {
+            // plain per-pixel stages with the full +-4 halo and clamped coordinates (frame border within reach)
             for (int r = wy; r < uh; r += NWARP)
                 for (int c = lane; c < bw; c += 32) {
                     const uint8_t* up = &S.U[r * UW + c];
                     S.HS[r * BW + c] = (uint16_t)(up[0] + up[1] + up[2] + up[3] + up[4]);
                 }
             __syncthreads();
+            piece_threshold_majority<false>(S, px0, py0, mw, mh, W, H, T, out, wpr);
+            if (wy == 0 && lane < 8) s_desc[slot ^ 1][lane] = dn;
+            if (tid == 0) s_next = nx;
+            __syncthreads();
+            if (s_next < total) {
+                if (use_win) piece_issue_window(win, s_desc[slot ^ 1], frames, fstride, W, H);
+                if (tid == 0) next = atomicAdd(&cw.counters[CN_PIECE_CUR], 1);
+            }
         }
-        uint32_t* out = cw.rows_out + (unsigned)ce[3] + (size_t)(py0 - cy0) * wpr + bx * (PIECE / 32);
-        if (packed) piece_threshold_majority_packed(S, mw, mh, hl, hr, ht, hb, T, out, wpr);
-        else piece_threshold_majority<false>(S, px0, py0, mw, mh, W, H, T, out, wpr);
+        if (s_next >= total) break;
+        slot ^= 1;
     }
 }
 
@@ -903,7 +1009,7 @@ size_t cluster_ws_bytes(int n, int H, int W, int max_contours, size_t* offs /*[1
     offs[0] = take((size_t)n * 4);                         // need_general
     offs[1] = take(64);                                    // counters
     offs[2] = take((size_t)cl_cap_of(n) * 32);             // clusters
-    offs[3] = take((size_t)pc_cap_of(n) * 8);              // pieces
+    offs[3] = take((size_t)pc_cap_of(n) * 32);             // pieces
     offs[4] = take((size_t)n * 4);                         // rec_count
     offs[5] = take((size_t)n * max_contours * 4);          // rec_start
     offs[6] = take((size_t)n * max_contours * 24);         // rec_a
@@ -956,11 +1062,7 @@ int launch_cluster_path(const uint8_t* frames, int n, int H, int W, int64_t fstr
     const int cells = tv.TX * tv.TY;
     size_t sm_form = (size_t)((cells + 7) & ~7) * 2 + (size_t)HOT_MAX * (2 + 4 + 16 + 8 + 8) + (size_t)ROOTS_MAX * (2 + 12) + 64;
 #ifndef MOCAP_EMU
-    static bool attr_done = false;
-    if (!attr_done) {
-        cudaFuncSetAttribute(form_clusters_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 64 * 1024);
-        attr_done = true;
-    }
+    CUDA_TRY(cudaFuncSetAttribute(form_clusters_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 64 * 1024));
 #endif
     stage_begin(timer, 1, s);
     LAUNCH(form_clusters_kernel, n, CL_THREADS, sm_form, s, cellbox, tv, cw);
