@@ -531,9 +531,10 @@ __device__ __forceinline__ void piece_issue_window(uint8_t* win, const int* d, c
     }
 }
 
-// Persistent CTAs over the piece list.  The loop is software-pipelined over pieces: while the packed stages of piece i run,
-// warp 0 fetches the descriptor of piece i + 1 and every thread posts that piece's source window into `win` (free again once
-// the remap of piece i is done), so that neither the descriptor nor the window latency is waited for.
+// Persistent CTAs over the piece list.  The loop is software-pipelined over pieces: as soon as the remap of piece i has
+// consumed `win`, every thread posts the source window of piece i + 1 into it (cp.async, lands while the stages of piece i
+// run), warp 0 fetches the descriptor of piece i + 2 and thread 0 draws the index of piece i + 3 -- no descriptor, window or
+// work-counter latency is waited for inside the loop.
 __global__ void __launch_bounds__(CL_THREADS, 8) piece_filter_kernel(const uint8_t* __restrict__ frames, int64_t fstride, TableView tv, int thresh,
                                                                   ClusterWs cw)
 {
@@ -550,10 +551,17 @@ __global__ void __launch_bounds__(CL_THREADS, 8) piece_filter_kernel(const uint8
     const int total = min(cw.counters[CN_PIECES], cw.pc_cap);
     if (tid == 0) s_next = atomicAdd(&cw.counters[CN_PIECE_CUR], 1);
     __syncthreads();
-    int item = s_next;
+    const int item = s_next;
     if (item >= total) return;
     if (tid < 8) s_desc[0][tid] = cw.pieces[8 * (size_t)item + tid];
-    int next = tid == 0 ? atomicAdd(&cw.counters[CN_PIECE_CUR], 1) : 0;      // in flight while the first piece is processed
+    // three pieces deep: piece i is processed from s_desc[slot], warp 0 holds the descriptor of piece i + 1 in registers (dn),
+    // thread 0 the index of piece i + 2 (next, an atomic in flight)
+    int nx = 0, dn = 0, next = 0;
+    if (wy == 0) {
+        nx = __shfl_sync(0xffffffffu, lane == 0 ? atomicAdd(&cw.counters[CN_PIECE_CUR], 1) : 0, 0);
+        if (lane < 8 && nx < total) dn = cw.pieces[8 * (size_t)nx + lane];
+        if (lane == 0) next = atomicAdd(&cw.counters[CN_PIECE_CUR], 1);
+    }
     __syncthreads();
     if (use_win) piece_issue_window(win, s_desc[0], frames, fstride, W, H);
     int slot = 0;
@@ -576,7 +584,9 @@ __global__ void __launch_bounds__(CL_THREADS, 8) piece_filter_kernel(const uint8
         const int uw = ux1 - ux0 + 1, uh = uy1 - uy0 + 1, bw = mw + 4;
         const uint8_t* fr = frames + (size_t)f * fstride;
         piece_copy_wait();
-        __syncthreads();                                            // the window of this piece has landed
+        __syncthreads();                                            // the window of this piece has landed; the other descriptor slot is free
+        if (wy == 0 && lane < 8) s_desc[slot ^ 1][lane] = dn;
+        if (tid == 0) s_next = nx;
         // ---- 1. undistorted pixels of the U box (zero outside the frame): the uw x uh box is walked as a flat index (all
         //         lanes busy whatever the box width), four pixels per thread per pass so that the map loads of a pass are
         //         in flight together; the bilinear taps come from the staged window. ----------------------------------------
@@ -644,23 +654,18 @@ __global__ void __launch_bounds__(CL_THREADS, 8) piece_filter_kernel(const uint8
             }
         }
         __syncthreads();                                            // U complete; the window is free again
-        // warp 0 starts fetching the next piece's descriptor (used two barriers further down)
-        int nx = 0, dn = 0;
+        // post the next piece's window (it lands while the stages below run), fetch the descriptor of the piece after it
+        if (s_next < total && use_win) piece_issue_window(win, s_desc[slot ^ 1], frames, fstride, W, H);
         if (wy == 0) {
             nx = __shfl_sync(0xffffffffu, next, 0);
-            if (lane < 8 && nx < total) dn = cw.pieces[8 * (size_t)nx + lane];
+            dn = (lane < 8 && nx < total) ? cw.pieces[8 * (size_t)nx + lane] : 0;
+            if (lane == 0) next = atomicAdd(&cw.counters[CN_PIECE_CUR], 1);
         }
         if (packed) {
             packed_stage_a(S, pd);
             __syncthreads();
-            if (wy == 0 && lane < 8) s_desc[slot ^ 1][lane] = dn;
-            if (tid == 0) s_next = nx;
             packed_stage_b(S, pd, T);
             __syncthreads();
-            if (s_next < total) {
-                if (use_win) piece_issue_window(win, s_desc[slot ^ 1], frames, fstride, W, H);
-                if (tid == 0) next = atomicAdd(&cw.counters[CN_PIECE_CUR], 1);
-            }
             packed_stage_c1(S, pd);
             __syncthreads();
             packed_stage_c2(S, pd, out, wpr);
@@ -673,13 +678,6 @@ __global__ void __launch_bounds__(CL_THREADS, 8) piece_filter_kernel(const uint8
                 }
             __syncthreads();
             piece_threshold_majority<false>(S, px0, py0, mw, mh, W, H, T, out, wpr);
-            if (wy == 0 && lane < 8) s_desc[slot ^ 1][lane] = dn;
-            if (tid == 0) s_next = nx;
-            __syncthreads();
-            if (s_next < total) {
-                if (use_win) piece_issue_window(win, s_desc[slot ^ 1], frames, fstride, W, H);
-                if (tid == 0) next = atomicAdd(&cw.counters[CN_PIECE_CUR], 1);
-            }
         }
         if (s_next >= total) break;
         slot ^= 1;
