@@ -452,17 +452,18 @@ __global__ void scan_hot_scalar_kernel(const uint8_t* __restrict__ frames, int n
     }
 }
 
-// general path: the output tiles the hot cells of a flagged frame can reach (one thread per source cell)
+// general path: the output tiles the hot cells of a flagged frame can reach (one CTA per frame; frames the cluster path
+// finished leave at once)
 __global__ void mark_active_kernel(const uint32_t* __restrict__ cellbox, TableView tv, int n_frames, uint32_t* __restrict__ active, int TXW,
                                    const int* __restrict__ need_general)
 {
     const int cells = tv.TX * tv.TY;
-    long long idx = (long long)blockIdx.x * blockDim.x + threadIdx.x;
-    if (idx >= (long long)n_frames * cells) return;
-    int f = (int)(idx / cells), c = (int)(idx - (long long)f * cells);
-    if (need_general && !need_general[f]) return;
-    if (cellbox[idx] == CELL_EMPTY) return;
-    mark_cell(tv, active, f, c / tv.TX, c % tv.TX, TXW);
+    for (int f = blockIdx.x; f < n_frames; f += gridDim.x) {
+        if (need_general && !need_general[f]) continue;
+        const uint32_t* cb = cellbox + (size_t)f * cells;
+        for (int c = threadIdx.x; c < cells; c += blockDim.x)
+            if (cb[c] != CELL_EMPTY) mark_cell(tv, active, f, c / tv.TX, c % tv.TX, TXW);
+    }
 }
 
 __global__ void compact_tiles_kernel(const uint32_t* __restrict__ active, long long n_words, int TX, int TY, int TXW,
@@ -720,8 +721,7 @@ int launch_tiles(const uint8_t* frames, int n, int H, int W, int64_t fstride, co
     cudaGetDevice(&dev);
     cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
     CUDA_TRY(cudaMemsetAsync(ws.active, 0, (size_t)n * TY * TXW * 4, s));
-    long long n_cells = (long long)n * TX * TY;
-    LAUNCH(mark_active_kernel, (unsigned)((n_cells + 255) / 256), 256, 0, s, ws.cellbox, tv, n, ws.active, TXW, need_general);
+    LAUNCH(mark_active_kernel, (unsigned)(n < 65535 ? n : 65535), 256, 0, s, ws.cellbox, tv, n, ws.active, TXW, need_general);
     long long n_words = (long long)n * TY * TXW;
     LAUNCH(compact_tiles_kernel, (unsigned)((n_words + 255) / 256), 256, 0, s, ws.active, n_words, TX, TY, TXW, ws.list, ws.counters, need_general);
     LAUNCH(filter_tiles_kernel, sms * 4, FT_WARPS * 32, 0, s, frames, fstride, tv, thresh, ws.list, ws.counters, ws.counters + 1,
