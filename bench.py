@@ -416,7 +416,7 @@ def run_b200(args):
     except Exception:
         pass
     det_ms = sum(stage_avg.values())
-    kernels = {"scan": "scan_hot_vec_kernel", "group": "form_clusters_kernel", "filter": "piece_filter_kernel",
+    kernels = {"scan": "scan_hot_vec32_kernel", "group": "form_clusters_kernel", "filter": "piece_filter_kernel",
                "borders": "candidates_kernel + borders_finalize_kernel (traces, filter/centroid/order)",
                "finish": "general path for flagged frames (mark_active/compact_tiles/filter_tiles/blobs)"}
     roofline = {"bound": "hbm", "kernel": kernels.get(dom, dom), "stage": dom, "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
