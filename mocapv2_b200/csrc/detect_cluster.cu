@@ -79,6 +79,9 @@ __device__ __forceinline__ void suf_union(int* parent, int a, int b)
 
 __device__ __forceinline__ int cdiv_dev(int a, int b) { return (a + b - 1) / b; }
 
+// u16 slots of form_clusters_kernel's cell -> hot-slot map; at least two int arrays of HOT_MAX (reused once the map is dead)
+__host__ __device__ __forceinline__ int form_idx_slots(int cells) { int a = (cells + 7) & ~7; return a > 4 * HOT_MAX ? a : 4 * HOT_MAX; }
+
 __device__ __forceinline__ bool boxes_touch(const int* a, const int* b)
 {
     return a[0] <= b[2] + 1 && b[0] <= a[2] + 1 && a[1] <= b[3] + 1 && b[1] <= a[3] + 1;
@@ -105,14 +108,17 @@ __device__ __forceinline__ void make_piece_desc(const TableView& tv, int f, int 
     const int ux1 = packed ? px1 + hr + 2 : px1 + 4, uy1 = packed ? py1 + hb + 2 : py1 + 4;
     const int tx0 = max(ux0 >> 5, 0), tx1 = min(ux1 >> 5, tv.TX - 1), ty0 = max(uy0 >> 5, 0), ty1 = min(uy1 >> 5, tv.TY - 1);
     int dx0 = 0x7fffffff, dx1 = -0x7fffffff, dy0 = 0x7fffffff, dy1 = -0x7fffffff;
-    for (int ty = ty0; ty <= ty1; ++ty)
-        for (int tx = tx0; tx <= tx1; ++tx) {
-            const int4 t = *(const int4*)(tv.tile + 8 * (ty * tv.TX + tx) + 4);
-            if (t.x <= t.y) { dx0 = min(dx0, t.x); dx1 = max(dx1, t.y); dy0 = min(dy0, t.z); dy1 = max(dy1, t.w); }
-        }
+    for (int ty = ty0; ty <= ty1; ++ty) {                                  // the U box (<= 72 wide) spans at most 4 tiles per row:
+        int4 t[4];                                                         // four loads in flight, surplus ones repeat the last tile
+#pragma unroll
+        for (int q = 0; q < 4; ++q) t[q] = *(const int4*)(tv.tile + 8 * (ty * tv.TX + min(tx0 + q, tx1)) + 4);
+#pragma unroll
+        for (int q = 0; q < 4; ++q)
+            if (t[q].x <= t[q].y) { dx0 = min(dx0, t[q].x); dx1 = max(dx1, t[q].y); dy0 = min(dy0, t[q].z); dy1 = max(dy1, t[q].w); }
+    }
     int wx0 = 0, wy0 = 0, wh = 0, nvec = 0;
     bool fits = false;
-    if (dx0 <= dx1) {
+    if (dx0 <= dx1 && tx1 - tx0 <= 3) {
         wx0 = (ux0 + dx0) & ~15; wy0 = uy0 + dy0;
         const int wx1 = ux1 + dx1 + 1, wy1 = uy1 + dy1 + 1;
         fits = wx1 - wx0 + 1 <= WIN_W && wy1 - wy0 + 1 <= WIN_H && wx0 >= -32768 && wy0 >= -32768;
@@ -141,8 +147,8 @@ __global__ void __launch_bounds__(CL_THREADS) form_clusters_kernel(const uint32_
     const int TX = tv.TX, TY = tv.TY, cells = TX * TY, W = tv.W, H = tv.H;
     if (cw.need_general[f]) return;
     // carve: idx_of[cells] u16 | hot_cell[HOT_MAX] u16 | parent[HOT_MAX] int | box[HOT_MAX][4] short | cbox[HOT_MAX][4] int | roots[ROOTS_MAX] u16
-    uint16_t* idx_of = (uint16_t*)smraw;
-    uint16_t* hot_cell = idx_of + ((cells + 7) & ~7);
+    uint16_t* idx_of = (uint16_t*)smraw;                // dead after the neighbour pass: its memory then holds fill[] and ymax[]
+    uint16_t* hot_cell = idx_of + form_idx_slots(cells);
     int* parent = (int*)(hot_cell + HOT_MAX);
     int* cbox = parent + HOT_MAX;
     short* box = (short*)(cbox + 4 * HOT_MAX);
@@ -216,15 +222,18 @@ __global__ void __launch_bounds__(CL_THREADS) form_clusters_kernel(const uint32_
     for (int h = tid; h < n_hot; h += nt) {
         cbox[4 * h] = 0x7fffffff; cbox[4 * h + 1] = 0x7fffffff; cbox[4 * h + 2] = -1; cbox[4 * h + 3] = 0;   // [3]: member count, then offset | count << 16
     }
+    int* fill = (int*)idx_of;                           // per root (hot slot): members written so far
+    int* ymax = fill + HOT_MAX;                         // per root: y1 of the bounding box
+    for (int h = tid; h < n_hot; h += nt) { fill[h] = 0; ymax[h] = -1; }
     if (tid == 0) s_nroots = 0;
     __syncthreads();
-    // bounding box per root: x0, y0, x1 in cbox[0..2]; y1 kept in a second pass to leave cbox[3] for the count
+    // bounding box per root: x0, y0, x1 in cbox[0..2], y1 in ymax[]; cbox[3] counts the members
     for (int h = tid; h < n_hot; h += nt) {
         if (box[4 * h] > box[4 * h + 2]) continue;
         int r = suf_find(parent, h);
         parent[h] = r;
         atomicMin(&cbox[4 * r], (int)tight[4 * h]); atomicMin(&cbox[4 * r + 1], (int)tight[4 * h + 1]);
-        atomicMax(&cbox[4 * r + 2], (int)tight[4 * h + 2]);
+        atomicMax(&cbox[4 * r + 2], (int)tight[4 * h + 2]); atomicMax(&ymax[r], (int)tight[4 * h + 3]);
         atomicAdd(&cbox[4 * r + 3], 1);
         if (r == h) { int k = atomicAdd(&s_nroots, 1); if (k < ROOTS_MAX) roots[k] = (uint16_t)h; }
     }
@@ -237,22 +246,19 @@ __global__ void __launch_bounds__(CL_THREADS) form_clusters_kernel(const uint32_
         for (int i = 0; i < nr; ++i) { int r = roots[i]; int c = cbox[4 * r + 3]; cbox[4 * r + 3] = acc | (c << 16); acc += c; }
     }
     __syncthreads();
-    // one thread per cluster gathers its member boxes (a few hundred hot cells per frame at most) and sizes its bit rows and
-    // filter pieces; the frame then reserves ONE contiguous block of cluster ids, bit-row words and pieces (three global
-    // atomics per frame instead of three per cluster)
+    // member boxes of a cluster, contiguous from its offset (their order inside a cluster is irrelevant: ownership = "inside
+    // any of them"); one thread per cluster sizes its bit rows and filter pieces.  The frame then reserves ONE contiguous
+    // block of cluster ids, bit-row words and pieces (three global atomics per frame instead of three per cluster).
     short* memb = cw.memb + (size_t)f * HOT_MAX * 4;
+    for (int h = tid; h < n_hot; h += nt) {
+        if (box[4 * h] > box[4 * h + 2]) continue;
+        const int r = parent[h];
+        const int k = (cbox[4 * r + 3] & 0xffff) + atomicAdd(&fill[r], 1);
+        *(uint2*)(memb + 4 * k) = *(const uint2*)(box + 4 * h);
+    }
     for (int i = tid; i < nr; i += nt) {
         int r = roots[i];
-        int off = cbox[4 * r + 3] & 0xffff, k = 0;
-        int y1 = -1;
-        for (int h = 0; h < n_hot; ++h) {
-            if (box[4 * h] > box[4 * h + 2] || parent[h] != r) continue;
-            short* m = memb + 4 * (off + k);
-            m[0] = box[4 * h]; m[1] = box[4 * h + 1]; m[2] = box[4 * h + 2]; m[3] = box[4 * h + 3];
-            y1 = max(y1, (int)tight[4 * h + 3]);
-            ++k;
-        }
-        cbox[4 * r + 3] = off | (k << 16);
+        int y1 = ymax[r];
         int mw = cbox[4 * r + 2] - cbox[4 * r] + 1, mh = y1 - cbox[4 * r + 1] + 1;
         int pbx = cdiv_dev(mw, PIECE), pby = cdiv_dev(mh, PIECE);
         r_y1[i] = y1;
@@ -1058,7 +1064,7 @@ int launch_cluster_path(const uint8_t* frames, int n, int H, int W, int64_t fstr
     cudaGetDevice(&dev);
     cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
     const int cells = tv.TX * tv.TY;
-    size_t sm_form = (size_t)((cells + 7) & ~7) * 2 + (size_t)HOT_MAX * (2 + 4 + 16 + 8 + 8) + (size_t)ROOTS_MAX * (2 + 12) + 64;
+    size_t sm_form = (size_t)form_idx_slots(cells) * 2 + (size_t)HOT_MAX * (2 + 4 + 16 + 8 + 8) + (size_t)ROOTS_MAX * (2 + 12) + 64;
 #ifndef MOCAP_EMU
     CUDA_TRY(cudaFuncSetAttribute(form_clusters_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 64 * 1024));
 #endif
