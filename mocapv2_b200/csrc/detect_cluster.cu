@@ -739,21 +739,28 @@ __global__ void __launch_bounds__(128) candidates_kernel(ClusterWs cw)
     const int lane = threadIdx.x & 31;
     const int warp = (blockIdx.x * blockDim.x + threadIdx.x) >> 5, nwarps = (gridDim.x * blockDim.x) >> 5;
     const int total = min(cw.counters[CN_CLUSTERS], cw.cl_cap);
+    // the cluster entry of the warp's next cluster is fetched while the current one is scanned
+    int4 ea = make_int4(0, 0, 0, 0), eb = ea;
+    if (warp < total) { ea = *(const int4*)(cw.clusters + 8 * (size_t)warp); eb = *(const int4*)(cw.clusters + 8 * (size_t)warp + 4); }
     for (int cid = warp; cid < total; cid += nwarps) {
-        const int* ce = cw.clusters + 8 * (size_t)cid;
-        const int f = ce[0];
-        const int cx0 = ce[1] & 0xffff, cy0 = ce[1] >> 16, cx1 = ce[2] & 0xffff, cy1 = ce[2] >> 16, wpr = ce[4];
+        const int4 ca = ea, cb = eb;
+        if (cid + nwarps < total) {
+            ea = *(const int4*)(cw.clusters + 8 * (size_t)(cid + nwarps)); eb = *(const int4*)(cw.clusters + 8 * (size_t)(cid + nwarps) + 4);
+        }
+        const int f = ca.x;
+        const int cx0 = ca.y & 0xffff, cy0 = ca.y >> 16, cx1 = ca.z & 0xffff, cy1 = ca.z >> 16, wpr = cb.x;
         const int mw = cx1 - cx0 + 1, mh = cy1 - cy0 + 1;
         if (mw <= 0 || cw.need_general[f]) continue;
-        const int m_off = ce[5] & 0xffff, m_cnt = ce[5] >> 16;
+        const int m_off = cb.y & 0xffff, m_cnt = cb.y >> 16;
         const short* memb = cw.memb + ((size_t)f * HOT_MAX + m_off) * 4;
-        BitImg im; im.p = cw.rows_out + (unsigned)ce[3]; im.W = mw; im.H = mh; im.WPR = wpr;
+        BitImg im; im.p = cw.rows_out + (unsigned)ca.w; im.W = mw; im.H = mh; im.WPR = wpr;
         for (int r = lane; r < mh; r += 32) {
             const uint32_t* row = im.p + (size_t)r * wpr;
             if (wpr == 2) {
                 // box at most 64 wide: the row and the row above are one 64-bit word each, runs and gaps come from bit scans
-                unsigned long long cur = (unsigned long long)row[0] | ((unsigned long long)row[1] << 32), up = 0ull;
-                if (r > 0) up = (unsigned long long)row[-2] | ((unsigned long long)row[-1] << 32);
+                // (bit-row storage is handed out in even word counts, so these rows are 8-byte aligned)
+                unsigned long long cur = *(const unsigned long long*)row, up = 0ull;
+                if (r > 0) up = *(const unsigned long long*)(row - 2);
                 int last_end = -2;
                 while (cur) {
                     int s0 = __ffsll((long long)cur) - 1;

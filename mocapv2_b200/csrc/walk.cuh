@@ -140,7 +140,7 @@ static __device__ int trace_contour64(const uint32_t* __restrict__ rows, int mh,
                                       long long* a, double* per, int* n_chain, int* overflow, int ox, int oy, int Wabs, int* bbox)
 {
     auto load = [&](int yy) -> unsigned long long {
-        return (unsigned)yy < (unsigned)mh ? ((unsigned long long)rows[2 * yy] | ((unsigned long long)rows[2 * yy + 1] << 32)) : 0ull;
+        return (unsigned)yy < (unsigned)mh ? *(const unsigned long long*)(rows + 2 * yy) : 0ull;    // rows of a two-word box are 8-byte aligned
     };
     auto nbr = [&](unsigned long long up, unsigned long long mid, unsigned long long dn, int xx) -> uint32_t {
         uint32_t u, m, d;
