@@ -24,7 +24,7 @@ extern "C" {
 #define MOCAP_ERR_INVALID (-1)     /* bad argument (null pointer, non-positive size, unsupported shape) */
 #define MOCAP_ERR_WORKSPACE (-2)   /* workspace smaller than mocap_*_workspace_bytes() */
 #define MOCAP_ERR_CUDA (-3)        /* a CUDA runtime call failed (cudaGetLastError() is preserved) */
-#define MOCAP_ERR_UNSUPPORTED (-4) /* shape outside the compiled limits (see mocap_limits) */
+#define MOCAP_ERR_UNSUPPORTED (-4) /* shape outside the compiled limits (frame side > 16384, > MOCAP_MAX_CAMS views, displacement > 1023 px) */
 
 /* per-frame flags written to out_flags[] of mocap_detect_batch */
 #define MOCAP_FLAG_RUN_OVERFLOW 1      /* more foreground runs than max_runs: frame outputs invalid */
