@@ -1,6 +1,7 @@
 """The N>1 path: cameras sharded over ranks, one all-gather of centroid records, frame-sets sharded for geometry.
 world_size 2 over gloo on the CPU (kernel sources through the emulation build); outputs must be bit-identical to the
-1-rank run.  The GPU-box variant of the same check runs under torchrun in bench.py --check."""
+1-rank run.  The same check runs over NCCL on real GPUs when the box has two of them
+(`-m gpu`, skipped on a one-GPU box)."""
 import os
 import sys
 
@@ -21,36 +22,37 @@ def _frames():
     return z["frames"][:2]                                   # [FS=2, C=2, 480, 640]
 
 
-def _run(rank, world, port, out_dir):
+def _run(rank, world, port, out_dir, backend="gloo"):
     sys.path.insert(0, REPO)
     sys.path.insert(0, os.path.join(REPO, "tests", "emu"))
-    import build_emu
     from mocapv2_b200.engine import CaptureEngine
     from mocapv2_b200.pipeline import CapturePipeline
-    if world > 1:
-        dist.init_process_group("gloo", init_method=f"tcp://127.0.0.1:{port}", rank=rank, world_size=world)
-    eng = CaptureEngine(_test_lib=build_emu.build())
+    if backend == "nccl":
+        torch.cuda.set_device(rank)
+        if world > 1:
+            dist.init_process_group("nccl", init_method=f"tcp://127.0.0.1:{port}", rank=rank, world_size=world,
+                                    device_id=torch.device(f"cuda:{rank}"))
+        eng = CaptureEngine(f"cuda:{rank}")
+    else:
+        import build_emu
+        if world > 1:
+            dist.init_process_group("gloo", init_method=f"tcp://127.0.0.1:{port}", rank=rank, world_size=world)
+        eng = CaptureEngine(_test_lib=build_emu.build())
     rig = S.config_rig("c1")
     pipe = CapturePipeline(eng, rig, max_blobs=8, obj_count=4, max_groups=16, fp64=False)
     frames = torch.from_numpy(_frames())
-    local = frames[:, pipe.cam_begin:pipe.cam_begin + pipe.cams_local].contiguous()
+    local = frames[:, pipe.cam_begin:pipe.cam_begin + pipe.cams_local].contiguous().to(eng.device)
     res = pipe.step(local)
-    torch.save({"b": res.fs_begin, "e": res.fs_end, "obj": res.corr.obj, "n_obj": res.corr.n_obj, "img": res.corr.img,
-                "n_valid": res.corr.n_valid, "err": res.corr.err, "count": res.det.count, "collectives": pipe.collectives},
+    cpu = lambda t: t.cpu()
+    torch.save({"b": res.fs_begin, "e": res.fs_end, "obj": cpu(res.corr.obj), "n_obj": cpu(res.corr.n_obj), "img": cpu(res.corr.img),
+                "n_valid": cpu(res.corr.n_valid), "err": cpu(res.corr.err), "count": cpu(res.det.count), "collectives": pipe.collectives},
                os.path.join(out_dir, f"rank{rank}_of{world}.pt"))
     if world > 1:
         dist.barrier()
         dist.destroy_process_group()
 
 
-def test_two_ranks_equal_one_rank(tmp_path):
-    sys.path.insert(0, os.path.join(REPO, "tests", "emu"))
-    import build_emu
-    build_emu.build()
-    out = str(tmp_path)
-    _run(0, 1, 0, out)
-    port = 29500 + os.getpid() % 2000
-    mp.spawn(_run, args=(2, port, out), nprocs=2, join=True)
+def _compare(out):
     one = torch.load(os.path.join(out, "rank0_of1.pt"))
     assert int(one["n_valid"].sum()) > 0 and one["collectives"] == 0
     for r in range(2):
@@ -65,3 +67,25 @@ def test_two_ranks_equal_one_rank(tmp_path):
             assert torch.equal(two["err"][s, :nv], one["err"][b + s, :nv])
         # each rank detected only its own camera
         assert torch.equal(two["count"], one["count"].view(2, 2)[:, r])
+
+
+def test_two_ranks_equal_one_rank(tmp_path):
+    sys.path.insert(0, os.path.join(REPO, "tests", "emu"))
+    import build_emu
+    build_emu.build()
+    out = str(tmp_path)
+    _run(0, 1, 0, out)
+    port = 29500 + os.getpid() % 2000
+    mp.spawn(_run, args=(2, port, out), nprocs=2, join=True)
+    _compare(out)
+
+
+@pytest.mark.gpu
+def test_two_gpus_over_nccl_equal_one_gpu(tmp_path):
+    if torch.cuda.device_count() < 2:
+        pytest.skip("needs two GPUs (the one-GPU suite covers the same logic over gloo)")
+    out = str(tmp_path)
+    port = 31500 + os.getpid() % 2000
+    mp.spawn(_run, args=(1, port, out, "nccl"), nprocs=1, join=True)
+    mp.spawn(_run, args=(2, port, out, "nccl"), nprocs=2, join=True)
+    _compare(out)
