@@ -248,6 +248,34 @@ def test_strong_lens_goes_to_the_general_path(engine):
     assert fl & 63 == 0 and fl & 64 and fl >> 8 == 10, fl
 
 
+def test_pincushion_lens_blobs_next_to_unmapped_pixels(engine):
+    """k1 > 0: output pixels near the frame border map outside the source (value 0).  Blobs that sit next to that band are
+    filtered by pieces whose tiles hold such pixels (the remap loop with the outside test), the ones in the middle by the
+    loop without it; both must match the oracle."""
+    rng = np.random.default_rng(11)
+    H, W = 240, 320
+    Kp = np.array([[400.0, 0, W / 2], [0, 400.0, H / 2], [0, 0, 1]])
+    Dp = np.array([0.30, 0.0, 0.0, 0.0, 0.0])
+    und0, _ = R.filter_frame(np.full((H, W), 255, np.uint8), Kp, Dp)
+    assert (und0 == 0).sum() > 500 and und0[H // 2, W // 2] == 255        # an unmapped band along the border, none in the middle
+    yy, xx = np.mgrid[:H, :W]
+    from util import oracle_contour_table
+    for it in range(3):
+        img = rng.integers(0, 40, (H, W)).astype(np.uint8)
+        for cx, cy, r in [(22, 25, 12), (W - 24, 30, 13), (30, H - 26, 12), (W - 26, H - 24, 11), (W // 2, H // 2, 14),
+                          (W // 2 + 60, 16, 9), (14, H // 2, 9)]:
+            cx += int(rng.integers(-3, 4)); cy += int(rng.integers(-3, 4))
+            img[(xx - cx) ** 2 + (yy - cy) ** 2 <= r * r] = 255
+        res = engine.detect(dev(engine, img[None]), Kp, Dp, min_area=30.0, outputs=("contours",))
+        _, binimg = R.filter_frame(img, Kp, Dp)
+        table, pts = oracle_contour_table(binimg, 30.0)
+        nc = int(res.extras["contour_count"][0])
+        assert nc == len(table) and np.array_equal(res.extras["contours"][0, :nc, :7].cpu().numpy(), table)
+        assert len(pts) >= 5 and res.points(0) == pts
+        lean = engine.detect(dev(engine, img[None]), Kp, Dp, min_area=30.0)       # the cluster path proper
+        assert lean.points(0) == pts and int(lean.flags[0]) & 63 == 0
+
+
 def test_blobs_deep_nesting_uses_general_ordering(engine):
     b = np.zeros((90, 90), np.uint8)
     for k in range(0, 44, 2):
