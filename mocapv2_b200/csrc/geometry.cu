@@ -330,8 +330,13 @@ __global__ void __launch_bounds__(CORR_THREADS) correspond_kernel(
         const int32_t* pp = fxy + (size_t)i * max_pts * 2;
         int np = min(fcount[i], max_pts), n = 0, fl = 0;
         double dist[MOCAP_MAX_CAND];
+        // points farther than cutoff + 2e-5 can neither pass the cutoff nor register as a tie: they are rejected on the
+        // numerator alone (the margin dwarfs the rounding of the division), so the FP64 divide runs for near points only
+        const double far = __dmul_rn(__dmul_rn(den, cutoff + 2e-5), 1.0 + 1e-12);
         for (int k = 0; k < np; ++k) {
-            double d = __ddiv_rn(fabs(__dadd_rn(__dadd_rn(__dmul_rn(a, (double)pp[2 * k]), __dmul_rn(b, (double)pp[2 * k + 1])), c)), den);
+            double num = fabs(__dadd_rn(__dadd_rn(__dmul_rn(a, (double)pp[2 * k]), __dmul_rn(b, (double)pp[2 * k + 1])), c));
+            if (num > far) continue;
+            double d = __ddiv_rn(num, den);
             if (fabs(d - cutoff) < 1e-5) fl |= MOCAP_CFLAG_TIE;
             if (!(d < cutoff)) continue;
             int pos;                                           // keep the MOCAP_MAX_CAND smallest, stable on ties
