@@ -391,6 +391,27 @@ def run_b200(args):
                     "peak_source": "148 SMs x 128 FP32 lanes x 2 x clocks.max.sm (no tensor cores: tiny independent solves)"}
         del pts5, xyz5, err5
 
+    # ---- the step in front of the path: raw Bayer GR sensor frames -> grey (RealtimeTracking_FLIR.py:103-104) ---------------
+    front = None
+    if rank == 0:
+        nb = 256                                                   # 1.07 GB in + 1.07 GB out: larger than L2
+        raw = torch.randint(0, 256, (nb, H, W), dtype=torch.uint8, device=device)
+        grey = torch.empty_like(raw)
+        for _ in range(3):
+            eng.bayer_gr2gray(raw, out=grey)
+        fa, fb = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        torch.cuda.synchronize()
+        fa.record()
+        for _ in range(10):
+            eng.bayer_gr2gray(raw, out=grey)
+        fb.record()
+        torch.cuda.synchronize()
+        fms = fa.elapsed_time(fb) / 10
+        front = {"workload": f"Bayer GR -> grey, {nb} frames {W}x{H} u8 (bilinear demosaic + BGR2GRAY, bit-identical to OpenCV)",
+                 "kernel": "bayer_gr2gray_rows_kernel", "ms": fms, "frames_per_s": nb / (fms * 1e-3),
+                 "algorithmic_bytes": 2 * nb * H * W, "achieved_gbs": 2 * nb * H * W / (fms * 1e-3) / 1e9}
+        del raw, grey
+
     if rank != 0:
         if world > 1:
             dist.barrier()
@@ -419,6 +440,9 @@ def run_b200(args):
     kernels = {"scan": "scan_hot_vec32_kernel", "group": "form_clusters_kernel", "filter": "piece_filter_kernel",
                "borders": "candidates_kernel + borders_finalize_kernel (traces, filter/centroid/order)",
                "finish": "general path for flagged frames (mark_active/compact_tiles/filter_tiles/blobs)"}
+    if front:
+        front["peak_gbs"] = peak
+        front["frac"] = front["achieved_gbs"] / peak
     roofline = {"bound": "hbm", "kernel": kernels.get(dom, dom), "stage": dom, "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
                 "traffic": traffic, "peak_source": peak_src, "algorithmic_bytes_per_launch": alg_bytes,
                 "stage_ms": stage_avg, "detect_ms": det_ms,
@@ -447,7 +471,7 @@ def run_b200(args):
         "points_per_s": points_per_step * args.steps / (ms_total * 1e-3),
         "frame_sets_with_group_cap": float(n_pts[1].item()), "centroids_per_frame": float(n_pts[2].item()) / (n_local * N),
         "e2e": e2e, "gpu_launches": gpu_launches, "collectives_per_step": 1 if N > 1 else 0,
-        "clocks": clocks, "roofline": roofline, "cpu_baseline": cpu, "geometry": geometry,
+        "clocks": clocks, "roofline": roofline, "cpu_baseline": cpu, "geometry": geometry, "front_step": front,
     }
     emit(line)
     if world > 1:

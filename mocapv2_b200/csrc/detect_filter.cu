@@ -820,9 +820,137 @@ __global__ void bayer_gr2gray_kernel(const uint8_t* __restrict__ in, int n, int 
     out[(size_t)f * H * W + (size_t)y * W + x] = (uint8_t)((R * 9798 + G * 19235 + B * 3735 + 16384) >> 15);
 }
 
+// The same conversion at streaming speed (rows that are a multiple of 4 bytes, 4-byte aligned buffers): a warp walks a
+// 128-pixel-wide strip of BAYER_ROWS rows top to bottom; a lane loads ONE 32-bit word per input row (every input byte is
+// loaded once, neighbours of the word come from the adjacent lanes by shuffle) and keeps the three rows around the output
+// row in registers, already split into even / odd pixels as two 16-bit lanes per register.  With the word on an even
+// column, even pixels of a row are all the same kind of site (red or green) and odd pixels the other, so the bilinear
+// means run on both pixels of a lane pair at once (sums <= 1022 fit 16 bits); the grey value of a pixel is one DP2A
+// (9798 R + 19235 G) on top of one IMAD (3735 B + 16384).  Border rows / columns copy their inner neighbour.
+#define BAYER_ROWS 64
+struct BayerRow { uint32_t wE, wO, lE, lO, rE, rO; };          // the word, its left- and its right-shifted copy: even / odd pixels
+
+// raw word of the lane + the bytes left and right of it (from the neighbouring lanes; the lanes at the ends of the warp
+// fetch theirs, pl / pr say whether there is one) -> the six even / odd pixel pairs the sums below need
+__device__ __forceinline__ BayerRow bayer_split(uint32_t w, const uint8_t* __restrict__ p, bool pl, bool pr)
+{
+    uint32_t lb = __shfl_up_sync(0xffffffffu, w, 1) >> 24, rb = __shfl_down_sync(0xffffffffu, w, 1) & 0xffu;
+    if (pl) lb = p[-1];
+    if (pr) rb = p[4];
+    const uint32_t L = __byte_perm(lb, w, 0x6540), R = __byte_perm(w, rb, 0x4321);      // pixels x-1 and x+1 of the word's four
+    BayerRow r;
+    r.wE = w & 0x00ff00ffu; r.wO = (w >> 8) & 0x00ff00ffu;
+    r.lE = L & 0x00ff00ffu; r.lO = (L >> 8) & 0x00ff00ffu;
+    r.rE = R & 0x00ff00ffu; r.rO = (R >> 8) & 0x00ff00ffu;
+    return r;
+}
+
+// two grey bytes (low / high 16-bit lane of the packed R, G, B) -> bits 0..7 and 16..23
+__device__ __forceinline__ uint32_t bayer_grey2(uint32_t Rp, uint32_t Gp, uint32_t Bp)
+{
+    const uint32_t WRG = 9798u | (19235u << 16);
+    uint32_t lo = __dp2a_lo(WRG, __byte_perm(Rp, Gp, 0x0040), (Bp & 0xffffu) * 3735u + 16384u) >> 15;
+    uint32_t hi = __dp2a_lo(WRG, __byte_perm(Rp, Gp, 0x0062), (Bp >> 16) * 3735u + 16384u) >> 15;
+    return lo | (hi << 16);
+}
+
+// grey word (4 pixels) of an output row from the rows above / at / below it; `odd`: row parity (red row)
+__device__ __forceinline__ uint32_t bayer_row_grey(const BayerRow& u, const BayerRow& c, const BayerRow& d, bool odd)
+{
+    const uint32_t M = 0x00ff00ffu;
+    uint32_t gE, gO;                                                   // grey of the even / odd pixels of the word
+    if (odd) {
+        // red row: even pixels are red sites (G = cross, B = diagonals), odd pixels green (R = horizontal, B = vertical)
+        uint32_t cross = ((u.wE + d.wE + c.lE + c.rE + 0x00020002u) >> 2) & M;
+        uint32_t diag = ((u.lE + u.rE + d.lE + d.rE + 0x00020002u) >> 2) & M;
+        uint32_t hor = ((c.lO + c.rO + 0x00010001u) >> 1) & M, ver = ((u.wO + d.wO + 0x00010001u) >> 1) & M;
+        gE = bayer_grey2(c.wE, cross, diag);
+        gO = bayer_grey2(hor, c.wO, ver);
+    } else {
+        // blue row: even pixels green (B = horizontal, R = vertical), odd pixels blue sites (G = cross, R = diagonals)
+        uint32_t hor = ((c.lE + c.rE + 0x00010001u) >> 1) & M, ver = ((u.wE + d.wE + 0x00010001u) >> 1) & M;
+        uint32_t cross = ((u.wO + d.wO + c.lO + c.rO + 0x00020002u) >> 2) & M;
+        uint32_t diag = ((u.lO + u.rO + d.lO + d.rO + 0x00020002u) >> 2) & M;
+        gE = bayer_grey2(ver, c.wE, hor);
+        gO = bayer_grey2(diag, cross, c.wO);
+    }
+    return gE | (gO << 8);
+}
+
+// interior rows 1 .. H-2 (rows 0 and H-1 are copies, bayer_border_rows_kernel)
+__global__ void __launch_bounds__(128) bayer_gr2gray_rows_kernel(const uint8_t* __restrict__ in, int H, int W, uint8_t* __restrict__ out)
+{
+    const int lane = threadIdx.x, x0 = (blockIdx.x * 32 + lane) * 4;
+    const int strip = blockIdx.y * blockDim.y + threadIdx.y;
+    const int ya = max(strip * BAYER_ROWS, 1), yb = min((strip + 1) * BAYER_ROWS, H - 1);     // interior output rows [ya, yb)
+    if (ya >= yb) return;
+    // lanes beyond the row end keep running (shuffles) on the last word and store nothing
+    const bool active = x0 < W;
+    const int xs = active ? x0 : W - 4;
+    const bool pl = lane == 0 && x0 > 0, pr31 = lane == 31 && x0 + 4 < W;          // lane 0 / 31 fetch the byte beyond the warp's 128
+    const uint8_t* p = in + (size_t)blockIdx.z * H * W + (size_t)(ya - 1) * W + xs;           // walks down the input rows
+    uint8_t* q = out + (size_t)blockIdx.z * H * W + (size_t)ya * W + xs;                      // walks down the output rows
+    const bool left_edge = x0 == 0, right_edge = x0 + 4 == W;
+    BayerRow r[3];
+    r[0] = bayer_split(*(const uint32_t*)p, p, pl, pr31);
+    p += W;
+    r[1] = bayer_split(*(const uint32_t*)p, p, pl, pr31);
+    p += W;
+    uint32_t wn = *(const uint32_t*)p;                                 // the next row's word is always one step ahead
+    int yl = ya + 1;                                                   // the row wn holds
+    auto fetch = [&]() -> BayerRow {
+        BayerRow t = bayer_split(wn, p, pl, pr31);
+        if (yl + 1 < H) { p += W; wn = *(const uint32_t*)p; ++yl; }
+        return t;
+    };
+    auto emit = [&](uint32_t g) {
+        if (left_edge) g = __byte_perm(g, 0, 0x3211);                  // column 0 copies column 1
+        if (right_edge) g = __byte_perm(g, 0, 0x2210);                 // column W-1 copies column W-2
+        if (active) *(uint32_t*)q = g;
+        q += W;
+    };
+    int y = ya;
+    if (y & 1) {                                                       // first strip: start the unrolled loop on an even row
+        r[2] = fetch();
+        emit(bayer_row_grey(r[0], r[1], r[2], true));
+        r[0] = r[1]; r[1] = r[2];
+        ++y;
+    }
+    // six rows per pass: the three row registers rotate back to where they started and the row parity is a constant
+    for (; y + 6 <= yb; y += 6) {
+#pragma unroll
+        for (int k = 0; k < 6; ++k) {
+            r[(k + 2) % 3] = fetch();
+            emit(bayer_row_grey(r[k % 3], r[(k + 1) % 3], r[(k + 2) % 3], (k & 1) != 0));
+        }
+    }
+    for (; y < yb; ++y) {
+        r[2] = fetch();
+        emit(bayer_row_grey(r[0], r[1], r[2], (y & 1) != 0));
+        r[0] = r[1]; r[1] = r[2];
+    }
+}
+
+// rows 0 and H-1 copy rows 1 and H-2
+__global__ void bayer_border_rows_kernel(uint8_t* __restrict__ out, int H, int W)
+{
+    const int x = blockIdx.x * blockDim.x + threadIdx.x;
+    if (x >= W) return;
+    uint8_t* fo = out + (size_t)blockIdx.z * H * W;
+    fo[x] = fo[(size_t)W + x];
+    fo[(size_t)(H - 1) * W + x] = fo[(size_t)(H - 2) * W + x];
+}
+
 extern "C" int mocap_bayer_gr2gray_batch(const uint8_t* raw_dev, int n, int H, int W, uint8_t* out_dev, void* stream)
 {
     if (!raw_dev || !out_dev || n <= 0 || H < 3 || W < 3 || n > 65535) return MOCAP_ERR_INVALID;
+    if (W % 4 == 0 && ((uintptr_t)raw_dev % 4) == 0 && ((uintptr_t)out_dev % 4) == 0) {
+        LAUNCH(bayer_gr2gray_rows_kernel, dim3(cdiv(W, 128), cdiv(cdiv(H, BAYER_ROWS), 4), n), dim3(32, 4), 0, (cudaStream_t)stream,
+               raw_dev, H, W, out_dev);
+        LAUNCH(bayer_border_rows_kernel, dim3(cdiv(W, 256), 1, n), 256, 0, (cudaStream_t)stream, out_dev, H, W);
+        CUDA_TRY(cudaGetLastError());
+        return MOCAP_OK;
+    }
     LAUNCH(bayer_gr2gray_kernel, dim3(cdiv(W, 64), cdiv(H, 4), n), dim3(64, 4), 0, (cudaStream_t)stream, raw_dev, n, H, W, out_dev);
     CUDA_TRY(cudaGetLastError());
     return MOCAP_OK;

@@ -255,14 +255,19 @@ class CaptureEngine:
         self.launches += 1
         return out
 
-    def bayer_gr2gray(self, raw: torch.Tensor) -> torch.Tensor:
+    def bayer_gr2gray(self, raw: torch.Tensor, out: torch.Tensor | None = None) -> torch.Tensor:
         """cvtColor(BAYER_GR2BGR) -> cvtColor(BGR2GRAY) (RealtimeTracking_FLIR.py:103-104) for raw sensor frames [n, H, W] uint8."""
         raw = self._check_dev(raw.contiguous(), torch.uint8, "raw")
         n, H, W = raw.shape
-        out = torch.empty_like(raw)
+        if out is None:
+            out = torch.empty_like(raw)
+        elif out.shape != raw.shape:
+            raise ValueError("out must have the shape of raw")
+        else:
+            self._check_dev(out, torch.uint8, "out")
         _cabi.check(self.lib, self.lib.mocap_bayer_gr2gray_batch(self._ptr(raw), n, H, W, self._ptr(out), self._stream()),
                     "mocap_bayer_gr2gray_batch")
-        self.launches += 1
+        self.launches += 2                      # interior rows + the two copied border rows
         return out
 
     def undistort(self, frames: torch.Tensor, K, dist) -> torch.Tensor:

@@ -160,6 +160,18 @@ static inline T __shfl_down_sync(unsigned, T v, int delta)
     return r;
 }
 
+template <typename T>
+static inline T __shfl_up_sync(unsigned, T v, int delta)
+{
+    unsigned long long s[32], raw = 0; int n;
+    memcpy(&raw, &v, sizeof(T));
+    emu::exchange(raw, s, &n);
+    int src = emu::my_lane() - delta;
+    if (src < 0) return v;
+    T r; memcpy(&r, &s[src], sizeof(T));
+    return r;
+}
+
 // ---- atomics ---------------------------------------------------------------------------------------------------
 static inline int atomicAdd(int* p, int v) { return __atomic_fetch_add(p, v, __ATOMIC_SEQ_CST); }
 static inline unsigned atomicAdd(unsigned* p, unsigned v) { return __atomic_fetch_add(p, v, __ATOMIC_SEQ_CST); }
@@ -186,6 +198,18 @@ static inline unsigned long long atomicMin(unsigned long long* p, unsigned long 
 }
 
 // ---- intrinsics (build with -ffp-contract=off so that a*b+c is never fused) ---------------------------------------
+static inline unsigned __byte_perm(unsigned x, unsigned y, unsigned sel)
+{
+    unsigned long long src = ((unsigned long long)y << 32) | x;
+    unsigned r = 0;
+    for (int i = 0; i < 4; ++i) {
+        unsigned n = (sel >> (4 * i)) & 0xf, b = (unsigned)(src >> (8 * (n & 7))) & 0xffu;
+        if (n & 8) b = (b & 0x80u) ? 0xffu : 0u;          // sign-replicate mode
+        r |= b << (8 * i);
+    }
+    return r;
+}
+static inline unsigned __dp2a_lo(unsigned a, unsigned b, unsigned c) { return c + (a & 0xffffu) * (b & 0xffu) + (a >> 16) * ((b >> 8) & 0xffu); }
 static inline int __popc(unsigned v) { return __builtin_popcount(v); }
 static inline int __popcll(unsigned long long v) { return __builtin_popcountll(v); }
 static inline int __ffs(int v) { return __builtin_ffs(v); }
