@@ -412,6 +412,26 @@ def run_b200(args):
                  "algorithmic_bytes": 2 * nb * H * W, "achieved_gbs": 2 * nb * H * W / (fms * 1e-3) / 1e9}
         del raw, grey
 
+    # ---- one frame through the drop-in the realtime loop calls: numpy image in, centroid list + undistorted image out ------
+    latency = None
+    if rank == 0:
+        from mocapv2_b200 import engine as E
+        from mocapv2_b200.lib import ImageOperations as IO
+        E.set_default_engine(eng)
+        IO.camera_params = rig["camera_params"]
+        IO.ANNOTATE = False                                        # the display-only overlays are host-side cv2 drawing
+        host_frame = frames[0, 0].cpu().numpy()
+        for _ in range(5):
+            IO._find_dot(host_frame)
+        lat = []
+        for _ in range(30):
+            t0 = time.perf_counter()
+            _, pts_one = IO._find_dot(host_frame)
+            lat.append((time.perf_counter() - t0) * 1e3)
+        lat.sort()
+        latency = {"call": "lib.ImageOperations._find_dot(img) on one 2048x2048 host frame (H2D + detect + undistorted image D2H)",
+                   "median_ms": lat[len(lat) // 2], "min_ms": lat[0], "centroids": len(pts_one)}
+
     if rank != 0:
         if world > 1:
             dist.barrier()
@@ -471,7 +491,7 @@ def run_b200(args):
         "points_per_s": points_per_step * args.steps / (ms_total * 1e-3),
         "frame_sets_with_group_cap": float(n_pts[1].item()), "centroids_per_frame": float(n_pts[2].item()) / (n_local * N),
         "e2e": e2e, "gpu_launches": gpu_launches, "collectives_per_step": 1 if N > 1 else 0,
-        "clocks": clocks, "roofline": roofline, "cpu_baseline": cpu, "geometry": geometry, "front_step": front,
+        "clocks": clocks, "roofline": roofline, "cpu_baseline": cpu, "geometry": geometry, "front_step": front, "find_dot_latency": latency,
     }
     emit(line)
     if world > 1:

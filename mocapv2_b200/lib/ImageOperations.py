@@ -31,18 +31,52 @@ def _params():
     return camera_params
 
 
+_tls = threading.local()               # per calling thread (one per camera in the realtime loop): pinned staging buffers
+
+
+def _staging(shape, eng):
+    """Pinned host buffers (in, out) and the device frame of one image shape, owned by the calling thread: the frame goes
+    numpy -> pinned -> HBM at PCIe speed instead of through a pageable copy, and comes back the same way."""
+    bufs = getattr(_tls, "bufs", None)
+    if bufs is None:
+        bufs = _tls.bufs = {}
+    key = (tuple(shape), str(eng.device))
+    if key not in bufs:
+        if len(bufs) > 8:
+            bufs.clear()
+        bufs[key] = (torch.empty(tuple(shape), dtype=torch.uint8, pin_memory=True),
+                     torch.empty(tuple(shape), dtype=torch.uint8, pin_memory=True),
+                     torch.empty((1,) + tuple(shape), dtype=torch.uint8, device=eng.device))
+    return bufs[key]
+
+
 def _to_device(img, eng):
     a = np.ascontiguousarray(img)
     if a.dtype != np.uint8 or a.ndim != 2:
         raise ValueError("expected a single-channel uint8 image (H, W)")
-    return torch.from_numpy(a)[None].to(eng.device, non_blocking=False)
+    if eng.device.type != "cuda":                              # tests: the CPU build of the kernels
+        return torch.from_numpy(a)[None].to(eng.device, non_blocking=False)
+    pin_in, _, dev = _staging(a.shape, eng)
+    pin_in.numpy()[...] = a
+    dev[0].copy_(pin_in, non_blocking=True)                   # stream-ordered in front of the kernels that read it
+    return dev
+
+
+def _to_host(t, eng):
+    """Device image (H, W) uint8 -> a NEW numpy array (callers draw on it), through the thread's pinned buffer."""
+    if eng.device.type != "cuda":
+        return t.cpu().numpy()
+    _, pin_out, _ = _staging(t.shape, eng)
+    pin_out.copy_(t, non_blocking=True)
+    torch.cuda.current_stream(eng.device).synchronize()
+    return pin_out.numpy().copy()
 
 
 def bayer_gr_to_gray(image):
     """The two cv2.cvtColor calls in front of _find_dot in the realtime loop (RealtimeTracking_FLIR.py:103-104), on the GPU:
     raw BayerGR sensor frame (H, W) uint8 -> grey (H, W) uint8, bit-identical to OpenCV's."""
     eng = _engine.default_engine()
-    return eng.bayer_gr2gray(_to_device(image, eng))[0].cpu().numpy()
+    return _to_host(eng.bayer_gr2gray(_to_device(image, eng))[0], eng)
 
 
 def image_filter_cpu(image, camera_number=0):
@@ -50,7 +84,7 @@ def image_filter_cpu(image, camera_number=0):
 
     Kept under its reference name; it runs on the GPU like everything else here.  `camera_number` is ignored."""
     eng = _engine.default_engine()
-    return eng.median5_threshold(_to_device(image, eng))[0].cpu().numpy()
+    return _to_host(eng.median5_threshold(_to_device(image, eng))[0], eng)
 
 
 def image_filter_gpu(image, camera_number=0):
@@ -82,7 +116,7 @@ def _find_dot(img, print_location=False, return_filtered=False):
         b = res.extras["bits"][0].cpu().numpy().view(np.uint8)
         out = (np.unpackbits(b, axis=1, bitorder="little")[:, :W] * 255).astype(np.uint8)
     else:
-        out = eng.undistort(fr, K, dist)[0].cpu().numpy()
+        out = _to_host(eng.undistort(fr, K, dist)[0], eng)
     if ANNOTATE and image_points:
         try:                                                  # display-only overlays (lib/ImageOperations.py:67-73)
             import cv2 as cv
