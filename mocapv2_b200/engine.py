@@ -87,7 +87,7 @@ class CaptureEngine:
             self.lib = _cabi.load(_test_lib)
         self._tables = {}
         self._ws = None
-        self._lock = threading.Lock()           # _find_dot is called from one thread per camera (RealtimeTracking_FLIR.py:309)
+        self._lock = threading.RLock()           # every library call of this engine is issued under it           # _find_dot is called from one thread per camera (RealtimeTracking_FLIR.py:309)
         self.launches = 0                       # kernels launched through this engine (bench bookkeeping)
 
     # ---- plumbing ------------------------------------------------------------------------------------------------
@@ -121,17 +121,18 @@ class CaptureEngine:
         dd = np.asarray(dist, dtype=np.float64).ravel()
         d[:min(5, dd.size)] = dd[:5]
         key = (K.tobytes(), d.tobytes(), H, W)
-        tab = self._tables.get(key)
-        if tab is None:
-            nbytes = self.lib.mocap_undistort_table_bytes(H, W)
-            if nbytes == 0:
-                raise _cabi.MocapError("unsupported frame size")
-            tab = torch.zeros(int(nbytes), dtype=torch.uint8, device=self.device)
-            with torch.cuda.device(self.device) if self.device.type == "cuda" else _nullctx():
-                st = self.lib.mocap_undistort_table_build(K.ctypes.data, d.ctypes.data, H, W, self._ptr(tab), nbytes, self._stream())
-            _cabi.check(self.lib, st, "mocap_undistort_table_build")
-            self.launches += 3
-            self._tables[key] = tab
+        with self._lock:                       # concurrent first calls (one thread per camera) build the table once
+            tab = self._tables.get(key)
+            if tab is None:
+                nbytes = self.lib.mocap_undistort_table_bytes(H, W)
+                if nbytes == 0:
+                    raise _cabi.MocapError("unsupported frame size")
+                tab = torch.zeros(int(nbytes), dtype=torch.uint8, device=self.device)
+                with torch.cuda.device(self.device) if self.device.type == "cuda" else _nullctx():
+                    st = self.lib.mocap_undistort_table_build(K.ctypes.data, d.ctypes.data, H, W, self._ptr(tab), nbytes, self._stream())
+                _cabi.check(self.lib, st, "mocap_undistort_table_build")
+                self.launches += 3
+                self._tables[key] = tab
         return tab
 
     # ---- detection ----------------------------------------------------------------------------------------------------------
@@ -241,7 +242,8 @@ class CaptureEngine:
         frames = self._check_dev(frames.contiguous(), torch.uint8, "frames")
         n, H, W = frames.shape
         out = torch.empty_like(frames)
-        _cabi.check(self.lib, self.lib.mocap_blur5_batch(self._ptr(frames), n, H, W, self._ptr(out), self._stream()), "mocap_blur5_batch")
+        with self._lock:
+            _cabi.check(self.lib, self.lib.mocap_blur5_batch(self._ptr(frames), n, H, W, self._ptr(out), self._stream()), "mocap_blur5_batch")
         self.launches += 1
         return out
 
@@ -250,8 +252,9 @@ class CaptureEngine:
         frames = self._check_dev(frames.contiguous(), torch.uint8, "frames")
         n, H, W = frames.shape
         out = torch.empty_like(frames)
-        _cabi.check(self.lib, self.lib.mocap_median5_threshold_batch(self._ptr(frames), n, H, W, int(thresh), self._ptr(out), self._stream()),
-                    "mocap_median5_threshold_batch")
+        with self._lock:
+            _cabi.check(self.lib, self.lib.mocap_median5_threshold_batch(self._ptr(frames), n, H, W, int(thresh), self._ptr(out), self._stream()),
+                        "mocap_median5_threshold_batch")
         self.launches += 1
         return out
 
@@ -265,8 +268,9 @@ class CaptureEngine:
             raise ValueError("out must have the shape of raw")
         else:
             self._check_dev(out, torch.uint8, "out")
-        _cabi.check(self.lib, self.lib.mocap_bayer_gr2gray_batch(self._ptr(raw), n, H, W, self._ptr(out), self._stream()),
-                    "mocap_bayer_gr2gray_batch")
+        with self._lock:
+            _cabi.check(self.lib, self.lib.mocap_bayer_gr2gray_batch(self._ptr(raw), n, H, W, self._ptr(out), self._stream()),
+                        "mocap_bayer_gr2gray_batch")
         self.launches += 2                      # interior rows + the two copied border rows
         return out
 
@@ -276,8 +280,9 @@ class CaptureEngine:
         n, H, W = frames.shape
         tab = self.table(K, dist, H, W)
         out = torch.empty_like(frames)
-        _cabi.check(self.lib, self.lib.mocap_undistort_batch(self._ptr(frames), n, H, W, self._ptr(tab), self._ptr(out), self._stream()),
-                    "mocap_undistort_batch")
+        with self._lock:
+            _cabi.check(self.lib, self.lib.mocap_undistort_batch(self._ptr(frames), n, H, W, self._ptr(tab), self._ptr(out), self._stream()),
+                        "mocap_undistort_batch")
         self.launches += 1
         return out
 
@@ -315,8 +320,9 @@ class CaptureEngine:
             err = self.empty((P,), pts.dtype)
         if P == 0:                                  # triangulate_points([]) -> np.array([]) (Helpers.py:87-99)
             return xyz, err
-        st = self.lib.mocap_triangulate_batch(self._ptr(pts), self._ptr(valid), self._ptr(cams), C, P,
-                                              1 if pts.dtype == torch.float64 else 0, self._ptr(xyz), self._ptr(err), self._stream())
+        with self._lock:
+            st = self.lib.mocap_triangulate_batch(self._ptr(pts), self._ptr(valid), self._ptr(cams), C, P,
+                                                  1 if pts.dtype == torch.float64 else 0, self._ptr(xyz), self._ptr(err), self._stream())
         _cabi.check(self.lib, st, "mocap_triangulate_batch")
         self.launches += 1 if P else 0
         return xyz, err
@@ -332,8 +338,9 @@ class CaptureEngine:
         err = self.empty((P,), pts.dtype)
         if P == 0:
             return err
-        st = self.lib.mocap_reproject_batch(self._ptr(pts), self._ptr(valid), self._ptr(xyz), self._ptr(cams), C, P,
-                                            1 if pts.dtype == torch.float64 else 0, self._ptr(err), self._stream())
+        with self._lock:
+            st = self.lib.mocap_reproject_batch(self._ptr(pts), self._ptr(valid), self._ptr(xyz), self._ptr(cams), C, P,
+                                                1 if pts.dtype == torch.float64 else 0, self._ptr(err), self._stream())
         _cabi.check(self.lib, st, "mocap_reproject_batch")
         self.launches += 1 if P else 0
         return err
