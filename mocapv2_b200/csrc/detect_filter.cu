@@ -830,18 +830,34 @@ __global__ void bayer_gr2gray_kernel(const uint8_t* __restrict__ in, int n, int 
 #define BAYER_ROWS 64
 struct BayerRow { uint32_t wE, wO, lE, lO, rE, rO; };          // the word, its left- and its right-shifted copy: even / odd pixels
 
-// raw word of the lane + the bytes left and right of it (from the neighbouring lanes; the lanes at the ends of the warp
-// fetch theirs, pl / pr say whether there is one) -> the six even / odd pixel pairs the sums below need
-__device__ __forceinline__ BayerRow bayer_split(uint32_t w, const uint8_t* __restrict__ p, bool pl, bool pr)
+// raw words of the lane (NW x 4 pixels) + the bytes left and right of them (from the neighbouring lanes; the lanes at the ends
+// of the warp fetch theirs, pl / pr say whether there is one) -> per word the six even / odd pixel pairs the sums below need
+template <int NW> struct BayerRows { BayerRow w[NW]; };
+
+template <int NW>
+__device__ __forceinline__ void bayer_load(const uint8_t* __restrict__ p, uint32_t raw[NW])
 {
-    uint32_t lb = __shfl_up_sync(0xffffffffu, w, 1) >> 24, rb = __shfl_down_sync(0xffffffffu, w, 1) & 0xffu;
+    if (NW == 2) { uint2 v = *(const uint2*)p; raw[0] = v.x; raw[NW - 1] = v.y; }
+    else raw[0] = *(const uint32_t*)p;
+}
+
+template <int NW>
+__device__ __forceinline__ BayerRows<NW> bayer_split(const uint32_t raw[NW], const uint8_t* __restrict__ p, bool pl, bool pr)
+{
+    uint32_t lb = __shfl_up_sync(0xffffffffu, raw[NW - 1], 1) >> 24, rb = __shfl_down_sync(0xffffffffu, raw[0], 1) & 0xffu;
     if (pl) lb = p[-1];
-    if (pr) rb = p[4];
-    const uint32_t L = __byte_perm(lb, w, 0x6540), R = __byte_perm(w, rb, 0x4321);      // pixels x-1 and x+1 of the word's four
-    BayerRow r;
-    r.wE = w & 0x00ff00ffu; r.wO = (w >> 8) & 0x00ff00ffu;
-    r.lE = L & 0x00ff00ffu; r.lO = (L >> 8) & 0x00ff00ffu;
-    r.rE = R & 0x00ff00ffu; r.rO = (R >> 8) & 0x00ff00ffu;
+    if (pr) rb = p[4 * NW];
+    BayerRows<NW> r;
+#pragma unroll
+    for (int k = 0; k < NW; ++k) {
+        const uint32_t w = raw[k];
+        // pixels x-1 and x+1 of the word's four
+        const uint32_t L = k == 0 ? __byte_perm(lb, w, 0x6540) : __byte_perm(raw[k > 0 ? k - 1 : 0], w, 0x6543);
+        const uint32_t R = k == NW - 1 ? __byte_perm(w, rb, 0x4321) : __byte_perm(w, raw[k < NW - 1 ? k + 1 : k], 0x4321);
+        r.w[k].wE = w & 0x00ff00ffu; r.w[k].wO = (w >> 8) & 0x00ff00ffu;
+        r.w[k].lE = L & 0x00ff00ffu; r.w[k].lO = (L >> 8) & 0x00ff00ffu;
+        r.w[k].rE = R & 0x00ff00ffu; r.w[k].rO = (R >> 8) & 0x00ff00ffu;
+    }
     return r;
 }
 
@@ -877,42 +893,52 @@ __device__ __forceinline__ uint32_t bayer_row_grey(const BayerRow& u, const Baye
     return gE | (gO << 8);
 }
 
-// interior rows 1 .. H-2 (rows 0 and H-1 are copies, bayer_border_rows_kernel)
+// interior rows 1 .. H-2 (rows 0 and H-1 are copies, bayer_border_rows_kernel); NW words (4 NW pixels) per lane and row
+template <int NW>
 __global__ void __launch_bounds__(128) bayer_gr2gray_rows_kernel(const uint8_t* __restrict__ in, int H, int W, uint8_t* __restrict__ out)
 {
-    const int lane = threadIdx.x, x0 = (blockIdx.x * 32 + lane) * 4;
+    const int lane = threadIdx.x, x0 = (blockIdx.x * 32 + lane) * 4 * NW;
     const int strip = blockIdx.y * blockDim.y + threadIdx.y;
     const int ya = max(strip * BAYER_ROWS, 1), yb = min((strip + 1) * BAYER_ROWS, H - 1);     // interior output rows [ya, yb)
     if (ya >= yb) return;
-    // lanes beyond the row end keep running (shuffles) on the last word and store nothing
+    // lanes beyond the row end keep running (shuffles) on the last words and store nothing
     const bool active = x0 < W;
-    const int xs = active ? x0 : W - 4;
-    const bool pl = lane == 0 && x0 > 0, pr31 = lane == 31 && x0 + 4 < W;          // lane 0 / 31 fetch the byte beyond the warp's 128
+    const int xs = active ? x0 : W - 4 * NW;
+    const bool pl = lane == 0 && x0 > 0, pr = lane == 31 && x0 + 4 * NW < W;       // lane 0 / 31 fetch the byte beyond the warp's span
     const uint8_t* p = in + (size_t)blockIdx.z * H * W + (size_t)(ya - 1) * W + xs;           // walks down the input rows
     uint8_t* q = out + (size_t)blockIdx.z * H * W + (size_t)ya * W + xs;                      // walks down the output rows
-    const bool left_edge = x0 == 0, right_edge = x0 + 4 == W;
-    BayerRow r[3];
-    r[0] = bayer_split(*(const uint32_t*)p, p, pl, pr31);
+    const bool left_edge = x0 == 0, right_edge = x0 + 4 * NW == W;
+    BayerRows<NW> r[3];
+    uint32_t wn[NW];
+    bayer_load<NW>(p, wn);
+    r[0] = bayer_split<NW>(wn, p, pl, pr);
     p += W;
-    r[1] = bayer_split(*(const uint32_t*)p, p, pl, pr31);
+    bayer_load<NW>(p, wn);
+    r[1] = bayer_split<NW>(wn, p, pl, pr);
     p += W;
-    uint32_t wn = *(const uint32_t*)p;                                 // the next row's word is always one step ahead
+    bayer_load<NW>(p, wn);                                             // the next row's words are always one step ahead
     int yl = ya + 1;                                                   // the row wn holds
-    auto fetch = [&]() -> BayerRow {
-        BayerRow t = bayer_split(wn, p, pl, pr31);
-        if (yl + 1 < H) { p += W; wn = *(const uint32_t*)p; ++yl; }
+    auto fetch = [&]() -> BayerRows<NW> {
+        BayerRows<NW> t = bayer_split<NW>(wn, p, pl, pr);
+        if (yl + 1 < H) { p += W; bayer_load<NW>(p, wn); ++yl; }
         return t;
     };
-    auto emit = [&](uint32_t g) {
-        if (left_edge) g = __byte_perm(g, 0, 0x3211);                  // column 0 copies column 1
-        if (right_edge) g = __byte_perm(g, 0, 0x2210);                 // column W-1 copies column W-2
-        if (active) *(uint32_t*)q = g;
+    auto emit = [&](const BayerRows<NW>& u, const BayerRows<NW>& c, const BayerRows<NW>& d, bool odd) {
+        uint32_t g[NW];
+#pragma unroll
+        for (int k = 0; k < NW; ++k) g[k] = bayer_row_grey(u.w[k], c.w[k], d.w[k], odd);
+        if (left_edge) g[0] = __byte_perm(g[0], 0, 0x3211);           // column 0 copies column 1
+        if (right_edge) g[NW - 1] = __byte_perm(g[NW - 1], 0, 0x2210); // column W-1 copies column W-2
+        if (active) {
+            if (NW == 2) *(uint2*)q = make_uint2(g[0], g[NW - 1]);
+            else *(uint32_t*)q = g[0];
+        }
         q += W;
     };
     int y = ya;
     if (y & 1) {                                                       // first strip: start the unrolled loop on an even row
         r[2] = fetch();
-        emit(bayer_row_grey(r[0], r[1], r[2], true));
+        emit(r[0], r[1], r[2], true);
         r[0] = r[1]; r[1] = r[2];
         ++y;
     }
@@ -921,12 +947,12 @@ __global__ void __launch_bounds__(128) bayer_gr2gray_rows_kernel(const uint8_t* 
 #pragma unroll
         for (int k = 0; k < 6; ++k) {
             r[(k + 2) % 3] = fetch();
-            emit(bayer_row_grey(r[k % 3], r[(k + 1) % 3], r[(k + 2) % 3], (k & 1) != 0));
+            emit(r[k % 3], r[(k + 1) % 3], r[(k + 2) % 3], (k & 1) != 0);
         }
     }
     for (; y < yb; ++y) {
         r[2] = fetch();
-        emit(bayer_row_grey(r[0], r[1], r[2], (y & 1) != 0));
+        emit(r[0], r[1], r[2], (y & 1) != 0);
         r[0] = r[1]; r[1] = r[2];
     }
 }
@@ -945,8 +971,11 @@ extern "C" int mocap_bayer_gr2gray_batch(const uint8_t* raw_dev, int n, int H, i
 {
     if (!raw_dev || !out_dev || n <= 0 || H < 3 || W < 3 || n > 65535) return MOCAP_ERR_INVALID;
     if (W % 4 == 0 && ((uintptr_t)raw_dev % 4) == 0 && ((uintptr_t)out_dev % 4) == 0) {
-        LAUNCH(bayer_gr2gray_rows_kernel, dim3(cdiv(W, 128), cdiv(cdiv(H, BAYER_ROWS), 4), n), dim3(32, 4), 0, (cudaStream_t)stream,
-               raw_dev, H, W, out_dev);
+        const bool wide = W % 8 == 0 && ((uintptr_t)raw_dev % 8) == 0 && ((uintptr_t)out_dev % 8) == 0;
+        auto k1 = bayer_gr2gray_rows_kernel<1>;
+        auto k2 = bayer_gr2gray_rows_kernel<2>;
+        if (wide) LAUNCH(k2, dim3(cdiv(W, 256), cdiv(cdiv(H, BAYER_ROWS), 4), n), dim3(32, 4), 0, (cudaStream_t)stream, raw_dev, H, W, out_dev);
+        else LAUNCH(k1, dim3(cdiv(W, 128), cdiv(cdiv(H, BAYER_ROWS), 4), n), dim3(32, 4), 0, (cudaStream_t)stream, raw_dev, H, W, out_dev);
         LAUNCH(bayer_border_rows_kernel, dim3(cdiv(W, 256), 1, n), 256, 0, (cudaStream_t)stream, out_dev, H, W);
         CUDA_TRY(cudaGetLastError());
         return MOCAP_OK;
