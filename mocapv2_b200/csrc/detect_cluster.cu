@@ -993,12 +993,14 @@ __device__ void frame_finalize(const ClusterWs& cw, int f, uint8_t* keepv /*[max
 
 // One CTA per frame: the traces of the frame's border-start candidates, the nesting check and -- unless the frame was
 // handed to the general path on the way -- the reference's filter / centroid / output order.
-__global__ void __launch_bounds__(CL_THREADS) borders_finalize_kernel(ClusterWs cw, int W, int max_contours, int max_blobs, double min_area, double min_circ,
+__global__ void __launch_bounds__(CL_THREADS) borders_finalize_kernel(ClusterWs cw, int W, int frame_step, int max_contours, int max_blobs, double min_area, double min_circ,
                                                                       int32_t* __restrict__ out_xy, int32_t* __restrict__ out_count, int32_t* __restrict__ out_flags,
                                                                       double* __restrict__ out_contours, int32_t* __restrict__ out_contour_count)
 {
     DYN_SHARED(smraw);
-    const int f = blockIdx.x;
+    // CTA b takes frame b * frame_step mod n (frame_step coprime to n): consecutive frames of a batch come from the same
+    // cameras in the same order, so a plain b -> frame map would hand every SM frames of the same few cameras
+    const int f = (int)(((long long)blockIdx.x * frame_step) % cw.n_frames);
     if (cw.need_general[f]) return;
     frame_traces(cw, f, W, max_contours);
     __syncthreads();
@@ -1083,7 +1085,9 @@ int launch_cluster_path(const uint8_t* frames, int n, int H, int W, int64_t fstr
     stage_end(timer, 2, s);
     stage_begin(timer, 3, s);
     LAUNCH(candidates_kernel, sms * 16, 128, 0, s, cw);
-    LAUNCH(borders_finalize_kernel, n, CL_THREADS, (size_t)max_contours + 16, s, cw, W, max_contours, max_blobs, min_area, min_circ,
+    int frame_step = 1;
+    for (int pr : {61, 67, 71, 73}) if (n % pr != 0) { frame_step = pr; break; }          // a prime that does not divide n
+    LAUNCH(borders_finalize_kernel, n, CL_THREADS, (size_t)max_contours + 16, s, cw, W, frame_step, max_contours, max_blobs, min_area, min_circ,
            out_xy, out_count, out_flags, out_contours, out_contour_count);
     stage_end(timer, 3, s);
     CUDA_TRY(cudaGetLastError());
