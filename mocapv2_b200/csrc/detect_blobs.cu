@@ -104,7 +104,7 @@ __global__ void __launch_bounds__(BLOB_THREADS) blobs_kernel(
     if (need_general && !need_general[f]) return;           // frame fully handled by the cluster path
     const int H = P.H, W = P.W, TX = P.TX;
     __shared__ int sh[BLOB_THREADS + 1];
-    __shared__ int s_nruns, s_nblobs, s_nholes, s_flag, s_ncont;
+    __shared__ int s_nblobs, s_nholes, s_flag, s_ncont;
 
     // carve the per-frame workspace
     char* p = ws_base + (size_t)f * ws_stride;

@@ -676,7 +676,7 @@ __global__ void materialize_bits_kernel(const uint32_t* __restrict__ bits, const
 // ---------------------------------------------------------------------------------------------------------
 // host-side launcher shared by mocap_filter_batch and mocap_detect_batch
 // ---------------------------------------------------------------------------------------------------------
-int launch_scan(const uint8_t* frames, int n, int H, int W, int64_t fstride, const TableView& tv, int thresh,
+int launch_scan(const uint8_t* frames, int n, int /*H*/, int W, int64_t fstride, const TableView& tv, int thresh,
                 const FilterWs& ws, cudaStream_t s, StageTimer* timer)
 {
     int dev = 0, sms = 148;
@@ -711,7 +711,7 @@ int launch_scan(const uint8_t* frames, int n, int H, int W, int64_t fstride, con
 }
 
 // general path, filter part: active tiles of the frames in need_general (all frames if null) -> packed binary image
-int launch_tiles(const uint8_t* frames, int n, int H, int W, int64_t fstride, const TableView& tv, int thresh,
+int launch_tiles(const uint8_t* frames, int n, int /*H*/, int W, int64_t fstride, const TableView& tv, int thresh,
                  const FilterWs& ws, int max_fg, int* flags, const int* need_general, cudaStream_t s)
 {
     const int TX = tv.TX, TY = tv.TY, TXW = cdiv(TX, 32);
