@@ -59,7 +59,27 @@ __device__ __forceinline__ void jacobi_min_eigvec(T b00, T b01, T b02, T b03, T 
                     T g = (T)100 * Num<T>::abs_(apq), dp = Num<T>::abs_(A[p][p]), dq = Num<T>::abs_(A[q][q]);
                     if (g + dp == dp && g + dq == dq) { A[p][q] = (T)0; A[q][p] = (T)0; apq = (T)0; }
                 }
-                if (apq != (T)0) {
+                if (sizeof(T) == 4 && apq != (T)0) {
+                    // FP32 main mode: the rotation from delta = aqq - app directly, t = 2 apq / (delta + sign(delta) sqrt(delta^2 +
+                    // 4 apq^2)), applied as (c, s) -- three SFU operations (sqrt, rcp, rsqrt) instead of the five of the theta /
+                    // tau form below, which the FP64 check mode keeps
+                    T dl = A[q][q] - A[p][p], two = (T)2 * apq;
+                    T r = Num<T>::sqrt_(dl * dl + two * two);
+                    T t = two * Num<T>::rcp_(dl + (dl < (T)0 ? -r : r));
+                    T c = Num<T>::rsqrt_(t * t + (T)1), s = t * c;
+                    A[p][p] -= t * apq; A[q][q] += t * apq; A[p][q] = (T)0; A[q][p] = (T)0;
+#pragma unroll
+                    for (int r2 = 0; r2 < 4; ++r2) {
+                        if (r2 != p && r2 != q) {
+                            T arp = A[r2][p], arq = A[r2][q];
+                            A[r2][p] = c * arp - s * arq; A[p][r2] = A[r2][p];
+                            A[r2][q] = s * arp + c * arq; A[q][r2] = A[r2][q];
+                        }
+                        T vrp = V[r2][p], vrq = V[r2][q];
+                        V[r2][p] = c * vrp - s * vrq;
+                        V[r2][q] = s * vrp + c * vrq;
+                    }
+                } else if (apq != (T)0) {
                     T theta = (A[q][q] - A[p][p]) * Num<T>::rcp_((T)2 * apq);
                     T at = Num<T>::abs_(theta);
                     T t;
