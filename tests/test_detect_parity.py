@@ -276,6 +276,32 @@ def test_pincushion_lens_blobs_next_to_unmapped_pixels(engine):
         assert lean.points(0) == pts and int(lean.flags[0]) & 63 == 0
 
 
+def test_moderate_barrel_lens_on_the_cluster_path(engine):
+    """A lens that bends enough for some pieces' source windows not to fit the staged shared-memory window (those pieces
+    take their taps from global memory) but little enough per cell to stay on the cluster path."""
+    rng = np.random.default_rng(21)
+    H, W = 240, 320
+    Kb = np.array([[300.0, 0, W / 2], [0, 300.0, H / 2], [0, 0, 1]])
+    Db = np.array([-0.20, 0.01, 0.001, -0.001, 0.0])
+    yy, xx = np.mgrid[:H, :W]
+    from util import oracle_contour_table
+    seen_cluster_path = False
+    for it in range(3):
+        img = rng.integers(0, 40, (H, W)).astype(np.uint8)
+        for _ in range(7):
+            cx, cy, r = int(rng.integers(20, W - 20)), int(rng.integers(20, H - 20)), int(rng.integers(7, 15))
+            img[(xx - cx) ** 2 + (yy - cy) ** 2 <= r * r] = 255
+        if it == 2:
+            img[40:200, 150:156] = 255                                   # a tall bar: a cluster of several pieces
+            img[60:170, 190:290] = 255                                   # a slab: full 64x64 pieces, windows wider than 96
+        _, binimg = R.filter_frame(img, Kb, Db)
+        _, pts = oracle_contour_table(binimg, 30.0)
+        lean = engine.detect(dev(engine, img[None]), Kb, Db, min_area=30.0)
+        assert lean.points(0) == (pts if pts else [[None, None]]) and int(lean.flags[0]) & 63 == 0
+        seen_cluster_path |= (int(lean.flags[0]) & 64) == 0
+    assert seen_cluster_path
+
+
 def test_blobs_deep_nesting_uses_general_ordering(engine):
     b = np.zeros((90, 90), np.uint8)
     for k in range(0, 44, 2):
