@@ -22,7 +22,20 @@ def _frames():
     return z["frames"][:2]                                   # [FS=2, C=2, 480, 640]
 
 
-def _run(rank, world, port, out_dir, backend="gloo"):
+def _ring4_scene():
+    """Four cameras on a ring, 480x360, two frame-sets of three markers (deterministic): with two ranks every rank owns TWO
+    cameras, so the (rank, local camera) -> camera order of the exchange is exercised."""
+    rig = S.ring_rig(4, 480, 360, radius=6.0)
+    rng = np.random.default_rng(404)
+    frames = []
+    for _ in range(2):
+        X = S.sample_markers(rig, 3, rng, spread=0.10, min_sep_px=75.0, margin=36.0, tries=400)
+        radii = rng.integers(17, 21, (4, len(X)))
+        frames.append(S.render_frameset(rig, X, radii, rng))
+    return rig, np.stack(frames)                              # [FS=2, C=4, 360, 480]
+
+
+def _run(rank, world, port, out_dir, backend="gloo", scene="c1"):
     sys.path.insert(0, REPO)
     sys.path.insert(0, os.path.join(REPO, "tests", "emu"))
     from mocapv2_b200.engine import CaptureEngine
@@ -38,9 +51,12 @@ def _run(rank, world, port, out_dir, backend="gloo"):
         if world > 1:
             dist.init_process_group("gloo", init_method=f"tcp://127.0.0.1:{port}", rank=rank, world_size=world)
         eng = CaptureEngine(_test_lib=build_emu.build())
-    rig = S.config_rig("c1")
+    if scene == "ring4":
+        rig, fr = _ring4_scene()
+    else:
+        rig, fr = S.config_rig("c1"), _frames()
     pipe = CapturePipeline(eng, rig, max_blobs=8, obj_count=4, max_groups=16, fp64=False)
-    frames = torch.from_numpy(_frames())
+    frames = torch.from_numpy(fr)
     local = frames[:, pipe.cam_begin:pipe.cam_begin + pipe.cams_local].contiguous().to(eng.device)
     res = pipe.step(local)
     cpu = lambda t: t.cpu()
@@ -52,7 +68,7 @@ def _run(rank, world, port, out_dir, backend="gloo"):
         dist.destroy_process_group()
 
 
-def _compare(out):
+def _compare(out, cams_per_rank=1):
     one = torch.load(os.path.join(out, "rank0_of1.pt"))
     assert int(one["n_valid"].sum()) > 0 and one["collectives"] == 0
     for r in range(2):
@@ -65,8 +81,9 @@ def _compare(out):
             assert torch.equal(two["img"][s, :nv], one["img"][b + s, :nv])
             assert torch.equal(two["obj"][s, :no], one["obj"][b + s, :no])  # bit-identical, no cross-rank reductions
             assert torch.equal(two["err"][s, :nv], one["err"][b + s, :nv])
-        # each rank detected only its own camera
-        assert torch.equal(two["count"], one["count"].view(2, 2)[:, r])
+        # each rank detected only its own cameras
+        cl = cams_per_rank
+        assert torch.equal(two["count"].view(2, cl), one["count"].view(2, 2 * cl)[:, r * cl:(r + 1) * cl])
 
 
 def test_two_ranks_equal_one_rank(tmp_path):
@@ -80,12 +97,25 @@ def test_two_ranks_equal_one_rank(tmp_path):
     _compare(out)
 
 
+def test_two_ranks_with_two_cameras_each(tmp_path):
+    sys.path.insert(0, os.path.join(REPO, "tests", "emu"))
+    import build_emu
+    build_emu.build()
+    out = str(tmp_path)
+    _run(0, 1, 0, out, "gloo", "ring4")
+    one = torch.load(os.path.join(out, "rank0_of1.pt"))
+    assert int(one["n_obj"].min()) >= 2                       # the scene triangulates in every frame-set
+    port = 33500 + os.getpid() % 2000
+    mp.spawn(_run, args=(2, port, out, "gloo", "ring4"), nprocs=2, join=True)
+    _compare(out, cams_per_rank=2)
+
+
 @pytest.mark.gpu
 def test_two_gpus_over_nccl_equal_one_gpu(tmp_path):
     if torch.cuda.device_count() < 2:
         pytest.skip("needs two GPUs (the one-GPU suite covers the same logic over gloo)")
     out = str(tmp_path)
     port = 31500 + os.getpid() % 2000
-    mp.spawn(_run, args=(1, port, out, "nccl"), nprocs=1, join=True)
-    mp.spawn(_run, args=(2, port, out, "nccl"), nprocs=2, join=True)
-    _compare(out)
+    mp.spawn(_run, args=(1, port, out, "nccl", "ring4"), nprocs=1, join=True)
+    mp.spawn(_run, args=(2, port, out, "nccl", "ring4"), nprocs=2, join=True)
+    _compare(out, cams_per_rank=2)
