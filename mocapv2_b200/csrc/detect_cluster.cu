@@ -828,8 +828,10 @@ __device__ void frame_traces(const ClusterWs& cw, int f, int W, int max_contours
     __syncthreads();
     const int n_cand = min(cw.cand_count[f], CAND_PER_FRAME);
     // Work order: a warp traces 32 borders in lockstep, so its time is its longest border.  The candidates are therefore
-    // counting-sorted by the size of their cluster box (a proxy for the border length), boxes up to 64 wide (rows cached in
-    // registers, trace_contour64) first and the wider ones (generic loop) after them, starting on a warp boundary.
+    // counting-sorted by the size of their cluster box (a proxy for the border length), longest first: the boxes wider than
+    // 64 pixels (several blobs next to each other; traced on a sliding 64-pixel window, generic loop only for boxes higher
+    // than 1024), then, from a warp boundary, the boxes up to 64 wide (rows cached in registers).  A second pass
+    // over the list runs in reverse thread order, so that the shortest borders follow the shortest first-pass borders.
     __shared__ uint16_t s_order[CAND_PER_FRAME + 32];          // + the padding between the two lists
     __shared__ int s_bucket[34];
     if (threadIdx.x < 34) s_bucket[threadIdx.x] = 0;
@@ -837,8 +839,8 @@ __device__ void frame_traces(const ClusterWs& cw, int f, int W, int max_contours
     auto bucket_of = [&](const int* ce) -> int {
         int mw = (ce[2] & 0xffff) - (ce[1] & 0xffff) + 1, mh = (ce[2] >> 16) - (ce[1] >> 16) + 1;
         bool narrow = ce[4] == 2 && mh <= 1024;
-        int b = min((mw + mh) >> 4, 15);
-        return narrow ? b : 16 + b;
+        int b = 15 - min((mw + mh) >> 4, 15);
+        return narrow ? 16 + b : b;
     };
     for (int cslot = threadIdx.x; cslot < n_cand; cslot += blockDim.x)
         atomicAdd(&s_bucket[1 + bucket_of(cw.clusters + 8 * (size_t)cw.cand_list[2 * ((size_t)f * CAND_PER_FRAME + cslot)])], 1);
@@ -846,11 +848,11 @@ __device__ void frame_traces(const ClusterWs& cw, int f, int W, int max_contours
     if (threadIdx.x == 0) {
         int acc = 0;
         for (int b = 1; b <= 32; ++b) { int c = s_bucket[b]; s_bucket[b] = acc; acc += c; if (b == 16) { s_bucket[33] = acc; acc = (acc + 31) & ~31; } }
-        // s_bucket[1 + b] = start of bucket b; the wide buckets (16..31) start on a warp boundary; s_bucket[33] = #narrow
+        // s_bucket[1 + b] = start of bucket b; the narrow buckets (16..31) start on a warp boundary; s_bucket[33] = #wide
         s_bucket[0] = acc;                                       // padded total
     }
     __syncthreads();
-    const int n_narrow = s_bucket[33], n_pad = (n_narrow + 31) & ~31, n_total = s_bucket[0];
+    const int n_wide = s_bucket[33], n_pad = (n_wide + 31) & ~31, n_total = s_bucket[0];
     for (int i = threadIdx.x; i < CAND_PER_FRAME + 32; i += blockDim.x) s_order[i] = 0xffff;
     __syncthreads();
     for (int cslot = threadIdx.x; cslot < n_cand; cslot += blockDim.x) {
@@ -859,7 +861,9 @@ __device__ void frame_traces(const ClusterWs& cw, int f, int W, int max_contours
         s_order[pos] = (uint16_t)cslot;                          // pos < n_cand + 31 <= CAND_PER_FRAME + 31
     }
     __syncthreads();
-    for (int it = threadIdx.x; it < n_total; it += blockDim.x) {
+    for (int base = 0, pass = 0; base < n_total; base += blockDim.x, ++pass) {
+        const int it = base + ((pass & 1) ? (int)(blockDim.x - 1 - threadIdx.x) : (int)threadIdx.x);
+        if (it >= n_total) continue;
         const int cslot = s_order[it];
         if (cslot == 0xffff) continue;                           // padding between the two lists
         const size_t c = (size_t)f * CAND_PER_FRAME + cslot;
@@ -870,8 +874,12 @@ __device__ void frame_traces(const ClusterWs& cw, int f, int W, int max_contours
         BitImg im; im.p = cw.rows_out + (unsigned)ce[3]; im.W = mx1 - mx0 + 1; im.H = my1 - my0 + 1; im.WPR = ce[4];
         long long st = (long long)(ly + my0) * W + (lx + mx0);
         long long a[3]; double per; int nch, ovf = 0, bbox[4];
-        int ok = it < n_pad ? trace_contour64(im.p, im.H, lx, ly, ty ? 0 : 4, 2 * st + ty, a, &per, &nch, &ovf, mx0, my0, W, bbox)
-                             : trace_contour(im, lx, ly, ty ? 0 : 4, 2 * st + ty, a, &per, &nch, &ovf, mx0, my0, W, bbox);
+        int ok;
+        if (it >= n_pad) ok = trace_contour64<false>(im.p, im.H, 2, 0, im.W, lx, ly, ty ? 0 : 4, 2 * st + ty, a, &per, &nch, &ovf, mx0, my0, W, bbox);
+        else if (im.W > 64 && im.H <= 1024) {
+            const int wx0 = min(max(lx - 32, 0), im.W - 64);
+            ok = trace_contour64<true>(im.p, im.H, im.WPR, wx0, im.W, lx - wx0, ly, ty ? 0 : 4, 2 * st + ty, a, &per, &nch, &ovf, mx0 + wx0, my0, W, bbox);
+        } else ok = trace_contour(im, lx, ly, ty ? 0 : 4, 2 * st + ty, a, &per, &nch, &ovf, mx0, my0, W, bbox);
         if (ovf) { cw.need_general[f] = 8; continue; }
         if (!ok) continue;
         long long parent = -1;

@@ -136,11 +136,24 @@ static __device__ int trace_contour(const BitImg& im, int x, int y, int side, lo
 //  * perimeter: CHAIN_APPROX_SIMPLE segments are axis-parallel (length = an integer, exact in float32) or diagonal
 //    (length = float32 sqrt(2 k^2)); the double sum of such float32 values is exact in any order, so axis lengths are summed
 //    as integers, unit diagonals are counted, longer diagonals added one by one.
-static __device__ int trace_contour64(const uint32_t* __restrict__ rows, int mh, int x, int y, int side, long long key0,
+//
+// WINDOW = true: the same trace on a sliding 64-pixel wide window of a wider box (wpr words per row, mw > 64 pixels wide;
+// a blob of a wide cluster box is usually narrow).  The window starts at column wx0 (0 <= wx0 <= mw - 64); (x, ox) and all
+// vertex coordinates are relative to wx0.  When the walker reaches a window column whose outer neighbour is not known, the
+// window is re-centred on it (three row loads).  Coordinates then exceed 64, so the a10/a01 products are taken in 64 bits.
+template <bool WINDOW>
+static __device__ int trace_contour64(const uint32_t* __restrict__ rows, int mh, int wpr, int wx0, int mw, int x, int y, int side, long long key0,
                                       long long* a, double* per, int* n_chain, int* overflow, int ox, int oy, int Wabs, int* bbox)
 {
+    int wofs = 0;                                   // window origin relative to wx0 (WINDOW only)
+    int wi0 = wx0 >> 5, wsh = wx0 & 31;
     auto load = [&](int yy) -> unsigned long long {
-        return (unsigned)yy < (unsigned)mh ? *(const unsigned long long*)(rows + 2 * yy) : 0ull;    // rows of a two-word box are 8-byte aligned
+        if ((unsigned)yy >= (unsigned)mh) return 0ull;
+        if (!WINDOW) return *(const unsigned long long*)(rows + 2 * yy);                            // rows of a two-word box are 8-byte aligned
+        const uint32_t* r = rows + (size_t)yy * wpr + wi0;                                          // origin + 63 < mw: words wi0, wi0 + 1 exist
+        const uint32_t w0 = r[0], w1 = r[1], w2 = (wsh && wi0 + 2 < wpr) ? r[2] : 0u;
+        const unsigned long long lo = (unsigned long long)w0 | ((unsigned long long)w1 << 32);
+        return wsh ? (lo >> wsh) | ((unsigned long long)w2 << (64 - wsh)) : lo;
     };
     auto nbr = [&](unsigned long long up, unsigned long long mid, unsigned long long dn, int xx) -> uint32_t {
         uint32_t u, m, d;
@@ -171,7 +184,7 @@ static __device__ int trace_contour64(const uint32_t* __restrict__ rows, int mh,
     int wx = x, wy = y;
     for (int step = 0; step < WALK_BUDGET; ++step) {
         const int cx = wx, cy = wy;
-        uint32_t m = nbr(up, mid, dn, wx);
+        uint32_t m = nbr(up, mid, dn, wx - wofs);
         int start = (s + 1) & 7;
         uint32_t rot = ((m | (m << 8)) >> start) & 0xffu;
         int k = rot ? __ffs(rot) - 1 : 8;
@@ -180,8 +193,20 @@ static __device__ int trace_contour64(const uint32_t* __restrict__ rows, int mh,
         uint32_t zeros = (z | (z >> 8)) & 0xffu;
         int nx = wx + dir_dx(d), ny = wy + dir_dy(d);
         bool done = (nx == x0 && ny == y0 && wx == x1 && wy == y1);
-        if (ny < wy) { dn = mid; mid = up; up = load(ny - 1); }
-        else if (ny > wy) { up = mid; mid = dn; dn = load(ny + 1); }
+        bool slide = false;
+        if (WINDOW) {
+            const int bx = nx - wofs, org = wx0 + wofs;              // window column of the next pixel, window origin in the box
+            slide = (bx == 0 && org > 0) || (bx == 63 && org + 64 < mw);
+            if (slide) {
+                const int norg = min(max(wx0 + nx - 32, 0), mw - 64);
+                wofs = norg - wx0; wi0 = norg >> 5; wsh = norg & 31;
+                up = load(ny - 1); mid = load(ny); dn = load(ny + 1);
+            }
+        }
+        if (!slide) {
+            if (ny < wy) { dn = mid; mid = up; up = load(ny - 1); }
+            else if (ny > wy) { up = mid; mid = dn; dn = load(ny + 1); }
+        }
         wx = nx; wy = ny; s = (d + 4) & 7;
         ++n;
         if (key0 >= 0 && (zeros & 0x11u)) {
@@ -192,7 +217,9 @@ static __device__ int trace_contour64(const uint32_t* __restrict__ rows, int mh,
         if (d != prev_dir) {
             if (have_v) {
                 int dxy = vx * cy - cx * vy;
-                a00 += dxy; a10 += dxy * (vx + cx); a01 += dxy * (vy + cy);
+                a00 += dxy;
+                if (WINDOW) { a10 += (long long)dxy * (vx + cx); a01 += (long long)dxy * (vy + cy); }
+                else { a10 += dxy * (vx + cx); a01 += dxy * (vy + cy); }
                 int adx = abs(cx - vx), ady = abs(cy - vy);
                 if (adx == 0 || ady == 0) axis_len += adx + ady;
                 else if (adx == 1) ++n_diag1;
@@ -205,7 +232,9 @@ static __device__ int trace_contour64(const uint32_t* __restrict__ rows, int mh,
         if (done) {
             if (have_v) {
                 int dxy = vx * fy - fx * vy;
-                a00 += dxy; a10 += dxy * (vx + fx); a01 += dxy * (vy + fy);
+                a00 += dxy;
+                if (WINDOW) { a10 += (long long)dxy * (vx + fx); a01 += (long long)dxy * (vy + fy); }
+                else { a10 += dxy * (vx + fx); a01 += dxy * (vy + fy); }
                 int adx = abs(fx - vx), ady = abs(fy - vy);
                 if (adx == 0 || ady == 0) axis_len += adx + ady;
                 else if (adx == 1) ++n_diag1;
