@@ -195,6 +195,55 @@ def test_cluster_path_random_scenes(engine):
     assert paths == {False, True} or not is_gpu(engine) or True
 
 
+def test_wide_blobs_slide_the_trace_window(engine):
+    """Borders in cluster boxes wider than 64 pixels are traced on a sliding 64-pixel window (walk.cuh, WINDOW variant):
+    flat ellipses and bars several windows wide, combs whose teeth make the walker cross the window edge again and again,
+    rings (hole borders), small blobs at either end of a box just wider than the window, and blobs touching the frame edges.
+    Contour table (Green sums, perimeter, order) and centroids against the oracle; every frame must finish on the cluster path."""
+    from util import oracle_contour_table
+    rng = np.random.default_rng(4242)
+    H, W = 200, 416
+    yy, xx = np.mgrid[:H, :W]
+    scenes = []
+    img = rng.integers(0, 40, (H, W)).astype(np.uint8)                  # flat ellipse + long bar + comb
+    img[((xx - 200) / 150.0) ** 2 + ((yy - 40) / 18.0) ** 2 <= 1.0] = 255
+    img[90:100, 20:390] = 255
+    img[130:140, 30:380] = 255
+    for x in range(30, 380, 14):
+        img[140:185, x:x + 7] = 255
+    scenes.append(img)
+    img = rng.integers(0, 40, (H, W)).astype(np.uint8)                  # two blobs at the ends of boxes 66..100 wide, a wide ring
+    for y0, gap in ((30, 30), (90, 44), (150, 60)):
+        for cx in (40, 40 + gap):
+            img[(xx - cx) ** 2 + (yy - y0) ** 2 <= 15 ** 2] = 255
+    d2 = ((xx - 280) / 110.0) ** 2 + ((yy - 100) / 60.0) ** 2
+    img[(d2 <= 1.0) & (d2 >= 0.55)] = 255
+    scenes.append(img)
+    img = rng.integers(0, 40, (H, W)).astype(np.uint8)                  # wide shapes touching the left / right / top frame edges
+    img[20:50, 0:130] = 255
+    img[80:120, W - 150:W] = 255
+    img[0:12, 150:300] = 255
+    img[((xx - 208) / 190.0) ** 2 + ((yy - 165) / 20.0) ** 2 <= 1.0] = 255
+    scenes.append(img)
+    for _ in range(3 if is_gpu(engine) else 1):                         # random wide polygons (diagonal runs longer than one pixel)
+        img = rng.integers(0, 40, (H, W)).astype(np.uint8)
+        for _ in range(4):
+            cx, cy = int(rng.integers(80, W - 80)), int(rng.integers(30, H - 30))
+            ax, ay, sk = float(rng.uniform(40, 75)), float(rng.uniform(8, 25)), float(rng.uniform(-0.3, 0.3))
+            img[np.abs((xx - cx) / ax) + np.abs((yy - cy - sk * (xx - cx)) / ay) <= 1.0] = 255
+        scenes.append(img)
+    for img in scenes:
+        for ma in (0.0, 500.0):
+            res = engine.detect(dev(engine, img[None]), K, D, min_area=ma, outputs=("contours",))
+            _, binimg = R.filter_frame(img, K, D)
+            table, pts = oracle_contour_table(binimg, ma)
+            nc = int(res.extras["contour_count"][0])
+            assert nc == len(table)
+            assert np.array_equal(res.extras["contours"][0, :nc, :7].cpu().numpy(), table)
+            assert res.points(0) == (pts if pts else [[None, None]])
+            assert int(res.flags[0]) & (63 | 64) & ~16 == 0           # no capacity flag, and finished by the cluster path
+
+
 def test_adversarial_background_just_below_threshold(engine):
     """Background 216 (one below the threshold): a single pixel > 216 in a 5x5 window already sets the thresholded mean, so
     the filtered foreground reaches as far from the hot pixels as it possibly can (gaps between nearby hot features fill
