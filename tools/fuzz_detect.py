@@ -33,7 +33,7 @@ def main():
         yy, xx = np.mgrid[:H, :W]
         for _ in range(int(rng.integers(0, 14))):
             cx, cy = int(rng.integers(0, W)), int(rng.integers(0, H))
-            kind = rng.integers(0, 4)
+            kind = rng.integers(0, 6)
             if kind == 0:
                 r = int(rng.integers(2, 30)); img[(xx - cx) ** 2 + (yy - cy) ** 2 <= r * r] = 255
             elif kind == 1:
@@ -41,8 +41,14 @@ def main():
                 img[(d2 <= r * r) & (d2 >= (r // 2) ** 2)] = 255                      # ring: a hole border
             elif kind == 2:
                 w, h = int(rng.integers(1, 120)), int(rng.integers(1, 90)); img[cy:cy + h, cx:cx + w] = 255
-            else:
+            elif kind == 3:
                 img[max(cy - 1, 0):cy + 2, max(cx - 1, 0):cx + 2] = int(rng.integers(217, 256))
+            elif kind == 4:                                                          # flat ellipse, several trace windows wide
+                ax, ay = float(rng.uniform(20, 140)), float(rng.uniform(4, 30))
+                img[((xx - cx) / ax) ** 2 + ((yy - cy) / ay) ** 2 <= 1.0] = 255
+            else:                                                                    # sheared diamond: long diagonal runs
+                ax, ay, sk = float(rng.uniform(20, 120)), float(rng.uniform(5, 40)), float(rng.uniform(-0.5, 0.5))
+                img[np.abs((xx - cx) / ax) + np.abs((yy - cy - sk * (xx - cx)) / ay) <= 1.0] = 255
         min_area = float(rng.choice([0.0, 30.0, 500.0]))
         _, binimg = R.filter_frame(img, K, D)
         _, pts = oracle_contour_table(binimg, min_area)
