@@ -1,0 +1,122 @@
+"""Design probe for a trace-free border stage (development tool, CPU only; not used by the product).
+
+Claim checked here against cv2.findContours(CHAIN_APPROX_NONE): the pixel-to-pixel steps ("links") of ALL borders of a
+binary image are determined by the 2x2 pixel configuration at each lattice corner:
+  1 or 4 or 0 foreground pixels : no link
+  2 edge-adjacent foreground    : one axis link between them
+  3 foreground                  : one diagonal link between the two pixels edge-adjacent to the background pixel
+  2 diagonal foreground         : two diagonal links (one each way)
+with the direction given by the orientation rule below.  The Green sums (a00, a10, a01 of cv.moments on a contour) are
+sums over links.  Every link keeps one background pixel on its right-hand side; the pair (8-connected foreground
+component of the link's pixels, 4-connected background component of that pixel) names the border the link belongs to, so
+the sums of every border -- outer and hole, any nesting -- can be accumulated with atomics per label pair, without
+following any border (second check below: the per-label-pair a00/a10/a01 against those of the cv2 contours).
+python tools/links_probe.py [n_images]
+"""
+import sys
+from collections import Counter
+
+import cv2
+import numpy as np
+from scipy import ndimage
+
+
+def local_links(img):
+    """Links from the 2x2 configuration at every lattice corner of the zero-padded image; returns Counter of (x0,y0,x1,y1)."""
+    H, W = img.shape
+    p = np.zeros((H + 2, W + 2), bool)
+    p[1:-1, 1:-1] = img != 0
+    out = Counter()
+    rights = {}
+    for vy in range(H + 1):                 # corner (vx, vy) touches padded pixels a=(vy,vx) NW, b=(vy,vx+1) NE, c=(vy+1,vx) SW, d=(vy+1,vx+1) SE
+        for vx in range(W + 1):
+            a, b, c, d = p[vy, vx], p[vy, vx + 1], p[vy + 1, vx], p[vy + 1, vx + 1]
+            A, B, C, D = (vx - 1, vy - 1), (vx, vy - 1), (vx - 1, vy), (vx, vy)      # unpadded pixel coordinates
+            n = int(a) + int(b) + int(c) + int(d)
+            def add(s, t):
+                out[(s[0], s[1], t[0], t[1])] += 1
+                # the background pixel on the right-hand side of the step s -> t, among the corner's four pixels
+                hx, hy = t[0] - s[0], t[1] - s[1]
+                for q, isfg in ((A, a), (B, b), (C, c), (D, d)):        # n == 3: the corner's only background pixel
+                    if not isfg and (n == 3 or (q[0] - s[0]) * hy - (q[1] - s[1]) * hx < 0):
+                        rights[(s[0], s[1], t[0], t[1])] = q
+            if n == 2:
+                if a and b: add(A, B)            # background below  (a border keeps the background on its right-hand side)
+                elif c and d: add(D, C)          # background above
+                elif a and c: add(C, A)          # background to the east
+                elif b and d: add(B, D)          # background to the west
+                elif a and d: add(A, D); add(D, A)
+                else: add(B, C); add(C, B)
+            elif n == 3:
+                if not d: add(C, B)              # links the two pixels edge-adjacent to the background pixel
+                elif not a: add(B, C)
+                elif not b: add(D, A)
+                else: add(A, D)
+    return out, rights
+
+
+def cv_links(img):
+    cs, _ = cv2.findContours((img != 0).astype(np.uint8), cv2.RETR_LIST, cv2.CHAIN_APPROX_NONE)
+    out = Counter()
+    for c in cs:
+        pts = c[:, 0, :]
+        if len(pts) == 1:
+            continue
+        for i in range(len(pts)):
+            s, t = pts[i], pts[(i + 1) % len(pts)]
+            out[(int(s[0]), int(s[1]), int(t[0]), int(t[1]))] += 1
+    return out
+
+
+def green(pts):
+    a00 = a10 = a01 = 0
+    for i in range(len(pts)):
+        (x0, y0), (x1, y1) = pts[i - 1], pts[i]
+        dxy = int(x0) * int(y1) - int(x1) * int(y0)
+        a00 += dxy; a10 += dxy * (int(x0) + int(x1)); a01 += dxy * (int(y0) + int(y1))
+    return a00, a10, a01
+
+
+def per_border_check(img, links, rights):
+    H, W = img.shape
+    fgp = np.zeros((H + 2, W + 2), bool)
+    fgp[1:-1, 1:-1] = img != 0
+    fl, _ = ndimage.label(fgp, structure=np.ones((3, 3)))                 # 8-connected foreground
+    bl, _ = ndimage.label(~fgp)                                           # 4-connected background (padded: one outer region)
+    acc = {}
+    for (x0, y0, x1, y1), cnt in links.items():
+        assert cnt == 1
+        r = rights[(x0, y0, x1, y1)]
+        key = (int(fl[y0 + 1, x0 + 1]), int(bl[r[1] + 1, r[0] + 1]))
+        dxy = x0 * y1 - x1 * y0
+        s = acc.setdefault(key, [0, 0, 0])
+        s[0] += dxy; s[1] += dxy * (x0 + x1); s[2] += dxy * (y0 + y1)
+    mine = sorted(tuple(v) for v in acc.values())
+    cs, _ = cv2.findContours((img != 0).astype(np.uint8), cv2.RETR_LIST, cv2.CHAIN_APPROX_SIMPLE)
+    ref = sorted(green(c[:, 0, :]) for c in cs if len(c) > 1)
+    return mine == ref
+
+
+def main():
+    n = int(sys.argv[1]) if len(sys.argv) > 1 else 200
+    rng = np.random.default_rng(5)
+    for it in range(n):
+        H, W = int(rng.integers(3, 40)), int(rng.integers(3, 40))
+        img = rng.random((H, W)) < rng.choice([0.2, 0.5, 0.8])
+        if it % 3 == 0:                                       # smoother shapes
+            img = cv2.blur(img.astype(np.float32), (5, 5)) > 0.5
+        (a, rights), b = local_links(img), cv_links(img)
+        if a != b:
+            print("MISMATCH at image", it, "only local:", list((a - b).items())[:5], "only cv:", list((b - a).items())[:5])
+            np.save("/tmp/links_fail.npy", img)
+            return 1
+        if not per_border_check(img, a, rights):
+            print("PER-BORDER MISMATCH at image", it)
+            np.save("/tmp/links_fail.npy", img)
+            return 1
+    print(n, "images: local link multiset == cv2 border steps; per-(fg, bg)-label sums == per-contour Green sums")
+    return 0
+
+
+if __name__ == "__main__":
+    sys.exit(main())
