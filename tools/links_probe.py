@@ -11,14 +11,22 @@ sums over links.  Every link keeps one background pixel on its right-hand side; 
 component of the link's pixels, 4-connected background component of that pixel) names the border the link belongs to, so
 the sums of every border -- outer and hole, any nesting -- can be accumulated with atomics per label pair, without
 following any border (second check below: the per-label-pair a00/a10/a01 against those of the cv2 contours).
+Third check: the whole per-border record (a00, a10, a01, perimeter of the CHAIN_APPROX_SIMPLE polygon, hole flag, start
+pixel) computed without following a border -- step sums per label pair, perimeter = axis steps + float32 sqrt(2 k^2) per
+diagonal run (a step's successor is one 3x3 lookup), hole flag = sign of a00, start = smallest west/east edge key of the
+label pair -- against the oracle's contour table (oracle/restate.py).
 python tools/links_probe.py [n_images]
 """
+import os
 import sys
 from collections import Counter
 
 import cv2
 import numpy as np
 from scipy import ndimage
+
+sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
+from oracle import restate as R                      # noqa: E402
 
 
 def local_links(img):
@@ -97,6 +105,78 @@ def per_border_check(img, links, rights):
     return mine == ref
 
 
+DX = (1, 1, 0, -1, -1, -1, 0, 1)                        # 0=E 1=NE 2=N 3=NW 4=W 5=SW 6=S 7=SE (y grows downwards)
+DY = (0, -1, -1, -1, 0, 1, 1, 1)
+
+
+def trace_free_records(img):
+    """Sorted [(a00, a10, a01, perimeter, is_hole, start_x, start_y)] of every border with more than one pixel."""
+    H, W = img.shape
+    links, rights = local_links(img)
+    fgp = np.zeros((H + 2, W + 2), bool)
+    fgp[1:-1, 1:-1] = img != 0
+    fl, _ = ndimage.label(fgp, structure=np.ones((3, 3)))
+    bl, _ = ndimage.label(~fgp)
+    fg = lambda x, y: bool(fgp[y + 1, x + 1])
+    key_of = {L: (int(fl[L[1] + 1, L[0] + 1]), int(bl[rights[L][1] + 1, rights[L][0] + 1])) for L in links}
+    dir_of = lambda L: [d for d in range(8) if (DX[d], DY[d]) == (L[2] - L[0], L[3] - L[1])][0]
+    succ = {}
+    for L in links:                                  # successor: one border-following step at the link's end pixel
+        x, y, d = L[2], L[3], dir_of(L)
+        back = (d + 4) & 7
+        for k in range(1, 9):
+            nd = (back + k) & 7
+            if fg(x + DX[nd], y + DY[nd]):
+                succ[L] = (x, y, x + DX[nd], y + DY[nd])
+                break
+    assert sorted(succ.values()) == sorted(links)    # a bijection on the links
+    pred_dir = {succ[L]: dir_of(L) for L in links}
+    rec = {}
+    for L in links:
+        x0, y0, x1, y1 = L
+        r = rec.setdefault(key_of[L], {"a": [0, 0, 0], "axis": 0, "diag": 0.0})
+        dxy = x0 * y1 - x1 * y0
+        r["a"][0] += dxy; r["a"][1] += dxy * (x0 + x1); r["a"][2] += dxy * (y0 + y1)
+        d = dir_of(L)
+        assert key_of[succ[L]] == key_of[L]
+        if d % 2 == 0:
+            r["axis"] += 1
+        elif pred_dir[L] != d:                       # start of a diagonal run: follow it
+            k, M = 1, L
+            while dir_of(succ[M]) == d and succ[M] != L:
+                M = succ[M]; k += 1
+            r["diag"] += float(np.sqrt(np.float32(2 * k * k)))
+    # start pixel: the smallest west / east edge (crack between a foreground pixel and the background pixel beside it)
+    start = {}
+    for y in range(H):
+        for x in range(W):
+            if not fg(x, y):
+                continue
+            for east, nx in ((0, x - 1), (1, x + 1)):
+                if not fg(nx, y):
+                    k = (int(fl[y + 1, x + 1]), int(bl[y + 1, nx + 1]))
+                    start[k] = min(start.get(k, (1 << 62,)), (2 * (y * W + x) + east, x, y))
+    out = []
+    for k, r in rec.items():
+        a00 = r["a"][0]
+        hole = int(start[k][0] & 1)                  # a border that starts on an east edge is a hole border
+        first = (start[k][1], start[k][2]) if not hole else (-1, -1)
+        out.append((a00, r["a"][1], r["a"][2], r["axis"] + r["diag"], hole) + first)
+    return sorted(out)
+
+
+def oracle_records(img):
+    contours, info = R.find_contours((img != 0).astype(np.uint8) * 255)
+    out = []
+    for c, inf in zip(contours, info):
+        if int(inf[2]) <= 1 and len(c) <= 1:
+            continue
+        a00, a10, a01, per = R.contour_stats(c)
+        first = (int(c[0][0]), int(c[0][1])) if not inf[0] else (-1, -1)   # cv2's first point of a hole border is not the pixel it was found at
+        out.append((int(a00), int(a10), int(a01), float(per), int(inf[0])) + first)
+    return sorted(out)
+
+
 def main():
     n = int(sys.argv[1]) if len(sys.argv) > 1 else 200
     rng = np.random.default_rng(5)
@@ -114,6 +194,12 @@ def main():
             print("PER-BORDER MISMATCH at image", it)
             np.save("/tmp/links_fail.npy", img)
             return 1
+        mine, ref = trace_free_records(img), oracle_records(img)
+        if mine != ref:
+            print("RECORD MISMATCH at image", it, [x for x in mine if x not in ref][:3], [x for x in ref if x not in mine][:3])
+            np.save("/tmp/links_fail.npy", img)
+            return 1
+    print(n, "images: trace-free border records == oracle contour records")
     print(n, "images: local link multiset == cv2 border steps; per-(fg, bg)-label sums == per-contour Green sums")
     return 0
 
