@@ -15,6 +15,8 @@ Third check: the whole per-border record (a00, a10, a01, perimeter of the CHAIN_
 pixel) computed without following a border -- step sums per label pair, perimeter = axis steps + float32 sqrt(2 k^2) per
 diagonal run (a step's successor is one 3x3 lookup), hole flag = sign of a00, start = smallest west/east edge key of the
 label pair -- against the oracle's contour table (oracle/restate.py).
+Fourth check: the bit-parallel form a kernel would use -- eight step masks per pair of adjacent bit rows from shifts and
+logic (step_masks) -- gives the same links.
 python tools/links_probe.py [n_images]
 """
 import os
@@ -61,6 +63,41 @@ def local_links(img):
                 elif not b: add(D, A)
                 else: add(A, D)
     return out, rights
+
+
+def step_masks(U, L):
+    """Bit rows U (row y) and L (row y + 1) of the zero-padded image, bit x = pixel x (Python ints = arbitrarily wide
+    words).  With a = U[x], b = U[x+1], c = L[x], d = L[x+1] the corner between them emits (bit x of each mask):
+      E  from (x, y)      a b ~c ~d      W  from (x+1, y+1)  c d ~a ~b      N  from (x, y+1)  a c ~b ~d      S  from (x+1, y)  b d ~a ~c
+      SE from (x, y)      a d ~c         NW from (x+1, y+1)  a d ~b         SW from (x+1, y)  b c ~a         NE from (x, y+1)  b c ~d
+    (the diagonal masks cover both the two-diagonal-pixel corner and the three-pixel corners)."""
+    a, b, c, d = U, U >> 1, L, L >> 1
+    n = lambda v: ~v
+    return {"E": a & b & n(c) & n(d), "W": c & d & n(a) & n(b), "N": a & c & n(b) & n(d), "S": b & d & n(a) & n(c),
+            "SE": a & d & n(c), "NW": a & d & n(b), "SW": b & c & n(a), "NE": b & c & n(d)}
+
+
+def bitrow_links(img):
+    H, W = img.shape
+    rows = [0] * (H + 2)                                  # padded rows -1 .. H; bit x + 1 = pixel x (one padding column on the left)
+    for y in range(H):
+        for x in range(W):
+            if img[y, x]:
+                rows[y + 1] |= 1 << (x + 1)
+    src = {"E": (0, 0, 1, 0), "W": (1, 1, -1, 0), "N": (0, 1, 0, -1), "S": (1, 0, 0, 1),
+           "SE": (0, 0, 1, 1), "NW": (1, 1, -1, -1), "SW": (1, 0, -1, 1), "NE": (0, 1, 1, -1)}   # source pixel offset from the corner's NW pixel, step
+    out = Counter()
+    for yy in range(H + 1):                               # corner row between padded rows yy and yy + 1, i.e. image rows yy - 1 and yy
+        for name, m in step_masks(rows[yy], rows[yy + 1]).items():
+            m &= (1 << (W + 2)) - 1
+            ox, oy, dx, dy = src[name]
+            x = 0
+            while m:
+                if m & 1:
+                    sx, sy = x - 1 + ox, yy - 1 + oy
+                    out[(sx, sy, sx + dx, sy + dy)] += 1
+                m >>= 1; x += 1
+    return out
 
 
 def cv_links(img):
@@ -186,6 +223,9 @@ def main():
         if it % 3 == 0:                                       # smoother shapes
             img = cv2.blur(img.astype(np.float32), (5, 5)) > 0.5
         (a, rights), b = local_links(img), cv_links(img)
+        if bitrow_links(img) != a:
+            print("BIT-ROW MASK MISMATCH at image", it)
+            return 1
         if a != b:
             print("MISMATCH at image", it, "only local:", list((a - b).items())[:5], "only cv:", list((b - a).items())[:5])
             np.save("/tmp/links_fail.npy", img)
@@ -199,7 +239,7 @@ def main():
             print("RECORD MISMATCH at image", it, [x for x in mine if x not in ref][:3], [x for x in ref if x not in mine][:3])
             np.save("/tmp/links_fail.npy", img)
             return 1
-    print(n, "images: trace-free border records == oracle contour records")
+    print(n, "images: trace-free border records == oracle contour records; bit-row step masks == corner enumeration")
     print(n, "images: local link multiset == cv2 border steps; per-(fg, bg)-label sums == per-contour Green sums")
     return 0
 
