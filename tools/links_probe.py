@@ -176,6 +176,13 @@ def trace_free_records(img):
         r["a"][0] += dxy; r["a"][1] += dxy * (x0 + x1); r["a"][2] += dxy * (y0 + y1)
         d = dir_of(L)
         assert key_of[succ[L]] == key_of[L]
+        if d % 2:
+            # a diagonal step is continued by a step of the same direction iff, at its end pixel q, the two neighbours after
+            # the right-hand background pixel in the search order are empty and the next pixel on the diagonal is set:
+            # SE: SW, S empty; NE: SE, E empty; NW: NE, N empty; SW: NW, W empty  (local: bit logic on three rows)
+            e1, e2 = (d + 6) & 7, (d + 7) & 7
+            local = not fg(x1 + DX[e1], y1 + DY[e1]) and not fg(x1 + DX[e2], y1 + DY[e2]) and fg(x1 + DX[d], y1 + DY[d])
+            assert local == (dir_of(succ[L]) == d)
         if d % 2 == 0:
             r["axis"] += 1
         elif pred_dir[L] != d:                       # start of a diagonal run: follow it
