@@ -45,6 +45,15 @@ def run():
         assert a.points(0) == b.points(0)
         c = eng.detect(torch.from_numpy(img[None].copy()), K, D, min_area=0.0)          # the cluster path proper
         assert c.points(0) == a.points(0)
+    img = rng.integers(0, 40, (200, 416)).astype(np.uint8)                               # borders several trace windows wide (walk.cuh, WINDOW)
+    yy, xx = np.mgrid[:200, :416]
+    img[((xx - 200) / 150.0) ** 2 + ((yy - 40) / 18.0) ** 2 <= 1.0] = 255
+    img[130:140, 30:416] = 255
+    for x in range(30, 400, 14):
+        img[140:185, x:x + 7] = 255
+    img[90:120, 0:130] = 255
+    assert eng.detect(torch.from_numpy(img[None].copy()), K, D, min_area=0.0).points(0) == \
+        eng.detect(torch.from_numpy(img[None].copy()), K, D, min_area=0.0, outputs=("bits", "labels")).points(0)
     for shape in [(3, 4), (5, 8), (34, 132), (64, 128), (97, 260), (7, 10), (33, 65)]:  # Bayer front step, both kernels
         eng.bayer_gr2gray(torch.from_numpy(rng.integers(0, 256, (2,) + shape).astype(np.uint8)))
     z = np.load(os.path.join(REPO, "tests", "golden", "c1_frames.npz"))["frames"].reshape(-1, 480, 640)[:2]
