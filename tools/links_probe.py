@@ -221,6 +221,30 @@ def oracle_records(img):
     return sorted(out)
 
 
+def euler_check(img):
+    """Holes of every 8-connected component from corner counts: (Q1 - Q3 - 2 QD) / 4 == 1 - holes, where Q1 / Q3 / QD count the
+    2x2 corners holding one / three / two diagonal pixels of the component (a component without holes needs no background
+    labels: all its steps belong to its outer border)."""
+    H, W = img.shape
+    p = np.zeros((H + 2, W + 2), bool)
+    p[1:-1, 1:-1] = img != 0
+    fl, nf = ndimage.label(p, structure=np.ones((3, 3)))
+    q = np.zeros((3, nf + 1), np.int64)
+    for y in range(H + 1):
+        for x in range(W + 1):
+            blk = p[y:y + 2, x:x + 2]
+            n = int(blk.sum())
+            if n in (1, 3) or (n == 2 and blk[0, 0] == blk[1, 1]):
+                q[{1: 0, 3: 1, 2: 2}[n], fl[y:y + 2, x:x + 2][blk][0]] += 1
+    holes = np.zeros(nf + 1, np.int64)
+    cs, hier = cv2.findContours((img != 0).astype(np.uint8), cv2.RETR_CCOMP, cv2.CHAIN_APPROX_NONE)
+    if hier is not None:
+        for c, h in zip(cs, hier[0]):
+            if h[3] >= 0:                                   # a hole border runs over pixels of the component around it
+                holes[fl[c[0][0][1] + 1, c[0][0][0] + 1]] += 1
+    return np.array_equal((q[0] - q[1] - 2 * q[2])[1:], 4 * (1 - holes[1:]))
+
+
 def main():
     n = int(sys.argv[1]) if len(sys.argv) > 1 else 200
     rng = np.random.default_rng(5)
@@ -241,12 +265,15 @@ def main():
             print("PER-BORDER MISMATCH at image", it)
             np.save("/tmp/links_fail.npy", img)
             return 1
+        if not euler_check(img):
+            print("EULER MISMATCH at image", it)
+            return 1
         mine, ref = trace_free_records(img), oracle_records(img)
         if mine != ref:
             print("RECORD MISMATCH at image", it, [x for x in mine if x not in ref][:3], [x for x in ref if x not in mine][:3])
             np.save("/tmp/links_fail.npy", img)
             return 1
-    print(n, "images: trace-free border records == oracle contour records; bit-row step masks == corner enumeration")
+    print(n, "images: trace-free border records == oracle contour records; bit-row step masks == corner enumeration; holes per component == 1 - Euler number")
     print(n, "images: local link multiset == cv2 border steps; per-(fg, bg)-label sums == per-contour Green sums")
     return 0
 
