@@ -1,5 +1,5 @@
 """Fuzz the detection path on the CUDA-on-CPU build against the oracle: random lenses, frame sizes and scenes
-(development tool; python tools/fuzz_detect.py [iterations] [seed])."""
+(development tool; python tests/fuzz_detect.py [iterations] [seed]; it uses the oracle, so it lives under tests/)."""
 import os
 import sys
 

@@ -17,7 +17,7 @@ diagonal run (a step's successor is one 3x3 lookup), hole flag = sign of a00, st
 label pair -- against the oracle's contour table (oracle/restate.py).
 Fourth check: the bit-parallel form a kernel would use -- eight step masks per pair of adjacent bit rows from shifts and
 logic (step_masks) -- gives the same links.
-python tools/links_probe.py [n_images]
+python tests/links_probe.py [n_images]
 """
 import os
 import sys
