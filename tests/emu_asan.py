@@ -1,5 +1,5 @@
 """AddressSanitizer pass over the kernel sources through the CUDA-on-CPU shim (tests/emu): compute-sanitizer is closed on the
-GPU pool, so out-of-bounds accesses are hunted here.  Usage:  python tools/emu_asan.py   (rebuilds into /tmp/emu_asan, then
+GPU pool, so out-of-bounds accesses are hunted here.  Usage:  python tests/emu_asan.py   (rebuilds into /tmp/emu_asan, then
 re-executes itself with libasan preloaded)."""
 import os
 import subprocess
