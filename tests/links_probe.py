@@ -96,6 +96,15 @@ def bitrow_links(img):
                 if m & 1:
                     sx, sy = x - 1 + ox, yy - 1 + oy
                     out[(sx, sy, sx + dx, sy + dy)] += 1
+                    # contribution of the step in closed form, (cx, cy) = the corner's NW pixel:
+                    #   dxy: E -cy, W cy+1, N -cx, S cx+1, SE cx-cy, NW cy-cx, SW cx+cy+1, NE -(cx+cy+1)
+                    #   a10 += dxy * (x0 + x1), a01 += dxy * (y0 + y1) with x0 + x1 = 2 cx + 1 (N: 2 cx, S: 2 cx + 2),
+                    #   y0 + y1 = 2 cy + 1 (E: 2 cy, W: 2 cy + 2)
+                    cx, cy = x - 1, yy - 1
+                    dxy = {"E": -cy, "W": cy + 1, "N": -cx, "S": cx + 1, "SE": cx - cy, "NW": cy - cx, "SW": cx + cy + 1, "NE": -(cx + cy + 1)}[name]
+                    sumx = {"N": 2 * cx, "S": 2 * cx + 2}.get(name, 2 * cx + 1)
+                    sumy = {"E": 2 * cy, "W": 2 * cy + 2}.get(name, 2 * cy + 1)
+                    assert dxy == sx * (sy + dy) - (sx + dx) * sy and sumx == 2 * sx + dx and sumy == 2 * sy + dy
                 m >>= 1; x += 1
     return out
 
