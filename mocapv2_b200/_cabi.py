@@ -43,6 +43,14 @@ SIGNATURES = {
     "mocap_stage_timer_destroy": (None, [_p]),
     "mocap_stage_timer_read": (_i, [_p, _p]),
     "mocap_stage_name": (C.c_char_p, [_i]),
+    "mocap_detect_pipe_create": (_p, [_i, _i]),
+    "mocap_detect_pipe_destroy": (None, [_p]),
+    "mocap_detect_pipelined_workspace_bytes": (_sz, [_i, _i, _i, _i, _i, _i, _i]),
+    "mocap_detect_batch_pipelined": (_i, [_p, _p, _i, _i, _i, _i64, _p, _i, _d, _d, _i, _i, _i,
+                                          _p, _p, _p, _p, _p, _p, _sz, _p, _p]),
+    "mocap_detect_pipe_timeline": (_i, [_p, _p, _i]),
+    "mocap_detect_pipe_info": (_i, [_p, _p]),
+    "mocap_scan_cells_batch": (_i, [_p, _i, _i, _i, _i64, _p, _i, _i, _p, _p, _sz, _p]),
     "mocap_filter_batch": (_i, [_p, _i, _i, _i, _i64, _p, _i, _p, _p, _sz, _p]),
     "mocap_blobs_batch": (_i, [_p, _i, _i, _i, _d, _d, _i, _i, _i, _p, _p, _p, _p, _p, _p, _p, _p, _p, _sz, _p]),
     "mocap_blur5_batch": (_i, [_p, _i, _i, _i, _p, _p]),
@@ -55,6 +63,12 @@ SIGNATURES = {
     "mocap_correspond_batch": (_i, [_p, _p, _i, _i, _i, _p, _p, _d, _i, _i, _i,
                                     _p, _p, _p, _p, _p, _p, _p, _p, _sz, _p]),
 }
+
+
+class PipeOpts(C.Structure):
+    """MocapPipeOpts of include/mocap_b200.h"""
+    _fields_ = [("chunk_frames", _i), ("sync_mode", _i), ("scan_variant", _i), ("filter_ctas_per_sm", _i),
+                ("cand_ctas_per_sm", _i), ("record_timeline", _i), ("stream_plan", _i), ("reserved", _i * 1)]
 
 
 class MocapError(RuntimeError):

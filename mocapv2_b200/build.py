@@ -9,7 +9,7 @@ import sys
 
 HERE = os.path.dirname(os.path.abspath(__file__))
 CSRC = os.path.join(HERE, "csrc")
-SOURCES = ["api.cu", "detect_filter.cu", "detect_cluster.cu", "detect_blobs.cu", "geometry.cu"]
+SOURCES = ["api.cu", "detect_filter.cu", "detect_scan_tma.cu", "detect_cluster.cu", "detect_blobs.cu", "geometry.cu"]
 LIB = os.path.join(HERE, "libmocap_b200.so")
 NVCC_FLAGS = ["-gencode", "arch=compute_100a,code=sm_100a", "-lineinfo", "-O3", "-std=c++17",
               "--fmad=true", "-Xcompiler", "-fPIC,-O2", "-Xptxas", "-v", "-shared", "-cudart", "shared"]

@@ -65,6 +65,56 @@ struct StageTimer {
 static inline void stage_begin(StageTimer* t, int stage, cudaStream_t s) { if (t) { cudaEventRecord(t->ev[2 * stage], s); } }
 static inline void stage_end(StageTimer* t, int stage, cudaStream_t s) { if (t) { cudaEventRecord(t->ev[2 * stage + 1], s); t->recorded[stage] = 1; } }
 
+#define CELL_EMPTY 0xffffffffu
+// ---------------------------------------------------------------------------------------------------------
+// hot-pixel test: byte > thresh, four bytes at a time.  T = thresh + 1.
+//   T in 129..255: bit7(b) & bit7((b & 0x7f) + (256 - T));   T in 1..128: bit7(b) | bit7((b & 0x7f) + (128 - T))
+// ---------------------------------------------------------------------------------------------------------
+struct HotTest { uint32_t add; int mode; };   // mode 0: and, 1: or, 2: never, 3: always
+static inline HotTest make_hot_test(int thresh)
+{
+    HotTest h; int T = thresh + 1;
+    if (T >= 256) { h.mode = 2; h.add = 0; }
+    else if (T <= 0) { h.mode = 3; h.add = 0; }
+    else if (T > 128) { h.mode = 0; h.add = 0x01010101u * (uint32_t)(256 - T); }
+    else { h.mode = 1; h.add = 0x01010101u * (uint32_t)(128 - T); }
+    return h;
+}
+template <int MODE>
+__device__ __forceinline__ uint32_t hot4(uint32_t w, uint32_t add)
+{
+    uint32_t t = (w & 0x7f7f7f7fu) + add;
+    if (MODE == 0) return w & t;        // caller masks with 0x80808080
+    if (MODE == 1) return w | t;
+    if (MODE == 2) return 0u;
+    return 0x80808080u;
+}
+
+// hot byte lanes of a 32-bit word (bit 7 of every byte of h) -> 4-bit mask, bit b = byte b
+__device__ __forceinline__ uint32_t hot_nibble(uint32_t h)
+{
+    h &= 0x80808080u;
+    return ((h >> 7) | (h >> 14) | (h >> 21) | (h >> 28)) & 0xfu;
+}
+
+// cell-local hot bounding box packed x0 | x1 << 8 | y0 << 16 | y1 << 24; CELL_EMPTY when the cell holds no pixel > thresh
+__device__ __forceinline__ uint32_t pack_cellbox(uint32_t xmask, uint32_t ymask)
+{
+    if (!xmask) return CELL_EMPTY;
+    uint32_t x0 = __ffs(xmask) - 1, x1 = 31 - __clz(xmask), y0 = __ffs(ymask) - 1, y1 = 31 - __clz(ymask);
+    return x0 | (x1 << 8) | (y0 << 16) | (y1 << 24);
+}
+
+// how launch_cluster_path runs a batch (or one chunk of the overlapped pipeline)
+struct ClusterLaunch {
+    int zero = 1;                    // clear the counters / lists of the workspace on the stream first
+    int filter_ctas_per_sm = 8;      // persistent piece-filter CTAs per SM (fewer when the TMA scan is co-resident)
+    int cand_ctas_per_sm = 16;
+    cudaEvent_t ev_group = nullptr, ev_filter = nullptr, ev_borders = nullptr;   // recorded after the stages (timeline marks; hand-over between streams)
+    cudaStream_t s_filter = nullptr, s_borders = nullptr;   // run the piece filter / the border stage on other streams than the grouping
+                                                             // (each waits for the event of the stage before it, which must then be set)
+};
+
 // workspace slices of the filter stage (carved by api.cu)
 struct FilterWs {
     uint32_t* active;    // [n][TY][TXW] bitmap of output tiles that can hold foreground

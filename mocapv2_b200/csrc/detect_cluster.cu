@@ -24,7 +24,6 @@
 #define WIN_W 96                // staged source window of a piece: up to 96 x 79 bytes (sized so that 8 CTAs fit one SM)
 #define WIN_H 79
 #define CAND_PER_FRAME 512      // border-start candidates per frame on the cluster path
-#define CELL_EMPTY 0xffffffffu
 
 // counters[] slots
 #define CN_CLUSTERS 0
@@ -1027,20 +1026,23 @@ size_t cluster_ws_bytes(int n, int H, int W, int max_contours, size_t* offs /*[1
 {
     size_t off = 0;
     auto take = [&](size_t bytes) { size_t r = off; off += align_up(bytes, 256); return r; };
-    offs[0] = take((size_t)n * 4);                         // need_general
+    offs[0] = take((size_t)n * 4);                         // need_general (the chunked path keeps one array for the whole batch instead)
+    // everything a call has to zero first lies in one block: offs[14] = its start, offs[15] = its size
+    offs[14] = off;
     offs[1] = take(64);                                    // counters
+    offs[4] = take((size_t)n * 4);                         // rec_count
+    offs[11] = take((size_t)n * 4);                        // cand_count
+    offs[13] = take((size_t)n * 8);                        // frame_clusters
+    offs[15] = off - offs[14];
     offs[2] = take((size_t)cl_cap_of(n) * 32);             // clusters
     offs[3] = take((size_t)pc_cap_of(n) * 32);             // pieces
-    offs[4] = take((size_t)n * 4);                         // rec_count
     offs[5] = take((size_t)n * max_contours * 4);          // rec_start
     offs[6] = take((size_t)n * max_contours * 24);         // rec_a
     offs[7] = take((size_t)n * max_contours * 8);          // rec_per
     offs[8] = take((size_t)n * HOT_MAX * 8);               // memb
     offs[9] = take(rows_cap_of(n, H, W) * 4);              // rows_out
     offs[10] = take((size_t)n * CAND_PER_FRAME * 8);       // cand_list
-    offs[11] = take((size_t)n * 4);                        // cand_count
     offs[12] = take((size_t)n * max_contours * 16);        // rec_info
-    offs[13] = take((size_t)n * 8);                        // frame_clusters
     return off;
 }
 
@@ -1050,13 +1052,13 @@ bool cluster_path_supported(int H, int W)
 }
 
 int launch_cluster_path(const uint8_t* frames, int n, int H, int W, int64_t fstride, const TableView& tv, int thresh,
-                        const uint32_t* cellbox, char* ws_base, const size_t* offs,
+                        const uint32_t* cellbox, char* ws_base, const size_t* offs, int* need_general,
                         int max_contours, int max_blobs, double min_area, double min_circ,
                         int32_t* out_xy, int32_t* out_count, int32_t* out_flags, double* out_contours, int32_t* out_contour_count,
-                        cudaStream_t s, StageTimer* timer)
+                        cudaStream_t s, StageTimer* timer, const ClusterLaunch& how)
 {
     ClusterWs cw;
-    cw.need_general = (int*)(ws_base + offs[0]);
+    cw.need_general = need_general;
     cw.counters = (int*)(ws_base + offs[1]);
     cw.clusters = (int*)(ws_base + offs[2]);
     cw.pieces = (int*)(ws_base + offs[3]);
@@ -1073,31 +1075,40 @@ int launch_cluster_path(const uint8_t* frames, int n, int H, int W, int64_t fstr
     cw.rec_info = (int*)(ws_base + offs[12]);
     cw.frame_clusters = (int*)(ws_base + offs[13]);
     cw.n_frames = n;
-    CUDA_TRY(cudaMemsetAsync(cw.counters, 0, 64, s));
-    CUDA_TRY(cudaMemsetAsync(cw.rec_count, 0, (size_t)n * 4, s));
-    CUDA_TRY(cudaMemsetAsync(cw.cand_count, 0, (size_t)n * 4, s));
-    CUDA_TRY(cudaMemsetAsync(cw.frame_clusters, 0, (size_t)n * 8, s));
+    if (how.zero) CUDA_TRY(cudaMemsetAsync(ws_base + offs[14], 0, offs[15], s));
     int dev = 0, sms = 148;
     cudaGetDevice(&dev);
     cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
     const int cells = tv.TX * tv.TY;
     size_t sm_form = (size_t)form_idx_slots(cells) * 2 + (size_t)HOT_MAX * (2 + 4 + 16 + 8 + 8) + (size_t)ROOTS_MAX * (2 + 12) + 64;
 #ifndef MOCAP_EMU
-    CUDA_TRY(cudaFuncSetAttribute(form_clusters_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 64 * 1024));
+    static bool attr_done = false;                          // (idempotent; a race only repeats the call)
+    if (!attr_done) { CUDA_TRY(cudaFuncSetAttribute(form_clusters_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 64 * 1024)); attr_done = true; }
 #endif
     stage_begin(timer, 1, s);
     LAUNCH(form_clusters_kernel, n, CL_THREADS, sm_form, s, cellbox, tv, cw);
     stage_end(timer, 1, s);
-    stage_begin(timer, 2, s);
-    LAUNCH(piece_filter_kernel, sms * 8, CL_THREADS, 0, s, frames, fstride, tv, thresh, cw);
-    stage_end(timer, 2, s);
-    stage_begin(timer, 3, s);
-    LAUNCH(candidates_kernel, sms * 16, 128, 0, s, cw);
+    if (how.ev_group) cudaEventRecord(how.ev_group, s);
+    cudaStream_t sf = how.s_filter ? how.s_filter : s;
+#ifndef MOCAP_EMU
+    if (sf != s) { if (!how.ev_group) return MOCAP_ERR_INVALID; CUDA_TRY(cudaStreamWaitEvent(sf, how.ev_group, 0)); }
+#endif
+    stage_begin(timer, 2, sf);
+    LAUNCH(piece_filter_kernel, sms * how.filter_ctas_per_sm, CL_THREADS, 0, sf, frames, fstride, tv, thresh, cw);
+    stage_end(timer, 2, sf);
+    if (how.ev_filter) cudaEventRecord(how.ev_filter, sf);
+    cudaStream_t sb = how.s_borders ? how.s_borders : sf;
+#ifndef MOCAP_EMU
+    if (sb != sf) { if (!how.ev_filter) return MOCAP_ERR_INVALID; CUDA_TRY(cudaStreamWaitEvent(sb, how.ev_filter, 0)); }
+#endif
+    stage_begin(timer, 3, sb);
+    LAUNCH(candidates_kernel, sms * how.cand_ctas_per_sm, 128, 0, sb, cw);
     int frame_step = 1;
     for (int pr : {61, 67, 71, 73}) if (n % pr != 0) { frame_step = pr; break; }          // a prime that does not divide n
-    LAUNCH(borders_finalize_kernel, n, CL_THREADS, (size_t)max_contours + 16, s, cw, W, frame_step, max_contours, max_blobs, min_area, min_circ,
+    LAUNCH(borders_finalize_kernel, n, CL_THREADS, (size_t)max_contours + 16, sb, cw, W, frame_step, max_contours, max_blobs, min_area, min_circ,
            out_xy, out_count, out_flags, out_contours, out_contour_count);
-    stage_end(timer, 3, s);
+    stage_end(timer, 3, sb);
+    if (how.ev_borders) cudaEventRecord(how.ev_borders, sb);
     CUDA_TRY(cudaGetLastError());
     return MOCAP_OK;
 }

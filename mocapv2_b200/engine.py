@@ -89,6 +89,10 @@ class CaptureEngine:
         self._ws = None
         self._lock = threading.RLock()           # every library call of this engine is issued under it           # _find_dot is called from one thread per camera (RealtimeTracking_FLIR.py:309)
         self.launches = 0                       # kernels launched through this engine (bench bookkeeping)
+        self.pipe_workers = 2                   # worker streams of the overlapped detection
+        self.pipe_prio_mode = 0
+        self._pipe_handle = None
+        self.last_pipe_info = None
 
     # ---- plumbing ------------------------------------------------------------------------------------------------
     def _stream(self):
@@ -188,6 +192,84 @@ class CaptureEngine:
             _cabi.check(self.lib, st, "mocap_detect_batch")
             # scan, group, filter pieces, candidates, traces+finalize + the general path's mark / compact / tiles / blobs
             self.launches += 9 + (1 if "bits" in ex else 0)
+        return out
+
+    # ---- overlapped detection (chunks: TMA scan of chunk k+1 beside the filter / border stages of chunk k) ----------------------
+    def _pipe(self):
+        if getattr(self, "_pipe_handle", None) is None:
+            h = self.lib.mocap_detect_pipe_create(int(self.pipe_workers), int(self.pipe_prio_mode))
+            if not h:
+                raise _cabi.MocapError("mocap_detect_pipe_create failed")
+            self._pipe_handle = h
+        return ctypes.c_void_p(self._pipe_handle)
+
+    def detect_pipelined(self, frames: torch.Tensor, K, dist, *, thresh=THRESH_U8, min_area=MIN_AREA, min_circ=MIN_CIRC,
+                         max_blobs=None, max_contours=None, max_runs=None, outputs=(), out: DetectResult | None = None,
+                         chunk_frames=128, sync_mode=1, scan_variant=1, filter_ctas_per_sm=0, cand_ctas_per_sm=0,
+                         stream_plan=0, timeline=False) -> DetectResult:
+        """Same results as detect() (centroid lists, optionally the contour table), computed chunk by chunk with the streaming
+        scan overlapped with the other stages (mocap_detect_batch_pipelined)."""
+        if frames.dim() != 3:
+            raise ValueError("frames must be [n, H, W]")
+        if frames.device != self.device or frames.dtype != torch.uint8:
+            raise ValueError(f"frames must be uint8 on {self.device}")
+        if any(o != "contours" for o in outputs):
+            raise ValueError("detect_pipelined offers the contour table only; use detect() for bits / labels / blob_sums")
+        n, H, W = frames.shape
+        if frames.stride(2) != 1 or frames.stride(1) != W:
+            frames = frames.contiguous()
+        stride = frames.stride(0) if n > 1 else H * W
+        max_blobs, max_contours, max_runs = self.default_caps(H, W, max_blobs, max_contours, max_runs)
+        tab = self.table(K, dist, H, W)
+        if out is None:
+            out = DetectResult(self.empty((n, max_blobs, 2), torch.int32), self.empty((n,), torch.int32),
+                               self.empty((n,), torch.int32))
+        ex = out.extras
+        if "contours" in outputs and "contours" not in ex:
+            ex["contours"] = torch.zeros((n, max_contours, 8), dtype=torch.float64, device=self.device)
+            ex["contour_count"] = self.empty((n,), torch.int32)
+        nbytes = self.lib.mocap_detect_pipelined_workspace_bytes(n, H, W, max_blobs, max_contours, max_runs, int(chunk_frames))
+        if nbytes == 0:
+            raise _cabi.MocapError("mocap_detect_pipelined_workspace_bytes: unsupported shape")
+        opts = _cabi.PipeOpts(int(chunk_frames), int(sync_mode), int(scan_variant), int(filter_ctas_per_sm), int(cand_ctas_per_sm),
+                              1 if timeline else 0, int(stream_plan))
+        with self._lock:
+            ws = self._workspace(nbytes)
+            st = self.lib.mocap_detect_batch_pipelined(
+                self._pipe(), self._ptr(frames), n, H, W, stride, self._ptr(tab), int(thresh), float(min_area), float(min_circ),
+                max_blobs, max_contours, max_runs, self._ptr(out.xy), self._ptr(out.count), self._ptr(out.flags),
+                self._ptr(ex.get("contours")), self._ptr(ex.get("contour_count")), self._ptr(ws), nbytes, self._stream(),
+                ctypes.byref(opts))
+            _cabi.check(self.lib, st, "mocap_detect_batch_pipelined")
+            info = (ctypes.c_int * 3)()
+            self.lib.mocap_detect_pipe_info(self._pipe(), info)
+            chunks = int(info[1])
+            scans = 1 if int(info[2]) == 1 else chunks
+            self.launches += scans + 4 * chunks + 4          # scan(s) + per chunk group/filter/candidates/borders + general path
+            self.last_pipe_info = {"tma_scan": bool(info[0]), "chunks": chunks, "sync_mode": int(info[2])}
+        return out
+
+    def pipe_timeline(self):
+        """ms since the fork of the last detect_pipelined(timeline=True): {"scan_done", "join", "chunks": [[seen, grouped, filtered, borders], ...]}"""
+        buf = (ctypes.c_float * (2 + 4 * 64))()
+        k = self.lib.mocap_detect_pipe_timeline(self._pipe(), buf, len(buf))
+        if k <= 0:
+            return None
+        v = [float(x) for x in buf[:k]]
+        return {"scan_done": v[0], "join": v[1], "chunks": [v[2 + 4 * c: 6 + 4 * c] for c in range((k - 2) // 4)]}
+
+    def scan_cells(self, frames: torch.Tensor, K, dist, *, thresh=THRESH_U8, variant=0) -> torch.Tensor:
+        """The streaming scan alone: hot bounding box of every 32x32 source cell, [n, ceil(H/32), ceil(W/32)] int32 (stage parity)."""
+        frames = self._check_dev(frames.contiguous(), torch.uint8, "frames")
+        n, H, W = frames.shape
+        tab = self.table(K, dist, H, W)
+        out = self.empty((n, (H + 31) // 32, (W + 31) // 32), torch.int32)
+        with self._lock:
+            ws = self._workspace(4096)
+            st = self.lib.mocap_scan_cells_batch(self._ptr(frames), n, H, W, H * W, self._ptr(tab), int(thresh), int(variant),
+                                                 self._ptr(out), self._ptr(ws), 4096, self._stream())
+            _cabi.check(self.lib, st, "mocap_scan_cells_batch")
+            self.launches += 1
         return out
 
     def blobs(self, bits: torch.Tensor, W: int, *, min_area=MIN_AREA, min_circ=MIN_CIRC, max_blobs=None, max_contours=None,

@@ -12,7 +12,7 @@ REPO = os.path.dirname(os.path.dirname(HERE))
 CSRC = os.path.join(REPO, "mocapv2_b200", "csrc")
 OUT = os.path.join(HERE, "_build")
 LIB = os.path.join(OUT, "libmocap_emu.so")
-SOURCES = ["api.cu", "detect_filter.cu", "detect_cluster.cu", "detect_blobs.cu", "geometry.cu"]
+SOURCES = ["api.cu", "detect_filter.cu", "detect_scan_tma.cu", "detect_cluster.cu", "detect_blobs.cu", "geometry.cu"]
 
 
 def build(force=False):
