@@ -38,35 +38,49 @@ SPREAD = 0.95              # half-extent (m) of the marker volume around the rig
 def parse():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
-    ap.add_argument("--steps", type=int, default=10)
+    ap.add_argument("--steps", type=int, default=None, help="timed steps (default: 300 = more than 0.5 s of device time; reference arm: 20)")
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
     ap.add_argument("--frame-sets", type=int, default=64, help="frame-sets per GPU per step (F0)")
     ap.add_argument("--e2e-steps", type=int, default=3)
     ap.add_argument("--cpu-sample", type=int, default=1, help="frame-sets timed for cpu_baseline (0 = skip)")
     ap.add_argument("--no-e2e", action="store_true")
-    return ap.parse_args()
+    ap.add_argument("--no-geometry", action="store_true", help="skip the config-5 geometry sweep")
+    ap.add_argument("--no-extra", action="store_true", help="skip front step, _find_dot latency and the C1 / C3 configs")
+    a = ap.parse_args()
+    if a.steps is None:
+        a.steps = 300 if a.impl == "b200" else 20
+    return a
 
 
 # ---------------------------------------------------------------------------------------------------------------------
 # synthetic rig + frames (data plumbing)
 # ---------------------------------------------------------------------------------------------------------------------
-def make_scene(n_frame_sets, seed=S.SEED0 + 4000):
-    """Marker positions per frame-set and their integer pixel centres per camera: (rig, centres [FS, C, M, 2] int64)."""
-    rig = S.config_rig(CONFIG)
+def make_scene(n_frame_sets, config=CONFIG, n_markers=N_MARKERS, spread=SPREAD, seed=S.SEED0 + 4000):
+    """Marker positions per frame-set and their integer pixel centres per camera: (rig, centres [FS, C, M, 2] int64, radius idx).
+
+    Everything a frame-set needs is drawn from ITS OWN generator (seed + 1 + s), so frame-set s is the same scene whatever the
+    number of frame-sets of the run: the first F0 frame-sets of an N-GPU run are the frame-sets of the 1-GPU run and the
+    output checksum of rank 0 can be compared across N."""
+    rig = S.config_rig(config)
     rng = np.random.default_rng(seed)
     # markers spread over the whole commonly visible volume, >= 2r+12 px apart in every view where that is achievable
     # (with 16 views and 128 markers some views inevitably show touching blobs; the detector handles them)
-    X0 = S.sample_markers(rig, N_MARKERS, rng, spread=SPREAD, min_sep_px=56.0, margin=40.0, tries=300)
-    cen = np.empty((n_frame_sets, len(rig["poses"]), N_MARKERS, 2), dtype=np.int64)
+    X0 = S.sample_markers(rig, n_markers, rng, spread=spread, min_sep_px=56.0, margin=40.0, tries=300)
+    C = len(rig["poses"])
+    cen = np.empty((n_frame_sets, C, n_markers, 2), dtype=np.int64)
+    radius_idx = np.empty((n_frame_sets, C, n_markers), dtype=np.int64)
     for s in range(n_frame_sets):
-        X = X0 + rng.uniform(-JITTER, JITTER, X0.shape)
+        rs = np.random.default_rng(seed + 1 + s)
+        X = X0 + rs.uniform(-JITTER, JITTER, X0.shape)
         cen[s] = np.rint(S.marker_pixels(rig, X)).astype(np.int64)
-    radius_idx = rng.integers(0, 9, (n_frame_sets, len(rig["poses"]), N_MARKERS))
+        radius_idx[s] = rs.integers(0, 9, (C, n_markers))
     return rig, cen, radius_idx
 
 
 def render_local(rig, cen, radius_idx, cam_begin, cams_local, device):
+    """Frames [FS, cams_local, H, W] of this rank's cameras; the background noise of a frame is seeded by (frame-set, camera)
+    alone, so a frame does not depend on how the cameras are sharded."""
     import torch
     FS = cen.shape[0]
     H, W = rig["H"], rig["W"]
@@ -75,7 +89,8 @@ def render_local(rig, cen, radius_idx, cam_begin, cams_local, device):
     for s in range(FS):
         c = torch.from_numpy(cen[s, cam_begin:cam_begin + cams_local]).to(device)
         r = torch.from_numpy(radius_idx[s, cam_begin:cam_begin + cams_local]).to(device)
-        S.render_batch_torch(H, W, c, r, 1000 + s * 64 + cam_begin, device, stamps=stamps, out=frames[s])
+        seeds = [1000 + s * 64 + cam_begin + k for k in range(cams_local)]
+        S.render_batch_torch(H, W, c, r, seeds, device, stamps=stamps, out=frames[s])
     return frames
 
 
@@ -166,9 +181,11 @@ def run_reference(args):
     if not cv2_port.available():
         emit({"impl": "reference", "unavailable": "opencv (cv2) is not importable on this host"})
         return 0
+    cvt = None
     try:
         import cv2
         cv2.setNumThreads(threads)
+        cvt = cv2.getNumThreads()
     except Exception:
         pass
     for _ in range(args.warmup):
@@ -189,7 +206,8 @@ def run_reference(args):
         "dtype": "u8 (detection) / f64 (geometry)", "data": "synthetic",
         "points_per_s": pts / t,
         "config": workload_config(1, 1, sample="1 frame-set (16 frames) per step"),
-        "cpu_baseline": {"value": value, "unit": "frames/s", "cores": threads, "kind": "port",
+        "cpu_baseline": {"value": value, "unit": "frames/s", "cores": threads, "os_cpu_count": os.cpu_count(),
+                         "cv2_num_threads": cvt, "kind": "port",
                          "sample": "1 frame-set (16 frames 2048x2048) per step; OpenCV calls of lib/ImageOperations.py:33-65 "
                                    "(numba blur -> integer restatement) + lib/Helpers.py:178-280 control flow in NumPy with the "
                                    f"same candidate cap (max_cand {MAX_CAND}, max_groups {MAX_GROUPS}); frames over a {threads}-thread pool"},
@@ -203,7 +221,7 @@ def run_reference(args):
 def workload_config(n, f0, sample=None):
     cfg = {"workload": "BASELINE config 4: 16 cameras 2048x2048 u8, 128 markers, detect+match+triangulate",
            "cameras": 16, "frame": [2048, 2048], "markers": N_MARKERS, "frame_sets_per_gpu_per_step": f0,
-           "frames_per_step": 16 * f0 * n, "parallelism": f"cameras sharded x{n} for detection, frame-sets sharded x{n} for geometry, 1 all-gather",
+           "frames_per_step": 16 * f0 * n, "parallelism": f"cameras sharded x{n} for detection, frame-sets sharded x{n} for geometry, 1 shard exchange (one grouped NCCL send/recv)",
            "group_cap": {"max_cand": MAX_CAND, "max_groups": MAX_GROUPS},
            "l2": "inputs per step (>=1 GB) exceed the 126 MB L2; the same resident batch is re-read every step"}
     if sample:
@@ -214,6 +232,108 @@ def workload_config(n, f0, sample=None):
 # ---------------------------------------------------------------------------------------------------------------------
 # GPU arm
 # ---------------------------------------------------------------------------------------------------------------------
+def _events(n):
+    import torch
+    return [torch.cuda.Event(enable_timing=True) for _ in range(n)]
+
+
+def _hash_tensors(*ts):
+    import hashlib
+    h = hashlib.sha1()
+    for t in ts:
+        h.update(np.ascontiguousarray(t.cpu().numpy()).tobytes())
+    return h.hexdigest()[:16]
+
+
+def _load_traffic():
+    try:
+        return json.load(open(os.path.join(REPO, "profiles", "traffic.json")))
+    except Exception:
+        return {}
+
+
+def _parity_check(rig, frames, det, corr, cams_local):
+    """GPU results of frame-set 0 against the CPU arm's (oracle/cv2_port.py) on the SAME frames, the same caps."""
+    from oracle import cv2_port
+    if not cv2_port.available():
+        return {"checked": False, "why": "opencv not importable on this host"}
+    host = frames[0].cpu().numpy()
+    pts, obj, ipa = cv2_port.frame_set(host, rig, N_MARKERS, max_cand=MAX_CAND, max_groups=MAX_GROUPS)
+    gpu_pts = [det.points(c) for c in range(cams_local)]
+    cen_ok = gpu_pts == [[list(map(int, q)) if q[0] is not None else q for q in p] for p in pts]
+    nv, no = int(corr.n_valid[0]), int(corr.n_obj[0])
+    img = corr.img[0, :nv].cpu().numpy()
+    got = corr.obj[0, :no].cpu().numpy()
+    ipa = np.asarray(ipa)
+    pairs_ok = bool(ipa.shape == img.shape and np.array_equal(ipa, img))
+    obj = np.asarray(obj, dtype=np.float64).reshape(-1, 3)
+    rel = None
+    # the returned object points are sorted by mean error; FP32 errors of neighbouring roots may swap places, so compare as sets
+    if len(obj) == len(got) and len(obj):
+        d = np.linalg.norm(got[:, None, :] - obj[None, :, :], axis=2)
+        rel = float((d.min(axis=1) / np.linalg.norm(got, axis=1)).max())
+    return {"checked": True, "frame_set": 0, "centroid_lists_equal": bool(cen_ok), "pairs_equal": pairs_ok,
+            "n_centroids": int(sum(len(p) for p in gpu_pts)), "n_roots": nv, "n_object_points": no,
+            "object_points_max_rel_err": rel, "tolerance": 1e-4,
+            "ok": bool(cen_ok and pairs_ok and rel is not None and rel < 1e-4)}
+
+
+def _time_loop(fn, reps, warm=3):
+    import torch
+    for _ in range(warm):
+        fn()
+    torch.cuda.synchronize()
+    a, b = _events(2)
+    a.record()
+    for _ in range(reps):
+        fn()
+    b.record()
+    torch.cuda.synchronize()
+    return a.elapsed_time(b) / reps
+
+
+def _extra_config(eng, name, n_markers, spread, frame_sets, device):
+    """frames/s and points/s of another BASELINE config on one GPU (resident inputs): detection chain fraction included."""
+    import torch
+    from mocapv2_b200.pipeline import CapturePipeline
+    rig, cen, ridx = make_scene(frame_sets, config=name, n_markers=n_markers, spread=spread, seed=S.SEED0 + 7000)
+    mb = max(8, n_markers + n_markers // 4)
+    pipe = CapturePipeline(eng, rig, max_blobs=mb, obj_count=n_markers, max_groups=MAX_GROUPS)
+    frames = render_local(rig, cen, ridx, 0, pipe.cams_local, device)
+    C = pipe.cams_local
+    H, W = rig["H"], rig["W"]
+    corr = [None]
+    marks = []
+
+    def step(rec=False):
+        ev = _events(3) if rec else None
+        if rec:
+            ev[0].record()
+        det = pipe.detect(frames)
+        if rec:
+            ev[1].record()
+        xy, count = pipe.exchange(det, frame_sets)
+        corr[0] = eng.correspond(xy, count, pipe.Fs, pipe.cams, obj_count=n_markers, max_groups=MAX_GROUPS, out=corr[0])
+        if rec:
+            ev[2].record()
+            marks.append(ev)
+        return det
+
+    ms = _time_loop(step, 10)
+    for _ in range(5):
+        det = step(rec=True)
+    torch.cuda.synchronize()
+    det_ms = float(np.mean([e[0].elapsed_time(e[1]) for e in marks]))
+    n = frame_sets * C
+    out = {"workload": f"{name}: {C} cameras {W}x{H}, {n_markers} markers, {frame_sets} frame-sets per step",
+           "ms_per_step": ms, "frames_per_s": n / (ms * 1e-3), "points_per_s": float(corr[0].n_valid.sum().item()) / (ms * 1e-3),
+           "detect_ms": det_ms, "detect_gbs": n * H * W / (det_ms * 1e-3) / 1e9,
+           "centroids_per_frame": float(det.count.float().mean().item()), "flags_or": int(det.flags.max().item()) & 63,
+           "frame_sets_with_group_cap": int((corr[0].flags & 1).sum().item()), "overlapped_detection": eng.last_pipe_info}
+    del frames
+    return out
+
+
 def run_b200(args):
     import torch
     import torch.distributed as dist
@@ -238,10 +358,20 @@ def run_b200(args):
     H, W = rig["H"], rig["W"]
     corr_out = [None]
 
-    def step(timer=None):
-        det = pipe.detect(frames, timer=timer)
+    def step(marks=None):
+        if marks is not None:
+            ev = _events(4)
+            ev[0].record()
+        det = pipe.detect(frames)
+        if marks is not None:
+            ev[1].record()
         xy, count = pipe.exchange(det, FS)
+        if marks is not None:
+            ev[2].record()
         corr_out[0] = eng.correspond(xy, count, pipe.Fs, pipe.cams, obj_count=N_MARKERS, max_groups=MAX_GROUPS, out=corr_out[0])
+        if marks is not None:
+            ev[3].record()
+            marks.append(ev)
         return det, corr_out[0]
 
     def barrier():
@@ -249,44 +379,70 @@ def run_b200(args):
             dist.barrier()
         torch.cuda.synchronize()
 
+    def rank_max(x):
+        t = torch.tensor([float(x)], device=device, dtype=torch.float64)
+        if world > 1:
+            dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        return float(t.item())
+
     sampler = ClockSampler(local)
     if rank == 0:
         sampler.start()                     # nvidia-smi needs ~100 ms to deliver its first sample: start before the warm-up
     for _ in range(max(args.warmup, 3)):
         step()
     barrier()
-    timers = [eng.stage_timer() for _ in range(args.steps)]
     launches0 = eng.launches
-    ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    marks = []
+    ev0, ev1 = _events(2)
     barrier()
     ev0.record()
     for k in range(args.steps):
-        det, corr = step(timers[k])
+        det, corr = step(marks)
     ev1.record()
     gpu_launches = eng.launches - launches0
     barrier()
-    # nvidia-smi delivers a sample every ~50-100 ms and the timed region may be shorter than that: keep the same step loop
-    # running (untimed) for about a second more so that the clock record is taken under this very load
+    # nvidia-smi delivers a sample every ~50-100 ms: if the timed region was shorter than a second keep the same step loop
+    # running (untimed) so that the clock record is taken under this very load
     t_sus = time.perf_counter()
-    while time.perf_counter() - t_sus < 1.0:
+    while time.perf_counter() - t_sus < max(0.0, 1.0 - ev0.elapsed_time(ev1) * 1e-3):
         for _ in range(5):
             step()
         torch.cuda.synchronize()
     clocks = sampler.stop() if rank == 0 else None
     if clocks is not None:
-        clocks["window"] = "warm-up + timed region + 1 s of the same step loop (untimed)"
+        clocks["window"] = "warm-up + timed region (+ the same step loop, untimed, up to 1 s in total)"
     barrier()
-    ms = torch.tensor([ev0.elapsed_time(ev1)], device=device, dtype=torch.float64)
-    if world > 1:
-        dist.all_reduce(ms, op=dist.ReduceOp.MAX)
-    ms_total = float(ms.item())
+    ms_total = rank_max(ev0.elapsed_time(ev1))
+    phase = {"detect_ms": rank_max(np.mean([e[0].elapsed_time(e[1]) for e in marks])),
+             "exchange_ms": rank_max(np.mean([e[1].elapsed_time(e[2]) for e in marks])),
+             "geometry_ms": rank_max(np.mean([e[2].elapsed_time(e[3]) for e in marks])),
+             "note": "CUDA events on the step's stream around detect / exchange / match+triangulate, mean over the timed steps, max over ranks"}
+    pipe_info = eng.last_pipe_info
+
+    # ---- the stages one after the other (the same kernels without overlap), and the overlapped call's timeline -------------------
+    timers = [eng.stage_timer() for _ in range(5)]
+    for t in timers:
+        pipe.detect(frames, timer=t)                          # a timer selects the one-shot call: stages are separable there
+    torch.cuda.synchronize()
     stage_ms = {}
     for t in timers:
         for k, v in eng.stage_timer_read(t).items():
             stage_ms.setdefault(k, []).append(v)
     stage_avg = {k: float(np.mean(v)) for k, v in stage_ms.items()}
+    serial_ms = sum(stage_avg.values())
+    timeline = None
+    if pipe_info is not None:
+        pipe.detect(frames, timeline=True)
+        torch.cuda.synchronize()
+        timeline = eng.pipe_timeline()
+        flat = frames.view(-1, H, W)
+        tma_scan_ms = _time_loop(lambda: eng.scan_cells(flat, pipe.K0, pipe.dist0, variant=1), 10)
+    else:
+        tma_scan_ms = None
+    det, corr = step()
+    torch.cuda.synchronize()
 
-    # work accounting
+    # work accounting + output checksum of rank 0 (its geometry shard = frame-sets [0, F0): the same scene at every N)
     n_pts = torch.tensor([float(corr.n_valid.sum().item()), float((corr.flags & 1).sum().item()), float(det.count.sum().item())],
                          device=device, dtype=torch.float64)
     if world > 1:
@@ -294,6 +450,21 @@ def run_b200(args):
     frames_per_step = 16 * F0 * N
     value = frames_per_step * args.steps / (ms_total * 1e-3)
     points_per_step = float(n_pts[0].item())
+    checksum = None
+    if rank == 0:
+        nv = corr.n_valid.cpu().numpy()
+        no = corr.n_obj.cpu().numpy()
+        img = corr.img.cpu().numpy()
+        obj = corr.obj.cpu().numpy()
+        import hashlib
+        h = hashlib.sha1()
+        h.update(nv.tobytes()); h.update(no.tobytes())
+        for s_ in range(len(nv)):
+            h.update(np.ascontiguousarray(img[s_, :nv[s_]]).tobytes())
+            h.update(np.ascontiguousarray(obj[s_, :no[s_]]).tobytes())
+        checksum = {"sha1_16": h.hexdigest()[:16], "frame_sets": [0, F0],
+                    "over": "rank 0's geometry shard: n_valid, n_obj, matched image points (all cameras, i.e. every rank's centroids) and object "
+                            "points (raw float64 bits) of frame-sets [0, F0) -- the same scene at every N, so the value must not change with N"}
 
     # ---- end to end: pinned host frames -> H2D -> pipeline -> D2H of the results, every step ----------------------------
     e2e = None
@@ -309,10 +480,14 @@ def run_b200(args):
         bounds = np.linspace(0, FS, chunks + 1).astype(int)
         eng2 = CaptureEngine(device)
         eng2._tables = eng._tables
-        dets = [None] * chunks
+        full = pipe._buffers(n_local)
+        cl = pipe.cams_local
+        dets = [type(det)(full.xy[bounds[c] * cl:bounds[c + 1] * cl], full.count[bounds[c] * cl:bounds[c + 1] * cl],
+                          full.flags[bounds[c] * cl:bounds[c + 1] * cl]) for c in range(chunks)]
 
         def e2e_step():
-            # chunked: the copy of chunk k+1 overlaps detection of chunk k (copy stream + compute stream)
+            # chunked: the copy of chunk k+1 overlaps detection of chunk k (copy stream + compute stream); the detection of a chunk
+            # writes its slice of the pipeline's output buffers, nothing is concatenated
             evs = []
             for c in range(chunks):
                 with torch.cuda.stream(copy_stream):
@@ -320,14 +495,10 @@ def run_b200(args):
                     e = torch.cuda.Event()
                     e.record(copy_stream)
                     evs.append(e)
-            xy_parts, cnt_parts = [], []
             for c in range(chunks):
                 torch.cuda.current_stream().wait_event(evs[c])
                 fr = stage_dev[bounds[c]:bounds[c + 1]].view(-1, H, W)
-                dets[c] = eng2.detect(fr, pipe.K0, pipe.dist0, max_blobs=MAX_BLOBS, out=dets[c])
-                xy_parts.append(dets[c].xy)
-                cnt_parts.append(dets[c].count)
-            full = type(det)(torch.cat(xy_parts), torch.cat(cnt_parts), det.flags)
+                eng2.detect(fr, pipe.K0, pipe.dist0, max_blobs=MAX_BLOBS, out=dets[c])
             xy, count = pipe.exchange(full, FS)
             co = eng.correspond(xy, count, pipe.Fs, pipe.cams, obj_count=N_MARKERS, max_groups=MAX_GROUPS, out=corr_out[0])
             host_obj.copy_(co.obj, non_blocking=True)
@@ -336,77 +507,101 @@ def run_b200(args):
             torch.cuda.current_stream().synchronize()          # the caller reads the result on the host
             return int(host_nobj.sum())
 
+        def copy_only():
+            with torch.cuda.stream(copy_stream):
+                stage_dev.copy_(host, non_blocking=True)
+            copy_stream.synchronize()
+
         e2e_step()
         barrier()
         l0 = eng.launches + eng2.launches
         t0 = time.perf_counter()
-        a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        a, b = _events(2)
         a.record()
         for _ in range(args.e2e_steps):
             e2e_step()
         b.record()
         barrier()
         wall = time.perf_counter() - t0
-        ems = torch.tensor([max(a.elapsed_time(b), 0.0)], device=device, dtype=torch.float64)
+        ems = rank_max(max(a.elapsed_time(b), 0.0))
+        # the host link alone: the same pinned bytes, one H2D copy per rank at the same time on every rank (the ceiling of e2e)
+        copy_only()
+        barrier()
+        t0 = time.perf_counter()
+        for _ in range(args.e2e_steps):
+            copy_only()
+        t_copy = torch.tensor([time.perf_counter() - t0], device=device, dtype=torch.float64)
         if world > 1:
-            dist.all_reduce(ems, op=dist.ReduceOp.MAX)
-        e2e = {"value": frames_per_step * args.e2e_steps / (float(ems.item()) * 1e-3), "unit": "frames/s",
-               "h2d_bytes_per_step": int(frames.numel()) * N, "d2h_bytes_per_step": int(host_obj.numel() * 8 + host_nobj.numel() * 4 + host_cnt.numel() * 4) * N,
+            dist.all_reduce(t_copy, op=dist.ReduceOp.MAX)
+        copy_s = float(t_copy.item()) / args.e2e_steps
+        h2d_bytes = int(frames.numel()) * N
+        e2e_val = frames_per_step * args.e2e_steps / (ems * 1e-3)
+        ceil_val = frames_per_step / copy_s
+        e2e = {"value": e2e_val, "unit": "frames/s",
+               "h2d_bytes_per_step": h2d_bytes, "d2h_bytes_per_step": int(host_obj.numel() * 8 + host_nobj.numel() * 4 + host_cnt.numel() * 4) * N,
                "steps": args.e2e_steps, "wall_s": wall, "gpu_launches": eng.launches + eng2.launches - l0,
-               "how": f"pinned host frames -> {chunks} chunked H2D copies on a copy stream overlapped with detection -> all-gather -> "
+               "h2d_copy_only": {"aggregate_gbs": h2d_bytes / copy_s / 1e9, "frames_per_s_ceiling": ceil_val,
+                                 "e2e_over_ceiling": e2e_val / ceil_val,
+                                 "how": "the step's pinned frames copied H2D on every rank at once, nothing else running (wall clock, max over ranks)"},
+               "how": f"pinned host frames -> {chunks} chunked H2D copies on a copy stream overlapped with detection -> shard exchange -> "
                       "match+triangulate -> D2H of object points/counts, host sync every step"}
         del host, stage_dev
 
-    # ---- geometry-only sweep (BASELINE config 5 shape): 8-view DLT + reprojection error, FP32 main mode, vs the FP32 pipe ------
+    # ---- geometry-only sweep (BASELINE config 5): P 8-view correspondences sharded over the ranks, DLT + reprojection error, FP32 ---
     geometry = None
-    if rank == 0:
+    if not args.no_geometry:
         rig5 = S.config_rig("c5")
         cams5 = eng.cameras(rig5["poses"], rig5["camera_params"])
-        P5 = 4_000_000
-        g5 = torch.Generator(device=device).manual_seed(5)
-        X5 = torch.tensor(np.asarray(rig5["centre"]), device=device) + (torch.rand((P5, 3), generator=g5, device=device, dtype=torch.float64) - 0.5)
         Pm = torch.tensor(cams5.cpu().numpy()[:, :12].reshape(8, 3, 4), device=device)
-        proj = torch.einsum("cij,pj->pci", Pm, torch.cat([X5, torch.ones((P5, 1), device=device, dtype=torch.float64)], dim=1))
-        pts5 = torch.floor(proj[..., :2] / proj[..., 2:3]).float().contiguous()
-        del proj, X5
-        xyz5 = torch.empty((P5, 3), device=device)
-        err5 = torch.empty((P5,), device=device)
-        for _ in range(3):
-            eng.triangulate(pts5, cams5, xyz=xyz5, err=err5)
-        ga, gb = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-        torch.cuda.synchronize()
-        ga.record()
-        for _ in range(10):
-            eng.triangulate(pts5, cams5, xyz=xyz5, err=err5)
-        gb.record()
-        torch.cuda.synchronize()
-        tms = ga.elapsed_time(gb) / 10
+        sweeps = []
         flops = 140 * 8 + 1609                                     # F(N) = 140 N + 1609 per point
+        for P_total in (1_000_000, 10_000_000, 100_000_000):
+            P5 = P_total // N
+            g5 = torch.Generator(device=device).manual_seed(5 + rank)
+            pts5 = torch.empty((P5, 8, 2), device=device, dtype=torch.float32)
+            blk = 2_000_000
+            for o in range(0, P5, blk):                            # projected in slices: the FP64 intermediates stay small
+                m = min(blk, P5 - o)
+                X5 = torch.tensor(np.asarray(rig5["centre"]), device=device) + (torch.rand((m, 3), generator=g5, device=device, dtype=torch.float64) - 0.5)
+                proj = torch.einsum("cij,pj->pci", Pm, torch.cat([X5, torch.ones((m, 1), device=device, dtype=torch.float64)], dim=1))
+                pts5[o:o + m] = torch.floor(proj[..., :2] / proj[..., 2:3]).float()
+            del X5, proj
+            xyz5 = torch.empty((P5, 3), device=device)
+            err5 = torch.empty((P5,), device=device)
+            reps = 20 if P_total <= 10_000_000 else 5
+            for _ in range(3):
+                eng.triangulate(pts5, cams5, xyz=xyz5, err=err5)
+            barrier()
+            ga, gb = _events(2)
+            ga.record()
+            for _ in range(reps):
+                eng.triangulate(pts5, cams5, xyz=xyz5, err=err5)
+            gb.record()
+            barrier()
+            tms = rank_max(ga.elapsed_time(gb) / reps)
+            finite = torch.tensor([float(torch.isfinite(err5).sum().item())], device=device, dtype=torch.float64)
+            if world > 1:
+                dist.all_reduce(finite)
+            sweeps.append({"points": P5 * N, "points_per_rank": P5, "ms": tms, "points_per_s": P5 * N / (tms * 1e-3),
+                           "achieved_tflops": P5 * N * flops / (tms * 1e-3) / 1e12, "finite_results": int(finite.item())})
+            del pts5, xyz5, err5
         sm_mhz = (clocks or {}).get("sm_max_mhz") or 1965.0
         peak32 = 148 * 128 * 2 * sm_mhz * 1e6 / 1e12
-        geometry = {"workload": "BASELINE config 5 shape: 8-view DLT triangulation + reprojection error, FP32", "points": P5, "views": 8,
-                    "ms": tms, "points_per_s": P5 / (tms * 1e-3), "flop_per_point": flops,
-                    "achieved_tflops": P5 * flops / (tms * 1e-3) / 1e12, "fp32_peak_tflops": peak32,
-                    "frac_of_fp32_pipe": P5 * flops / (tms * 1e-3) / 1e12 / peak32,
-                    "peak_source": "148 SMs x 128 FP32 lanes x 2 x clocks.max.sm (no tensor cores: tiny independent solves)"}
-        del pts5, xyz5, err5
+        best = max(sweeps, key=lambda r: r["points_per_s"])
+        geometry = {"workload": "BASELINE config 5: 8-view DLT triangulation + reprojection error, FP32, points sharded over the ranks, no exchange",
+                    "views": 8, "flop_per_point": flops, "sweep": sweeps, "points_per_s": best["points_per_s"],
+                    "fp32_peak_tflops_per_gpu": peak32, "frac_of_fp32_pipe": best["achieved_tflops"] / (peak32 * N),
+                    "peak_source": "148 SMs x 128 FP32 lanes x 2 x clocks.max.sm per GPU (no tensor cores: tiny independent solves); the fraction is "
+                                   "algorithmic flops (SURVEY 8d) / time.  The pipe counters of the same kernel (ncu sm__inst_executed_pipe_fma*) are "
+                                   "in profiles/ (r2_ncu_summary.md)"}
 
     # ---- the step in front of the path: raw Bayer GR sensor frames -> grey (RealtimeTracking_FLIR.py:103-104) ---------------
     front = None
-    if rank == 0:
+    if rank == 0 and not args.no_extra:
         nb = 256                                                   # 1.07 GB in + 1.07 GB out: larger than L2
         raw = torch.randint(0, 256, (nb, H, W), dtype=torch.uint8, device=device)
         grey = torch.empty_like(raw)
-        for _ in range(3):
-            eng.bayer_gr2gray(raw, out=grey)
-        fa, fb = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-        torch.cuda.synchronize()
-        fa.record()
-        for _ in range(10):
-            eng.bayer_gr2gray(raw, out=grey)
-        fb.record()
-        torch.cuda.synchronize()
-        fms = fa.elapsed_time(fb) / 10
+        fms = _time_loop(lambda: eng.bayer_gr2gray(raw, out=grey), 10)
         front = {"workload": f"Bayer GR -> grey, {nb} frames {W}x{H} u8 (bilinear demosaic + BGR2GRAY, bit-identical to OpenCV)",
                  "kernel": "bayer_gr2gray_rows_kernel", "ms": fms, "frames_per_s": nb / (fms * 1e-3),
                  "algorithmic_bytes": 2 * nb * H * W, "achieved_gbs": 2 * nb * H * W / (fms * 1e-3) / 1e9}
@@ -414,7 +609,7 @@ def run_b200(args):
 
     # ---- one frame through the drop-in the realtime loop calls: numpy image in, centroid list + undistorted image out ------
     latency = None
-    if rank == 0:
+    if rank == 0 and not args.no_extra:
         from mocapv2_b200 import engine as E
         from mocapv2_b200.lib import ImageOperations as IO
         E.set_default_engine(eng)
@@ -432,13 +627,19 @@ def run_b200(args):
         latency = {"call": "lib.ImageOperations._find_dot(img) on one 2048x2048 host frame (H2D + detect + undistorted image D2H)",
                    "median_ms": lat[len(lat) // 2], "min_ms": lat[0], "centroids": len(pts_one)}
 
+    # ---- the other BASELINE configs on one GPU (C1: the reference's own 2-camera case, C3: 6 x 1440x1080) ---------------------
+    others = None
+    if world == 1 and not args.no_extra:
+        others = {"c1": _extra_config(eng, "c1", 4, 0.0, 1024, device),
+                  "c3": _extra_config(eng, "c3", 32, 0.42, 1024, device)}
+
     if rank != 0:
         if world > 1:
             dist.barrier()
             dist.destroy_process_group()
         return 0
 
-    # ---- roofline of the dominant kernel --------------------------------------------------------------------------------------
+    # ---- roofline: the detection chain (what a step pays for its H*W bytes), and every kernel against ITS OWN traffic --------------
     peaks = {}
     try:
         peaks = json.load(open(os.path.join(REPO, "MEASURED_PEAKS.json")))
@@ -446,41 +647,66 @@ def run_b200(args):
         pass
     peak = float(peaks.get("hbm_gbs", 6650.0))
     peak_src = "MEASURED_PEAKS.json hbm_gbs (measured copy bandwidth)" if "hbm_gbs" in peaks else "fallback 6650 GB/s (B200_PROFILING.md)"
-    dom = max(stage_avg, key=lambda k: stage_avg[k])
     alg_bytes = n_local * H * W + n_local * (4 + 8 * MAX_BLOBS)          # H*W read + (4 + 8 n_blobs) written per frame
-    achieved = alg_bytes / (stage_avg[dom] * 1e-3) / 1e9
-    traffic = None
-    try:
-        tr = json.load(open(os.path.join(REPO, "profiles", "traffic.json")))
-        if dom in tr:
-            traffic = tr[dom]["dram_bytes_per_frame"] * n_local
-    except Exception:
-        pass
-    det_ms = sum(stage_avg.values())
-    kernels = {"scan": "scan_hot_vec32_kernel", "group": "form_clusters_kernel", "filter": "piece_filter_kernel",
-               "borders": "candidates_kernel + borders_finalize_kernel (traces, filter/centroid/order)",
+    det_ms = phase["detect_ms"]
+    achieved = alg_bytes / (det_ms * 1e-3) / 1e9
+    tr = _load_traffic()
+    kernels = {"scan": "scan_hot_vec32_kernel (one-shot call) / scan_tma_kernel (overlapped call)", "group": "form_clusters_kernel",
+               "filter": "piece_filter_kernel", "borders": "candidates_kernel + borders_finalize_kernel (traces, filter/centroid/order)",
                "finish": "general path for flagged frames (mark_active/compact_tiles/filter_tiles/blobs)"}
+    per_kernel = {}
+    for st_name, ms_ in stage_avg.items():
+        ent = {"kernel": kernels.get(st_name, st_name), "ms_serial": ms_}
+        t_ = tr.get(st_name)
+        if t_ and ms_ > 0:
+            dram = t_["dram_bytes_per_frame"] * n_local
+            ent.update({"dram_bytes": dram, "dram_gbs": dram / (ms_ * 1e-3) / 1e9, "frac_of_hbm_peak": dram / (ms_ * 1e-3) / 1e9 / peak,
+                        "bound": t_.get("bound", "hbm")})
+        per_kernel[st_name] = ent
+    if tma_scan_ms:
+        per_kernel["scan_tma_alone"] = {"kernel": "scan_tma_kernel (TMA ring, timed alone)", "ms_serial": tma_scan_ms,
+                                        "dram_gbs": n_local * H * W / (tma_scan_ms * 1e-3) / 1e9,
+                                        "frac_of_hbm_peak": n_local * H * W / (tma_scan_ms * 1e-3) / 1e9 / peak, "bound": "hbm"}
     if front:
         front["peak_gbs"] = peak
         front["frac"] = front["achieved_gbs"] / peak
-    roofline = {"bound": "hbm", "kernel": kernels.get(dom, dom), "stage": dom, "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
-                "traffic": traffic, "peak_source": peak_src, "algorithmic_bytes_per_launch": alg_bytes,
-                "stage_ms": stage_avg, "detect_ms": det_ms,
-                "detect_pipeline": {"achieved": alg_bytes / (det_ms * 1e-3) / 1e9, "frac": alg_bytes / (det_ms * 1e-3) / 1e9 / peak,
-                                    "note": "all detection kernels of a step together (scan+group+filter+borders+finish) against the same H*W bytes"}}
+    chain_traffic = None
+    if tr:
+        chain_traffic = sum(v.get("dram_bytes_per_frame", 0) for k, v in tr.items() if isinstance(v, dict) and k in stage_avg) * n_local
+    roofline = {"bound": "hbm", "kernel": "detection chain of a step (scan, group, filter, borders, finish; the scan overlapped with the other stages)",
+                "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak, "traffic": chain_traffic,
+                "peak_source": peak_src, "algorithmic_bytes_per_launch": alg_bytes, "detect_ms": det_ms,
+                "definition": "frames x (H*W + 4 + 8*max_blobs) bytes / time of ALL detection kernels of a step (CUDA events around the detect "
+                              "call inside the timed loop, max over ranks)",
+                "stages_one_after_the_other": {"ms": stage_avg, "sum_ms": serial_ms, "frac": alg_bytes / (serial_ms * 1e-3) / 1e9 / peak,
+                                               "note": "the same kernels through the one-shot call (no overlap), per-stage CUDA events"},
+                "overlapped_detection": pipe_info, "timeline_ms": timeline,
+                "kernels": per_kernel,
+                "whole_step": {"ms": ms_total / args.steps, "frac": alg_bytes / (ms_total / args.steps * 1e-3) / 1e9 / peak}}
 
-    # ---- CPU baseline on this host (N=1 only) -------------------------------------------------------------------------------------
+    # ---- CPU baseline on this host (N=1 only) + parity of the timed workload against it ------------------------------------------------
     cpu = None
+    parity = None
     if world == 1 and args.cpu_sample > 0:
         threads = os.cpu_count() or 1
         hf = frames[:args.cpu_sample].cpu().numpy()
         r = cpu_frame_sets(rig, hf, args.cpu_sample, threads)
         if r is not None:
             dt, nf, npts = r
-            cpu = {"value": nf / dt, "unit": "frames/s", "cores": threads, "kind": "port",
+            cvt = None
+            try:
+                import cv2
+                cvt = cv2.getNumThreads()
+            except Exception:
+                pass
+            cpu = {"value": nf / dt, "unit": "frames/s", "cores": threads, "os_cpu_count": os.cpu_count(), "cv2_num_threads": cvt, "kind": "port",
                    "sample": f"{args.cpu_sample} frame-set(s) = {nf} frames of this workload in {dt:.2f} s: OpenCV calls of "
                              "lib/ImageOperations.py:33-65 (numba blur -> its integer restatement) + lib/Helpers.py:178-280 in NumPy "
                              f"with the same candidate cap; frames over a {threads}-thread pool", "points_per_s": npts / dt}
+        try:
+            parity = _parity_check(rig, frames, det, corr, pipe.cams_local)
+        except Exception as ex:                                  # the check must never cost the bench line
+            parity = {"checked": False, "why": repr(ex)}
 
     line = {
         "metric": "frames/s (detect+match+triangulate, 16-camera 2048x2048 rig, 128 markers)",
@@ -490,8 +716,10 @@ def run_b200(args):
         "config": workload_config(N, F0),
         "points_per_s": points_per_step * args.steps / (ms_total * 1e-3),
         "frame_sets_with_group_cap": float(n_pts[1].item()), "centroids_per_frame": float(n_pts[2].item()) / (n_local * N),
+        "phase_ms": phase, "output_checksum": checksum, "parity_check": parity,
         "e2e": e2e, "gpu_launches": gpu_launches, "collectives_per_step": 1 if N > 1 else 0,
         "clocks": clocks, "roofline": roofline, "cpu_baseline": cpu, "geometry": geometry, "front_step": front, "find_dot_latency": latency,
+        "other_configs": others,
     }
     emit(line)
     if world > 1:

@@ -111,8 +111,9 @@ typedef struct {
     int cand_ctas_per_sm;      /* <= 0: 12 */
     int record_timeline;       /* record CUDA events for mocap_detect_pipe_timeline */
     int stream_plan;           /* 0: a chunk's stages run as a chain on worker (chunk mod workers); 1: stage streams -- worker 0 groups,
-                                  worker 1 filters, workers 2.. take the border stages of alternate chunks (needs >= 3 workers) */
-    int reserved[1];
+                                  worker 1 filters, workers 2.. take the border stages of alternate chunks (needs >= 3 workers);
+                                  2: worker 0 groups and filters, workers 1.. take the borders; 3: like 2, grouping one chunk ahead */
+    int scan_stages;           /* 8 KB ring slots of the TMA scan per SM: 6 (default) or 3 (leaves room for seven filter CTAs) */
 } MocapPipeOpts;
 /* prio_mode 0: all workers at the lowest stream priority; 1 / 2 (for stream_plan 1): earlier / later stages first */
 void* mocap_detect_pipe_create(int n_worker_streams, int prio_mode);
@@ -188,6 +189,16 @@ int mocap_correspond_batch(const int32_t* xy_dev, const int32_t* count_dev, int 
                            double* obj_out, int32_t* n_obj_out, int32_t* img_out, int32_t* n_valid_out,
                            double* err_out, int32_t* cand_out, int32_t* flags_out,
                            void* workspace, size_t workspace_bytes, void* stream);
+
+/* The same on centroid lists stored in camera blocks: xy_dev [C / cams_per_block][S][cams_per_block][max_pts][2], count_dev
+ * [C / cams_per_block][S][cams_per_block] -- the buffer a rank holds after the shard exchange of the multi-GPU pipeline (one block per
+ * source rank: that rank's cameras, this rank's frame-sets), read in place.  cams_per_block == C is mocap_correspond_batch. */
+int mocap_correspond_batch_blocked(const int32_t* xy_dev, const int32_t* count_dev, int S, int C, int max_pts, int cams_per_block,
+                                   const double* F_dev, const double* cams_dev, double cutoff, int obj_count,
+                                   int max_groups, int fp64_mode,
+                                   double* obj_out, int32_t* n_obj_out, int32_t* img_out, int32_t* n_valid_out,
+                                   double* err_out, int32_t* cand_out, int32_t* flags_out,
+                                   void* workspace, size_t workspace_bytes, void* stream);
 
 #ifdef __cplusplus
 }

@@ -62,13 +62,15 @@ SIGNATURES = {
     "mocap_correspond_workspace_bytes": (_sz, [_i, _i, _i, _i]),
     "mocap_correspond_batch": (_i, [_p, _p, _i, _i, _i, _p, _p, _d, _i, _i, _i,
                                     _p, _p, _p, _p, _p, _p, _p, _p, _sz, _p]),
+    "mocap_correspond_batch_blocked": (_i, [_p, _p, _i, _i, _i, _i, _p, _p, _d, _i, _i, _i,
+                                            _p, _p, _p, _p, _p, _p, _p, _p, _sz, _p]),
 }
 
 
 class PipeOpts(C.Structure):
     """MocapPipeOpts of include/mocap_b200.h"""
     _fields_ = [("chunk_frames", _i), ("sync_mode", _i), ("scan_variant", _i), ("filter_ctas_per_sm", _i),
-                ("cand_ctas_per_sm", _i), ("record_timeline", _i), ("stream_plan", _i), ("reserved", _i * 1)]
+                ("cand_ctas_per_sm", _i), ("record_timeline", _i), ("stream_plan", _i), ("scan_stages", _i)]
 
 
 class MocapError(RuntimeError):

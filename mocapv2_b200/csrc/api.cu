@@ -22,7 +22,7 @@ int launch_materialize_bits(const FilterWs& ws, int n, int H, int W, const Table
 bool scan_tma_supported(const uint8_t* frames, int n, int H, int W, int64_t fstride, int thresh);
 size_t scan_tma_ctrl_bytes(int chunks);
 int launch_scan_tma(const uint8_t* frames, int n, int H, int W, int64_t fstride, const TableView& tv, int thresh, uint32_t* cellbox,
-                    int* ctrl, int chunks, int chunk_frames, int widx, int item_begin, int item_end, cudaStream_t s);
+                    int* ctrl, int chunks, int chunk_frames, int widx, int item_begin, int item_end, int stages, cudaStream_t s);
 int stream_wait_geq(cudaStream_t s, const int* addr_dev, int value);
 bool stream_wait_supported();
 // detect_blobs.cu
@@ -406,17 +406,40 @@ extern "C" int mocap_detect_batch_pipelined(void* pipe, const uint8_t* frames_de
     CUDA_TRY(cudaEventRecord(dp->ev_fork, s));
     CUDA_TRY(cudaStreamWaitEvent(dp->s_scan, dp->ev_fork, 0));
     if (mode == 1) {
-        st = launch_scan_tma(frames_dev, n_frames, H, W, frame_stride, tv, thresh, ws.cellbox, ctrl, chunks, cf, 0, 0, -1, dp->s_scan);
+        st = launch_scan_tma(frames_dev, n_frames, H, W, frame_stride, tv, thresh, ws.cellbox, ctrl, chunks, cf, 0, 0, -1, opts->scan_stages, dp->s_scan);
         if (st != MOCAP_OK) return st;
     }
+    // Stream plans (which worker stream runs which stage of which chunk):
+    //   0  a chunk's stages as one chain on worker (chunk mod workers)
+    //   1  stage streams: worker 0 groups, worker 1 filters, workers 2.. take the borders of alternate chunks
+    //   2  worker 0 groups and filters chunk after chunk; workers 1.. take the borders (they fill the filter kernels' tails)
+    //   3  like 2, grouping one chunk ahead of the filter (group(k+1) is issued before filter(k): never waits for filter CTAs to leave)
+    int plan = opts->stream_plan;
+    if ((plan == 1 && dp->n_proc < 3) || ((plan == 2 || plan == 3) && dp->n_proc < 2) || plan < 0 || plan > 3) plan = 0;
+    for (int i = 0; i < dp->n_proc; ++i) CUDA_TRY(cudaStreamWaitEvent(dp->s_proc[i], dp->ev_fork, 0));
+    auto group_stream = [&](int c) { return plan == 0 ? dp->s_proc[c % dp->n_proc] : dp->s_proc[0]; };
+    auto run_stages = [&](int c, int stages) -> int {
+        const int f0 = c * cf, nc = (n_frames - f0) < cf ? (n_frames - f0) : cf;
+        char* cws = base + P.off_chunks + (size_t)c * P.chunk_bytes;
+        uint32_t* cb = ws.cellbox + (size_t)f0 * tv.TX * tv.TY;
+        cudaStream_t ps = group_stream(c);
+        ClusterLaunch hc = how;
+        hc.zero = 0;
+        hc.stages = stages;
+        hc.ev_group = dp->ev_tl[c][1]; hc.ev_filter = dp->ev_tl[c][2]; hc.ev_borders = dp->ev_tl[c][3];
+        if (plan == 1) { hc.s_filter = dp->s_proc[1]; hc.s_borders = dp->s_proc[2 + c % (dp->n_proc - 2)]; }
+        if (plan == 2 || plan == 3) { hc.s_filter = dp->s_proc[0]; hc.s_borders = dp->s_proc[1 + c % (dp->n_proc - 1)]; }
+        return launch_cluster_path(frames_dev + (size_t)f0 * frame_stride, nc, H, W, frame_stride, tv, thresh, cb, cws, P.cl_offs, need_general + f0,
+                                   max_contours, max_blobs, min_area, min_circ,
+                                   out_xy + (size_t)f0 * max_blobs * 2, out_count + f0, out_flags + f0,
+                                   out_contours ? out_contours + (size_t)f0 * max_contours * 8 : nullptr, out_contour_count ? out_contour_count + f0 : nullptr,
+                                   ps, nullptr, hc);
+    };
     for (int c = 0; c < chunks; ++c) {
         const int f0 = c * cf, nc = (n_frames - f0) < cf ? (n_frames - f0) : cf;
-        const bool staged = opts->stream_plan == 1 && dp->n_proc >= 3;       // stage streams: 0 groups, 1 filters, 2.. take the borders
-        cudaStream_t ps = staged ? dp->s_proc[0] : dp->s_proc[c % dp->n_proc];
-        if (c == 0) for (int i = 0; i < dp->n_proc; ++i) CUDA_TRY(cudaStreamWaitEvent(dp->s_proc[i], dp->ev_fork, 0));
+        cudaStream_t ps = group_stream(c);
         char* cws = base + P.off_chunks + (size_t)c * P.chunk_bytes;
         CUDA_TRY(cudaMemsetAsync(cws + P.cl_offs[14], 0, P.cl_offs[15], ps));     // the chunk's counters / lists, off the critical path
-        uint32_t* cb = ws.cellbox + (size_t)f0 * tv.TX * tv.TY;
         if (mode == 1) {
             st = stream_wait_geq(ps, ctrl + PIPE_CTRL_WORK + chunks + c, 1);
             if (st != MOCAP_OK) return st;
@@ -424,9 +447,9 @@ extern "C" int mocap_detect_batch_pipelined(void* pipe, const uint8_t* frames_de
             if (tma) {
                 // all launches share the batch-wide tensor map and item numbering; launch c covers the boxes of chunk c
                 const int ib = f0 * per_frame_items, ie = (f0 + nc) * per_frame_items;
-                st = launch_scan_tma(frames_dev, n_frames, H, W, frame_stride, tv, thresh, ws.cellbox, ctrl, chunks, cf, c, ib, ie, dp->s_scan);
+                st = launch_scan_tma(frames_dev, n_frames, H, W, frame_stride, tv, thresh, ws.cellbox, ctrl, chunks, cf, c, ib, ie, opts->scan_stages, dp->s_scan);
             } else {
-                FilterWs wc = ws; wc.cellbox = cb;
+                FilterWs wc = ws; wc.cellbox = ws.cellbox + (size_t)f0 * tv.TX * tv.TY;
                 st = launch_scan(frames_dev + (size_t)f0 * frame_stride, nc, H, W, frame_stride, tv, thresh, wc, dp->s_scan, nullptr);
             }
             if (st != MOCAP_OK) return st;
@@ -434,15 +457,13 @@ extern "C" int mocap_detect_batch_pipelined(void* pipe, const uint8_t* frames_de
             CUDA_TRY(cudaStreamWaitEvent(ps, dp->ev_scan[c], 0));
         }
         if (tl) CUDA_TRY(cudaEventRecord(dp->ev_tl[c][0], ps));
-        ClusterLaunch hc = how;
-        hc.zero = 0;
-        if (tl || staged) { hc.ev_group = dp->ev_tl[c][1]; hc.ev_filter = dp->ev_tl[c][2]; hc.ev_borders = dp->ev_tl[c][3]; }
-        if (staged) { hc.s_filter = dp->s_proc[1]; hc.s_borders = dp->s_proc[2 + c % (dp->n_proc - 2)]; }
-        st = launch_cluster_path(frames_dev + (size_t)f0 * frame_stride, nc, H, W, frame_stride, tv, thresh, cb, cws, P.cl_offs, need_general + f0,
-                                 max_contours, max_blobs, min_area, min_circ,
-                                 out_xy + (size_t)f0 * max_blobs * 2, out_count + f0, out_flags + f0,
-                                 out_contours ? out_contours + (size_t)f0 * max_contours * 8 : nullptr, out_contour_count ? out_contour_count + f0 : nullptr,
-                                 ps, nullptr, hc);
+        if (plan == 3) {
+            st = run_stages(c, 1);
+            if (st == MOCAP_OK && c > 0) st = run_stages(c - 1, 2 | 4);
+            if (st == MOCAP_OK && c == chunks - 1) st = run_stages(c, 2 | 4);
+        } else {
+            st = run_stages(c, 1 | 2 | 4);
+        }
         if (st != MOCAP_OK) return st;
     }
     CUDA_TRY(cudaEventRecord(dp->ev_scan_done, dp->s_scan));
@@ -511,5 +532,5 @@ extern "C" int mocap_scan_cells_batch(const uint8_t* frames_dev, int n_frames, i
     if (!scan_tma_supported(frames_dev, n_frames, H, W, frame_stride, thresh)) return MOCAP_ERR_UNSUPPORTED;
     if (!workspace || workspace_bytes < scan_tma_ctrl_bytes(1)) return MOCAP_ERR_WORKSPACE;
     CUDA_TRY(cudaMemsetAsync(workspace, 0, scan_tma_ctrl_bytes(1), s));
-    return launch_scan_tma(frames_dev, n_frames, H, W, frame_stride, tv, thresh, cellbox_out, (int*)workspace, 1, n_frames, 0, 0, -1, s);
+    return launch_scan_tma(frames_dev, n_frames, H, W, frame_stride, tv, thresh, cellbox_out, (int*)workspace, 1, n_frames, 0, 0, -1, variant == 2 ? 3 : 6, s);
 }

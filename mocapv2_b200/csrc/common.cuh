@@ -108,6 +108,7 @@ __device__ __forceinline__ uint32_t pack_cellbox(uint32_t xmask, uint32_t ymask)
 // how launch_cluster_path runs a batch (or one chunk of the overlapped pipeline)
 struct ClusterLaunch {
     int zero = 1;                    // clear the counters / lists of the workspace on the stream first
+    int stages = 7;                  // which stages this call issues: 1 group, 2 piece filter, 4 borders (a chunk may be issued in parts)
     int filter_ctas_per_sm = 8;      // persistent piece-filter CTAs per SM (fewer when the TMA scan is co-resident)
     int cand_ctas_per_sm = 16;
     cudaEvent_t ev_group = nullptr, ev_filter = nullptr, ev_borders = nullptr;   // recorded after the stages (timeline marks; hand-over between streams)

@@ -1085,30 +1085,36 @@ int launch_cluster_path(const uint8_t* frames, int n, int H, int W, int64_t fstr
     static bool attr_done = false;                          // (idempotent; a race only repeats the call)
     if (!attr_done) { CUDA_TRY(cudaFuncSetAttribute(form_clusters_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 64 * 1024)); attr_done = true; }
 #endif
-    stage_begin(timer, 1, s);
-    LAUNCH(form_clusters_kernel, n, CL_THREADS, sm_form, s, cellbox, tv, cw);
-    stage_end(timer, 1, s);
-    if (how.ev_group) cudaEventRecord(how.ev_group, s);
+    if (how.stages & 1) {
+        stage_begin(timer, 1, s);
+        LAUNCH(form_clusters_kernel, n, CL_THREADS, sm_form, s, cellbox, tv, cw);
+        stage_end(timer, 1, s);
+        if (how.ev_group) cudaEventRecord(how.ev_group, s);
+    }
     cudaStream_t sf = how.s_filter ? how.s_filter : s;
+    if (how.stages & 2) {
 #ifndef MOCAP_EMU
-    if (sf != s) { if (!how.ev_group) return MOCAP_ERR_INVALID; CUDA_TRY(cudaStreamWaitEvent(sf, how.ev_group, 0)); }
+        if (sf != s) { if (!how.ev_group) return MOCAP_ERR_INVALID; CUDA_TRY(cudaStreamWaitEvent(sf, how.ev_group, 0)); }
 #endif
-    stage_begin(timer, 2, sf);
-    LAUNCH(piece_filter_kernel, sms * how.filter_ctas_per_sm, CL_THREADS, 0, sf, frames, fstride, tv, thresh, cw);
-    stage_end(timer, 2, sf);
-    if (how.ev_filter) cudaEventRecord(how.ev_filter, sf);
+        stage_begin(timer, 2, sf);
+        LAUNCH(piece_filter_kernel, sms * how.filter_ctas_per_sm, CL_THREADS, 0, sf, frames, fstride, tv, thresh, cw);
+        stage_end(timer, 2, sf);
+        if (how.ev_filter) cudaEventRecord(how.ev_filter, sf);
+    }
     cudaStream_t sb = how.s_borders ? how.s_borders : sf;
+    if (how.stages & 4) {
 #ifndef MOCAP_EMU
-    if (sb != sf) { if (!how.ev_filter) return MOCAP_ERR_INVALID; CUDA_TRY(cudaStreamWaitEvent(sb, how.ev_filter, 0)); }
+        if (sb != sf) { if (!how.ev_filter) return MOCAP_ERR_INVALID; CUDA_TRY(cudaStreamWaitEvent(sb, how.ev_filter, 0)); }
 #endif
-    stage_begin(timer, 3, sb);
-    LAUNCH(candidates_kernel, sms * how.cand_ctas_per_sm, 128, 0, sb, cw);
-    int frame_step = 1;
-    for (int pr : {61, 67, 71, 73}) if (n % pr != 0) { frame_step = pr; break; }          // a prime that does not divide n
-    LAUNCH(borders_finalize_kernel, n, CL_THREADS, (size_t)max_contours + 16, sb, cw, W, frame_step, max_contours, max_blobs, min_area, min_circ,
-           out_xy, out_count, out_flags, out_contours, out_contour_count);
-    stage_end(timer, 3, sb);
-    if (how.ev_borders) cudaEventRecord(how.ev_borders, sb);
+        stage_begin(timer, 3, sb);
+        LAUNCH(candidates_kernel, sms * how.cand_ctas_per_sm, 128, 0, sb, cw);
+        int frame_step = 1;
+        for (int pr : {61, 67, 71, 73}) if (n % pr != 0) { frame_step = pr; break; }          // a prime that does not divide n
+        LAUNCH(borders_finalize_kernel, n, CL_THREADS, (size_t)max_contours + 16, sb, cw, W, frame_step, max_contours, max_blobs, min_area, min_circ,
+               out_xy, out_count, out_flags, out_contours, out_contour_count);
+        stage_end(timer, 3, sb);
+        if (how.ev_borders) cudaEventRecord(how.ev_borders, sb);
+    }
     CUDA_TRY(cudaGetLastError());
     return MOCAP_OK;
 }

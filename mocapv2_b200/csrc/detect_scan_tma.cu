@@ -28,7 +28,7 @@
 #define ST_BOX_H 32
 #define ST_STAGE_BYTES (ST_BOX_W * ST_BOX_H)
 #define ST_CONSUMERS 4
-#define ST_STAGES 6
+#define ST_STAGES_MAX 6            // ring slots of 8 KB: 6 when the scan has the SM (almost) to itself, 3 beside seven filter CTAs
 #define ST_GRAB 8                  // boxes a producer draws from the work counter at a time (one 2048-pixel band of cells)
 #define ST_THREADS (32 * (ST_CONSUMERS + 1))
 
@@ -80,22 +80,25 @@ __device__ __forceinline__ void scan_publish(const ScanTmaArgs& a, int ch, int c
     }
 }
 
-template <int MODE>
+template <int MODE, int ST_STAGES>
 __global__ void __launch_bounds__(ST_THREADS, 8) scan_tma_kernel(const __grid_constant__ CUtensorMap tmap, ScanTmaArgs a)
 {
     extern __shared__ unsigned char st_raw[];
     unsigned char* st = st_raw + ((128u - (smem_u32(st_raw) & 127u)) & 127u);          // TMA destinations: 128-byte aligned
     uint8_t* ring = st;
-    // "box landed" barriers: TWO per ring slot, used by alternate fills.  Consumer warps take the boxes round-robin, so successive
-    // fills of a slot are waited for by different warps, and TMA completions arrive out of order: the warp waiting for fill k+1 of a
-    // slot may start waiting while fill k has not landed yet -- on a single barrier its parity test would pass at once (parity only
-    // tells odd from even phases).  With a barrier per alternate fill, a waiter is never more than one phase away from its barrier.
+    // "box landed" barriers: NB per ring slot, used by successive fills in turn.  Consumer warps take the boxes round-robin, so
+    // successive fills of a slot are waited for by different warps, and TMA completions arrive out of order: a warp that has finished
+    // box q starts waiting for box q + C (C consumer warps) while older boxes may still be in flight -- if the barrier it waits on were
+    // still in the phase of an older, unfinished fill, its parity test would pass at once (parity only tells odd from even phases).
+    // A barrier is reused every NB * S boxes (S slots); its previous fill q + C - NB * S is certainly complete when box q has been
+    // ISSUED (its slot was handed back before box q + C - (NB - 1) * S went into it), i.e. when C <= (NB - 1) * S.
+    constexpr int NB = (ST_CONSUMERS + ST_STAGES - 1) / ST_STAGES + 1;
     uint64_t* full = (uint64_t*)(st + ST_STAGES * ST_STAGE_BYTES);
-    uint64_t* empty = full + 2 * ST_STAGES;
-    StageRec* rec = (StageRec*)(empty + ST_STAGES);
+    uint64_t* empty = full + NB * ST_STAGES;
+    StageRec* rec = (StageRec*)(st + ST_STAGES * ST_STAGE_BYTES + (((NB + 1) * ST_STAGES * 8 + 15) & ~15));
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     if (threadIdx.x == 0) {
-        for (int s = 0; s < ST_STAGES; ++s) { mbar_init(&full[2 * s], 1); mbar_init(&full[2 * s + 1], 1); mbar_init(&empty[s], 1); }
+        for (int s = 0; s < ST_STAGES; ++s) { for (int b = 0; b < NB; ++b) mbar_init(&full[NB * s + b], 1); mbar_init(&empty[s], 1); }
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
     }
     __syncthreads();
@@ -117,7 +120,7 @@ __global__ void __launch_bounds__(ST_THREADS, 8) scan_tma_kernel(const __grid_co
             int chunk = base / a.items_per_chunk, left = (chunk + 1) * a.items_per_chunk - base;
             for (int it = base; it < end; ++it, ++q) {
                 const int stage = q % ST_STAGES, fill = q / ST_STAGES;
-                uint64_t* fb = &full[2 * stage + (fill & 1)];
+                uint64_t* fb = &full[NB * stage + fill % NB];
                 mbar_wait(&empty[stage], (fill & 1) ^ 1);
                 StageRec r;
                 r.cb_index = (f * a.TY + cy) * a.TX + xb * (ST_BOX_W / 32); r.ncell = min(ST_BOX_W / 32, a.TX - xb * (ST_BOX_W / 32));
@@ -133,7 +136,7 @@ __global__ void __launch_bounds__(ST_THREADS, 8) scan_tma_kernel(const __grid_co
             const int stage = q % ST_STAGES, fill = q / ST_STAGES;
             mbar_wait(&empty[stage], (fill & 1) ^ 1);
             rec[stage].ncell = -1;
-            mbar_arrive(&full[2 * stage + (fill & 1)]);
+            mbar_arrive(&full[NB * stage + fill % NB]);
         }
         return;
     }
@@ -146,9 +149,13 @@ __global__ void __launch_bounds__(ST_THREADS, 8) scan_tma_kernel(const __grid_co
     int cur_chunk = -1, cur_cnt = 0;
     for (int q = cw;; q += ST_CONSUMERS) {
         const int stage = q % ST_STAGES, fill = q / ST_STAGES;
-        mbar_wait(&full[2 * stage + (fill & 1)], (fill >> 1) & 1);
+        mbar_wait(&full[NB * stage + fill % NB], (fill / NB) & 1);
         const StageRec r = rec[stage];
-        if (r.ncell < 0) break;
+        if (r.ncell < 0) {                                                   // end mark: hand the slot back (the ring may be shorter than
+            __syncwarp();                                                    // the number of consumer warps, the next mark needs a slot)
+            if (lane == 0) mbar_arrive(&empty[stage]);
+            break;
+        }
         const uint8_t* src = ring + stage * ST_STAGE_BYTES + rpar * ST_BOX_W + chunkl * 16;
         uint32_t a0 = 0, a1 = 0, a2 = 0, a3 = 0, rowbits = 0;
 #pragma unroll
@@ -209,7 +216,7 @@ size_t scan_tma_ctrl_bytes(int chunks) { return align_up((size_t)(SCAN_CTRL_WORK
 // One launch over the boxes [item_begin, item_end) of the batch (all of them: item_end < 0).  ctrl: int [SCAN_CTRL_WORK + 2 chunks],
 // zeroed by the caller on an earlier point of the stream: work counters (one per launch index `widx`), then chunk_done[], chunk_flag[].
 int launch_scan_tma(const uint8_t* frames, int n, int H, int W, int64_t fstride, const TableView& tv, int thresh, uint32_t* cellbox,
-                    int* ctrl, int chunks, int chunk_frames, int widx, int item_begin, int item_end, cudaStream_t s)
+                    int* ctrl, int chunks, int chunk_frames, int widx, int item_begin, int item_end, int stages, cudaStream_t s)
 {
     static PFN_encodeTiled encode = (PFN_encodeTiled)driver_entry("cuTensorMapEncodeTiled");
     if (!encode) return MOCAP_ERR_UNSUPPORTED;
@@ -237,15 +244,22 @@ int launch_scan_tma(const uint8_t* frames, int n, int H, int W, int64_t fstride,
     a.items_per_chunk = (int)(per_frame * chunk_frames);
     a.item_begin = item_begin; a.item_end = item_end < 0 ? a.total_items : item_end;
     a.add = ht.add;
-    const size_t smem = (size_t)ST_STAGES * ST_STAGE_BYTES + 3 * ST_STAGES * 8 + ST_STAGES * sizeof(StageRec) + 128;
+    const int S = stages == 3 ? 3 : ST_STAGES_MAX;
+    const size_t smem = (size_t)S * ST_STAGE_BYTES + 4 * S * 8 + 16 + S * sizeof(StageRec) + 128;
     static bool attr_done = false;
     if (!attr_done) {
-        CUDA_TRY(cudaFuncSetAttribute(scan_tma_kernel<0>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-        CUDA_TRY(cudaFuncSetAttribute(scan_tma_kernel<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+        const int big = ST_STAGES_MAX * ST_STAGE_BYTES + 4 * ST_STAGES_MAX * 8 + 16 + ST_STAGES_MAX * (int)sizeof(StageRec) + 128;
+        CUDA_TRY(cudaFuncSetAttribute(scan_tma_kernel<0, ST_STAGES_MAX>, cudaFuncAttributeMaxDynamicSharedMemorySize, big));
+        CUDA_TRY(cudaFuncSetAttribute(scan_tma_kernel<1, ST_STAGES_MAX>, cudaFuncAttributeMaxDynamicSharedMemorySize, big));
         attr_done = true;
     }
-    if (ht.mode == 0) scan_tma_kernel<0><<<sms, ST_THREADS, smem, s>>>(map, a);
-    else scan_tma_kernel<1><<<sms, ST_THREADS, smem, s>>>(map, a);
+    if (S == 3) {
+        if (ht.mode == 0) scan_tma_kernel<0, 3><<<sms, ST_THREADS, smem, s>>>(map, a);
+        else scan_tma_kernel<1, 3><<<sms, ST_THREADS, smem, s>>>(map, a);
+    } else {
+        if (ht.mode == 0) scan_tma_kernel<0, ST_STAGES_MAX><<<sms, ST_THREADS, smem, s>>>(map, a);
+        else scan_tma_kernel<1, ST_STAGES_MAX><<<sms, ST_THREADS, smem, s>>>(map, a);
+    }
     CUDA_TRY(cudaGetLastError());
     return MOCAP_OK;
 }
@@ -267,7 +281,7 @@ bool stream_wait_supported()
 
 bool scan_tma_supported(const uint8_t*, int, int, int, int64_t, int) { return false; }
 size_t scan_tma_ctrl_bytes(int chunks) { return align_up((size_t)(SCAN_CTRL_WORK + 2 * chunks) * 4, 256); }
-int launch_scan_tma(const uint8_t*, int, int, int, int64_t, const TableView&, int, uint32_t*, int*, int, int, int, int, int, cudaStream_t) { return MOCAP_ERR_UNSUPPORTED; }
+int launch_scan_tma(const uint8_t*, int, int, int, int64_t, const TableView&, int, uint32_t*, int*, int, int, int, int, int, int, cudaStream_t) { return MOCAP_ERR_UNSUPPORTED; }
 int stream_wait_geq(cudaStream_t, const int*, int) { return MOCAP_ERR_UNSUPPORTED; }
 bool stream_wait_supported() { return false; }
 

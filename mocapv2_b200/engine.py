@@ -206,7 +206,7 @@ class CaptureEngine:
     def detect_pipelined(self, frames: torch.Tensor, K, dist, *, thresh=THRESH_U8, min_area=MIN_AREA, min_circ=MIN_CIRC,
                          max_blobs=None, max_contours=None, max_runs=None, outputs=(), out: DetectResult | None = None,
                          chunk_frames=128, sync_mode=1, scan_variant=1, filter_ctas_per_sm=0, cand_ctas_per_sm=0,
-                         stream_plan=0, timeline=False) -> DetectResult:
+                         stream_plan=0, scan_stages=6, timeline=False) -> DetectResult:
         """Same results as detect() (centroid lists, optionally the contour table), computed chunk by chunk with the streaming
         scan overlapped with the other stages (mocap_detect_batch_pipelined)."""
         if frames.dim() != 3:
@@ -232,7 +232,7 @@ class CaptureEngine:
         if nbytes == 0:
             raise _cabi.MocapError("mocap_detect_pipelined_workspace_bytes: unsupported shape")
         opts = _cabi.PipeOpts(int(chunk_frames), int(sync_mode), int(scan_variant), int(filter_ctas_per_sm), int(cand_ctas_per_sm),
-                              1 if timeline else 0, int(stream_plan))
+                              1 if timeline else 0, int(stream_plan), int(scan_stages))
         with self._lock:
             ws = self._workspace(nbytes)
             st = self.lib.mocap_detect_batch_pipelined(
@@ -432,11 +432,20 @@ class CaptureEngine:
         """find_point_correspondance_and_object_points (lib/Helpers.py:178-280) for S frame-sets.
 
         xy [S, C, max_pts, 2] int32 centroid lists, count [S, C] int32, Fs [C-1, 3, 3] float64 (Fs[i-1]: camera 0 -> camera i).
+        Camera-blocked input (what the shard exchange of the multi-GPU pipeline delivers) is read in place:
+        xy [B, S, C/B, max_pts, 2], count [B, S, C/B] with block b holding cameras b*C/B .. (b+1)*C/B - 1.
         """
         xy = self._check_dev(xy, torch.int32, "xy")
         count = self._check_dev(count, torch.int32, "count")
         cams = self._check_dev(cams, torch.float64, "cams")
-        S, C, max_pts, _ = xy.shape
+        if xy.dim() == 5:
+            B, S, cpb, max_pts, _ = xy.shape
+            C = B * cpb
+            if tuple(count.shape) != (B, S, cpb):
+                raise ValueError("count must be [B, S, C/B] for camera-blocked xy")
+        else:
+            S, C, max_pts, _ = xy.shape
+            cpb = C
         if C > 1:
             Fs = self._check_dev(Fs, torch.float64, "Fs")
             if Fs.shape[0] < C - 1:
@@ -451,12 +460,12 @@ class CaptureEngine:
         nbytes = self.lib.mocap_correspond_workspace_bytes(S, C, max_pts, max_groups)
         with self._lock:
             ws = self._workspace(nbytes)
-            st = self.lib.mocap_correspond_batch(
-                self._ptr(xy), self._ptr(count), S, C, max_pts, self._ptr(Fs) if C > 1 else ctypes.c_void_p(0), self._ptr(cams),
+            st = self.lib.mocap_correspond_batch_blocked(
+                self._ptr(xy), self._ptr(count), S, C, max_pts, cpb, self._ptr(Fs) if C > 1 else ctypes.c_void_p(0), self._ptr(cams),
                 float(cutoff), int(obj_count), int(max_groups), 1 if fp64 else 0,
                 self._ptr(res.obj), self._ptr(res.n_obj), self._ptr(res.img), self._ptr(res.n_valid), self._ptr(res.err),
                 self._ptr(res.cand), self._ptr(res.flags), self._ptr(ws), nbytes, self._stream())
-            _cabi.check(self.lib, st, "mocap_correspond_batch")
+            _cabi.check(self.lib, st, "mocap_correspond_batch_blocked")
             self.launches += 2
         return res
 

@@ -1,10 +1,13 @@
-"""Batched capture pipeline over one or several GPUs: detect -> (all-gather centroid lists) -> match + triangulate.
+"""Batched capture pipeline over one or several GPUs: detect -> (exchange centroid lists) -> match + triangulate.
 
 Sharding: detection is independent per (camera, frame) and is sharded by CAMERA, so a rank keeps
 its cameras' frames (and their undistortion table) resident; matching needs every camera's centroid list of a
-frame-set, so the fixed-stride records [count | xy] are exchanged with ONE all-gather (NCCL over NVLink on the GPU
-box, gloo in the CPU tests); matching + triangulation are then sharded by FRAME-SET with no further exchange.
-No floating-point reduction crosses ranks, so N-rank outputs are bit-identical to 1-rank outputs.
+frame-set and is sharded by FRAME-SET.  The one exchange step in between moves, per pair of ranks, exactly the records
+the receiver needs -- the sender's cameras of the receiver's frame-sets, a contiguous slice of the detection output --
+as ONE grouped NCCL send/recv (ncclGroupStart/End: a single launch over NVLink; gloo in the CPU tests).  Each rank
+receives 1/N of what an all-gather would deliver, and the receive buffer [source rank][frame-set][camera][blob] is read
+in place by the correspondence kernels (camera-blocked layout, mocap_correspond_batch_blocked): no pack, permute or copy
+kernels on the step path.  No floating-point reduction crosses ranks, so N-rank outputs are bit-identical to 1-rank.
 """
 from __future__ import annotations
 
@@ -49,9 +52,11 @@ class CapturePipeline:
         self.cams = engine.cameras(rig["poses"], rig["camera_params"])
         self.Fs = torch.from_numpy(np.asarray(rig["Fs"], dtype=np.float64).reshape(-1, 3, 3).copy()).to(engine.device)
         self._det = None
-        self._flat = None
-        self._gath = None
+        self._rx = None
         self.collectives = 0
+        # overlapped detection (engine.detect_pipelined) for batches large enough to pipeline: 4 chunks, 3 worker streams
+        self.pipelined_min_frames = 256
+        self.engine_pipe = {"workers": 3, "chunks": 4}
 
     def frame_set_shard(self, n_frame_sets: int):
         if n_frame_sets % self.world:
@@ -60,42 +65,61 @@ class CapturePipeline:
         return self.rank * per, (self.rank + 1) * per
 
     def _buffers(self, n: int):
-        """Detection outputs of n frames as two views of ONE flat int32 buffer [xy (n*mb*2) | count (n)]: the exchange
-        all-gathers that buffer as it is, nothing is packed."""
+        """Detection outputs of n frames [FS * cams_local, ...] (frame-set major: the slice of a destination rank is contiguous)."""
         if self._det is None or self._det.xy.shape[0] != n:
             mb = self.max_blobs
-            self._flat = torch.zeros(n * (2 * mb + 1), dtype=torch.int32, device=self.eng.device)
-            self._det = DetectResult(self._flat[: n * mb * 2].view(n, mb, 2), self._flat[n * mb * 2:],
+            self._det = DetectResult(torch.zeros((n, mb, 2), dtype=torch.int32, device=self.eng.device),
+                                     torch.zeros(n, dtype=torch.int32, device=self.eng.device),
                                      torch.zeros(n, dtype=torch.int32, device=self.eng.device))
-            self._gath = None
+            self._rx = None
         return self._det
 
-    def detect(self, frames: torch.Tensor, timer=None) -> DetectResult:
+    def detect(self, frames: torch.Tensor, timer=None, pipelined=None, timeline=False) -> DetectResult:
         """frames [FS, cams_local, H, W] uint8 on the device -> centroid lists of this rank's cameras."""
         FS, cl, H, W = frames.shape
         assert cl == self.cams_local and (H, W) == (self.H, self.W)
         flat = frames.view(FS * cl, H, W)
-        self._det = self.eng.detect(flat, self.K0, self.dist0, max_blobs=self.max_blobs, out=self._buffers(FS * cl), timer=timer)
+        n = FS * cl
+        if pipelined is None:
+            pipelined = timer is None and self.eng.device.type == "cuda" and n >= self.pipelined_min_frames
+        if pipelined:
+            self.eng.pipe_workers = self.engine_pipe["workers"]
+            chunk = -(-n // self.engine_pipe["chunks"])
+            self._det = self.eng.detect_pipelined(flat, self.K0, self.dist0, max_blobs=self.max_blobs, out=self._buffers(n),
+                                                  chunk_frames=chunk, timeline=timeline)
+        else:
+            self._det = self.eng.detect(flat, self.K0, self.dist0, max_blobs=self.max_blobs, out=self._buffers(n), timer=timer)
         return self._det
 
     def exchange(self, det: DetectResult, FS: int):
-        """One all-gather of the fixed-stride records; returns (xy [F0, C, max_blobs, 2], count [F0, C]) of this rank's shard."""
+        """The exchange step: returns (xy, count) of this rank's frame-set shard for ALL cameras, camera-blocked by source rank:
+        xy [world, F0, cams_local, max_blobs, 2], count [world, F0, cams_local] (world == 1: [F0, C, ...], nothing moves)."""
         cl, mb = self.cams_local, self.max_blobs
         b, e = self.frame_set_shard(FS)
+        per = e - b
         if self.world == 1:
             return det.xy.view(FS, cl, mb, 2), det.count.view(FS, cl)
-        n = FS * cl
-        if det is not self._det:                               # results that do not live in the pipeline's flat buffer
-            self._buffers(n)
-            self._det.xy.copy_(det.xy)
-            self._det.count.copy_(det.count)
-        if self._gath is None:
-            self._gath = torch.empty((self.world, self._flat.numel()), dtype=torch.int32, device=self.eng.device)
-        dist.all_gather_into_tensor(self._gath.view(-1), self._flat, group=self.group)
+        if self._rx is None or self._rx[0].shape[1] != per:
+            self._rx = (torch.empty((self.world, per, cl, mb, 2), dtype=torch.int32, device=self.eng.device),
+                        torch.empty((self.world, per, cl), dtype=torch.int32, device=self.eng.device))
+        rxy, rcnt = self._rx
+        sxy = det.xy.view(self.world, per, cl, mb, 2)                  # [destination rank][its frame-sets][my cameras]
+        scnt = det.count.view(self.world, per, cl)
+        ops = []
+        for k in range(1, self.world):                                 # every pair once per direction, self excluded
+            dst = (self.rank + k) % self.world
+            src = (self.rank - k) % self.world
+            gd = dist.get_global_rank(self.group, dst) if self.group is not None else dst
+            gs = dist.get_global_rank(self.group, src) if self.group is not None else src
+            ops += [dist.P2POp(dist.isend, sxy[dst], gd, self.group), dist.P2POp(dist.isend, scnt[dst], gd, self.group),
+                    dist.P2POp(dist.irecv, rxy[src], gs, self.group), dist.P2POp(dist.irecv, rcnt[src], gs, self.group)]
+        reqs = dist.batch_isend_irecv(ops)                             # NCCL: one group = one launch
+        rxy[self.rank].copy_(sxy[self.rank])                           # my own cameras of my own frame-sets: two small local copies
+        rcnt[self.rank].copy_(scnt[self.rank])
+        for r in reqs:
+            r.wait()                                                   # (NCCL: orders the current stream after the transfer, no host sync)
         self.collectives += 1
-        xy = self._gath[:, : n * mb * 2].view(self.world, FS, cl, mb, 2)[:, b:e].permute(1, 0, 2, 3, 4).reshape(e - b, self.C, mb, 2)
-        count = self._gath[:, n * mb * 2:].view(self.world, FS, cl)[:, b:e].permute(1, 0, 2).reshape(e - b, self.C)
-        return xy.contiguous(), count.contiguous()                      # camera index = rank * cams_local + local
+        return rxy, rcnt
 
     def step(self, frames: torch.Tensor) -> StepResult:
         FS = frames.shape[0]

@@ -246,7 +246,8 @@ def disc_stamps(radii=range(14, 23), sigma=1.2, side=57):
 def render_batch_torch(H, W, centres_px, radius_idx, seed, device, stamps=None, out=None):
     """Frames [n,H,W] uint8 on `device`: U[0,40) background, max-composited pre-blurred disc stamps.
 
-    centres_px: int64 tensor [n, M, 2] (x, y) integer disc centres; radius_idx: int64 [n, M] index into stamps.
+    centres_px: int64 tensor [n, M, 2] (x, y) integer disc centres; radius_idx: int64 [n, M] index into stamps;
+    seed: one int for the batch or a list of n ints (per-frame background noise).
     A cheaper on-device variant of render_frame (the blur is applied to the discs only); every arm of the
     bench consumes the same frames, so only determinism matters here.
     """
@@ -256,10 +257,15 @@ def render_batch_torch(H, W, centres_px, radius_idx, seed, device, stamps=None, 
     n, M, _ = centres_px.shape
     side = stamps.shape[-1]
     g = torch.Generator(device=device)
-    g.manual_seed(int(seed))
     if out is None:
         out = torch.empty((n, H, W), dtype=torch.uint8, device=device)
-    out.copy_(torch.randint(0, 40, (n, H, W), dtype=torch.uint8, device=device, generator=g))
+    if isinstance(seed, (list, tuple)):                      # one seed per frame: a frame does not depend on its batch
+        for i, sd in enumerate(seed):
+            g.manual_seed(int(sd))
+            out[i].copy_(torch.randint(0, 40, (H, W), dtype=torch.uint8, device=device, generator=g))
+    else:
+        g.manual_seed(int(seed))
+        out.copy_(torch.randint(0, 40, (n, H, W), dtype=torch.uint8, device=device, generator=g))
     d = torch.arange(side, device=device) - side // 2
     ys = centres_px[:, :, 1, None, None] + d[None, None, :, None]           # [n,M,side,1]
     xs = centres_px[:, :, 0, None, None] + d[None, None, None, :]           # [n,M,1,side]

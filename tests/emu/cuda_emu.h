@@ -210,6 +210,9 @@ static inline unsigned __byte_perm(unsigned x, unsigned y, unsigned sel)
     }
     return r;
 }
+static inline unsigned __umulhi(unsigned a, unsigned b) { return (unsigned)(((unsigned long long)a * b) >> 32); }
+static inline uint32_t __funnelshift_rc(uint32_t lo, uint32_t hi, uint32_t sh) { return sh >= 32 ? hi : (sh ? (lo >> sh) | (hi << (32 - sh)) : lo); }
+static inline unsigned __dp2a_hi(unsigned a, unsigned b, unsigned c) { return c + (a & 0xffffu) * ((b >> 16) & 0xffu) + (a >> 16) * (b >> 24); }
 static inline unsigned __dp2a_lo(unsigned a, unsigned b, unsigned c) { return c + (a & 0xffffu) * (b & 0xffu) + (a >> 16) * ((b >> 8) & 0xffu); }
 static inline int __popc(unsigned v) { return __builtin_popcount(v); }
 static inline int __popcll(unsigned long long v) { return __builtin_popcountll(v); }

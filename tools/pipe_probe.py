@@ -36,6 +36,8 @@ def main():
     ap.add_argument("--frame-sets", type=int, default=64)
     ap.add_argument("--reps", type=int, default=20)
     ap.add_argument("--quick", action="store_true")
+    ap.add_argument("--grid", default="", help="semicolon list of chunk,workers,filter_ctas,sync,scan,plan,prio tuples (overrides the built-in sweep)")
+    ap.add_argument("--timelines", action="store_true", help="print the stage timeline of every variant")
     a = ap.parse_args()
     dev = torch.device("cuda:0")
     torch.cuda.set_device(dev)
@@ -67,8 +69,11 @@ def main():
         grid = [(256, 3, 0, 1, 1, 0, 0), (128, 3, 0, 1, 1, 0, 0)]
         grid += [(cf, w, fc, 1, 1, 1, pm) for cf in (64, 128, 256) for w in (3, 4, 5) for fc in (4, 5) for pm in (0, 1, 2)]
         grid += [(128, 4, 3, 1, 1, 1, 2), (128, 4, 6, 1, 1, 1, 2), (128, 4, 5, 0, 1, 1, 2), (128, 4, 5, 0, 0, 1, 2)]
+    if a.grid:
+        grid = [tuple(int(x) for x in g.split(",")) for g in a.grid.split(";") if g]
     engines = {}
-    for (cf, w, fc, sm, sv, plan, pm) in grid:
+    for (cf, w, fc, sm, sv, plan, pm, *rest) in grid:
+        ss = rest[0] if rest else 6
         e = engines.get((w, pm))
         if e is None:
             e = CaptureEngine(dev)
@@ -76,20 +81,28 @@ def main():
             e.pipe_workers = w
             e.pipe_prio_mode = pm
             engines[(w, pm)] = e
-        kw = dict(max_blobs=mb, chunk_frames=cf, sync_mode=sm, scan_variant=sv, filter_ctas_per_sm=fc, stream_plan=plan)
+        kw = dict(max_blobs=mb, chunk_frames=cf, sync_mode=sm, scan_variant=sv, filter_ctas_per_sm=fc, stream_plan=plan, scan_stages=ss)
         res = e.detect_pipelined(frames, K, D, **kw)
         torch.cuda.synchronize()
         okk = bool(torch.equal(res.count, refc)) and bool(torch.equal(res.xy[:, :1], refxy[:, :1]))
         full_ok = all(torch.equal(res.xy[i, :int(refc[i])], refxy[i, :int(refc[i])]) for i in range(0, n, 37))
         t = timed(lambda: e.detect_pipelined(frames, K, D, out=res, **kw), a.reps)
-        rows.append({"chunk_frames": cf, "workers": w, "filter_ctas": fc, "sync_mode": sm, "scan_variant": sv, "stream_plan": plan, "prio_mode": pm,
+        rows.append({"chunk_frames": cf, "workers": w, "filter_ctas": fc, "sync_mode": sm, "scan_variant": sv, "stream_plan": plan, "prio_mode": pm, "scan_stages": ss,
                      "ms": t, "same": okk and full_ok, "info": e.last_pipe_info})
-        print(f"chunk {cf:4d} workers {w} filter_ctas {fc} sync {sm} scan {sv} plan {plan} prio {pm}: {t:7.3f} ms  {gb / t * 1e3:6.0f} GB/s  same={okk and full_ok}", flush=True)
+        print(f"chunk {cf:4d} workers {w} filter_ctas {fc} sync {sm} scan {sv} plan {plan} prio {pm} ring {ss}: {t:7.3f} ms  {gb / t * 1e3:6.0f} GB/s  same={okk and full_ok}", flush=True)
+        if a.timelines:
+            e.detect_pipelined(frames, K, D, out=res, timeline=True, **kw)
+            torch.cuda.synchronize()
+            tl = e.pipe_timeline()
+            rows[-1]["timeline_ms"] = tl
+            print("    scan done %.3f join %.3f | per chunk: seen, +group, +filter, +borders(end)" % (tl["scan_done"], tl["join"]))
+            for c, r in enumerate(tl["chunks"]):
+                print(f"    {c:2d}: {r[0]:.3f}  +{r[1] - r[0]:.3f}  +{r[2] - r[1]:.3f}  +{r[3] - r[2]:.3f} ({r[3]:.3f})")
     out["variants"] = rows
     best = min(rows, key=lambda r: r["ms"])
     e = engines[(best["workers"], best["prio_mode"])]
     e.detect_pipelined(frames, K, D, max_blobs=mb, chunk_frames=best["chunk_frames"], sync_mode=best["sync_mode"], scan_variant=best["scan_variant"],
-                       filter_ctas_per_sm=best["filter_ctas"], stream_plan=best["stream_plan"], timeline=True)
+                       filter_ctas_per_sm=best["filter_ctas"], stream_plan=best["stream_plan"], scan_stages=best["scan_stages"], timeline=True)
     torch.cuda.synchronize()
     tl = e.pipe_timeline()
     out["best"] = best
