@@ -38,6 +38,56 @@ template <> struct Num<double> {
 };
 
 // Smallest-eigenvalue eigenvector of a symmetric PSD 4x4 (upper triangle a[10]: 00 01 02 03 11 12 13 22 23 33).
+// FP32 main mode: FIVE cyclic sweeps, no data-dependent branch (the lanes of a warp never diverge, nothing is tested between
+// rotations).  Five is the budget of the flop count in SURVEY 8d; on the rigs of BASELINE configs 1-5 the smallest eigenvector has
+// converged to FP32 round-off after three to four (max relative error of X against the FP64 SVD 7e-7 at every count >= 4).
+// Rotation from delta = aqq - app: t = 2 apq / (delta + sign(delta) sqrt(delta^2 + 4 apq^2)), c = rsqrt(t^2 + 1), s = t c -- three
+// SFU operations (rsqrt, rcp, rsqrt), approximate on purpose: Jacobi rotations are self-correcting, an angle that is off by a few ulp
+// leaves a slightly larger off-diagonal for the next sweep.  apq == 0 gives t = 0 (the tiny terms keep 0 / 0 away): identity.
+__device__ __forceinline__ void jacobi_min_eigvec_f32(float b00, float b01, float b02, float b03, float b11, float b12, float b13,
+                                                      float b22, float b23, float b33, float v[4])
+{
+    float A[4][4] = {{b00, b01, b02, b03}, {b01, b11, b12, b13}, {b02, b12, b22, b23}, {b03, b13, b23, b33}};
+    float V[4][4] = {{1, 0, 0, 0}, {0, 1, 0, 0}, {0, 0, 1, 0}, {0, 0, 0, 1}};
+#pragma unroll 1
+    for (int sweep = 0; sweep < 5; ++sweep) {
+#pragma unroll
+        for (int p = 0; p < 3; ++p) {
+#pragma unroll
+            for (int q = p + 1; q < 4; ++q) {
+                const float apq = A[p][q];
+                const float dl = A[q][q] - A[p][p], two = apq + apq;
+                const float ss = dl * dl + two * two;
+                const float r = ss * rsqrtf(ss + 1e-37f);
+                const float t = __fdividef(two, dl + copysignf(r + 1e-30f, dl));
+                const float c = rsqrtf(t * t + 1.0f), s = t * c;
+                A[p][p] -= t * apq; A[q][q] += t * apq; A[p][q] = 0.0f; A[q][p] = 0.0f;
+#pragma unroll
+                for (int r2 = 0; r2 < 4; ++r2) {
+                    if (r2 != p && r2 != q) {
+                        const float arp = A[r2][p], arq = A[r2][q];
+                        A[r2][p] = c * arp - s * arq; A[p][r2] = A[r2][p];
+                        A[r2][q] = s * arp + c * arq; A[q][r2] = A[r2][q];
+                    }
+                    const float vrp = V[r2][p], vrq = V[r2][q];
+                    V[r2][p] = c * vrp - s * vrq;
+                    V[r2][q] = s * vrp + c * vrq;
+                }
+            }
+        }
+    }
+    // column of the smallest |eigenvalue| by selects
+    const float e0 = fabsf(A[0][0]), e1 = fabsf(A[1][1]), e2 = fabsf(A[2][2]), e3 = fabsf(A[3][3]);
+    const bool k01 = e1 < e0, k23 = e3 < e2;
+    const float m01 = k01 ? e1 : e0, m23 = k23 ? e3 : e2;
+    const bool hi = m23 < m01;
+#pragma unroll
+    for (int r = 0; r < 4; ++r) {
+        const float a = k01 ? V[r][1] : V[r][0], b = k23 ? V[r][3] : V[r][2];
+        v[r] = hi ? b : a;
+    }
+}
+
 template <typename T>
 __device__ __forceinline__ void jacobi_min_eigvec(T b00, T b01, T b02, T b03, T b11, T b12, T b13, T b22, T b23, T b33, T v[4])
 {
@@ -111,6 +161,26 @@ __device__ __forceinline__ void jacobi_min_eigvec(T b00, T b01, T b02, T b03, T 
     for (int r = 0; r < 4; ++r) v[r] = (k == 0) ? V[r][0] : (k == 1) ? V[r][1] : (k == 2) ? V[r][2] : V[r][3];
 }
 
+// twelve consecutive values (a 3x4 P, or R | t of a camera record): three 128-bit loads for floats that are 16-byte aligned
+template <typename T> __device__ __forceinline__ void load12(const T* p, T out[12])
+{
+#pragma unroll
+    for (int i = 0; i < 12; ++i) out[i] = p[i];
+}
+#ifndef MOCAP_EMU
+template <> __device__ __forceinline__ void load12<float>(const float* p, float out[12])
+{
+    if ((((size_t)p) & 15) == 0) {
+        const float4 a = ((const float4*)p)[0], b = ((const float4*)p)[1], c = ((const float4*)p)[2];
+        out[0] = a.x; out[1] = a.y; out[2] = a.z; out[3] = a.w; out[4] = b.x; out[5] = b.y; out[6] = b.z; out[7] = b.w;
+        out[8] = c.x; out[9] = c.y; out[10] = c.z; out[11] = c.w;
+    } else {
+#pragma unroll
+        for (int i = 0; i < 12; ++i) out[i] = p[i];
+    }
+}
+#endif
+
 template <typename T>
 struct Accum {                          // B = A^T A accumulated view by view
     T b[10];
@@ -123,14 +193,24 @@ struct Accum {                          // B = A^T A accumulated view by view
         b[4] += r[1] * r[1]; b[5] += r[1] * r[2]; b[6] += r[1] * r[3];
         b[7] += r[2] * r[2]; b[8] += r[2] * r[3]; b[9] += r[3] * r[3];
     }
-    __device__ __forceinline__ void add_view(const T* P, T x, T y) {   // P row-major 3x4
+    __device__ __forceinline__ void add_view(const T* P, T x, T y) {   // P row-major 3x4 (16-byte aligned for T = float)
+        T Pv[12];
+        load12(P, Pv);
         T r1[4], r2[4];
 #pragma unroll
-        for (int c = 0; c < 4; ++c) { r1[c] = y * P[8 + c] - P[4 + c]; r2[c] = P[c] - x * P[8 + c]; }
+        for (int c = 0; c < 4; ++c) { r1[c] = y * Pv[8 + c] - Pv[4 + c]; r2[c] = Pv[c] - x * Pv[8 + c]; }
         add_row(r1); add_row(r2);
     }
     __device__ __forceinline__ void solve(T X[3]) {
         T v[4];
+        if (sizeof(T) == 4) {
+            float w[4];
+            jacobi_min_eigvec_f32((float)b[0], (float)b[1], (float)b[2], (float)b[3], (float)b[4], (float)b[5], (float)b[6], (float)b[7],
+                                  (float)b[8], (float)b[9], w);
+            const float iw = 1.0f / w[3];                      // one IEEE reciprocal instead of three divisions
+            X[0] = (T)(w[0] * iw); X[1] = (T)(w[1] * iw); X[2] = (T)(w[2] * iw);
+            return;
+        }
         jacobi_min_eigvec<T>(b[0], b[1], b[2], b[3], b[4], b[5], b[6], b[7], b[8], b[9], v);
         X[0] = v[0] / v[3]; X[1] = v[1] / v[3]; X[2] = v[2] / v[3];
     }
@@ -167,7 +247,9 @@ __device__ __forceinline__ void project<double>(const double* pose, const double
 template <>
 __device__ __forceinline__ void project<float>(const float* pose, const float* kd, const float X[3], float& u, float& v)
 {
-    const float* R = pose; const float* t = pose + 9;
+    float Rt[12];
+    load12(pose, Rt);
+    const float* R = Rt; const float* t = Rt + 9;
     float Yx = R[0] * X[0] + R[1] * X[1] + R[2] * X[2] + t[0];
     float Yy = R[3] * X[0] + R[4] * X[1] + R[5] * X[2] + t[1];
     float Yz = R[6] * X[0] + R[7] * X[1] + R[8] * X[2] + t[2];
@@ -184,13 +266,13 @@ __device__ __forceinline__ void project<float>(const float* pose, const float* k
 }
 
 // camera records in shared memory, converted to T: per camera 38 values (P 12, R 9, t 3, K 9, dist 5)
-#define CAM_T_STRIDE 38
+#define CAM_T_STRIDE 40            // 38 values + padding: P and R | t of every camera start on a 16-byte boundary (floats)
 template <typename T>
 __device__ __forceinline__ void load_cams(const double* __restrict__ cams, int C, T* sm)
 {
     for (int i = threadIdx.x; i < C * CAM_T_STRIDE; i += blockDim.x) {
         int c = i / CAM_T_STRIDE, k = i - c * CAM_T_STRIDE;
-        sm[i] = (T)cams[(size_t)c * MOCAP_CAM_STRIDE + k];
+        sm[i] = k < 38 ? (T)cams[(size_t)c * MOCAP_CAM_STRIDE + k] : (T)0;
     }
     __syncthreads();
 }
@@ -207,6 +289,16 @@ __device__ __forceinline__ void make_P(const T* camK, const T* camPose, T* P)
         P[4 * r + 3] = K[3 * r] * t[0] + K[3 * r + 1] * t[1] + K[3 * r + 2] * t[2];
     }
 }
+
+// one image point (x, y): a single 64-bit load for floats (a point list [P][C][2] is 8-byte aligned)
+template <typename T> __device__ __forceinline__ void load_xy(const T* p, T& x, T& y) { x = p[0]; y = p[1]; }
+#ifndef MOCAP_EMU
+template <> __device__ __forceinline__ void load_xy<float>(const float* p, float& x, float& y)
+{
+    const float2 v = __ldg((const float2*)p);
+    x = v.x; y = v.y;
+}
+#endif
 
 template <typename T, bool TRIANGULATE>
 __global__ void __launch_bounds__(128) triangulate_kernel(const T* __restrict__ pts, const uint8_t* __restrict__ valid,
@@ -226,7 +318,8 @@ __global__ void __launch_bounds__(128) triangulate_kernel(const T* __restrict__ 
             Accum<T> acc; acc.clear();
             for (int c = 0; c < C; ++c) {
                 if (vm && !vm[c]) continue;
-                T x = p[2 * c], y = p[2 * c + 1];
+                T x, y;
+                load_xy(p + 2 * c, x, y);
                 if (vm) { T P[12]; make_P<T>(sm + nv * CAM_T_STRIDE, sm + c * CAM_T_STRIDE, P); acc.add_view(P, x, y); }
                 else acc.add_view(sm + c * CAM_T_STRIDE + CAM_P, x, y);
                 ++nv;
@@ -247,7 +340,9 @@ __global__ void __launch_bounds__(128) triangulate_kernel(const T* __restrict__ 
                     if (vm && !vm[c]) continue;
                     T u, v;
                     project<T>(sm + c * CAM_T_STRIDE + CAM_R, sm + (vm ? rank : c) * CAM_T_STRIDE + CAM_K, X, u, v);
-                    T dx = p[2 * c] - u, dy = p[2 * c + 1] - v;
+                    T ox, oy;
+                    load_xy(p + 2 * c, ox, oy);
+                    T dx = ox - u, dy = oy - v;
                     s += dx * dx; s += dy * dy;
                     ++rank;
                 }

@@ -2,8 +2,8 @@
 
 PyTorch is plumbing here (HBM allocations, the current CUDA stream, torch.distributed); every computation of the
 path happens inside libmocap_b200.so.  `CaptureEngine()` refuses to exist without a CUDA device and the built
-library -- there is no CPU path.  (`_test_lib`/`device` exist so that tests/ can drive the same host logic against
-the CPU emulation build of the kernel sources, tests/emu; the package itself never does that.)
+library -- there is no CPU path.  (tests/emu/emu_engine.py subclasses the engine to drive the same host logic against the
+CPU emulation build of the kernel sources; that is test infrastructure, the package never loads it.)
 """
 from __future__ import annotations
 
@@ -74,31 +74,79 @@ class CorrespondResult:
 
 
 class CaptureEngine:
-    def __init__(self, device=None, *, _test_lib: str | None = None):
-        if _test_lib is None:
-            if not torch.cuda.is_available():
-                raise _cabi.MocapError("mocapv2_b200 needs a CUDA device (B200, sm_100a); there is no CPU fallback")
-            self.device = torch.device(device if device is not None else f"cuda:{torch.cuda.current_device()}")
-            if self.device.type != "cuda":
-                raise _cabi.MocapError("mocapv2_b200 runs on CUDA devices only")
-            self.lib = _cabi.load()
-        else:                                   # tests/ only: CPU emulation build of the same kernel sources
-            self.device = torch.device("cpu")
-            self.lib = _cabi.load(_test_lib)
+    def __init__(self, device=None):
+        if not torch.cuda.is_available():
+            raise _cabi.MocapError("mocapv2_b200 needs a CUDA device (B200, sm_100a); there is no CPU fallback")
+        self.device = torch.device(device if device is not None else f"cuda:{torch.cuda.current_device()}")
+        if self.device.type != "cuda":
+            raise _cabi.MocapError("mocapv2_b200 runs on CUDA devices only")
+        self.lib = _cabi.load()
+        self._init_state()
+
+    def _init_state(self):
         self._tables = {}
-        self._ws = None
-        self._lock = threading.RLock()           # every library call of this engine is issued under it           # _find_dot is called from one thread per camera (RealtimeTracking_FLIR.py:309)
+        # _find_dot is called from one thread per camera (RealtimeTracking_FLIR.py:309): every calling thread owns its workspace
+        # (and its detection pipe), keyed by the CUDA stream it launches on, so concurrent calls never share scratch memory and
+        # need no lock -- the C-ABI keeps no state.  The lock only guards the shared table cache.
+        self._tls = threading.local()
+        self._lock = threading.RLock()
         self.launches = 0                       # kernels launched through this engine (bench bookkeeping)
-        self.pipe_workers = 2                   # worker streams of the overlapped detection
+        self.pipe_workers = 3                   # worker streams of the overlapped detection
         self.pipe_prio_mode = 0
-        self._pipe_handle = None
         self.last_pipe_info = None
 
     # ---- plumbing ------------------------------------------------------------------------------------------------
     def _stream(self):
-        if self.device.type == "cuda":
-            return ctypes.c_void_p(torch.cuda.current_stream(self.device).cuda_stream)
-        return ctypes.c_void_p(0)
+        return ctypes.c_void_p(torch.cuda.current_stream(self.device).cuda_stream)
+
+    def _device_ctx(self):
+        return torch.cuda.device(self.device)
+
+    def _retire(self, t: torch.Tensor):
+        """A buffer about to be dropped stays alive until the current stream has passed the kernels that used it."""
+        t.record_stream(torch.cuda.current_stream(self.device))
+
+    # ---- one image from / to the host (the drop-in's per-frame calls; a calling thread owns its stream and staging buffers) ----
+    def thread_stream(self):
+        """Context manager: the calling thread's own CUDA stream.  The realtime loop calls _find_dot from one thread per camera
+        (RealtimeTracking_FLIR.py:309-312); on their own streams the cameras' copies and kernels overlap."""
+        st = getattr(self._tls, "stream", None)
+        if st is None:
+            st = self._tls.stream = torch.cuda.Stream(self.device)
+        return torch.cuda.stream(st)
+
+    def _staging(self, shape):
+        """Pinned host buffers (in, out) and the device frame of one image shape, owned by the calling thread: the frame goes
+        numpy -> pinned -> HBM at PCIe speed instead of through a pageable copy, and comes back the same way."""
+        bufs = getattr(self._tls, "bufs", None)
+        if bufs is None:
+            bufs = self._tls.bufs = {}
+        key = tuple(shape)
+        if key not in bufs:
+            if len(bufs) > 8:
+                bufs.clear()
+            bufs[key] = (torch.empty(key, dtype=torch.uint8, pin_memory=True), torch.empty(key, dtype=torch.uint8, pin_memory=True),
+                         torch.empty((1,) + key, dtype=torch.uint8, device=self.device))
+        return bufs[key]
+
+    def upload_image(self, a: np.ndarray) -> torch.Tensor:
+        """(H, W) uint8 numpy -> [1, H, W] device tensor, stream-ordered in front of the kernels that read it."""
+        pin_in, _, dev = self._staging(a.shape)
+        pin_in.numpy()[...] = a
+        dev[0].copy_(pin_in, non_blocking=True)
+        return dev
+
+    def download_image_async(self, t: torch.Tensor):
+        """Queue the copy of a device image (H, W) into the thread's pinned buffer; returns a function that waits for the stream
+        and hands out a NEW numpy array (callers draw on it)."""
+        _, pin_out, _ = self._staging(t.shape)
+        pin_out.copy_(t, non_blocking=True)
+        stream = torch.cuda.current_stream(self.device)
+
+        def fetch():
+            stream.synchronize()
+            return pin_out.numpy().copy()
+        return fetch
 
     def _check_dev(self, t: torch.Tensor, dtype, name):
         if t.device != self.device or t.dtype != dtype or not t.is_contiguous():
@@ -110,10 +158,18 @@ class CaptureEngine:
         return ctypes.c_void_p(t.data_ptr()) if t is not None else ctypes.c_void_p(0)
 
     def _workspace(self, nbytes: int) -> torch.Tensor:
-        if self._ws is None or self._ws.numel() < nbytes:
-            self._ws = None
-            self._ws = torch.empty(int(nbytes), dtype=torch.uint8, device=self.device)
-        return self._ws
+        """Scratch memory of the calling thread for the stream it is launching on (grown on demand; a buffer that is replaced
+        stays alive until the stream has passed the kernels that used it: record_stream)."""
+        d = getattr(self._tls, "ws", None)
+        if d is None:
+            d = self._tls.ws = {}
+        key = int(self._stream().value or 0)
+        ws = d.get(key)
+        if ws is None or ws.numel() < nbytes:
+            if ws is not None:
+                self._retire(ws)
+            ws = d[key] = torch.empty(int(nbytes), dtype=torch.uint8, device=self.device)
+        return ws
 
     def empty(self, shape, dtype):
         return torch.empty(shape, dtype=dtype, device=self.device)
@@ -132,7 +188,7 @@ class CaptureEngine:
                 if nbytes == 0:
                     raise _cabi.MocapError("unsupported frame size")
                 tab = torch.zeros(int(nbytes), dtype=torch.uint8, device=self.device)
-                with torch.cuda.device(self.device) if self.device.type == "cuda" else _nullctx():
+                with self._device_ctx():
                     st = self.lib.mocap_undistort_table_build(K.ctypes.data, d.ctypes.data, H, W, self._ptr(tab), nbytes, self._stream())
                 _cabi.check(self.lib, st, "mocap_undistort_table_build")
                 self.launches += 3
@@ -181,27 +237,31 @@ class CaptureEngine:
         nbytes = self.lib.mocap_detect_workspace_bytes(n, H, W, max_blobs, max_contours, max_runs)
         if nbytes == 0:
             raise _cabi.MocapError("mocap_detect_workspace_bytes: unsupported shape")
-        with self._lock:
-            ws = self._workspace(nbytes)
-            st = self.lib.mocap_detect_batch(
-                self._ptr(frames), n, H, W, stride, self._ptr(tab), int(thresh), float(min_area), float(min_circ),
-                max_blobs, max_contours, max_runs, self._ptr(out.xy), self._ptr(out.count), self._ptr(out.flags),
-                self._ptr(ex.get("bits")), self._ptr(ex.get("labels")), self._ptr(ex.get("blob_sums")),
-                self._ptr(ex.get("blob_count")), self._ptr(ex.get("contours")), self._ptr(ex.get("contour_count")),
-                self._ptr(ws), nbytes, self._stream(), ctypes.c_void_p(timer) if timer else ctypes.c_void_p(0))
-            _cabi.check(self.lib, st, "mocap_detect_batch")
-            # scan, group, filter pieces, candidates, traces+finalize + the general path's mark / compact / tiles / blobs
-            self.launches += 9 + (1 if "bits" in ex else 0)
+        ws = self._workspace(nbytes)
+        st = self.lib.mocap_detect_batch(
+            self._ptr(frames), n, H, W, stride, self._ptr(tab), int(thresh), float(min_area), float(min_circ),
+            max_blobs, max_contours, max_runs, self._ptr(out.xy), self._ptr(out.count), self._ptr(out.flags),
+            self._ptr(ex.get("bits")), self._ptr(ex.get("labels")), self._ptr(ex.get("blob_sums")),
+            self._ptr(ex.get("blob_count")), self._ptr(ex.get("contours")), self._ptr(ex.get("contour_count")),
+            self._ptr(ws), nbytes, self._stream(), ctypes.c_void_p(timer) if timer else ctypes.c_void_p(0))
+        _cabi.check(self.lib, st, "mocap_detect_batch")
+        # scan, group, filter pieces, candidates, traces+finalize + the general path's mark / compact / tiles / blobs
+        self.launches += 9 + (1 if "bits" in ex else 0)
         return out
 
     # ---- overlapped detection (chunks: TMA scan of chunk k+1 beside the filter / border stages of chunk k) ----------------------
     def _pipe(self):
-        if getattr(self, "_pipe_handle", None) is None:
-            h = self.lib.mocap_detect_pipe_create(int(self.pipe_workers), int(self.pipe_prio_mode))
+        """The calling thread's detection pipe (worker streams + events of the overlapped detection)."""
+        key = (int(self.pipe_workers), int(self.pipe_prio_mode))
+        pipes = getattr(self._tls, "pipes", None)
+        if pipes is None:
+            pipes = self._tls.pipes = {}
+        if key not in pipes:
+            h = self.lib.mocap_detect_pipe_create(*key)
             if not h:
                 raise _cabi.MocapError("mocap_detect_pipe_create failed")
-            self._pipe_handle = h
-        return ctypes.c_void_p(self._pipe_handle)
+            pipes[key] = h
+        return ctypes.c_void_p(pipes[key])
 
     def detect_pipelined(self, frames: torch.Tensor, K, dist, *, thresh=THRESH_U8, min_area=MIN_AREA, min_circ=MIN_CIRC,
                          max_blobs=None, max_contours=None, max_runs=None, outputs=(), out: DetectResult | None = None,
@@ -233,20 +293,19 @@ class CaptureEngine:
             raise _cabi.MocapError("mocap_detect_pipelined_workspace_bytes: unsupported shape")
         opts = _cabi.PipeOpts(int(chunk_frames), int(sync_mode), int(scan_variant), int(filter_ctas_per_sm), int(cand_ctas_per_sm),
                               1 if timeline else 0, int(stream_plan), int(scan_stages))
-        with self._lock:
-            ws = self._workspace(nbytes)
-            st = self.lib.mocap_detect_batch_pipelined(
-                self._pipe(), self._ptr(frames), n, H, W, stride, self._ptr(tab), int(thresh), float(min_area), float(min_circ),
-                max_blobs, max_contours, max_runs, self._ptr(out.xy), self._ptr(out.count), self._ptr(out.flags),
-                self._ptr(ex.get("contours")), self._ptr(ex.get("contour_count")), self._ptr(ws), nbytes, self._stream(),
-                ctypes.byref(opts))
-            _cabi.check(self.lib, st, "mocap_detect_batch_pipelined")
-            info = (ctypes.c_int * 3)()
-            self.lib.mocap_detect_pipe_info(self._pipe(), info)
-            chunks = int(info[1])
-            scans = 1 if int(info[2]) == 1 else chunks
-            self.launches += scans + 4 * chunks + 4          # scan(s) + per chunk group/filter/candidates/borders + general path
-            self.last_pipe_info = {"tma_scan": bool(info[0]), "chunks": chunks, "sync_mode": int(info[2])}
+        ws = self._workspace(nbytes)
+        st = self.lib.mocap_detect_batch_pipelined(
+            self._pipe(), self._ptr(frames), n, H, W, stride, self._ptr(tab), int(thresh), float(min_area), float(min_circ),
+            max_blobs, max_contours, max_runs, self._ptr(out.xy), self._ptr(out.count), self._ptr(out.flags),
+            self._ptr(ex.get("contours")), self._ptr(ex.get("contour_count")), self._ptr(ws), nbytes, self._stream(),
+            ctypes.byref(opts))
+        _cabi.check(self.lib, st, "mocap_detect_batch_pipelined")
+        info = (ctypes.c_int * 3)()
+        self.lib.mocap_detect_pipe_info(self._pipe(), info)
+        chunks = int(info[1])
+        scans = 1 if int(info[2]) == 1 else chunks
+        self.launches += scans + 4 * chunks + 4          # scan(s) + per chunk group/filter/candidates/borders + general path
+        self.last_pipe_info = {"tma_scan": bool(info[0]), "chunks": chunks, "sync_mode": int(info[2])}
         return out
 
     def pipe_timeline(self):
@@ -264,12 +323,11 @@ class CaptureEngine:
         n, H, W = frames.shape
         tab = self.table(K, dist, H, W)
         out = self.empty((n, (H + 31) // 32, (W + 31) // 32), torch.int32)
-        with self._lock:
-            ws = self._workspace(4096)
-            st = self.lib.mocap_scan_cells_batch(self._ptr(frames), n, H, W, H * W, self._ptr(tab), int(thresh), int(variant),
-                                                 self._ptr(out), self._ptr(ws), 4096, self._stream())
-            _cabi.check(self.lib, st, "mocap_scan_cells_batch")
-            self.launches += 1
+        ws = self._workspace(4096)
+        st = self.lib.mocap_scan_cells_batch(self._ptr(frames), n, H, W, H * W, self._ptr(tab), int(thresh), int(variant),
+                                             self._ptr(out), self._ptr(ws), 4096, self._stream())
+        _cabi.check(self.lib, st, "mocap_scan_cells_batch")
+        self.launches += 1
         return out
 
     def blobs(self, bits: torch.Tensor, W: int, *, min_area=MIN_AREA, min_circ=MIN_CIRC, max_blobs=None, max_contours=None,
@@ -293,15 +351,14 @@ class CaptureEngine:
         nbytes = self.lib.mocap_detect_workspace_bytes(n, H, W, max_blobs, max_contours, max_runs)
         if nbytes == 0:
             raise _cabi.MocapError("mocap_detect_workspace_bytes: unsupported shape")
-        with self._lock:
-            ws = self._workspace(nbytes)
-            st = self.lib.mocap_blobs_batch(
-                self._ptr(bits), n, H, W, float(min_area), float(min_circ), max_blobs, max_contours, max_runs,
-                self._ptr(out.xy), self._ptr(out.count), self._ptr(out.flags), self._ptr(ex.get("labels")),
-                self._ptr(ex.get("blob_sums")), self._ptr(ex.get("blob_count")), self._ptr(ex.get("contours")),
-                self._ptr(ex.get("contour_count")), self._ptr(ws), nbytes, self._stream())
-            _cabi.check(self.lib, st, "mocap_blobs_batch")
-            self.launches += 2
+        ws = self._workspace(nbytes)
+        st = self.lib.mocap_blobs_batch(
+            self._ptr(bits), n, H, W, float(min_area), float(min_circ), max_blobs, max_contours, max_runs,
+            self._ptr(out.xy), self._ptr(out.count), self._ptr(out.flags), self._ptr(ex.get("labels")),
+            self._ptr(ex.get("blob_sums")), self._ptr(ex.get("blob_count")), self._ptr(ex.get("contours")),
+            self._ptr(ex.get("contour_count")), self._ptr(ws), nbytes, self._stream())
+        _cabi.check(self.lib, st, "mocap_blobs_batch")
+        self.launches += 2
         return out
 
     def filter(self, frames: torch.Tensor, K, dist, *, thresh=THRESH_U8) -> torch.Tensor:
@@ -311,12 +368,11 @@ class CaptureEngine:
         tab = self.table(K, dist, H, W)
         bits = self.empty((n, H, (W + 31) // 32), torch.int32)
         nbytes = self.lib.mocap_detect_workspace_bytes(n, H, W, 1, 1, 1)
-        with self._lock:
-            ws = self._workspace(nbytes)
-            st = self.lib.mocap_filter_batch(self._ptr(frames), n, H, W, H * W, self._ptr(tab), int(thresh), self._ptr(bits),
-                                             self._ptr(ws), nbytes, self._stream())
-            _cabi.check(self.lib, st, "mocap_filter_batch")
-            self.launches += 4
+        ws = self._workspace(nbytes)
+        st = self.lib.mocap_filter_batch(self._ptr(frames), n, H, W, H * W, self._ptr(tab), int(thresh), self._ptr(bits),
+                                         self._ptr(ws), nbytes, self._stream())
+        _cabi.check(self.lib, st, "mocap_filter_batch")
+        self.launches += 4
         return bits
 
     def blur5(self, frames: torch.Tensor) -> torch.Tensor:
@@ -324,8 +380,7 @@ class CaptureEngine:
         frames = self._check_dev(frames.contiguous(), torch.uint8, "frames")
         n, H, W = frames.shape
         out = torch.empty_like(frames)
-        with self._lock:
-            _cabi.check(self.lib, self.lib.mocap_blur5_batch(self._ptr(frames), n, H, W, self._ptr(out), self._stream()), "mocap_blur5_batch")
+        _cabi.check(self.lib, self.lib.mocap_blur5_batch(self._ptr(frames), n, H, W, self._ptr(out), self._stream()), "mocap_blur5_batch")
         self.launches += 1
         return out
 
@@ -334,9 +389,8 @@ class CaptureEngine:
         frames = self._check_dev(frames.contiguous(), torch.uint8, "frames")
         n, H, W = frames.shape
         out = torch.empty_like(frames)
-        with self._lock:
-            _cabi.check(self.lib, self.lib.mocap_median5_threshold_batch(self._ptr(frames), n, H, W, int(thresh), self._ptr(out), self._stream()),
-                        "mocap_median5_threshold_batch")
+        _cabi.check(self.lib, self.lib.mocap_median5_threshold_batch(self._ptr(frames), n, H, W, int(thresh), self._ptr(out), self._stream()),
+                    "mocap_median5_threshold_batch")
         self.launches += 1
         return out
 
@@ -350,9 +404,8 @@ class CaptureEngine:
             raise ValueError("out must have the shape of raw")
         else:
             self._check_dev(out, torch.uint8, "out")
-        with self._lock:
-            _cabi.check(self.lib, self.lib.mocap_bayer_gr2gray_batch(self._ptr(raw), n, H, W, self._ptr(out), self._stream()),
-                        "mocap_bayer_gr2gray_batch")
+        _cabi.check(self.lib, self.lib.mocap_bayer_gr2gray_batch(self._ptr(raw), n, H, W, self._ptr(out), self._stream()),
+                    "mocap_bayer_gr2gray_batch")
         self.launches += 2                      # interior rows + the two copied border rows
         return out
 
@@ -362,9 +415,8 @@ class CaptureEngine:
         n, H, W = frames.shape
         tab = self.table(K, dist, H, W)
         out = torch.empty_like(frames)
-        with self._lock:
-            _cabi.check(self.lib, self.lib.mocap_undistort_batch(self._ptr(frames), n, H, W, self._ptr(tab), self._ptr(out), self._stream()),
-                        "mocap_undistort_batch")
+        _cabi.check(self.lib, self.lib.mocap_undistort_batch(self._ptr(frames), n, H, W, self._ptr(tab), self._ptr(out), self._stream()),
+                    "mocap_undistort_batch")
         self.launches += 1
         return out
 
@@ -402,9 +454,8 @@ class CaptureEngine:
             err = self.empty((P,), pts.dtype)
         if P == 0:                                  # triangulate_points([]) -> np.array([]) (Helpers.py:87-99)
             return xyz, err
-        with self._lock:
-            st = self.lib.mocap_triangulate_batch(self._ptr(pts), self._ptr(valid), self._ptr(cams), C, P,
-                                                  1 if pts.dtype == torch.float64 else 0, self._ptr(xyz), self._ptr(err), self._stream())
+        st = self.lib.mocap_triangulate_batch(self._ptr(pts), self._ptr(valid), self._ptr(cams), C, P,
+                                              1 if pts.dtype == torch.float64 else 0, self._ptr(xyz), self._ptr(err), self._stream())
         _cabi.check(self.lib, st, "mocap_triangulate_batch")
         self.launches += 1 if P else 0
         return xyz, err
@@ -420,9 +471,8 @@ class CaptureEngine:
         err = self.empty((P,), pts.dtype)
         if P == 0:
             return err
-        with self._lock:
-            st = self.lib.mocap_reproject_batch(self._ptr(pts), self._ptr(valid), self._ptr(xyz), self._ptr(cams), C, P,
-                                                1 if pts.dtype == torch.float64 else 0, self._ptr(err), self._stream())
+        st = self.lib.mocap_reproject_batch(self._ptr(pts), self._ptr(valid), self._ptr(xyz), self._ptr(cams), C, P,
+                                            1 if pts.dtype == torch.float64 else 0, self._ptr(err), self._stream())
         _cabi.check(self.lib, st, "mocap_reproject_batch")
         self.launches += 1 if P else 0
         return err
@@ -458,24 +508,15 @@ class CaptureEngine:
         if S == 0:
             return res
         nbytes = self.lib.mocap_correspond_workspace_bytes(S, C, max_pts, max_groups)
-        with self._lock:
-            ws = self._workspace(nbytes)
-            st = self.lib.mocap_correspond_batch_blocked(
-                self._ptr(xy), self._ptr(count), S, C, max_pts, cpb, self._ptr(Fs) if C > 1 else ctypes.c_void_p(0), self._ptr(cams),
-                float(cutoff), int(obj_count), int(max_groups), 1 if fp64 else 0,
-                self._ptr(res.obj), self._ptr(res.n_obj), self._ptr(res.img), self._ptr(res.n_valid), self._ptr(res.err),
-                self._ptr(res.cand), self._ptr(res.flags), self._ptr(ws), nbytes, self._stream())
-            _cabi.check(self.lib, st, "mocap_correspond_batch_blocked")
-            self.launches += 2
+        ws = self._workspace(nbytes)
+        st = self.lib.mocap_correspond_batch_blocked(
+            self._ptr(xy), self._ptr(count), S, C, max_pts, cpb, self._ptr(Fs) if C > 1 else ctypes.c_void_p(0), self._ptr(cams),
+            float(cutoff), int(obj_count), int(max_groups), 1 if fp64 else 0,
+            self._ptr(res.obj), self._ptr(res.n_obj), self._ptr(res.img), self._ptr(res.n_valid), self._ptr(res.err),
+            self._ptr(res.cand), self._ptr(res.flags), self._ptr(ws), nbytes, self._stream())
+        _cabi.check(self.lib, st, "mocap_correspond_batch_blocked")
+        self.launches += 2
         return res
-
-
-class _nullctx:
-    def __enter__(self):
-        return self
-
-    def __exit__(self, *a):
-        return False
 
 
 _default_engine = None

@@ -183,6 +183,8 @@ def find_point_correspondance_and_object_points(image_points, camera_poses, obj_
     read_fundamental_matrix()
     eng = _engine.default_engine()
     C = len(camera_poses)
+    if len(image_points) < C:
+        raise IndexError("list index out of range")              # image_points[i], Helpers.py:203-216
     if C > 1 and len(Fs) < C - 1:
         raise IndexError("list index out of range")              # Fs[i-1], Helpers.py:206
     lists = []

@@ -11,8 +11,8 @@ import json
 import threading
 
 import numpy as np
-import torch
 
+from .. import _cabi
 from .. import engine as _engine
 
 cuda_lock = threading.Lock()           # kept for API compatibility (lib/ImageOperations.py:9); the engine serialises itself
@@ -31,45 +31,16 @@ def _params():
     return camera_params
 
 
-_tls = threading.local()               # per calling thread (one per camera in the realtime loop): pinned staging buffers
-
-
-def _staging(shape, eng):
-    """Pinned host buffers (in, out) and the device frame of one image shape, owned by the calling thread: the frame goes
-    numpy -> pinned -> HBM at PCIe speed instead of through a pageable copy, and comes back the same way."""
-    bufs = getattr(_tls, "bufs", None)
-    if bufs is None:
-        bufs = _tls.bufs = {}
-    key = (tuple(shape), str(eng.device))
-    if key not in bufs:
-        if len(bufs) > 8:
-            bufs.clear()
-        bufs[key] = (torch.empty(tuple(shape), dtype=torch.uint8, pin_memory=True),
-                     torch.empty(tuple(shape), dtype=torch.uint8, pin_memory=True),
-                     torch.empty((1,) + tuple(shape), dtype=torch.uint8, device=eng.device))
-    return bufs[key]
-
-
 def _to_device(img, eng):
     a = np.ascontiguousarray(img)
     if a.dtype != np.uint8 or a.ndim != 2:
         raise ValueError("expected a single-channel uint8 image (H, W)")
-    if eng.device.type != "cuda":                              # tests: the CPU build of the kernels
-        return torch.from_numpy(a)[None].to(eng.device, non_blocking=False)
-    pin_in, _, dev = _staging(a.shape, eng)
-    pin_in.numpy()[...] = a
-    dev[0].copy_(pin_in, non_blocking=True)                   # stream-ordered in front of the kernels that read it
-    return dev
+    return eng.upload_image(a)
 
 
 def _to_host(t, eng):
-    """Device image (H, W) uint8 -> a NEW numpy array (callers draw on it), through the thread's pinned buffer."""
-    if eng.device.type != "cuda":
-        return t.cpu().numpy()
-    _, pin_out, _ = _staging(t.shape, eng)
-    pin_out.copy_(t, non_blocking=True)
-    torch.cuda.current_stream(eng.device).synchronize()
-    return pin_out.numpy().copy()
+    """Device image (H, W) uint8 -> a NEW numpy array (callers draw on it), through the calling thread's pinned buffer."""
+    return eng.download_image_async(t)()
 
 
 def bayer_gr_to_gray(image):
@@ -99,6 +70,22 @@ def image_filter_gpu(image, camera_number=0):
     return (np.unpackbits(b, axis=1, bitorder="little")[:, :W] * 255).astype(np.uint8)
 
 
+def _detect_one(eng, fr, K, dist, outputs):
+    """eng.detect on one frame; capacity overflows (MOCAP_FLAG_*_OVERFLOW: more blobs / contours / runs than the default
+    caps hold) are never returned as a silently short list -- the call is repeated with larger caps, like the reference,
+    which has none (lib/ImageOperations.py:41-65)."""
+    caps = {}
+    for attempt in range(6):
+        res = eng.detect(fr, K, dist, outputs=outputs, **caps)
+        flags = int(res.flags[0])                              # device -> host read of the result
+        if not flags & _cabi.FLAG_ERRORS:
+            return res
+        H, W = fr.shape[1:]
+        mb, mc, mr = eng.default_caps(H, W, caps.get("max_blobs"), caps.get("max_contours"), caps.get("max_runs"))
+        caps = {"max_blobs": 4 * mb, "max_contours": 4 * mc, "max_runs": 4 * mr}
+    raise _cabi.MocapError(f"_find_dot: detection capacity exceeded even with caps {caps} (flags {flags})")
+
+
 def _find_dot(img, print_location=False, return_filtered=False):
     """output: image with dot and dot coordinates -- (img, [[x, y], ...]) or (img, [[None, None]]).
 
@@ -107,16 +94,19 @@ def _find_dot(img, print_location=False, return_filtered=False):
     cp = _params()[0]
     K = np.array(cp["intrinsic_matrix"], dtype=np.float64)
     dist = np.array(cp["distortion_coef"], dtype=np.float64)
-    fr = _to_device(img, eng)
-    H, W = fr.shape[1:]
-    res = eng.detect(fr, K, dist, outputs=("bits",) if return_filtered else ())
-    n = int(res.count[0])                                     # device -> host read of the result
-    image_points = res.xy[0, :n].tolist() if n else []
-    if return_filtered:
-        b = res.extras["bits"][0].cpu().numpy().view(np.uint8)
-        out = (np.unpackbits(b, axis=1, bitorder="little")[:, :W] * 255).astype(np.uint8)
-    else:
-        out = _to_host(eng.undistort(fr, K, dist)[0], eng)
+    with eng.thread_stream():
+        fr = _to_device(img, eng)
+        H, W = fr.shape[1:]
+        # everything of the call is queued before the first host read: H2D, the undistorted image and its way back, detection
+        fetch = None if return_filtered else eng.download_image_async(eng.undistort(fr, K, dist)[0])
+        res = _detect_one(eng, fr, K, dist, ("bits",) if return_filtered else ())
+        n = int(res.count[0])
+        image_points = res.xy[0, :n].tolist() if n else []
+        if return_filtered:
+            b = res.extras["bits"][0].cpu().numpy().view(np.uint8)
+            out = (np.unpackbits(b, axis=1, bitorder="little")[:, :W] * 255).astype(np.uint8)
+        else:
+            out = fetch()
     if ANNOTATE and image_points:
         try:                                                  # display-only overlays (lib/ImageOperations.py:67-73)
             import cv2 as cv

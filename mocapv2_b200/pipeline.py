@@ -81,7 +81,7 @@ class CapturePipeline:
         flat = frames.view(FS * cl, H, W)
         n = FS * cl
         if pipelined is None:
-            pipelined = timer is None and self.eng.device.type == "cuda" and n >= self.pipelined_min_frames
+            pipelined = timer is None and n >= self.pipelined_min_frames
         if pipelined:
             self.eng.pipe_workers = self.engine_pipe["workers"]
             chunk = -(-n // self.engine_pipe["chunks"])

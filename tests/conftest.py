@@ -37,8 +37,8 @@ def emu_engine():
     """CaptureEngine over the CPU emulation build of the kernel sources (test infrastructure, see tests/emu)."""
     sys.path.insert(0, os.path.join(REPO, "tests", "emu"))
     import build_emu
-    from mocapv2_b200.engine import CaptureEngine
-    return CaptureEngine(_test_lib=build_emu.build())
+    from emu_engine import EmuEngine
+    return EmuEngine(build_emu.build())
 
 
 @pytest.fixture(scope="session")

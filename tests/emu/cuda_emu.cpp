@@ -2,6 +2,7 @@
 #include "cuda_emu.h"
 
 #include <chrono>
+#include <mutex>
 double emu_now_ms()
 {
     return std::chrono::duration<double, std::milli>(std::chrono::steady_clock::now().time_since_epoch()).count();
@@ -13,10 +14,13 @@ std::vector<unsigned char> g_dyn_smem;
 thread_local uint3_emu t_threadIdx, t_blockIdx;
 dim3 g_blockDim, g_gridDim;
 
+static std::mutex g_launch_mutex;      // one "device": launches from several host threads run one after the other
+
 void launch(dim3 grid, dim3 block, size_t smem, const std::function<void()>& body)
 {
     const int nt = (int)(block.x * block.y * block.z);
     if (nt <= 0 || grid.x * grid.y * grid.z == 0) return;
+    std::lock_guard<std::mutex> guard(g_launch_mutex);
     g_blockDim = block;
     g_gridDim = grid;
     g_dyn_smem.assign(smem + 64, 0);

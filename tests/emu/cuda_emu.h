@@ -239,6 +239,7 @@ static inline double __fma_rn(double a, double b, double c) { return fma(a, b, c
 static inline float __fmaf_rn(float a, float b, float c) { return fmaf(a, b, c); }
 static inline float __frcp_rn(float a) { return 1.0f / a; }
 static inline float rsqrtf(float a) { return 1.0f / sqrtf(a); }
+static inline float __fdividef(float a, float b) { return a / b; }
 static inline double rsqrt(double a) { return 1.0 / sqrt(a); }
 static inline unsigned __vsetgtu4_emu(unsigned a, unsigned b)
 {

@@ -29,10 +29,12 @@ def run():
     import torch
     sys.path.insert(0, REPO)
     sys.path.insert(0, os.path.join(REPO, "tests"))
+    sys.path.insert(0, os.path.join(REPO, "tests", "emu"))
     from mocapv2_b200 import synth as S
     from mocapv2_b200.engine import CaptureEngine
     from test_detect_parity import random_scene
-    eng = CaptureEngine(_test_lib=LIB)
+    from emu_engine import EmuEngine
+    eng = EmuEngine(LIB)
     K, D = S.SHIPPED_K, S.SHIPPED_DIST
     rng = np.random.default_rng(5)
     for it in range(10):

@@ -19,7 +19,8 @@ from util import oracle_contour_table               # noqa: E402
 def main():
     iters = int(sys.argv[1]) if len(sys.argv) > 1 else 40
     rng = np.random.default_rng(int(sys.argv[2]) if len(sys.argv) > 2 else 1)
-    eng = CaptureEngine(_test_lib=build_emu.build())
+    from emu_engine import EmuEngine
+    eng = EmuEngine(build_emu.build())
     reasons = {}
     for it in range(iters):
         H, W = int(rng.integers(40, 300)), int(rng.integers(40, 360))

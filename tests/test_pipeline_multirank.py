@@ -50,7 +50,8 @@ def _run(rank, world, port, out_dir, backend="gloo", scene="c1"):
         import build_emu
         if world > 1:
             dist.init_process_group("gloo", init_method=f"tcp://127.0.0.1:{port}", rank=rank, world_size=world)
-        eng = CaptureEngine(_test_lib=build_emu.build())
+        from emu_engine import EmuEngine
+        eng = EmuEngine(build_emu.build())
     if scene == "ring4":
         rig, fr = _ring4_scene()
     else:
