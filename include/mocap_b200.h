@@ -173,6 +173,13 @@ int mocap_triangulate_batch(const void* pts_dev, const uint8_t* valid_dev, const
 int mocap_reproject_batch(const void* pts_dev, const uint8_t* valid_dev, const void* xyz_dev,
                           const double* cams_dev, int C, int64_t P, int fp64_mode, void* err_out, void* stream);
 
+/* The residual of bundle_adjustment (lib/Helpers.py:158-176; residual :160-167 = triangulate_points + calculate_reprojection_errors on
+ * all points) under n_sets pose hypotheses in one launch, FP64: cams_sets_dev [n_sets][C][MOCAP_CAM_STRIDE], pts_dev [P][C][2] (every view
+ * valid), err_out [n_sets][P].  One call per optimiser iteration evaluates the residual at x and at every x + h e_i of scipy's 2-point
+ * finite-difference Jacobian. */
+int mocap_ba_residuals_batch(const double* pts_dev, const double* cams_sets_dev, int n_sets, int C, int64_t P,
+                             double* err_out, void* stream);
+
 /* ---- epipolar correspondence + candidate groups + ranking ---------------------------------------------------
  * find_point_correspondance_and_object_points (lib/Helpers.py:178-280) for S frame-sets.
  * xy_dev [S][C][max_pts][2] int32 centroid lists (the [None, None] entry already dropped), count_dev [S][C].

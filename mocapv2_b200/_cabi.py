@@ -58,6 +58,7 @@ SIGNATURES = {
     "mocap_bayer_gr2gray_batch": (_i, [_p, _i, _i, _i, _p, _p]),
     "mocap_undistort_batch": (_i, [_p, _i, _i, _i, _p, _p, _p]),
     "mocap_triangulate_batch": (_i, [_p, _p, _p, _i, _i64, _i, _p, _p, _p]),
+    "mocap_ba_residuals_batch": (_i, [_p, _p, _i, _i, _i64, _p, _p]),
     "mocap_reproject_batch": (_i, [_p, _p, _p, _p, _i, _i64, _i, _p, _p]),
     "mocap_correspond_workspace_bytes": (_sz, [_i, _i, _i, _i]),
     "mocap_correspond_batch": (_i, [_p, _p, _i, _i, _i, _p, _p, _d, _i, _i, _i,

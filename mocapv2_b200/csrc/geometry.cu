@@ -307,6 +307,10 @@ __global__ void __launch_bounds__(128) triangulate_kernel(const T* __restrict__ 
 {
     DYN_SHARED(smraw);
     T* sm = (T*)smraw;
+    // blockIdx.y: camera set (mocap_ba_residuals_batch evaluates the same points under several pose hypotheses in one launch)
+    cams += (size_t)blockIdx.y * C * MOCAP_CAM_STRIDE;
+    if (err_out) err_out += (size_t)blockIdx.y * n;
+    if (xyz_out) xyz_out += (size_t)blockIdx.y * n * 3;
     load_cams<T>(cams, C, sm);
     const T nan = (T)NAN;
     for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (long long)gridDim.x * blockDim.x) {
@@ -326,7 +330,7 @@ __global__ void __launch_bounds__(128) triangulate_kernel(const T* __restrict__ 
             }
             if (nv <= 1) { X[0] = X[1] = X[2] = nan; }
             else acc.solve(X);
-            xyz_out[(size_t)i * 3] = X[0]; xyz_out[(size_t)i * 3 + 1] = X[1]; xyz_out[(size_t)i * 3 + 2] = X[2];
+            if (xyz_out) { xyz_out[(size_t)i * 3] = X[0]; xyz_out[(size_t)i * 3 + 1] = X[1]; xyz_out[(size_t)i * 3 + 2] = X[2]; }
         } else {
             X[0] = xyz_in[(size_t)i * 3]; X[1] = xyz_in[(size_t)i * 3 + 1]; X[2] = xyz_in[(size_t)i * 3 + 2];
             for (int c = 0; c < C; ++c) nv += (!vm || vm[c]);
@@ -355,7 +359,7 @@ __global__ void __launch_bounds__(128) triangulate_kernel(const T* __restrict__ 
 
 template <typename T>
 static int launch_tri(const void* pts, const uint8_t* valid, const void* xyz_in, const double* cams, int C, int64_t n,
-                      void* xyz_out, void* err_out, bool tri, cudaStream_t s)
+                      void* xyz_out, void* err_out, bool tri, cudaStream_t s, int n_sets = 1)
 {
     int dev = 0, sms = 148;
     cudaGetDevice(&dev);
@@ -368,7 +372,7 @@ static int launch_tri(const void* pts, const uint8_t* valid, const void* xyz_in,
     auto k_rep = triangulate_kernel<T, false>;
     const T* no_in = nullptr;
     T* no_out = nullptr;
-    if (tri) LAUNCH(k_tri, (unsigned)blocks, 128, smem, s, (const T*)pts, valid, no_in, cams, C, n, (T*)xyz_out, (T*)err_out);
+    if (tri) LAUNCH(k_tri, dim3((unsigned)blocks, (unsigned)n_sets), 128, smem, s, (const T*)pts, valid, no_in, cams, C, n, (T*)xyz_out, (T*)err_out);
     else LAUNCH(k_rep, (unsigned)blocks, 128, smem, s, (const T*)pts, valid, (const T*)xyz_in, cams, C, n, no_out, (T*)err_out);
     CUDA_TRY(cudaGetLastError());
     return MOCAP_OK;
@@ -381,6 +385,17 @@ extern "C" int mocap_triangulate_batch(const void* pts_dev, const uint8_t* valid
     if (P == 0) return MOCAP_OK;
     if (fp64_mode) return launch_tri<double>(pts_dev, valid_dev, nullptr, cams_dev, C, P, xyz_out, err_out, true, (cudaStream_t)stream);
     return launch_tri<float>(pts_dev, valid_dev, nullptr, cams_dev, C, P, xyz_out, err_out, true, (cudaStream_t)stream);
+}
+
+// The residual of bundle_adjustment (lib/Helpers.py:160-167: triangulate_points + calculate_reprojection_errors on all points) for
+// n_sets pose hypotheses in ONE launch, FP64 with the reference's roundings: scipy's 2-point finite-difference Jacobian needs the
+// residual at x and at x + h e_i for every parameter, i.e. 7 hypotheses per iteration for the 6 parameters of the second camera.
+extern "C" int mocap_ba_residuals_batch(const double* pts_dev, const double* cams_sets_dev, int n_sets, int C, int64_t P,
+                                        double* err_out, void* stream)
+{
+    if (!pts_dev || !cams_sets_dev || !err_out || n_sets < 1 || n_sets > 65535 || C < 2 || C > MOCAP_MAX_CAMS || P < 0) return MOCAP_ERR_INVALID;
+    if (P == 0) return MOCAP_OK;
+    return launch_tri<double>(pts_dev, nullptr, nullptr, cams_sets_dev, C, P, nullptr, err_out, true, (cudaStream_t)stream, n_sets);
 }
 
 extern "C" int mocap_reproject_batch(const void* pts_dev, const uint8_t* valid_dev, const void* xyz_dev,

@@ -460,6 +460,21 @@ class CaptureEngine:
         self.launches += 1 if P else 0
         return xyz, err
 
+    def ba_residuals(self, pts: torch.Tensor, cams_sets: torch.Tensor) -> torch.Tensor:
+        """bundle_adjustment's residual (lib/Helpers.py:160-167) for several pose hypotheses in one launch, FP64:
+        pts [P, C, 2] float64 (all views valid), cams_sets [S, C, 40] float64 -> mean squared reprojection errors [S, P]."""
+        pts = self._check_dev(pts, torch.float64, "pts")
+        cams_sets = self._check_dev(cams_sets, torch.float64, "cams_sets")
+        P, C, _ = pts.shape
+        S = cams_sets.shape[0]
+        err = self.empty((S, P), torch.float64)
+        if P == 0:
+            return err
+        st = self.lib.mocap_ba_residuals_batch(self._ptr(pts), self._ptr(cams_sets), S, C, P, self._ptr(err), self._stream())
+        _cabi.check(self.lib, st, "mocap_ba_residuals_batch")
+        self.launches += 1
+        return err
+
     def reproject(self, pts: torch.Tensor, xyz: torch.Tensor, cams: torch.Tensor, valid: torch.Tensor | None = None):
         """calculate_reprojection_errors (lib/Helpers.py:102-143) for given object points."""
         pts = self._check_dev(pts, pts.dtype, "pts")

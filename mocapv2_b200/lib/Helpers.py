@@ -145,28 +145,60 @@ def params_to_camera_poses(params, num_cameras=2):
 
 
 def bundle_adjustment(image_points, camera_poses):
-    """Refine the second camera's pose (lib/Helpers.py:158-176): scipy least_squares (TRF, 2-point finite differences)
-    over the mean squared reprojection errors, cast to float32 like the reference; the residual -- triangulate_points +
-    calculate_reprojection_errors on all points -- is the GPU path, in its FP64 check mode (finite differences need it).
-    Same quirks: two cameras hard-coded (:162, :174)."""
+    """Refine the second camera's pose (lib/Helpers.py:158-176): scipy least_squares (TRF, 2-point finite differences) over the
+    mean squared reprojection errors, cast to float32 like the reference.  Same quirks: two cameras hard-coded (:162, :174).
+
+    The residual -- triangulate_points + calculate_reprojection_errors on all points (:160-167) -- runs on the GPU in FP64 with the
+    reference's roundings, and an optimiser iteration costs ONE launch: scipy hands the perturbed parameter vectors of its
+    finite-difference Jacobian to `workers`, here a map that evaluates all of them as pose hypotheses of a single
+    mocap_ba_residuals_batch call (x and the six x + h e_i).  The optimiser itself, its step sizes and its arithmetic on the
+    residuals are scipy's, exactly as in the reference, so jsons/before_ba_extrinsics.json still gives after_ba_extrinsics.json."""
     from scipy import optimize
     from scipy.spatial.transform import Rotation
-    global precision
-    saved, precision = precision, "fp64"
-    try:
-        def residual_function(params):
-            poses = params_to_camera_poses(params, 2)
-            object_points = triangulate_points(image_points, poses)
-            errors = calculate_reprojection_errors(image_points, object_points, poses)
-            return errors.astype(np.float32)
+    eng = _engine.default_engine()
+    read_camera_params()
+    groups = [list(g) for g in image_points]
+    fused = len(groups) > 0 and all(len(g) == 2 and not any(_is_none(p) for p in g) for g in groups)
+    stats = {"launches": 0, "hypotheses": 0}
 
-        init_params = np.array([])
-        for camera_pose in camera_poses[1:]:
-            init_params = np.concatenate([init_params, Rotation.from_matrix(camera_pose["R"]).as_rotvec(),
-                                          np.asarray(camera_pose["t"]).flatten()])
-        result = optimize.least_squares(residual_function, init_params, verbose=0, loss="linear", method="trf", ftol=1E-5, xtol=1E-15)
-    finally:
-        precision = saved
+    if fused:
+        pts_dev = torch.from_numpy(np.asarray(groups, dtype=np.float64).reshape(len(groups), 2, 2)).to(eng.device)
+
+        def residuals_of(params_list):
+            cams = np.stack([_engine.pack_cameras(params_to_camera_poses(np.asarray(p), 2), camera_params) for p in params_list])
+            err = eng.ba_residuals(pts_dev, torch.from_numpy(cams).to(eng.device))
+            stats["launches"] += 1
+            stats["hypotheses"] += len(params_list)
+            return [e.astype(np.float32) for e in err.cpu().numpy()]
+
+        def residual_function(params):
+            return residuals_of([params])[0]
+
+        def hypotheses_map(fun, xs):                       # scipy's `workers`: all finite-difference points of an iteration at once
+            return [np.atleast_1d(r) for r in residuals_of(list(xs))]
+    else:                                                  # groups with missing views: the reference's per-call path (:93, :125)
+        global precision
+        saved = precision
+
+        def residual_function(params):
+            global precision
+            precision = "fp64"
+            try:
+                poses = params_to_camera_poses(params, 2)
+                object_points = triangulate_points(image_points, poses)
+                errors = calculate_reprojection_errors(image_points, object_points, poses)
+            finally:
+                precision = saved
+            return errors.astype(np.float32)
+        hypotheses_map = None
+
+    init_params = np.array([])
+    for camera_pose in camera_poses[1:]:
+        init_params = np.concatenate([init_params, Rotation.from_matrix(camera_pose["R"]).as_rotvec(),
+                                      np.asarray(camera_pose["t"]).flatten()])
+    result = optimize.least_squares(residual_function, init_params, verbose=0, loss="linear", method="trf", ftol=1E-5, xtol=1E-15,
+                                    workers=hypotheses_map)
+    bundle_adjustment.last_stats = dict(stats, nfev=int(result.nfev), njev=int(result.njev) if result.njev is not None else None)
     return params_to_camera_poses(result.x)
 
 

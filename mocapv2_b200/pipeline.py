@@ -54,9 +54,10 @@ class CapturePipeline:
         self._det = None
         self._rx = None
         self.collectives = 0
-        # overlapped detection (engine.detect_pipelined) for batches large enough to pipeline: 4 chunks, 3 worker streams
+        # overlapped detection (engine.detect_pipelined) for batches large enough to pipeline: 8 chunks on 6 worker streams
+        # (tools/pipe_probe.py on the C4 batch: 1.75 ms against 2.03 ms for the one-shot call; 4 chunks / 4 workers 1.78 ms)
         self.pipelined_min_frames = 256
-        self.engine_pipe = {"workers": 3, "chunks": 4}
+        self.engine_pipe = {"workers": 6, "chunks": 8}
 
     def frame_set_shard(self, n_frame_sets: int):
         if n_frame_sets % self.world:

@@ -521,3 +521,31 @@ def test_full_size_batches_against_oracle_sample(gpu_engine, name, n):
     assert torch.equal(res2.xy * live, res.xy[perm] * live)
     # blobs overlap at random, so only a loose sanity bound on the count
     assert int(res.count.min()) > M // 4
+
+
+def test_detect_c2_video_wide(engine):
+    """BASELINE config 2 on a wide sample of the reference's videos (every 10th frame of cam1-6.mp4 and all 25 frames in which
+    the reference keeps a blob; tests/golden/c2_wide.*, generated by oracle/gen_golden_c2.py running the reference): kept
+    centroids, contour count and the pre-filter contour statistics (a00, perimeter, kept flag) of every frame -- the filter
+    keeps a blob in 25 frames only, so the pre-filter table is what makes this config bite."""
+    z = np.load(os.path.join(GOLDEN, "c2_wide.npz"))
+    meta = json.load(open(os.path.join(GOLDEN, "c2_wide.json")))
+    frames, counts, tab = z["frames"], z["contour_counts"], z["contours"]
+    offs = np.concatenate([[0], np.cumsum(counts)])
+    kept_idx = [i for i, p in enumerate(meta["points"]) if p != [[None, None]]]
+    assert len(frames) >= 120 and len(kept_idx) == 25
+    idx = list(range(len(frames))) if is_gpu(engine) else kept_idx[:2] + [0]
+    fr = dev(engine, frames[idx])
+    res = engine.detect(fr, K, D, outputs=("contours",))
+    runs = [res]
+    if is_gpu(engine):
+        runs.append(engine.detect_pipelined(fr, K, D, outputs=("contours",), chunk_frames=36))
+    for r in runs:
+        for k, i in enumerate(idx):
+            assert r.points(k) == meta["points"][i], f"frame {i} (cam, frame) = {z['ids'][i]}"
+            gold = tab[offs[i]:offs[i + 1]]
+            assert int(r.extras["contour_count"][k]) == len(gold)
+            got = r.extras["contours"][k, : len(gold)].cpu().numpy()
+            assert np.array_equal(got[:, 0], gold[:, 0])                       # a00 (oriented area x 2), exact
+            assert np.array_equal(got[:, 3], gold[:, 4])                       # perimeter (float32 sqrt sums in double), exact
+            assert np.array_equal(got[:, 6], gold[:, 6])                       # kept by the area / circularity filter

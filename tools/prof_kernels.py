@@ -25,7 +25,7 @@ def main():
     ap.add_argument("--frame-sets", type=int, default=64)
     ap.add_argument("--points", type=int, default=4_000_000)
     ap.add_argument("--bayer-frames", type=int, default=256)
-    ap.add_argument("--skip", default="", help="comma list of: detect,geometry,bayer")
+    ap.add_argument("--skip", default="", help="comma list of: detect,geometry,bayer,overlapped")
     a = ap.parse_args()
     skip = set(a.skip.split(",")) if a.skip else set()
     dev = torch.device("cuda:0")
@@ -38,10 +38,16 @@ def main():
     H, W = rig["H"], rig["W"]
     corr = [None]
 
+    flat = frames.view(-1, H, W)
+
     def step():
-        det = pipe.detect(frames)
+        det = pipe.detect(frames, pipelined=False)                 # the stages one after the other: every kernel profiled alone
         xy, count = pipe.exchange(det, FS)
         corr[0] = eng.correspond(xy, count, pipe.Fs, pipe.cams, obj_count=B.N_MARKERS, max_groups=B.MAX_GROUPS, out=corr[0])
+        eng.scan_cells(flat, pipe.K0, pipe.dist0, variant=1)       # the TMA ring scan of the overlapped call, alone
+
+    def overlapped():
+        pipe.detect(frames, pipelined=True)                        # the product call of the bench: scan beside the other stages
 
     rig5 = S.config_rig("c5")
     cams5 = eng.cameras(rig5["poses"], rig5["camera_params"])
@@ -60,11 +66,13 @@ def main():
         eng.bayer_gr2gray(raw, out=grey)
 
     for _ in range(3):
-        step(); geometry(); bayer()
+        step(); geometry(); bayer(); overlapped()
     torch.cuda.synchronize()
     torch.cuda.profiler.start()
     if "detect" not in skip:
         step()
+    if "overlapped" not in skip:
+        overlapped()
     if "geometry" not in skip:
         geometry()
     if "bayer" not in skip:
