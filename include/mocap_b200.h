@@ -150,6 +150,12 @@ int mocap_blobs_batch(const uint32_t* bits_dev, int n_frames, int H, int W,
                       double* out_contours, int32_t* out_contour_count,
                       void* workspace, size_t workspace_bytes, void* stream);
 
+/* cv.drawContours(img, contours_filtered, -1, (0,0,255), 2) of _find_dot (lib/ImageOperations.py:52-55; display only): paints `value`
+ * (the reference's colour on a one-channel image: 0) over the thickness-2 outline of every KEPT contour of the table returned by
+ * mocap_detect_batch (out_contours / out_contour_count, with the packed binary image out_bits of the same call) into img_dev [n][H][W]. */
+int mocap_draw_contours_batch(const uint32_t* bits_dev, const double* contours_dev, const int32_t* contour_count_dev,
+                              int n_frames, int H, int W, int max_contours, uint8_t* img_dev, int value, void* stream);
+
 /* ---- the reference's own GPU op: fast_cuda_blur(image, 5) (lib/CudaOperations.py:24-41) -------------------- */
 int mocap_blur5_batch(const uint8_t* frames_dev, int n_frames, int H, int W, uint8_t* out_dev, void* stream);
 /* image_filter_cpu (lib/ImageOperations.py:15-21): cv.medianBlur(image, 5) then cv.threshold(., thresh, 255, BINARY) -> u8 {0,255} */

@@ -53,6 +53,7 @@ SIGNATURES = {
     "mocap_scan_cells_batch": (_i, [_p, _i, _i, _i, _i64, _p, _i, _i, _p, _p, _sz, _p]),
     "mocap_filter_batch": (_i, [_p, _i, _i, _i, _i64, _p, _i, _p, _p, _sz, _p]),
     "mocap_blobs_batch": (_i, [_p, _i, _i, _i, _d, _d, _i, _i, _i, _p, _p, _p, _p, _p, _p, _p, _p, _p, _sz, _p]),
+    "mocap_draw_contours_batch": (_i, [_p, _p, _p, _i, _i, _i, _i, _p, _i, _p]),
     "mocap_blur5_batch": (_i, [_p, _i, _i, _i, _p, _p]),
     "mocap_median5_threshold_batch": (_i, [_p, _i, _i, _i, _i, _p, _p]),
     "mocap_bayer_gr2gray_batch": (_i, [_p, _i, _i, _i, _p, _p]),

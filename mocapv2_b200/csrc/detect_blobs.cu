@@ -578,3 +578,52 @@ int launch_blobs(const uint32_t* bits, const uint32_t* fg_tiles, const int* n_fg
     CUDA_TRY(cudaGetLastError());
     return MOCAP_OK;
 }
+
+
+// ---------------------------------------------------------------------------------------------------------
+// cv.drawContours(img, contours_filtered, -1, (0, 0, 255), 2) of _find_dot (lib/ImageOperations.py:52-55), display only: on the
+// one-channel image the colour is its first component, 0.  A thickness-2 polyline through the CHAIN_APPROX_SIMPLE vertices of a
+// border (OpenCV widens every segment by one pixel to each side and rounds its ends with a radius-1 disc) covers exactly: the plus-
+// shaped neighbourhood of every border pixel and, for every diagonal step (x, y) -> (x + dx, y + dy), the pixels (x + dx, y),
+// (x, y + dy), (x + dx, y - dy), (x - dx, y + dy), (x + 2 dx, y), (x, y + 2 dy) (checked against cv2 on random images with holes and
+// nesting, tests/test_dropin.py).  One thread per kept contour of the table re-walks its border on the packed binary image.
+// ---------------------------------------------------------------------------------------------------------
+__global__ void draw_contours_kernel(const uint32_t* __restrict__ bits, const double* __restrict__ contours, const int32_t* __restrict__ contour_count,
+                                     int max_contours, int H, int W, int TX, uint8_t* __restrict__ img, int value)
+{
+    const int f = blockIdx.y, c = blockIdx.x * blockDim.x + threadIdx.x;
+    if (c >= min(contour_count[f], max_contours)) return;
+    const double* o = contours + ((size_t)f * max_contours + c) * 8;
+    if (o[6] == 0.0) return;                                   // not kept by the area / circularity filter
+    const int st = (int)o[7], hole = o[4] != 0.0;
+    BitImg im; im.p = bits + (size_t)f * H * TX; im.W = W; im.H = H; im.WPR = TX;
+    uint8_t* out = img + (size_t)f * H * W;
+    auto put = [&](int x, int y) { if ((unsigned)x < (unsigned)W && (unsigned)y < (unsigned)H) out[(size_t)y * W + x] = (uint8_t)value; };
+    auto plus = [&](int x, int y) { put(x, y); put(x - 1, y); put(x + 1, y); put(x, y - 1); put(x, y + 1); };
+    const int y0 = st / W, x0 = st - y0 * W;
+    Walk w; walk_init(im, w, x0, y0, hole ? 0 : 4);           // outer borders start on a west edge, hole borders on an east edge
+    plus(x0, y0);
+    if (w.single) return;
+    for (int step = 0; step < WALK_BUDGET; ++step) {
+        const int cx = w.x, cy = w.y;
+        unsigned zeros; bool done;
+        const int d = walk_step(im, w, zeros, done);
+        plus(cx, cy);
+        if (d & 1) {
+            const int dx = dir_dx(d), dy = dir_dy(d);
+            put(cx + dx, cy); put(cx, cy + dy); put(cx + dx, cy - dy); put(cx - dx, cy + dy); put(cx + 2 * dx, cy); put(cx, cy + 2 * dy);
+        }
+        if (done) break;
+    }
+}
+
+extern "C" int mocap_draw_contours_batch(const uint32_t* bits_dev, const double* contours_dev, const int32_t* contour_count_dev,
+                                         int n_frames, int H, int W, int max_contours, uint8_t* img_dev, int value, void* stream)
+{
+    if (!bits_dev || !contours_dev || !contour_count_dev || !img_dev || n_frames <= 0 || n_frames > 65535 || H <= 0 || W <= 0 || max_contours <= 0)
+        return MOCAP_ERR_INVALID;
+    LAUNCH(draw_contours_kernel, dim3(cdiv(max_contours, 64), n_frames), 64, 0, (cudaStream_t)stream, bits_dev, contours_dev, contour_count_dev,
+           max_contours, H, W, cdiv(W, TILE), img_dev, value);
+    CUDA_TRY(cudaGetLastError());
+    return MOCAP_OK;
+}

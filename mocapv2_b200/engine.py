@@ -375,6 +375,20 @@ class CaptureEngine:
         self.launches += 4
         return bits
 
+    def draw_contours(self, img: torch.Tensor, res: DetectResult, value=0) -> torch.Tensor:
+        """cv.drawContours(img, kept contours, -1, colour, 2) of _find_dot (lib/ImageOperations.py:52-55), in place on img [n, H, W]
+        uint8; res must carry the "bits" and "contours" outputs of detect()."""
+        img = self._check_dev(img, torch.uint8, "img")
+        n, H, W = img.shape
+        ex = res.extras
+        if "bits" not in ex or "contours" not in ex:
+            raise ValueError('draw_contours needs detect(..., outputs=("bits", "contours"))')
+        st = self.lib.mocap_draw_contours_batch(self._ptr(ex["bits"]), self._ptr(ex["contours"]), self._ptr(ex["contour_count"]), n, H, W,
+                                                int(ex["contours"].shape[1]), self._ptr(img), int(value), self._stream())
+        _cabi.check(self.lib, st, "mocap_draw_contours_batch")
+        self.launches += 1
+        return img
+
     def blur5(self, frames: torch.Tensor) -> torch.Tensor:
         """fast_cuda_blur(image, 5) (lib/CudaOperations.py:24-41) for a batch [n, H, W] uint8."""
         frames = self._check_dev(frames.contiguous(), torch.uint8, "frames")

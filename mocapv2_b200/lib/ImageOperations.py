@@ -97,16 +97,24 @@ def _find_dot(img, print_location=False, return_filtered=False):
     with eng.thread_stream():
         fr = _to_device(img, eng)
         H, W = fr.shape[1:]
-        # everything of the call is queued before the first host read: H2D, the undistorted image and its way back, detection
-        fetch = None if return_filtered else eng.download_image_async(eng.undistort(fr, K, dist)[0])
-        res = _detect_one(eng, fr, K, dist, ("bits",) if return_filtered else ())
+        if not ANNOTATE and not return_filtered:
+            # everything of the call is queued before the first host read: H2D, the undistorted image and its way back, detection
+            fetch = eng.download_image_async(eng.undistort(fr, K, dist)[0])
+            res = _detect_one(eng, fr, K, dist, ())
+        else:
+            # with the reference's overlays: the contour outline needs the binary image and the contour table of the same call
+            res = _detect_one(eng, fr, K, dist, ("bits", "contours"))
+            if return_filtered:                               # the reference then draws on (and returns) the filtered image (:53)
+                b = res.extras["bits"][0].cpu().numpy().view(np.uint8)
+                canvas = eng.upload_image((np.unpackbits(b, axis=1, bitorder="little")[:, :W] * 255).astype(np.uint8))
+            else:
+                canvas = eng.undistort(fr, K, dist)
+            if ANNOTATE:
+                eng.draw_contours(canvas, res)                # cv.drawContours(..., (0, 0, 255), 2): 0 on a one-channel image
+            fetch = eng.download_image_async(canvas[0])
         n = int(res.count[0])
         image_points = res.xy[0, :n].tolist() if n else []
-        if return_filtered:
-            b = res.extras["bits"][0].cpu().numpy().view(np.uint8)
-            out = (np.unpackbits(b, axis=1, bitorder="little")[:, :W] * 255).astype(np.uint8)
-        else:
-            out = fetch()
+        out = fetch()
     if ANNOTATE and image_points:
         try:                                                  # display-only overlays (lib/ImageOperations.py:67-73)
             import cv2 as cv
