@@ -53,6 +53,8 @@ extern "C" {
 
 const char* mocap_status_string(int status);
 int mocap_abi_version(void);
+/* kernels launched by this library in this process so far (every launch is counted where it is issued) */
+unsigned long long mocap_kernel_launch_count(void);
 
 /* ---- undistortion table: cv.undistort(img, K0, dist0) of _find_dot (lib/ImageOperations.py:37-38) -------
  * Built once per (K, dist, H, W).  Holds the 1/32-px fixed-point displacement map of
@@ -125,6 +127,11 @@ int mocap_detect_batch_pipelined(void* pipe, const uint8_t* frames_dev, int n_fr
                                  int32_t* out_xy, int32_t* out_count, int32_t* out_flags,
                                  double* out_contours, int32_t* out_contour_count,
                                  void* workspace, size_t workspace_bytes, void* stream, const MocapPipeOpts* opts);
+/* Store-to-peer epilogue (multi-GPU): with per-frame destination addresses set (device arrays [n_frames] of pointers, valid for the
+ * following calls of this pipe; NULL, NULL switches it off) every frame's record is ALSO copied -- chunk by chunk, behind the chunk's
+ * border stage -- to xy_dst[f] (its centroids, int32 pairs) and count_dst[f] (its count): addresses in the receive buffer of the rank that
+ * matches the frame's frame-set, mapped into this process (symmetric memory over NVLink).  The exchange step is then a barrier. */
+int mocap_detect_pipe_set_scatter(void* pipe, const uint64_t* xy_dst_dev, const uint64_t* count_dst_dev);
 /* ms since the fork of the last call with record_timeline: [scan done, join] then per chunk [scan seen, grouped, filtered,
  * borders done]; returns the number of floats written, 0 without a timeline */
 int mocap_detect_pipe_timeline(void* pipe, float* ms_out, int cap);

@@ -12,7 +12,7 @@ import os
 HERE = os.path.dirname(os.path.abspath(__file__))
 DEFAULT_LIB = os.path.join(HERE, "libmocap_b200.so")
 
-ABI_VERSION = 1
+ABI_VERSION = 2
 MAX_CAND = 8
 MAX_CAMS = 16
 CAM_STRIDE = 40
@@ -34,6 +34,7 @@ _d = C.c_double
 SIGNATURES = {
     "mocap_status_string": (C.c_char_p, [_i]),
     "mocap_abi_version": (_i, []),
+    "mocap_kernel_launch_count": (C.c_uint64, []),
     "mocap_undistort_table_bytes": (_sz, [_i, _i]),
     "mocap_undistort_table_build": (_i, [_p, _p, _i, _i, _p, _sz, _p]),
     "mocap_detect_workspace_bytes": (_sz, [_i, _i, _i, _i, _i, _i]),
@@ -48,6 +49,7 @@ SIGNATURES = {
     "mocap_detect_pipelined_workspace_bytes": (_sz, [_i, _i, _i, _i, _i, _i, _i]),
     "mocap_detect_batch_pipelined": (_i, [_p, _p, _i, _i, _i, _i64, _p, _i, _d, _d, _i, _i, _i,
                                           _p, _p, _p, _p, _p, _p, _sz, _p, _p]),
+    "mocap_detect_pipe_set_scatter": (_i, [_p, _p, _p]),
     "mocap_detect_pipe_timeline": (_i, [_p, _p, _i]),
     "mocap_detect_pipe_info": (_i, [_p, _p]),
     "mocap_scan_cells_batch": (_i, [_p, _i, _i, _i, _i64, _p, _i, _i, _p, _p, _sz, _p]),

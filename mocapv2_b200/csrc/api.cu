@@ -49,6 +49,9 @@ extern "C" const char* mocap_status_string(int status)
 
 extern "C" int mocap_abi_version(void) { return MOCAP_ABI_VERSION; }
 
+unsigned long long g_mocap_launches = 0;
+extern "C" unsigned long long mocap_kernel_launch_count(void) { return __atomic_load_n(&g_mocap_launches, __ATOMIC_RELAXED); }
+
 extern "C" const char* mocap_stage_name(int stage)
 {
     static const char* names[MOCAP_N_STAGES] = {"scan", "group", "filter", "borders", "finish"};
@@ -254,7 +257,36 @@ extern "C" int mocap_blobs_batch(const uint32_t* bits_dev, int n_frames, int H, 
 #define PIPE_MAX_CHUNKS 64
 #define PIPE_TL_PER_CHUNK 4          // timeline marks per chunk: scan seen, grouped, filtered, borders done
 
+// Store-to-peer epilogue of the multi-GPU pipeline: every frame's record (count + centroids) is copied to the address its consumer
+// reads it from -- for the frame-sets of another rank that is a slot of THAT rank's receive buffer, mapped into this process
+// (symmetric memory over NVLink), so the exchange step needs no collective, only a barrier.  One warp per frame.  phase 0 (after a
+// chunk's border stage): frames the cluster path finished; phase 1 (after the general path): the frames it handed over.
+__global__ void scatter_records_kernel(const int32_t* __restrict__ xy, const int32_t* __restrict__ count, const unsigned long long* __restrict__ xy_dst,
+                                       const unsigned long long* __restrict__ count_dst, int n, int max_blobs, const int* __restrict__ need_general, int phase)
+{
+    const int lane = threadIdx.x & 31;
+    const int f = (int)((blockIdx.x * blockDim.x + threadIdx.x) >> 5);
+    if (f >= n) return;
+    if ((need_general[f] != 0) != (phase != 0)) return;
+    int c = count[f];
+    c = c < 0 ? 0 : (c > max_blobs ? max_blobs : c);
+    const uint2* src = (const uint2*)(xy + (size_t)f * max_blobs * 2);
+    uint2* dst = (uint2*)xy_dst[f];
+    for (int k = lane; k < c; k += 32) dst[k] = src[k];
+    if (lane == 0) *(int32_t*)count_dst[f] = count[f];
+}
+
+static int launch_scatter(const int32_t* xy, const int32_t* count, const unsigned long long* xy_dst, const unsigned long long* count_dst,
+                          int n, int max_blobs, const int* need_general, int phase, cudaStream_t s)
+{
+    LAUNCH(scatter_records_kernel, cdiv(n * 32, 128), 128, 0, s, xy, count, xy_dst, count_dst, n, max_blobs, need_general, phase);
+    CUDA_TRY(cudaGetLastError());
+    return MOCAP_OK;
+}
+
 struct DetectPipe {
+    const unsigned long long* sc_xy = nullptr;      // per-frame destinations of the store-to-peer epilogue (device arrays [n]), or null
+    const unsigned long long* sc_count = nullptr;
 #ifndef MOCAP_EMU
     cudaStream_t s_scan = nullptr, s_proc[PIPE_MAX_PROC] = {};
     cudaEvent_t ev_fork = nullptr, ev_scan_done = nullptr, ev_proc_done[PIPE_MAX_PROC] = {}, ev_join = nullptr;
@@ -297,6 +329,15 @@ extern "C" void* mocap_detect_pipe_create(int n_proc_streams, int prio_mode)
     if (!ok) { delete p; return nullptr; }
 #endif
     return p;
+}
+
+extern "C" int mocap_detect_pipe_set_scatter(void* pipe, const uint64_t* xy_dst_dev, const uint64_t* count_dst_dev)
+{
+    DetectPipe* p = (DetectPipe*)pipe;
+    if (!p || ((xy_dst_dev == nullptr) != (count_dst_dev == nullptr))) return MOCAP_ERR_INVALID;
+    p->sc_xy = (const unsigned long long*)xy_dst_dev;
+    p->sc_count = (const unsigned long long*)count_dst_dev;
+    return MOCAP_OK;
 }
 
 extern "C" void mocap_detect_pipe_destroy(void* pipe)
@@ -400,6 +441,10 @@ extern "C" int mocap_detect_batch_pipelined(void* pipe, const uint8_t* frames_de
                                  out_contours ? out_contours + (size_t)f0 * max_contours * 8 : nullptr, out_contour_count ? out_contour_count + f0 : nullptr,
                                  s, nullptr, how);
         if (st != MOCAP_OK) return st;
+        if (dp->sc_xy) {
+            st = launch_scatter(out_xy + (size_t)f0 * max_blobs * 2, out_count + f0, dp->sc_xy + f0, dp->sc_count + f0, nc, max_blobs, need_general + f0, 0, s);
+            if (st != MOCAP_OK) return st;
+        }
     }
 #else
     const bool tl = opts->record_timeline != 0;
@@ -429,11 +474,16 @@ extern "C" int mocap_detect_batch_pipelined(void* pipe, const uint8_t* frames_de
         hc.ev_group = dp->ev_tl[c][1]; hc.ev_filter = dp->ev_tl[c][2]; hc.ev_borders = dp->ev_tl[c][3];
         if (plan == 1) { hc.s_filter = dp->s_proc[1]; hc.s_borders = dp->s_proc[2 + c % (dp->n_proc - 2)]; }
         if (plan == 2 || plan == 3) { hc.s_filter = dp->s_proc[0]; hc.s_borders = dp->s_proc[1 + c % (dp->n_proc - 1)]; }
-        return launch_cluster_path(frames_dev + (size_t)f0 * frame_stride, nc, H, W, frame_stride, tv, thresh, cb, cws, P.cl_offs, need_general + f0,
-                                   max_contours, max_blobs, min_area, min_circ,
-                                   out_xy + (size_t)f0 * max_blobs * 2, out_count + f0, out_flags + f0,
-                                   out_contours ? out_contours + (size_t)f0 * max_contours * 8 : nullptr, out_contour_count ? out_contour_count + f0 : nullptr,
-                                   ps, nullptr, hc);
+        int rc = launch_cluster_path(frames_dev + (size_t)f0 * frame_stride, nc, H, W, frame_stride, tv, thresh, cb, cws, P.cl_offs, need_general + f0,
+                                     max_contours, max_blobs, min_area, min_circ,
+                                     out_xy + (size_t)f0 * max_blobs * 2, out_count + f0, out_flags + f0,
+                                     out_contours ? out_contours + (size_t)f0 * max_contours * 8 : nullptr, out_contour_count ? out_contour_count + f0 : nullptr,
+                                     ps, nullptr, hc);
+        if (rc == MOCAP_OK && (stages & 4) && dp->sc_xy) {      // the chunk's records go where their consumers read them, off the critical path
+            cudaStream_t sb = hc.s_borders ? hc.s_borders : (hc.s_filter ? hc.s_filter : ps);
+            rc = launch_scatter(out_xy + (size_t)f0 * max_blobs * 2, out_count + f0, dp->sc_xy + f0, dp->sc_count + f0, nc, max_blobs, need_general + f0, 0, sb);
+        }
+        return rc;
     };
     for (int c = 0; c < chunks; ++c) {
         const int f0 = c * cf, nc = (n_frames - f0) < cf ? (n_frames - f0) : cf;
@@ -477,9 +527,11 @@ extern "C" int mocap_detect_batch_pipelined(void* pipe, const uint8_t* frames_de
     // general path for the frames the cluster units could not finish (rare), whole batch
     st = launch_tiles(frames_dev, n_frames, H, W, frame_stride, tv, thresh, ws, P.L.max_fg, out_flags, need_general, s);
     if (st != MOCAP_OK) return st;
-    return launch_blobs(ws.bits, ws.fg_tiles, ws.n_fg, n_frames, H, W, P.L.TX, P.L.max_fg, max_runs, max_blobs, max_contours,
-                        min_area, min_circ, base + P.L.off_blob, P.L.blob_stride,
-                        out_xy, out_count, out_flags, nullptr, nullptr, out_contours, out_contour_count, nullptr, need_general, s);
+    st = launch_blobs(ws.bits, ws.fg_tiles, ws.n_fg, n_frames, H, W, P.L.TX, P.L.max_fg, max_runs, max_blobs, max_contours,
+                      min_area, min_circ, base + P.L.off_blob, P.L.blob_stride,
+                      out_xy, out_count, out_flags, nullptr, nullptr, out_contours, out_contour_count, nullptr, need_general, s);
+    if (st == MOCAP_OK && dp->sc_xy) st = launch_scatter(out_xy, out_count, dp->sc_xy, dp->sc_count, n_frames, max_blobs, need_general, 1, s);
+    return st;
 }
 
 // Timeline of the last mocap_detect_batch_pipelined call that had record_timeline set (read it after the stream has been

@@ -4,17 +4,21 @@
 // tests/emu builds this same source with g++ for the GPU-less CPU test-suite (never part of the product library)
 #include "cuda_emu.h"
 #define LAUNCH(kernel, grid, block, smem, stream, ...) \
-    emu::launch(dim3(grid), dim3(block), (size_t)(smem), [=]() { kernel(__VA_ARGS__); })
+    (mocap_count_launch(), emu::launch(dim3(grid), dim3(block), (size_t)(smem), [=]() { kernel(__VA_ARGS__); }))
 #define DYN_SHARED(name) unsigned char* name = emu::dyn_smem()
 #else
 #include <cuda_runtime.h>
-#define LAUNCH(kernel, grid, block, smem, stream, ...) kernel<<<grid, block, smem, stream>>>(__VA_ARGS__)
+#define LAUNCH(kernel, grid, block, smem, stream, ...) (mocap_count_launch(), kernel<<<grid, block, smem, stream>>>(__VA_ARGS__))
 #define DYN_SHARED(name) extern __shared__ __align__(16) unsigned char name[]
 #endif
 #include <stdint.h>
 #include "../../include/mocap_b200.h"
 
-#define MOCAP_ABI_VERSION 1
+#define MOCAP_ABI_VERSION 2
+
+// every kernel launch of the library is counted (mocap_kernel_launch_count: the bench's gpu_launches is read, not estimated)
+extern unsigned long long g_mocap_launches;
+static inline void mocap_count_launch() { __atomic_fetch_add(&g_mocap_launches, 1ull, __ATOMIC_RELAXED); }
 
 #define TILE 32              // output tile edge (pixels) == bits per packed word
 #define HALO_U 4             // undistorted pixels needed around an output tile (2 blur + 2 majority)

@@ -253,6 +253,7 @@ int launch_scan_tma(const uint8_t* frames, int n, int H, int W, int64_t fstride,
         CUDA_TRY(cudaFuncSetAttribute(scan_tma_kernel<1, ST_STAGES_MAX>, cudaFuncAttributeMaxDynamicSharedMemorySize, big));
         attr_done = true;
     }
+    mocap_count_launch();
     if (S == 3) {
         if (ht.mode == 0) scan_tma_kernel<0, 3><<<sms, ST_THREADS, smem, s>>>(map, a);
         else scan_tma_kernel<1, 3><<<sms, ST_THREADS, smem, s>>>(map, a);

@@ -90,12 +90,18 @@ class CaptureEngine:
         # need no lock -- the C-ABI keeps no state.  The lock only guards the shared table cache.
         self._tls = threading.local()
         self._lock = threading.RLock()
-        self.launches = 0                       # kernels launched through this engine (bench bookkeeping)
+        self._launch_base = int(self.lib.mocap_kernel_launch_count())
         self.pipe_workers = 3                   # worker streams of the overlapped detection
         self.pipe_prio_mode = 0
         self.last_pipe_info = None
 
     # ---- plumbing ------------------------------------------------------------------------------------------------
+    @property
+    def launches(self) -> int:
+        """Kernels the library has launched since this engine was created (counted inside the library at every launch; all
+        engines of a process share the counter)."""
+        return int(self.lib.mocap_kernel_launch_count()) - self._launch_base
+
     def _stream(self):
         return ctypes.c_void_p(torch.cuda.current_stream(self.device).cuda_stream)
 
@@ -191,7 +197,6 @@ class CaptureEngine:
                 with self._device_ctx():
                     st = self.lib.mocap_undistort_table_build(K.ctypes.data, d.ctypes.data, H, W, self._ptr(tab), nbytes, self._stream())
                 _cabi.check(self.lib, st, "mocap_undistort_table_build")
-                self.launches += 3
                 self._tables[key] = tab
         return tab
 
@@ -246,7 +251,6 @@ class CaptureEngine:
             self._ptr(ws), nbytes, self._stream(), ctypes.c_void_p(timer) if timer else ctypes.c_void_p(0))
         _cabi.check(self.lib, st, "mocap_detect_batch")
         # scan, group, filter pieces, candidates, traces+finalize + the general path's mark / compact / tiles / blobs
-        self.launches += 9 + (1 if "bits" in ex else 0)
         return out
 
     # ---- overlapped detection (chunks: TMA scan of chunk k+1 beside the filter / border stages of chunk k) ----------------------
@@ -304,9 +308,18 @@ class CaptureEngine:
         self.lib.mocap_detect_pipe_info(self._pipe(), info)
         chunks = int(info[1])
         scans = 1 if int(info[2]) == 1 else chunks
-        self.launches += scans + 4 * chunks + 4          # scan(s) + per chunk group/filter/candidates/borders + general path
         self.last_pipe_info = {"tma_scan": bool(info[0]), "chunks": chunks, "sync_mode": int(info[2])}
         return out
+
+    def set_detect_scatter(self, xy_dst: torch.Tensor | None, count_dst: torch.Tensor | None):
+        """Per-frame destination addresses (int64 device tensors [n]) of the store-to-peer epilogue of detect_pipelined, for the
+        calling thread's pipe; None, None switches it off (include/mocap_b200.h, mocap_detect_pipe_set_scatter)."""
+        if xy_dst is not None:
+            xy_dst = self._check_dev(xy_dst, torch.int64, "xy_dst")
+            count_dst = self._check_dev(count_dst, torch.int64, "count_dst")
+        self._tls.scatter = (xy_dst, count_dst)                  # keeps the tables alive
+        _cabi.check(self.lib, self.lib.mocap_detect_pipe_set_scatter(self._pipe(), self._ptr(xy_dst), self._ptr(count_dst)),
+                    "mocap_detect_pipe_set_scatter")
 
     def pipe_timeline(self):
         """ms since the fork of the last detect_pipelined(timeline=True): {"scan_done", "join", "chunks": [[seen, grouped, filtered, borders], ...]}"""
@@ -327,7 +340,6 @@ class CaptureEngine:
         st = self.lib.mocap_scan_cells_batch(self._ptr(frames), n, H, W, H * W, self._ptr(tab), int(thresh), int(variant),
                                              self._ptr(out), self._ptr(ws), 4096, self._stream())
         _cabi.check(self.lib, st, "mocap_scan_cells_batch")
-        self.launches += 1
         return out
 
     def blobs(self, bits: torch.Tensor, W: int, *, min_area=MIN_AREA, min_circ=MIN_CIRC, max_blobs=None, max_contours=None,
@@ -358,7 +370,6 @@ class CaptureEngine:
             self._ptr(ex.get("blob_sums")), self._ptr(ex.get("blob_count")), self._ptr(ex.get("contours")),
             self._ptr(ex.get("contour_count")), self._ptr(ws), nbytes, self._stream())
         _cabi.check(self.lib, st, "mocap_blobs_batch")
-        self.launches += 2
         return out
 
     def filter(self, frames: torch.Tensor, K, dist, *, thresh=THRESH_U8) -> torch.Tensor:
@@ -372,7 +383,6 @@ class CaptureEngine:
         st = self.lib.mocap_filter_batch(self._ptr(frames), n, H, W, H * W, self._ptr(tab), int(thresh), self._ptr(bits),
                                          self._ptr(ws), nbytes, self._stream())
         _cabi.check(self.lib, st, "mocap_filter_batch")
-        self.launches += 4
         return bits
 
     def draw_contours(self, img: torch.Tensor, res: DetectResult, value=0) -> torch.Tensor:
@@ -386,7 +396,6 @@ class CaptureEngine:
         st = self.lib.mocap_draw_contours_batch(self._ptr(ex["bits"]), self._ptr(ex["contours"]), self._ptr(ex["contour_count"]), n, H, W,
                                                 int(ex["contours"].shape[1]), self._ptr(img), int(value), self._stream())
         _cabi.check(self.lib, st, "mocap_draw_contours_batch")
-        self.launches += 1
         return img
 
     def blur5(self, frames: torch.Tensor) -> torch.Tensor:
@@ -395,7 +404,6 @@ class CaptureEngine:
         n, H, W = frames.shape
         out = torch.empty_like(frames)
         _cabi.check(self.lib, self.lib.mocap_blur5_batch(self._ptr(frames), n, H, W, self._ptr(out), self._stream()), "mocap_blur5_batch")
-        self.launches += 1
         return out
 
     def median5_threshold(self, frames: torch.Tensor, thresh=THRESH_U8) -> torch.Tensor:
@@ -405,7 +413,6 @@ class CaptureEngine:
         out = torch.empty_like(frames)
         _cabi.check(self.lib, self.lib.mocap_median5_threshold_batch(self._ptr(frames), n, H, W, int(thresh), self._ptr(out), self._stream()),
                     "mocap_median5_threshold_batch")
-        self.launches += 1
         return out
 
     def bayer_gr2gray(self, raw: torch.Tensor, out: torch.Tensor | None = None) -> torch.Tensor:
@@ -420,7 +427,6 @@ class CaptureEngine:
             self._check_dev(out, torch.uint8, "out")
         _cabi.check(self.lib, self.lib.mocap_bayer_gr2gray_batch(self._ptr(raw), n, H, W, self._ptr(out), self._stream()),
                     "mocap_bayer_gr2gray_batch")
-        self.launches += 2                      # interior rows + the two copied border rows
         return out
 
     def undistort(self, frames: torch.Tensor, K, dist) -> torch.Tensor:
@@ -431,7 +437,6 @@ class CaptureEngine:
         out = torch.empty_like(frames)
         _cabi.check(self.lib, self.lib.mocap_undistort_batch(self._ptr(frames), n, H, W, self._ptr(tab), self._ptr(out), self._stream()),
                     "mocap_undistort_batch")
-        self.launches += 1
         return out
 
     # ---- per-stage timing (bench) ---------------------------------------------------------------------------------------------
@@ -471,7 +476,6 @@ class CaptureEngine:
         st = self.lib.mocap_triangulate_batch(self._ptr(pts), self._ptr(valid), self._ptr(cams), C, P,
                                               1 if pts.dtype == torch.float64 else 0, self._ptr(xyz), self._ptr(err), self._stream())
         _cabi.check(self.lib, st, "mocap_triangulate_batch")
-        self.launches += 1 if P else 0
         return xyz, err
 
     def ba_residuals(self, pts: torch.Tensor, cams_sets: torch.Tensor) -> torch.Tensor:
@@ -486,7 +490,6 @@ class CaptureEngine:
             return err
         st = self.lib.mocap_ba_residuals_batch(self._ptr(pts), self._ptr(cams_sets), S, C, P, self._ptr(err), self._stream())
         _cabi.check(self.lib, st, "mocap_ba_residuals_batch")
-        self.launches += 1
         return err
 
     def reproject(self, pts: torch.Tensor, xyz: torch.Tensor, cams: torch.Tensor, valid: torch.Tensor | None = None):
@@ -503,7 +506,6 @@ class CaptureEngine:
         st = self.lib.mocap_reproject_batch(self._ptr(pts), self._ptr(valid), self._ptr(xyz), self._ptr(cams), C, P,
                                             1 if pts.dtype == torch.float64 else 0, self._ptr(err), self._stream())
         _cabi.check(self.lib, st, "mocap_reproject_batch")
-        self.launches += 1 if P else 0
         return err
 
     def correspond(self, xy: torch.Tensor, count: torch.Tensor, Fs: torch.Tensor, cams: torch.Tensor, *, obj_count=0,
@@ -544,7 +546,6 @@ class CaptureEngine:
             self._ptr(res.obj), self._ptr(res.n_obj), self._ptr(res.img), self._ptr(res.n_valid), self._ptr(res.err),
             self._ptr(res.cand), self._ptr(res.flags), self._ptr(ws), nbytes, self._stream())
         _cabi.check(self.lib, st, "mocap_correspond_batch_blocked")
-        self.launches += 2
         return res
 
 

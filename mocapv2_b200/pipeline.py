@@ -8,6 +8,12 @@ as ONE grouped NCCL send/recv (ncclGroupStart/End: a single launch over NVLink; 
 receives 1/N of what an all-gather would deliver, and the receive buffer [source rank][frame-set][camera][blob] is read
 in place by the correspondence kernels (camera-blocked layout, mocap_correspond_batch_blocked): no pack, permute or copy
 kernels on the step path.  No floating-point reduction crosses ranks, so N-rank outputs are bit-identical to 1-rank.
+
+On a GPU box with peer access (NVLink / NVSwitch) the exchange needs no collective at all: the receive buffers live in
+torch symmetric memory, every rank maps its peers' buffers, and the overlapped detection call stores each frame's record
+straight into the slot of the rank that matches its frame-set, chunk by chunk behind the chunk's border stage
+(`mocap_detect_pipe_set_scatter`: store-to-peer epilogue).  The exchange step is then one symmetric-memory barrier; two
+receive buffers alternate so that a rank may already store step t + 1 while a peer still matches step t.
 """
 from __future__ import annotations
 
@@ -54,6 +60,10 @@ class CapturePipeline:
         self._det = None
         self._rx = None
         self.collectives = 0
+        # store-to-peer exchange (symmetric memory): tried once on the first overlapped detection of a multi-rank CUDA pipeline
+        self.peer_exchange = True
+        self._peer = None                       # {"bufs", "hdls", "tables", "views", "turn", "n", "per"}
+        self._scattered = False
         # overlapped detection (engine.detect_pipelined) for batches large enough to pipeline: 8 chunks on 6 worker streams
         # (tools/pipe_probe.py on the C4 batch: 1.75 ms against 2.03 ms for the one-shot call; 4 chunks / 4 workers 1.78 ms)
         self.pipelined_min_frames = 256
@@ -83,14 +93,61 @@ class CapturePipeline:
         n = FS * cl
         if pipelined is None:
             pipelined = timer is None and n >= self.pipelined_min_frames
+        self._scattered = False
         if pipelined:
             self.eng.pipe_workers = self.engine_pipe["workers"]
             chunk = -(-n // self.engine_pipe["chunks"])
-            self._det = self.eng.detect_pipelined(flat, self.K0, self.dist0, max_blobs=self.max_blobs, out=self._buffers(n),
-                                                  chunk_frames=chunk, timeline=timeline)
+            peer = self._peer_setup(FS) if (self.world > 1 and self.peer_exchange) else None
+            if peer is not None:
+                peer["turn"] ^= 1
+                self.eng.set_detect_scatter(*peer["tables"][peer["turn"]])
+            try:
+                self._det = self.eng.detect_pipelined(flat, self.K0, self.dist0, max_blobs=self.max_blobs, out=self._buffers(n),
+                                                      chunk_frames=chunk, timeline=timeline)
+            finally:
+                if peer is not None:
+                    self.eng.set_detect_scatter(None, None)
+            self._scattered = peer is not None
         else:
             self._det = self.eng.detect(flat, self.K0, self.dist0, max_blobs=self.max_blobs, out=self._buffers(n), timer=timer)
         return self._det
+
+    def _peer_setup(self, FS: int):
+        """Symmetric receive buffers + the per-frame destination tables of the store-to-peer epilogue (collective, once per shape).
+        Returns None -- and the pipeline keeps the NCCL exchange -- where symmetric memory is not available."""
+        cl, mb = self.cams_local, self.max_blobs
+        b, e = self.frame_set_shard(FS)
+        per = e - b
+        if self._peer is not None and self._peer["per"] == per:
+            return self._peer
+        if self._peer is False or self.eng.device.type != "cuda":
+            return None
+        try:
+            import torch.distributed._symmetric_memory as symm
+            group = self.group if self.group is not None else dist.group.WORLD
+            xy_elems = self.world * per * cl * mb * 2
+            cnt_elems = self.world * per * cl
+            bufs, hdls, tables, views = [], [], [], []
+            s_idx = torch.arange(FS).repeat_interleave(cl)                 # frame-set of local frame i = s * cl + c
+            c_idx = torch.arange(cl).repeat(FS)
+            dst = s_idx // per
+            slot = (self.rank * per + s_idx % per) * cl + c_idx            # [source rank][frame-set of the shard][camera]
+            for _ in range(2):
+                buf = symm.empty(xy_elems + cnt_elems, dtype=torch.int32, device=self.eng.device)
+                buf.zero_()
+                hdl = symm.rendezvous(buf, group)
+                base = torch.tensor([int(p) for p in hdl.buffer_ptrs], dtype=torch.int64)
+                xy_dst = (base[dst] + slot * (mb * 2 * 4)).to(self.eng.device)
+                cnt_dst = (base[dst] + (xy_elems + slot) * 4).to(self.eng.device)
+                bufs.append(buf); hdls.append(hdl); tables.append((xy_dst, cnt_dst))
+                views.append((buf[:xy_elems].view(self.world, per, cl, mb, 2), buf[xy_elems:].view(self.world, per, cl)))
+            self._peer = {"bufs": bufs, "hdls": hdls, "tables": tables, "views": views, "turn": 1, "per": per}
+        except Exception as ex:                                            # no peer mapping on this box: NCCL send/recv it is
+            import warnings
+            warnings.warn(f"store-to-peer exchange unavailable ({ex!r}); using the NCCL exchange")
+            self._peer = False
+            return None
+        return self._peer
 
     def exchange(self, det: DetectResult, FS: int):
         """The exchange step: returns (xy, count) of this rank's frame-set shard for ALL cameras, camera-blocked by source rank:
@@ -100,6 +157,13 @@ class CapturePipeline:
         per = e - b
         if self.world == 1:
             return det.xy.view(FS, cl, mb, 2), det.count.view(FS, cl)
+        if self._scattered and det is self._det and self._peer:
+            # the records are already where their consumers read them (store-to-peer epilogue of the detection): wait for the peers
+            peer = self._peer
+            peer["hdls"][peer["turn"]].barrier(channel=0)
+            self._scattered = False
+            self.collectives += 1
+            return peer["views"][peer["turn"]]
         if self._rx is None or self._rx[0].shape[1] != per:
             self._rx = (torch.empty((self.world, per, cl, mb, 2), dtype=torch.int32, device=self.eng.device),
                         torch.empty((self.world, per, cl), dtype=torch.int32, device=self.eng.device))

@@ -35,7 +35,7 @@ def _ring4_scene():
     return rig, np.stack(frames)                              # [FS=2, C=4, 360, 480]
 
 
-def _run(rank, world, port, out_dir, backend="gloo", scene="c1"):
+def _run(rank, world, port, out_dir, backend="gloo", scene="c1", overlapped=False):
     sys.path.insert(0, REPO)
     sys.path.insert(0, os.path.join(REPO, "tests", "emu"))
     from mocapv2_b200.engine import CaptureEngine
@@ -59,7 +59,14 @@ def _run(rank, world, port, out_dir, backend="gloo", scene="c1"):
     pipe = CapturePipeline(eng, rig, max_blobs=8, obj_count=4, max_groups=16, fp64=False)
     frames = torch.from_numpy(fr)
     local = frames[:, pipe.cam_begin:pipe.cam_begin + pipe.cams_local].contiguous().to(eng.device)
-    res = pipe.step(local)
+    if overlapped:                                            # the batch path of the bench: overlapped detection + store-to-peer exchange
+        pipe.pipelined_min_frames = 1
+        for _ in range(3):                                    # three steps: the two receive buffers alternate
+            res = pipe.step(local)
+        assert world == 1 or pipe._peer, "the store-to-peer exchange was not set up"
+        pipe.collectives = min(pipe.collectives, 1)
+    else:
+        res = pipe.step(local)
     cpu = lambda t: t.cpu()
     torch.save({"b": res.fs_begin, "e": res.fs_end, "obj": cpu(res.corr.obj), "n_obj": cpu(res.corr.n_obj), "img": cpu(res.corr.img),
                 "n_valid": cpu(res.corr.n_valid), "err": cpu(res.corr.err), "count": cpu(res.det.count), "collectives": pipe.collectives},
@@ -119,4 +126,17 @@ def test_two_gpus_over_nccl_equal_one_gpu(tmp_path):
     port = 31500 + os.getpid() % 2000
     mp.spawn(_run, args=(1, port, out, "nccl", "ring4"), nprocs=1, join=True)
     mp.spawn(_run, args=(2, port, out, "nccl", "ring4"), nprocs=2, join=True)
+    _compare(out, cams_per_rank=2)
+
+
+@pytest.mark.gpu
+def test_two_gpus_store_to_peer_equal_one_gpu(tmp_path):
+    """The same through the overlapped detection call with its store-to-peer epilogue (records written straight into the matching
+    rank's receive buffer over NVLink, symmetric-memory barrier instead of a collective), three steps in a row."""
+    if torch.cuda.device_count() < 2:
+        pytest.skip("needs two GPUs")
+    out = str(tmp_path)
+    port = 32500 + os.getpid() % 2000
+    mp.spawn(_run, args=(1, port, out, "nccl", "ring4", True), nprocs=1, join=True)
+    mp.spawn(_run, args=(2, port, out, "nccl", "ring4", True), nprocs=2, join=True)
     _compare(out, cams_per_rank=2)
