@@ -48,16 +48,24 @@ struct TableHeader {
     uint64_t off_cell;       // int32 [TY][TX][4]: output-tile rectangle (tx0,ty0,tx1,ty1) that samples this source cell
     uint64_t off_tile;       // int32 [TY][TX][8]: source box sx0,sy0,sx1,sy1 and displacement bounds dxmin,dxmax,dymin,dymax
     uint64_t off_cellinv;    // int32 [TY][TX][4]: bounds dxmin,dxmax,dymin,dymax of (source - output) over every output pixel that can sample the cell
+    uint64_t off_fast;       // int32 [H][W] (+ 16 bytes): the map in the form the piece filter consumes: fx | fy << 8 | tap offset << 16, where
+                             // tap offset = (dv >> 5) * WIN_W + (du >> 5) is where the pixel's first tap lies in a staged source window relative to the
+                             // pixel's own place in it; FAST_INVALID where the pixel maps outside or the offset does not fit 16 bits
+    uint64_t off_tflag;      // int32 [TY][TX]: != 0 when an output pixel of the tile has no valid fast-map entry
     uint64_t total_bytes;
 };
 #define TABLE_MAGIC 0x4d43424bu
 #define MAP_OUTSIDE 0x80008000u
+#define WIN_W 96             // row stride of the staged source window of a filter piece (detect_cluster.cu); the fast map is built for it
+#define FAST_INVALID 0x80000000u
 
 struct TableView {
     const int32_t* map;
     const int32_t* cell;
     const int32_t* tile;
     const int32_t* cellinv;
+    const int32_t* fast;
+    const int32_t* tflag;
     int H, W, TX, TY;
 };
 

@@ -15,14 +15,24 @@
 #include "common.cuh"
 #include "remap.cuh"
 #include "walk.cuh"
+#include "tma.cuh"
 
 #define CL_THREADS 128
+#ifndef PF_BATCH
+#define PF_BATCH 0              // fast remap: quads per thread whose map words are requested up front (0: none)
+#endif
+#ifndef PF_PREFETCH_LOOP
+#define PF_PREFETCH_LOOP 0      // fast remap: the map words of a thread's next quad are loaded while the current quad is computed
+#endif
+#ifndef PF_PREFETCH_PIECE
+#define PF_PREFETCH_PIECE 0     // ... and those of its first quad of the next piece during the stages of the current piece
+#endif
 #define HOT_MAX 1024            // hot cells per frame on the cluster path
 #define CELLS_MAX 8192          // TX*TY limit of the dense cell -> slot map held in shared memory
 #define ROOTS_MAX 512
 #define PIECE 64                // a cluster box is filtered in pieces of at most PIECE x PIECE output pixels
-#define WIN_W 96                // staged source window of a piece: up to 96 x 79 bytes (sized so that 8 CTAs fit one SM)
-#define WIN_H 79
+                                // staged source window of a piece: up to WIN_W (96, common.cuh) x 78 bytes (sized so that 8 CTAs fit one SM)
+#define WIN_H 78
 #define CAND_PER_FRAME 512      // border-start candidates per frame on the cluster path
 
 // counters[] slots
@@ -88,7 +98,7 @@ __device__ __forceinline__ bool boxes_touch(const int* a, const int* b)
 
 // Descriptor of one filter piece (<= 64x64 output pixels of a cluster box), everything piece_filter_kernel needs in 32 bytes:
 //   [0] frame            [1] px0 | py0 << 16 (piece origin)
-//   [2] mw | mh << 8 | hl << 16 | hr << 18 | ht << 20 | hb << 22 | packed << 24 | window fits << 25
+//   [2] mw | mh << 8 | hl << 16 | hr << 18 | ht << 20 | hb << 22 | packed << 24 | window fits << 25 | fast map usable << 26
 //   [3] word offset of the piece's first bit-row word      [4] words per row | window rows << 16 | 16-byte vectors per row << 24
 //   [5] window origin x (s16) | y << 16
 // hl, hr, ht, hb (0 or 2): how far the thresholded-mean box extends beyond the piece; it stops at the cluster box.
@@ -104,21 +114,33 @@ __device__ __forceinline__ void make_piece_desc(const TableView& tv, int f, int 
     const int hl = px0 - max(px0 - 2, cx0), hr = min(px1 + 2, cx1) - px1, ht = py0 - max(py0 - 2, cy0), hb = min(py1 + 2, cy1) - py1;
     const bool packed = px0 - hl >= 2 && py0 - ht >= 2 && px1 + hr + 2 < W && py1 + hb + 2 < H;
     const int ux0 = packed ? px0 - hl - 2 : px0 - 4, uy0 = packed ? py0 - ht - 2 : py0 - 4;
-    const int ux1 = packed ? px1 + hr + 2 : px1 + 4, uy1 = packed ? py1 + hb + 2 : py1 + 4;
-    const int tx0 = max(ux0 >> 5, 0), tx1 = min(ux1 >> 5, tv.TX - 1), ty0 = max(uy0 >> 5, 0), ty1 = min(uy1 >> 5, tv.TY - 1);
-    int dx0 = 0x7fffffff, dx1 = -0x7fffffff, dy0 = 0x7fffffff, dy1 = -0x7fffffff;
+    int ux1 = packed ? px1 + hr + 2 : px1 + 4;
+    const int uy1 = packed ? py1 + hb + 2 : py1 + 4;
+    // the fast remap of the piece filter works on quads of four pixels: its box is padded to a multiple of four columns, and the window
+    // and the fast-map test below cover the padding (pixels right of the box: computed, never used)
+    const int ux0p = ux0 & ~3, ux1p = ((ux1 + 4) & ~3) - 1;                // quads are aligned to frame columns that are multiples of 4
+    const bool padded = packed && ux1p < W;
+    const int ux0w = padded ? ux0p : ux0;                                  // the box the window and the fast-map test have to cover
+    if (padded) ux1 = ux1p;
+    const int tx0 = max(ux0w >> 5, 0), tx1 = min(ux1 >> 5, tv.TX - 1), ty0 = max(uy0 >> 5, 0), ty1 = min(uy1 >> 5, tv.TY - 1);
+    int dx0 = 0x7fffffff, dx1 = -0x7fffffff, dy0 = 0x7fffffff, dy1 = -0x7fffffff, no_fast = 0;
     for (int ty = ty0; ty <= ty1; ++ty) {                                  // the U box (<= 72 wide) spans at most 4 tiles per row:
-        int4 t[4];                                                         // four loads in flight, surplus ones repeat the last tile
+        int4 t[4]; int tf[4];                                              // four loads in flight, surplus ones repeat the last tile
 #pragma unroll
-        for (int q = 0; q < 4; ++q) t[q] = *(const int4*)(tv.tile + 8 * (ty * tv.TX + min(tx0 + q, tx1)) + 4);
+        for (int q = 0; q < 4; ++q) {
+            t[q] = *(const int4*)(tv.tile + 8 * (ty * tv.TX + min(tx0 + q, tx1)) + 4);
+            tf[q] = tv.tflag[ty * tv.TX + min(tx0 + q, tx1)];
+        }
 #pragma unroll
-        for (int q = 0; q < 4; ++q)
+        for (int q = 0; q < 4; ++q) {
             if (t[q].x <= t[q].y) { dx0 = min(dx0, t[q].x); dx1 = max(dx1, t[q].y); dy0 = min(dy0, t[q].z); dy1 = max(dy1, t[q].w); }
+            no_fast |= tf[q];
+        }
     }
     int wx0 = 0, wy0 = 0, wh = 0, nvec = 0;
     bool fits = false;
     if (dx0 <= dx1 && tx1 - tx0 <= 3) {
-        wx0 = (ux0 + dx0) & ~15; wy0 = uy0 + dy0;
+        wx0 = (ux0w + dx0) & ~15; wy0 = uy0 + dy0;
         const int wx1 = ux1 + dx1 + 1, wy1 = uy1 + dy1 + 1;
         fits = wx1 - wx0 + 1 <= WIN_W && wy1 - wy0 + 1 <= WIN_H && wx0 >= -32768 && wy0 >= -32768;
         if (fits) { wh = wy1 - wy0 + 1; nvec = (wx1 - wx0 + 16) >> 4; }
@@ -127,7 +149,8 @@ __device__ __forceinline__ void make_piece_desc(const TableView& tv, int f, int 
     int4 lo, hi;
     lo.x = f;
     lo.y = px0 | (py0 << 16);
-    lo.z = mw | (mh << 8) | (hl << 16) | (hr << 18) | (ht << 20) | (hb << 22) | ((int)packed << 24) | ((int)fits << 25);
+    lo.z = mw | (mh << 8) | (hl << 16) | (hr << 18) | (ht << 20) | (hb << 22) | ((int)packed << 24) | ((int)fits << 25) |
+           ((int)(padded && fits && !no_fast) << 26);
     lo.w = (int)(cluster_rows + (unsigned)(py0 - cy0) * (unsigned)wpr + (unsigned)(bx * (PIECE / 32)));
     hi.x = wpr | (wh << 16) | (nvec << 24);
     hi.y = (wx0 & 0xffff) | (wy0 << 16);
@@ -313,9 +336,10 @@ __global__ void __launch_bounds__(CL_THREADS) form_clusters_kernel(const uint32_
 // per piece: filter <= 64x64 output pixels of a cluster box in shared memory -> bit rows of the cluster (global)
 // ---------------------------------------------------------------------------------------------------------
 struct __align__(16) PieceSmem {
-    static constexpr int UW = PIECE + 8, BW = PIECE + 4;
-    uint8_t U[UW * UW];            // undistorted pixels, origin (px0 - 4, py0 - 4); 0 outside the frame
-    uint16_t HS[UW * BW];          // horizontal 5-sums of U (U rows x B cols)
+    static constexpr int UH = PIECE + 8, UW = PIECE + 12, BW = PIECE + 4, HSW = PIECE + 8;
+    uint8_t U[UH * UW];            // undistorted pixels, origin (px0 - 4, py0 - 4); 0 outside the frame.  Row stride UW: the fast remap stores
+                                   // quads aligned to frame columns that are multiples of 4, its rows start `lead` (0..3) pixels left of the box
+    uint16_t HS[UH * HSW];         // horizontal 5-sums of U (U rows x B cols), rows 16-byte aligned
     uint8_t B[BW * BW];            // thresholded floor-mean, origin (px0 - 2, py0 - 2)
     // the horizontal 5-counts of B (B rows x output cols, BW * PIECE bytes) reuse U, which is dead by then; the packed path
     // keeps its bit planes in HS
@@ -340,14 +364,14 @@ __device__ __forceinline__ void count5(uint32_t a, uint32_t b, uint32_t c, uint3
 // hl, hr, ht, hb (0 or 2): how far the thresholded-mean box extends beyond the piece on each side.  It stops at the
 // cluster box: outside of it the thresholded mean cannot be set by this cluster's hot pixels (it would lie more than 2 from
 // them), and whatever foreign hot pixels set there can only influence pixels that are not this cluster's foreground.
-struct PackedDims { int mw, mh, hl, hr, ht, hb; };
+struct PackedDims { int mw, mh, hl, hr, ht, hb, lead; };   // lead: columns of U / HS / the bit rows left of the box (fast remap)
 
 // ---- A ----  horizontal 5-sums of U -> HS
 __device__ __forceinline__ void packed_stage_a(PieceSmem& S, const PackedDims& d)
 {
-    constexpr int UW = PieceSmem::UW, BW = PieceSmem::BW;
+    constexpr int UW = PieceSmem::UW, HSW = PieceSmem::HSW;
     const int tid = threadIdx.x;
-    const int bw = d.mw + d.hl + d.hr, uh = d.mh + d.ht + d.hb + 4;
+    const int bw = d.mw + d.hl + d.hr + d.lead, uh = d.mh + d.ht + d.hb + 4;
     const int nq = (bw + 3) >> 2;
     const unsigned inv_q = (1u << 20) / (unsigned)nq + 1u;                        // t / nq == (t * inv_q) >> 20 (t * nq < 2^20)
     for (int t = tid; t < uh * nq; t += CL_THREADS) {
@@ -359,16 +383,16 @@ __device__ __forceinline__ void packed_stage_a(PieceSmem& S, const PackedDims& d
         uint32_t s2 = s1 - ((w0 >> 8) & 0xff) + ((w1 >> 16) & 0xff);
         uint32_t s3 = s2 - ((w0 >> 16) & 0xff) + (w1 >> 24);
         uint2 v; v.x = s0 | (s1 << 16); v.y = s2 | (s3 << 16);
-        *(uint2*)&S.HS[r * BW + 4 * q] = v;
+        *(uint2*)&S.HS[r * HSW + 4 * q] = v;
     }
 }
 
 // ---- B ----  bit rows of the thresholded mean: 16 bytes per row in S.B (72 bits used)
 __device__ __forceinline__ void packed_stage_b(PieceSmem& S, const PackedDims& d, int T)
 {
-    constexpr int BW = PieceSmem::BW;
+    constexpr int HSW = PieceSmem::HSW;
     const int tid = threadIdx.x;
-    const int bw = d.mw + d.hl + d.hr, bh = d.mh + d.ht + d.hb;
+    const int bw = d.mw + d.hl + d.hr + d.lead, bh = d.mh + d.ht + d.hb;
     uint8_t* bbits = S.B;
     const int no = (bw + 7) >> 3;
     const uint32_t bias = (0x8000u - (uint32_t)(25 * T)) * 0x00010001u;          // bit 15 of (v + bias) set  <=>  v >= 25 T
@@ -378,9 +402,8 @@ __device__ __forceinline__ void packed_stage_b(PieceSmem& S, const PackedDims& d
         uint32_t a0 = 0, a1 = 0, a2 = 0, a3 = 0;
 #pragma unroll
         for (int k = 0; k < 5; ++k) {
-            const uint2* hp = (const uint2*)&S.HS[(r + k) * BW + 8 * o];
-            uint2 lo = hp[0], hi = hp[1];
-            a0 += lo.x; a1 += lo.y; a2 += hi.x; a3 += hi.y;                       // packed u16 adds: sums <= 6375, no carry across halves
+            const uint4 h = *(const uint4*)&S.HS[(r + k) * HSW + 8 * o];     // one 128-bit load: eight sums
+            a0 += h.x; a1 += h.y; a2 += h.z; a3 += h.w;                       // packed u16 adds: sums <= 6375, no carry across halves
         }
         uint32_t m0 = (a0 + bias) & 0x80008000u, m1 = (a1 + bias) & 0x80008000u;
         uint32_t m2 = (a2 + bias) & 0x80008000u, m3 = (a3 + bias) & 0x80008000u;
@@ -403,7 +426,9 @@ __device__ __forceinline__ void packed_stage_c1(PieceSmem& S, const PackedDims& 
         uint32_t w0 = 0, w1 = 0, w2 = 0;
         if (rb >= 0 && rb < bh) {
             const uint32_t* bp = (const uint32_t*)&bbits[rb * 16];
-            w0 = bp[0]; w1 = bp[1]; w2 = bp[2] & 0xffu;                           // bits 0..31, 32..63, 64..71
+            w0 = bp[0]; w1 = bp[1]; w2 = bp[2];                                   // bits 0..31, 32..63, 64..95
+            if (d.lead) { w0 = __funnelshift_r(w0, w1, d.lead); w1 = __funnelshift_r(w1, w2, d.lead); w2 >>= d.lead; }   // drop the lead columns
+            w2 &= 0xffu;
             if (bw < 32) { w0 &= (1u << bw) - 1u; w1 = 0; w2 = 0; }               // drop the surplus bits of the last byte
             else if (bw < 64) { w1 &= bw == 32 ? 0u : (1u << (bw - 32)) - 1u; w2 = 0; }
             else w2 &= bw == 64 ? 0u : (1u << (bw - 64)) - 1u;
@@ -453,7 +478,7 @@ template <bool INTERIOR>
 __device__ __forceinline__ void piece_threshold_majority(PieceSmem& S, int px0, int py0, int mw, int mh, int W, int H, int T,
                                                          uint32_t* __restrict__ out, int wpr)
 {
-    constexpr int BW = PieceSmem::BW;
+    constexpr int BW = PieceSmem::BW, HSW = PieceSmem::HSW;
     uint8_t* MH = S.U;                                             // U is dead once HS is complete
     const int tid = threadIdx.x, lane = tid & 31, wy = tid >> 5, NWARP = CL_THREADS / 32;
     const int bw = mw + 4, bh = mh + 4;
@@ -464,8 +489,8 @@ __device__ __forceinline__ void piece_threshold_majority(PieceSmem& S, int px0, 
         for (int c = lane; c < bw; c += 32) {
             int j = px0 - 2 + c, b = 0;
             if (rowin && (INTERIOR || (unsigned)j < (unsigned)W)) {
-                const uint16_t* h = &S.HS[r * BW + c];
-                int s = h[0] + h[BW] + h[2 * BW] + h[3 * BW] + h[4 * BW];
+                const uint16_t* h = &S.HS[r * HSW + c];
+                int s = h[0] + h[HSW] + h[2 * HSW] + h[3 * HSW] + h[4 * HSW];
                 int cnt = INTERIOR ? 25 : cnty * (min(j + 2, W - 1) - max(j - 2, 0) + 1);
                 b = s >= T * cnt;
             }
@@ -501,6 +526,42 @@ __device__ __forceinline__ void piece_threshold_majority(PieceSmem& S, int px0, 
             if (lane == 0) out[(size_t)r * wpr + (c0 >> 5)] = wv;
         }
     }
+}
+
+// one undistorted pixel from the staged window: m = fast-map word (fx | fy << 8 | tap offset << 16), p = the pixel's own place in the window
+__device__ __forceinline__ uint32_t fast_tap(const uint8_t* p, uint32_t m)
+{
+    const uint8_t* q = p + ((int)m >> 16);
+#ifdef MOCAP_EMU
+    const int fx = (int)(m & 0xffu), fy = (int)((m >> 8) & 0xffu);
+#else
+    const int fx = (int)(m & 0xffu), fy = (int)__byte_perm(m, 0, 0x4441);      // byte 1, one PRMT
+#endif
+    const int r0 = (32 - fx) * q[0] + fx * q[1];
+    const int r1 = (32 - fx) * q[WIN_W] + fx * q[WIN_W + 1];
+    return (uint32_t)(((32 - fy) * r0 + fy * r1 + 512) >> 10);
+}
+
+// work split of the fast remap: the quads of the U box (four pixels of a row each) as a flat index, thread t takes quads t, t + 128, ...:
+// first quad (row r, quad column q), the step of 128 quads as (dr rows, dq quads) and the first map address
+struct FastIter { int r, q, nq, dr, dq, uh; const int32_t* mp; bool on; };
+__device__ __forceinline__ FastIter fast_iter_init(const int* d, const TableView& tv, int tid)
+{
+    const int px0 = d[1] & 0xffff, py0 = d[1] >> 16, dims = d[2];
+    const int hl = (dims >> 16) & 3, hr = (dims >> 18) & 3, ht = (dims >> 20) & 3, hb = (dims >> 22) & 3;
+    const int ux0 = px0 - hl - 2, lead = ux0 & 3;                              // quads are aligned to frame columns that are multiples of 4
+    const int uw = (dims & 0xff) + hl + hr + 4 + lead;
+    FastIter it;
+    it.uh = ((dims >> 8) & 0xff) + ht + hb + 4;
+    it.nq = (uw + 3) >> 2;                                                     // quads per row, <= 19
+    const unsigned inv = (1u << 16) / (unsigned)it.nq + 1u;                    // t / nq == (t * inv) >> 16 for t <= 128
+    it.on = ((dims >> 26) & 1) != 0;
+    it.r = (int)(((unsigned)tid * inv) >> 16);
+    it.q = tid - it.r * it.nq;
+    it.dr = (int)(((unsigned)CL_THREADS * inv) >> 16);
+    it.dq = CL_THREADS - it.dr * it.nq;
+    it.mp = tv.fast + (size_t)(py0 - ht - 2 + it.r) * tv.W + (ux0 - lead) + 4 * it.q;
+    return it;
 }
 
 // 16 bytes global -> shared without a register round trip (lands asynchronously; piece_copy_wait before the data is used)
@@ -540,14 +601,44 @@ __device__ __forceinline__ void piece_issue_window(uint8_t* win, const int* d, c
 // consumed `win`, every thread posts the source window of piece i + 1 into it (cp.async, lands while the stages of piece i
 // run), warp 0 fetches the descriptor of piece i + 2 and thread 0 draws the index of piece i + 3 -- no descriptor, window or
 // work-counter latency is waited for inside the loop.
+#ifdef MOCAP_EMU
+#define PF_ISSUE_WINDOW(desc) piece_issue_window(win, desc, frames, fstride, W, H)
+#else
+#define PF_ISSUE_WINDOW(desc)                                                                                                   \
+    do {                                                                                                                        \
+        if (!PF_USE_TMA) piece_issue_window(win, desc, frames, fstride, W, H);                                                  \
+        else if (tid == 0 && (((desc)[2] >> 25) & 1)) {                                                                         \
+            mbar_expect_tx(&wbar, WIN_W * WIN_H);                                                                               \
+            tma_load_box(win, &tmap, (int)(int16_t)((desc)[5] & 0xffff), (desc)[5] >> 16, (desc)[0], &wbar);                     \
+        }                                                                                                                       \
+    } while (0)
+#endif
+#ifdef MOCAP_EMU
+#define PF_TMA_PARAM
+#define PF_USE_TMA false
+#else
+#define PF_TMA_PARAM , const __grid_constant__ CUtensorMap tmap, int use_tma
+#define PF_USE_TMA (use_tma != 0)
+#endif
+// The source window of a piece comes in as ONE TMA box (cp.async.bulk.tensor.3d of the frame batch viewed as [n][H][W], WIN_W x WIN_H
+// bytes at (wx0, wy0, frame); what lies outside the frame is zero-filled by the TMA unit) issued by thread 0 and completing on an
+// mbarrier; batches the tensor map cannot describe use 16-byte cp.async copies per thread instead.
 __global__ void __launch_bounds__(CL_THREADS, 8) piece_filter_kernel(const uint8_t* __restrict__ frames, int64_t fstride, TableView tv, int thresh,
-                                                                  ClusterWs cw)
+                                                                  ClusterWs cw PF_TMA_PARAM)
 {
     __shared__ PieceSmem S;
-    __align__(16) __shared__ uint8_t win[WIN_W * WIN_H];           // staged source window
+    __align__(128) __shared__ uint8_t win[WIN_W * WIN_H];          // staged source window
+#ifndef MOCAP_EMU
+    __shared__ uint64_t wbar;                                      // "window landed" barrier of the TMA path
+    unsigned wphase = 0;
+    if (threadIdx.x == 0 && PF_USE_TMA) {
+        mbar_init(&wbar, 1);
+        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    }
+#endif
     __align__(16) __shared__ int s_desc[2][8];
     __shared__ int s_next;
-    constexpr int UW = PieceSmem::UW, BW = PieceSmem::BW;
+    constexpr int UW = PieceSmem::UW, HSW = PieceSmem::HSW;
     const bool vec_ok = (tv.W % 16 == 0) && (fstride % 16 == 0) && (((uintptr_t)frames) % 16 == 0);
     const int tid = threadIdx.x, lane = tid & 31, wy = tid >> 5, NWARP = CL_THREADS / 32;
     const int H = tv.H, W = tv.W, T = thresh + 1;
@@ -568,7 +659,12 @@ __global__ void __launch_bounds__(CL_THREADS, 8) piece_filter_kernel(const uint8
         if (lane == 0) next = atomicAdd(&cw.counters[CN_PIECE_CUR], 1);
     }
     __syncthreads();
-    if (use_win) piece_issue_window(win, s_desc[0], frames, fstride, W, H);
+    if (use_win) PF_ISSUE_WINDOW(s_desc[0]);
+    uint32_t a0 = 0, a1 = 0, a2 = 0, a3 = 0;                       // fast-map words of the thread's first quad of the coming piece
+    if (use_win && PF_PREFETCH_PIECE) {
+        const FastIter fi = fast_iter_init(s_desc[0], tv, tid);
+        if (fi.on && fi.r < fi.uh) { a0 = (uint32_t)fi.mp[0]; a1 = (uint32_t)fi.mp[1]; a2 = (uint32_t)fi.mp[2]; a3 = (uint32_t)fi.mp[3]; }
+    }
     int slot = 0;
     for (;;) {
         const int* d = s_desc[slot];
@@ -577,9 +673,11 @@ __global__ void __launch_bounds__(CL_THREADS, 8) piece_filter_kernel(const uint8
         PackedDims pd;
         pd.mw = dims & 0xff; pd.mh = (dims >> 8) & 0xff;
         pd.hl = (dims >> 16) & 3; pd.hr = (dims >> 18) & 3; pd.ht = (dims >> 20) & 3; pd.hb = (dims >> 22) & 3;
+        pd.lead = 0;
         const int mw = pd.mw, mh = pd.mh;
         const bool packed = ((dims >> 24) & 1) && t_ok;
         const bool staged = ((dims >> 25) & 1) && use_win;
+        const bool fastp = ((dims >> 26) & 1) && use_win;
         const int wpr = d[4] & 0xffff;
         const int wx0 = (int)(int16_t)(d[5] & 0xffff), wy0 = d[5] >> 16;
         uint32_t* out = cw.rows_out + (unsigned)d[3];
@@ -588,6 +686,10 @@ __global__ void __launch_bounds__(CL_THREADS, 8) piece_filter_kernel(const uint8
         const int ux1 = packed ? px1 + pd.hr + 2 : px1 + 4, uy1 = packed ? py1 + pd.hb + 2 : py1 + 4;
         const int uw = ux1 - ux0 + 1, uh = uy1 - uy0 + 1, bw = mw + 4;
         const uint8_t* fr = frames + (size_t)f * fstride;
+#ifndef MOCAP_EMU
+        if (PF_USE_TMA) { if (((dims >> 25) & 1) && use_win) { mbar_wait(&wbar, wphase); wphase ^= 1; } }
+        else
+#endif
         piece_copy_wait();
         __syncthreads();                                            // the window of this piece has landed; the other descriptor slot is free
         if (wy == 0 && lane < 8) s_desc[slot ^ 1][lane] = dn;
@@ -595,35 +697,67 @@ __global__ void __launch_bounds__(CL_THREADS, 8) piece_filter_kernel(const uint8
         // ---- 1. undistorted pixels of the U box (zero outside the frame): the uw x uh box is walked as a flat index (all
         //         lanes busy whatever the box width), four pixels per thread per pass so that the map loads of a pass are
         //         in flight together; the bilinear taps come from the staged window. ----------------------------------------
-        if (packed && staged) {
-            // fast path: the box lies inside the frame and its source window is staged; everything in piece-local
-            // coordinates (source column in the window = c + (du >> 5) + const, fraction = du & 31)
-            const int n_u = uw * uh;
-            const unsigned inv = (1u << 20) / (unsigned)uw + 1u;
-            const int32_t* mbase = tv.map + (size_t)uy0 * W + ux0;
-            const uint8_t* wbase = win + (uy0 - wy0) * WIN_W + (ux0 - wx0);
-            for (int base = tid; base < n_u; base += 4 * CL_THREADS) {
-                uint32_t m[4]; int rr[4], cc[4];
+        if (fastp) {
+            // fast path: the box lies inside the frame, its source window is staged and every pixel has a fast-map entry (fx, fy and
+            // the place of its first tap in the window relative to the pixel's own).  The quads (four pixels of a row) of the box are
+            // a flat index, a thread takes every 128th (pointer steps with one wrap test; four map loads, one 32-bit store of the four
+            // results per quad); the map words of its next quad are in flight while this one is computed, and those of its first quad were
+            // fetched during the stages of the piece before (a0..a3), so no L2 latency is waited for inside a piece.  The surplus
+            // pixels of a row's last quad are real pixels right of the box (the descriptor's window covers them).
+            FastIter fi = fast_iter_init(d, tv, tid);
+            pd.lead = ux0 & 3;
+            const uint8_t* pw = win + (uy0 - wy0 + fi.r) * WIN_W + (ux0 - pd.lead - wx0) + 4 * fi.q;
+            uint8_t* pu = S.U + fi.r * UW + 4 * fi.q;
+            const int dw = fi.dr * WIN_W + 4 * fi.dq, du = fi.dr * UW + 4 * fi.dq, dm = fi.dr * W + 4 * fi.dq;
+            const int dwx = WIN_W - 4 * fi.nq, dux = UW - 4 * fi.nq, dmx = W - 4 * fi.nq;          // the wrap into the next row
+#if PF_BATCH
+            // the map words of the thread's first PF_BATCH quads are all requested before the first one is used: one L2 latency per piece
+            {
+                uint32_t m[PF_BATCH][4];
+                int r2 = fi.r, q2 = fi.q;
+                const int32_t* mp2 = fi.mp;
 #pragma unroll
-                for (int k = 0; k < 4; ++k) {
-                    int idx = min(base + k * CL_THREADS, n_u - 1);             // the surplus lanes redo the last pixel
-                    int r = (int)(((unsigned)idx * inv) >> 20), c = idx - r * uw;
-                    rr[k] = r; cc[k] = c;
-                    m[k] = (uint32_t)mbase[r * W + c];
+                for (int k = 0; k < PF_BATCH; ++k) {
+                    if (r2 < uh) { m[k][0] = (uint32_t)mp2[0]; m[k][1] = (uint32_t)mp2[1]; m[k][2] = (uint32_t)mp2[2]; m[k][3] = (uint32_t)mp2[3]; }
+                    q2 += fi.dq; r2 += fi.dr; mp2 += dm;
+                    if (q2 >= fi.nq) { q2 -= fi.nq; ++r2; mp2 += dmx; }
                 }
 #pragma unroll
-                for (int k = 0; k < 4; ++k) {
-                    uint32_t mm = m[k];
-                    int du = (int)(int16_t)(mm & 0xffff), dv = (int)(int16_t)(mm >> 16);
-                    int fx = du & 31, fy = dv & 31;
-                    const uint8_t* p = wbase + (rr[k] + (dv >> 5)) * WIN_W + cc[k] + (du >> 5);
-                    if (mm == MAP_OUTSIDE) p = win;                            // any valid address; the value is discarded
-                    int r0 = (32 - fx) * p[0] + fx * p[1];
-                    int r1 = (32 - fx) * p[WIN_W] + fx * p[WIN_W + 1];
-                    int val = ((32 - fy) * r0 + fy * r1 + 512) >> 10;
-                    S.U[rr[k] * UW + cc[k]] = (uint8_t)(mm == MAP_OUTSIDE ? 0 : val);
+                for (int k = 0; k < PF_BATCH; ++k) {
+                    if (fi.r < uh)
+                        *(uint32_t*)pu = fast_tap(pw, m[k][0]) | (fast_tap(pw + 1, m[k][1]) << 8) | (fast_tap(pw + 2, m[k][2]) << 16) | (fast_tap(pw + 3, m[k][3]) << 24);
+                    fi.q += fi.dq; fi.r += fi.dr; fi.mp += dm; pw += dw; pu += du;
+                    if (fi.q >= fi.nq) { fi.q -= fi.nq; ++fi.r; fi.mp += dmx; pw += dwx; pu += dux; }
                 }
             }
+#endif
+#if PF_PREFETCH_LOOP
+#if !PF_PREFETCH_PIECE
+            if (fi.r < uh) { a0 = (uint32_t)fi.mp[0]; a1 = (uint32_t)fi.mp[1]; a2 = (uint32_t)fi.mp[2]; a3 = (uint32_t)fi.mp[3]; }
+#endif
+            uint32_t b0, b1, b2, b3;
+            while (fi.r < uh) {
+                const uint8_t* cw_ = pw; uint8_t* cu_ = pu;
+                fi.q += fi.dq; fi.r += fi.dr; fi.mp += dm; pw += dw; pu += du;
+                if (fi.q >= fi.nq) { fi.q -= fi.nq; ++fi.r; fi.mp += dmx; pw += dwx; pu += dux; }
+                if (fi.r < uh) { b0 = (uint32_t)fi.mp[0]; b1 = (uint32_t)fi.mp[1]; b2 = (uint32_t)fi.mp[2]; b3 = (uint32_t)fi.mp[3]; }
+                *(uint32_t*)cu_ = fast_tap(cw_, a0) | (fast_tap(cw_ + 1, a1) << 8) | (fast_tap(cw_ + 2, a2) << 16) | (fast_tap(cw_ + 3, a3) << 24);
+                if (fi.r >= uh) break;
+                cw_ = pw; cu_ = pu;
+                fi.q += fi.dq; fi.r += fi.dr; fi.mp += dm; pw += dw; pu += du;
+                if (fi.q >= fi.nq) { fi.q -= fi.nq; ++fi.r; fi.mp += dmx; pw += dwx; pu += dux; }
+                if (fi.r < uh) { a0 = (uint32_t)fi.mp[0]; a1 = (uint32_t)fi.mp[1]; a2 = (uint32_t)fi.mp[2]; a3 = (uint32_t)fi.mp[3]; }
+                *(uint32_t*)cu_ = fast_tap(cw_, b0) | (fast_tap(cw_ + 1, b1) << 8) | (fast_tap(cw_ + 2, b2) << 16) | (fast_tap(cw_ + 3, b3) << 24);
+            }
+#else
+            while (fi.r < uh) {
+                const int4 m = *(const int4*)fi.mp;                             // 16-byte aligned: W, the table and the quad column are
+                *(uint32_t*)pu = fast_tap(pw, (uint32_t)m.x) | (fast_tap(pw + 1, (uint32_t)m.y) << 8) | (fast_tap(pw + 2, (uint32_t)m.z) << 16) |
+                                 (fast_tap(pw + 3, (uint32_t)m.w) << 24);
+                fi.q += fi.dq; fi.r += fi.dr; fi.mp += dm; pw += dw; pu += du;
+                if (fi.q >= fi.nq) { fi.q -= fi.nq; ++fi.r; fi.mp += dmx; pw += dwx; pu += dux; }
+            }
+#endif
         } else {
             const int n_u = uw * uh;
             const unsigned inv = (1u << 20) / (unsigned)uw + 1u;              // idx / uw == (idx * inv) >> 20 for idx * uw < 2^20
@@ -660,7 +794,11 @@ __global__ void __launch_bounds__(CL_THREADS, 8) piece_filter_kernel(const uint8
         }
         __syncthreads();                                            // U complete; the window is free again
         // post the next piece's window (it lands while the stages below run), fetch the descriptor of the piece after it
-        if (s_next < total && use_win) piece_issue_window(win, s_desc[slot ^ 1], frames, fstride, W, H);
+        if (s_next < total && use_win) {
+            PF_ISSUE_WINDOW(s_desc[slot ^ 1]);
+            const FastIter fi = fast_iter_init(s_desc[slot ^ 1], tv, tid);
+            if (PF_PREFETCH_PIECE && fi.on && fi.r < fi.uh) { a0 = (uint32_t)fi.mp[0]; a1 = (uint32_t)fi.mp[1]; a2 = (uint32_t)fi.mp[2]; a3 = (uint32_t)fi.mp[3]; }
+        }
         if (wy == 0) {
             nx = __shfl_sync(0xffffffffu, next, 0);
             dn = (lane < 8 && nx < total) ? cw.pieces[8 * (size_t)nx + lane] : 0;
@@ -679,7 +817,7 @@ __global__ void __launch_bounds__(CL_THREADS, 8) piece_filter_kernel(const uint8
             for (int r = wy; r < uh; r += NWARP)
                 for (int c = lane; c < bw; c += 32) {
                     const uint8_t* up = &S.U[r * UW + c];
-                    S.HS[r * BW + c] = (uint16_t)(up[0] + up[1] + up[2] + up[3] + up[4]);
+                    S.HS[r * HSW + c] = (uint16_t)(up[0] + up[1] + up[2] + up[3] + up[4]);
                 }
             __syncthreads();
             piece_threshold_majority<false>(S, px0, py0, mw, mh, W, H, T, out, wpr);
@@ -1097,7 +1235,17 @@ int launch_cluster_path(const uint8_t* frames, int n, int H, int W, int64_t fstr
         if (sf != s) { if (!how.ev_group) return MOCAP_ERR_INVALID; CUDA_TRY(cudaStreamWaitEvent(sf, how.ev_group, 0)); }
 #endif
         stage_begin(timer, 2, sf);
+#ifdef MOCAP_EMU
         LAUNCH(piece_filter_kernel, sms * how.filter_ctas_per_sm, CL_THREADS, 0, sf, frames, fstride, tv, thresh, cw);
+#else
+        {
+            CUtensorMap tmap;
+            memset(&tmap, 0, sizeof(tmap));
+            const int T = thresh + 1;
+            const int use_tma = (T >= 0 && T <= 256 && frames_tensor_map(&tmap, frames, n, H, W, fstride, WIN_W, WIN_H)) ? 1 : 0;
+            LAUNCH(piece_filter_kernel, sms * how.filter_ctas_per_sm, CL_THREADS, 0, sf, frames, fstride, tv, thresh, cw, tmap, use_tma);
+        }
+#endif
         stage_end(timer, 2, sf);
         if (how.ev_filter) cudaEventRecord(how.ev_filter, sf);
     }

@@ -112,6 +112,33 @@ __global__ void build_tile_kernel(const int32_t* __restrict__ map, int H, int W,
     }
 }
 
+// The map in the form the piece filter's fast path consumes (TableHeader::off_fast) + per output tile whether all of its pixels have one.
+// One CTA per output tile.
+__global__ void build_fast_kernel(const int32_t* __restrict__ map, int H, int W, int TX, int32_t* __restrict__ fast, int32_t* __restrict__ tflag)
+{
+    const int tx = blockIdx.x, ty = blockIdx.y;
+    __shared__ int s_bad;
+    if (threadIdx.x == 0) s_bad = 0;
+    __syncthreads();
+    int bad = 0;
+    for (int idx = threadIdx.x; idx < TILE * TILE; idx += blockDim.x) {
+        int i = ty * TILE + idx / TILE, j = tx * TILE + idx % TILE;
+        if (i >= H || j >= W) continue;
+        uint32_t m = (uint32_t)map[(size_t)i * W + j], enc = FAST_INVALID;
+        if (m != MAP_OUTSIDE) {
+            int du = (int16_t)(m & 0xffff), dv = (int16_t)(m >> 16);
+            int off = (dv >> 5) * WIN_W + (du >> 5);
+            if (off >= -32768 && off <= 32767) enc = (uint32_t)(du & 31) | ((uint32_t)(dv & 31) << 8) | ((uint32_t)off << 16);
+        }
+        if (enc == FAST_INVALID) bad = 1;
+        fast[(size_t)i * W + j] = (int32_t)enc;
+    }
+    if (tx == 0 && ty == 0 && threadIdx.x < 4) fast[(size_t)H * W + threadIdx.x] = 0;      // the pad behind the last row
+    if (bad) atomicOr(&s_bad, 1);
+    __syncthreads();
+    if (threadIdx.x == 0) tflag[ty * TX + tx] = s_bad;
+}
+
 // Per 32x32 source cell: exact bounds of (source - output) integer displacement over every output pixel whose 2x2 tap
 // footprint touches the cell.  One thread per output pixel; pixels of a warp mostly hit the same cell, so the atomics are
 // few per address and this runs once per calibration.
@@ -163,6 +190,8 @@ static void table_layout(int H, int W, TableHeader* h)
     h->off_cell = off; off += align_up((size_t)h->TX * h->TY * 16, 256);
     h->off_tile = off; off += align_up((size_t)h->TX * h->TY * 32, 256);
     h->off_cellinv = off; off += align_up((size_t)h->TX * h->TY * 16, 256);
+    h->off_fast = off; off += align_up((size_t)H * W * 4 + 16, 256);
+    h->off_tflag = off; off += align_up((size_t)h->TX * h->TY * 4, 256);
     h->total_bytes = off;
 }
 
@@ -197,6 +226,7 @@ extern "C" int mocap_undistort_table_build(const double* K9, const double* dist5
     LAUNCH(init_tables_kernel, cdiv(nt, 256), 256, 0, s, cell, tile, cellinv, nt);
     LAUNCH(build_tile_kernel, dim3(h.TX, h.TY), 256, 0, s, map, H, W, h.TX, h.TY, cell, tile, cellinv);
     LAUNCH(build_cellinv_kernel, grd, blk, 0, s, map, H, W, h.TX, cellinv);
+    LAUNCH(build_fast_kernel, dim3(h.TX, h.TY), 256, 0, s, map, H, W, h.TX, (int32_t*)(base + h.off_fast), (int32_t*)(base + h.off_tflag));
     CUDA_TRY(cudaGetLastError());
     TableHeader back;
     CUDA_TRY(cudaMemcpyAsync(&back, base, sizeof(back), cudaMemcpyDeviceToHost, s));
@@ -214,6 +244,8 @@ int table_view(const void* table_dev, int H, int W, TableView* tv)
     tv->cell = (const int32_t*)(base + h.off_cell);
     tv->tile = (const int32_t*)(base + h.off_tile);
     tv->cellinv = (const int32_t*)(base + h.off_cellinv);
+    tv->fast = (const int32_t*)(base + h.off_fast);
+    tv->tflag = (const int32_t*)(base + h.off_tflag);
     tv->H = H; tv->W = W; tv->TX = h.TX; tv->TY = h.TY;
     return MOCAP_OK;
 }

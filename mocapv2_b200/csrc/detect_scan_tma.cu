@@ -21,8 +21,8 @@
 
 #define SCAN_CTRL_WORK 64          // work-counter slots at the head of the control block (one per scan launch of a call)
 
+#include "tma.cuh"
 #ifndef MOCAP_EMU
-#include <cuda.h>
 
 #define ST_BOX_W 256
 #define ST_BOX_H 32
@@ -42,30 +42,6 @@ struct ScanTmaArgs {
     uint32_t add;                  // SWAR constant of the hot test (make_hot_test)
 };
 struct __align__(16) StageRec { int cb_index, ncell, chunk, pad; };
-
-__device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
-__device__ __forceinline__ void mbar_init(uint64_t* bar, unsigned count)
-{
-    asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" :: "r"(smem_u32(bar)), "r"(count) : "memory");
-}
-__device__ __forceinline__ void mbar_expect_tx(uint64_t* bar, unsigned bytes)
-{
-    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" :: "r"(smem_u32(bar)), "r"(bytes) : "memory");
-}
-__device__ __forceinline__ void mbar_arrive(uint64_t* bar)
-{
-    asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" :: "r"(smem_u32(bar)) : "memory");
-}
-__device__ __forceinline__ void mbar_wait(uint64_t* bar, unsigned parity)
-{
-    asm volatile("{\n\t.reg .pred P1;\n\tLAB_WAIT:\n\tmbarrier.try_wait.parity.shared::cta.b64 P1, [%0], %1;\n\t@P1 bra DONE;\n\tbra LAB_WAIT;\n\tDONE:\n\t}"
-                 :: "r"(smem_u32(bar)), "r"(parity) : "memory");
-}
-__device__ __forceinline__ void tma_load_box(void* dst, const CUtensorMap* map, int x, int y, int z, uint64_t* bar, uint64_t policy)
-{
-    asm volatile("cp.async.bulk.tensor.3d.shared::cluster.global.mbarrier::complete_tx::bytes.L2::cache_hint [%0], [%1, {%3, %4, %5}], [%2], %6;"
-                 :: "r"(smem_u32(dst)), "l"(map), "r"(smem_u32(bar)), "r"(x), "r"(y), "r"(z), "l"(policy) : "memory");
-}
 
 // publish `cnt` finished boxes of chunk `ch` (whole warp calls; every cellbox store of those boxes precedes it)
 __device__ __forceinline__ void scan_publish(const ScanTmaArgs& a, int ch, int cnt, int lane)
@@ -201,6 +177,19 @@ static void* driver_entry(const char* name)
     return fn;
 }
 
+bool frames_tensor_map(CUtensorMap* out, const uint8_t* frames, int n, int H, int W, int64_t fstride, int box_w, int box_h)
+{
+    static PFN_encodeTiled encode = (PFN_encodeTiled)driver_entry("cuTensorMapEncodeTiled");
+    if (!encode || n <= 0 || H <= 0 || W <= 0) return false;
+    if (W % 16 || fstride % 16 || ((uintptr_t)frames) % 16) return false;    // tensor-map strides are multiples of 16 bytes
+    const cuuint64_t gdim[3] = {(cuuint64_t)W, (cuuint64_t)H, (cuuint64_t)n};
+    const cuuint64_t gstr[2] = {(cuuint64_t)W, (cuuint64_t)fstride};
+    const cuuint32_t box[3] = {(cuuint32_t)box_w, (cuuint32_t)box_h, 1};
+    const cuuint32_t estr[3] = {1, 1, 1};
+    return encode(out, CU_TENSOR_MAP_DATA_TYPE_UINT8, 3, (void*)frames, gdim, gstr, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE,
+                  CU_TENSOR_MAP_SWIZZLE_NONE, CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE) == CUDA_SUCCESS;
+}
+
 bool scan_tma_supported(const uint8_t* frames, int n, int H, int W, int64_t fstride, int thresh)
 {
     const int T = thresh + 1;
@@ -218,16 +207,8 @@ size_t scan_tma_ctrl_bytes(int chunks) { return align_up((size_t)(SCAN_CTRL_WORK
 int launch_scan_tma(const uint8_t* frames, int n, int H, int W, int64_t fstride, const TableView& tv, int thresh, uint32_t* cellbox,
                     int* ctrl, int chunks, int chunk_frames, int widx, int item_begin, int item_end, int stages, cudaStream_t s)
 {
-    static PFN_encodeTiled encode = (PFN_encodeTiled)driver_entry("cuTensorMapEncodeTiled");
-    if (!encode) return MOCAP_ERR_UNSUPPORTED;
     CUtensorMap map;
-    const cuuint64_t gdim[3] = {(cuuint64_t)W, (cuuint64_t)H, (cuuint64_t)n};
-    const cuuint64_t gstr[2] = {(cuuint64_t)W, (cuuint64_t)fstride};
-    const cuuint32_t box[3] = {ST_BOX_W, ST_BOX_H, 1};
-    const cuuint32_t estr[3] = {1, 1, 1};
-    if (encode(&map, CU_TENSOR_MAP_DATA_TYPE_UINT8, 3, (void*)frames, gdim, gstr, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE,
-               CU_TENSOR_MAP_SWIZZLE_NONE, CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE) != CUDA_SUCCESS)
-        return MOCAP_ERR_CUDA;
+    if (!frames_tensor_map(&map, frames, n, H, W, fstride, ST_BOX_W, ST_BOX_H)) return MOCAP_ERR_UNSUPPORTED;
     int dev = 0, sms = 148;
     cudaGetDevice(&dev);
     cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
