@@ -44,6 +44,7 @@ def parse():
     ap.add_argument("--frame-sets", type=int, default=64, help="frame-sets per GPU per step (F0)")
     ap.add_argument("--e2e-steps", type=int, default=3)
     ap.add_argument("--cpu-sample", type=int, default=1, help="frame-sets timed for cpu_baseline (0 = skip)")
+    ap.add_argument("--in-flight", type=int, default=2, help="steps in flight in the timed loop (each on its own lane: stream, detection pipe, buffers)")
     ap.add_argument("--no-e2e", action="store_true")
     ap.add_argument("--no-geometry", action="store_true", help="skip the config-5 geometry sweep")
     ap.add_argument("--no-extra", action="store_true", help="skip front step, _find_dot latency and the C1 / C3 configs")
@@ -221,7 +222,7 @@ def run_reference(args):
 def workload_config(n, f0, sample=None):
     cfg = {"workload": "BASELINE config 4: 16 cameras 2048x2048 u8, 128 markers, detect+match+triangulate",
            "cameras": 16, "frame": [2048, 2048], "markers": N_MARKERS, "frame_sets_per_gpu_per_step": f0,
-           "frames_per_step": 16 * f0 * n, "parallelism": f"cameras sharded x{n} for detection, frame-sets sharded x{n} for geometry, 1 shard exchange (one grouped NCCL send/recv)",
+           "frames_per_step": 16 * f0 * n, "parallelism": f"cameras sharded x{n} for detection, frame-sets sharded x{n} for geometry, 1 shard exchange (records stored straight into the matching rank's buffer over NVLink + a barrier; NCCL send/recv where peer memory is unavailable)",
            "group_cap": {"max_cand": MAX_CAND, "max_groups": MAX_GROUPS},
            "l2": "inputs per step (>=1 GB) exceed the 126 MB L2; the same resident batch is re-read every step"}
     if sample:
@@ -383,7 +384,7 @@ def run_b200(args):
     import torch
     import torch.distributed as dist
     from mocapv2_b200.engine import CaptureEngine
-    from mocapv2_b200.pipeline import CapturePipeline
+    from mocapv2_b200.pipeline import CapturePipeline, StepsInFlight
 
     world = int(os.environ.get("WORLD_SIZE", "1"))
     rank = int(os.environ.get("RANK", "0"))
@@ -401,23 +402,33 @@ def run_b200(args):
     frames = render_local(rig, cen, ridx, pipe.cam_begin, pipe.cams_local, device)
     n_local = FS * pipe.cams_local
     H, W = rig["H"], rig["W"]
-    corr_out = [None]
+    flight = StepsInFlight(pipe, args.in_flight)
+    corr_outs = {}
 
-    def step(marks=None):
+    def step_on(lane, marks=None):
         if marks is not None:
             ev = _events(4)
             ev[0].record()
-        det = pipe.detect(frames)
+        det = lane.detect(frames)
         if marks is not None:
             ev[1].record()
-        xy, count = pipe.exchange(det, FS)
+        xy, count = lane.exchange(det, FS)
         if marks is not None:
             ev[2].record()
-        corr_out[0] = eng.correspond(xy, count, pipe.Fs, pipe.cams, obj_count=N_MARKERS, max_groups=MAX_GROUPS, out=corr_out[0])
+        corr = corr_outs[id(lane)] = lane.eng.correspond(xy, count, lane.Fs, lane.cams, obj_count=N_MARKERS, max_groups=MAX_GROUPS,
+                                                         out=corr_outs.get(id(lane)))
         if marks is not None:
             ev[3].record()
             marks.append(ev)
-        return det, corr_out[0]
+        return det, corr
+
+    def step(marks=None):
+        """one step on the next lane (its own stream when several steps are in flight)"""
+        lane, st = flight.next_lane()
+        if st is None:
+            return step_on(lane, marks)
+        with torch.cuda.stream(st):
+            return step_on(lane, marks)
 
     def barrier():
         if world > 1:
@@ -441,18 +452,20 @@ def run_b200(args):
     ev0, ev1 = _events(2)
     barrier()
     ev0.record()
+    flight.fork()                           # the lanes start behind ev0 ...
     for k in range(args.steps):
         det, corr = step(marks)
+    flight.join()                           # ... and ev1 lies behind the last step of every lane
     ev1.record()
     gpu_launches = eng.launches - launches0
     barrier()
     # nvidia-smi delivers a sample every ~50-100 ms: if the timed region was shorter than a second keep the same step loop
     # running (untimed) so that the clock record is taken under this very load
-    t_sus = time.perf_counter()
-    while time.perf_counter() - t_sus < max(0.0, 1.0 - ev0.elapsed_time(ev1) * 1e-3):
-        for _ in range(5):
-            step()
-        torch.cuda.synchronize()
+    # (the number of extra steps follows from the all-reduced time: every rank runs the same number of steps and lane turns)
+    ms_timed = rank_max(ev0.elapsed_time(ev1))
+    for _ in range(int(max(0.0, 1000.0 - ms_timed) / max(ms_timed / args.steps, 1e-3)) + 1):
+        step()
+    torch.cuda.synchronize()
     clocks = sampler.stop() if rank == 0 else None
     if clocks is not None:
         clocks["window"] = "warm-up + timed region (+ the same step loop, untimed, up to 1 s in total)"
@@ -463,6 +476,34 @@ def run_b200(args):
              "geometry_ms": rank_max(np.mean([e[2].elapsed_time(e[3]) for e in marks])),
              "note": "CUDA events on the step's stream around detect / exchange / match+triangulate, mean over the timed steps, max over ranks"}
     pipe_info = eng.last_pipe_info
+
+    # ---- the detection chain alone at the bench's own operating point: K detect calls, `in_flight` of them in flight (lanes) --------
+    def detect_rate(reps, lanes_on):
+        a_, b_ = _events(2)
+        barrier()
+        a_.record()
+        if lanes_on:
+            flight.fork()
+        for _ in range(reps):
+            lane, st = flight.next_lane() if lanes_on else (pipe, None)
+            if st is None:
+                lane.detect(frames)
+            else:
+                with torch.cuda.stream(st):
+                    lane.detect(frames)
+        if lanes_on:
+            flight.join()
+        b_.record()
+        barrier()
+        return rank_max(a_.elapsed_time(b_)) / reps
+    reps_d = 2 * flight.depth * max(5, min(args.steps, 50) // (2 * flight.depth))
+    detect_rate(2 * flight.depth, True)
+    detect_rate(3, False)                   # (the caller's stream gets its own workspace on first use)
+    phase["detect_in_flight_ms"] = detect_rate(reps_d, True)
+    phase["detect_single_call_ms"] = detect_rate(reps_d, False)
+    phase["steps_in_flight"] = flight.depth
+    phase["note"] += ("; with several steps in flight the per-step marks are latencies under overlap -- detect_in_flight_ms is the time per detect "
+                      "call of a loop of detect calls alone with the same number in flight, detect_single_call_ms one call after the other")
 
     # ---- the stages one after the other (the same kernels without overlap), and the overlapped call's timeline -------------------
     timers = [eng.stage_timer() for _ in range(5)]
@@ -530,6 +571,8 @@ def run_b200(args):
         dets = [type(det)(full.xy[bounds[c] * cl:bounds[c + 1] * cl], full.count[bounds[c] * cl:bounds[c + 1] * cl],
                           full.flags[bounds[c] * cl:bounds[c + 1] * cl]) for c in range(chunks)]
 
+        e2e_corr = [None]
+
         def e2e_step():
             # chunked: the copy of chunk k+1 overlaps detection of chunk k (copy stream + compute stream); the detection of a chunk
             # writes its slice of the pipeline's output buffers, nothing is concatenated
@@ -545,7 +588,7 @@ def run_b200(args):
                 fr = stage_dev[bounds[c]:bounds[c + 1]].view(-1, H, W)
                 eng2.detect(fr, pipe.K0, pipe.dist0, max_blobs=MAX_BLOBS, out=dets[c])
             xy, count = pipe.exchange(full, FS)
-            co = eng.correspond(xy, count, pipe.Fs, pipe.cams, obj_count=N_MARKERS, max_groups=MAX_GROUPS, out=corr_out[0])
+            co = e2e_corr[0] = eng.correspond(xy, count, pipe.Fs, pipe.cams, obj_count=N_MARKERS, max_groups=MAX_GROUPS, out=e2e_corr[0])
             host_obj.copy_(co.obj, non_blocking=True)
             host_nobj.copy_(co.n_obj, non_blocking=True)
             host_cnt.copy_(full.count, non_blocking=True)
@@ -701,7 +744,7 @@ def run_b200(args):
     peak = float(peaks.get("hbm_gbs", 6650.0))
     peak_src = "MEASURED_PEAKS.json hbm_gbs (measured copy bandwidth)" if "hbm_gbs" in peaks else "fallback 6650 GB/s (B200_PROFILING.md)"
     alg_bytes = n_local * H * W + n_local * (4 + 8 * MAX_BLOBS)          # H*W read + (4 + 8 n_blobs) written per frame
-    det_ms = phase["detect_ms"]
+    det_ms = phase["detect_in_flight_ms"]
     achieved = alg_bytes / (det_ms * 1e-3) / 1e9
     tr = _load_traffic()
     kernels = {"scan": "scan_hot_vec32_kernel (one-shot call) / scan_tma_kernel (overlapped call)", "group": "form_clusters_kernel",
@@ -729,8 +772,11 @@ def run_b200(args):
     roofline = {"bound": "hbm", "kernel": "detection chain of a step (scan, group, filter, borders, finish; the scan overlapped with the other stages)",
                 "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak, "traffic": chain_traffic,
                 "peak_source": peak_src, "algorithmic_bytes_per_launch": alg_bytes, "detect_ms": det_ms,
-                "definition": "frames x (H*W + 4 + 8*max_blobs) bytes / time of ALL detection kernels of a step (CUDA events around the detect "
-                              "call inside the timed loop, max over ranks)",
+                "definition": "frames x (H*W + 4 + 8*max_blobs) bytes / time per step of ALL detection kernels of a step: CUDA events around a loop "
+                              "of detect calls at the operating point of the timed loop (phase_ms.steps_in_flight calls in flight, each on its "
+                              "own lane), max over ranks; single_call = one call after the other; whole_step = the timed loop itself "
+                              "(detection + exchange + match + triangulate)",
+                "single_call": {"ms": phase["detect_single_call_ms"], "frac": alg_bytes / (phase["detect_single_call_ms"] * 1e-3) / 1e9 / peak},
                 "stages_one_after_the_other": {"ms": stage_avg, "sum_ms": serial_ms, "frac": alg_bytes / (serial_ms * 1e-3) / 1e9 / peak,
                                                "note": "the same kernels through the one-shot call (no overlap), per-stage CUDA events"},
                 "overlapped_detection": pipe_info, "timeline_ms": timeline,
@@ -766,7 +812,9 @@ def run_b200(args):
         "value": value, "unit": "frames/s", "n_gpus": N, "steps": args.steps, "warmup": max(args.warmup, 3),
         "ms_per_step": ms_total / args.steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
         "dtype": "u8 (detection, integer exact) / f32 (geometry)", "data": "synthetic",
-        "config": workload_config(N, F0),
+        "config": dict(workload_config(N, F0), steps_in_flight=flight.depth,
+                       in_flight_note="the timed loop keeps this many steps in flight, each on its own lane (stream, detection pipe, buffers); "
+                                      "every step is complete when the timed region ends"),
         "points_per_s": points_per_step * args.steps / (ms_total * 1e-3),
         "frame_sets_with_group_cap": float(n_pts[1].item()), "centroids_per_frame": float(n_pts[2].item()) / (n_local * N),
         "phase_ms": phase, "output_checksum": checksum, "parity_check": parity,

@@ -95,6 +95,18 @@ class CaptureEngine:
         self.pipe_prio_mode = 0
         self.last_pipe_info = None
 
+    def clone(self) -> "CaptureEngine":
+        """A second engine over the same library, device and undistortion tables with its own per-thread state (workspaces, detection
+        pipe): a lane of pipeline.StepsInFlight."""
+        other = object.__new__(type(self))
+        other.device = self.device
+        other.lib = self.lib
+        other._init_state()
+        other._tables = self._tables
+        other._lock = self._lock                 # one lock for the shared table cache
+        other.pipe_workers, other.pipe_prio_mode = self.pipe_workers, self.pipe_prio_mode
+        return other
+
     # ---- plumbing ------------------------------------------------------------------------------------------------
     @property
     def launches(self) -> int:

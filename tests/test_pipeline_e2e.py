@@ -7,7 +7,7 @@ import pytest
 import torch
 
 from mocapv2_b200 import synth as S
-from mocapv2_b200.pipeline import CapturePipeline
+from mocapv2_b200.pipeline import CapturePipeline, StepsInFlight
 from oracle import restate as R
 
 
@@ -65,3 +65,30 @@ def test_config3_six_cameras_1440x1080(gpu_engine):
 def test_config4_sixteen_cameras_2048_reduced_markers(gpu_engine):
     """Config 4 at full frame size with a marker count the reference's group enumeration can finish."""
     assert check(gpu_engine, "c4", 2, 12, 104, 0.9, 4096) > 0
+
+
+def test_steps_in_flight_equal_one_step_after_the_other(engine):
+    """StepsInFlight: five steps over two lanes (own engine state, buffers and -- on the GPU -- streams) give what pipe.step gives."""
+    rig, frames = scene("c1", 2, 4, 105, 0.0)
+    batches = [torch.from_numpy(np.roll(frames, k, axis=0).copy()).to(engine.device) for k in range(2)]
+    pipe = CapturePipeline(engine, rig, max_blobs=64, obj_count=4, max_groups=64)
+    pipe.pipelined_min_frames = 1                                  # the overlapped detection call on every lane
+    want = []
+    for k in range(2):
+        r = pipe.step(batches[k])
+        want.append((r.det.count.clone(), r.det.xy.clone(), r.corr.n_obj.clone(), r.corr.obj.clone(), r.corr.img.clone()))
+    flight = StepsInFlight(pipe, depth=2)
+    flight.fork()
+    got = [flight.submit(batches[i % 2]) for i in range(5)]
+    flight.join()
+    if engine.device.type == "cuda":
+        torch.cuda.synchronize()
+    assert len(flight.lanes) == 2 and flight.lanes[1].eng is not pipe.eng
+    for i in (3, 4):                                               # the last result of each lane is still in its buffers
+        r, w = got[i], want[i % 2]
+        assert torch.equal(r.det.count, w[0]) and torch.equal(r.corr.n_obj, w[2])
+        for f in range(len(w[0])):
+            assert torch.equal(r.det.xy[f, :int(w[0][f])], w[1][f, :int(w[0][f])])
+        for s_ in range(len(w[2])):
+            no = int(w[2][s_])
+            assert torch.equal(r.corr.obj[s_, :no], w[3][s_, :no]) and torch.equal(r.corr.img[s_, :no], w[4][s_, :no])
