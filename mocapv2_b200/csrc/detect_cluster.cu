@@ -18,15 +18,6 @@
 #include "tma.cuh"
 
 #define CL_THREADS 128
-#ifndef PF_BATCH
-#define PF_BATCH 0              // fast remap: quads per thread whose map words are requested up front (0: none)
-#endif
-#ifndef PF_PREFETCH_LOOP
-#define PF_PREFETCH_LOOP 0      // fast remap: the map words of a thread's next quad are loaded while the current quad is computed
-#endif
-#ifndef PF_PREFETCH_PIECE
-#define PF_PREFETCH_PIECE 0     // ... and those of its first quad of the next piece during the stages of the current piece
-#endif
 #define HOT_MAX 1024            // hot cells per frame on the cluster path
 #define CELLS_MAX 8192          // TX*TY limit of the dense cell -> slot map held in shared memory
 #define ROOTS_MAX 512
@@ -660,11 +651,6 @@ __global__ void __launch_bounds__(CL_THREADS, 8) piece_filter_kernel(const uint8
     }
     __syncthreads();
     if (use_win) PF_ISSUE_WINDOW(s_desc[0]);
-    uint32_t a0 = 0, a1 = 0, a2 = 0, a3 = 0;                       // fast-map words of the thread's first quad of the coming piece
-    if (use_win && PF_PREFETCH_PIECE) {
-        const FastIter fi = fast_iter_init(s_desc[0], tv, tid);
-        if (fi.on && fi.r < fi.uh) { a0 = (uint32_t)fi.mp[0]; a1 = (uint32_t)fi.mp[1]; a2 = (uint32_t)fi.mp[2]; a3 = (uint32_t)fi.mp[3]; }
-    }
     int slot = 0;
     for (;;) {
         const int* d = s_desc[slot];
@@ -699,57 +685,19 @@ __global__ void __launch_bounds__(CL_THREADS, 8) piece_filter_kernel(const uint8
         //         in flight together; the bilinear taps come from the staged window. ----------------------------------------
         if (fastp) {
             // fast path: the box lies inside the frame, its source window is staged and every pixel has a fast-map entry (fx, fy and
-            // the place of its first tap in the window relative to the pixel's own).  The quads (four pixels of a row) of the box are
-            // a flat index, a thread takes every 128th (pointer steps with one wrap test; four map loads, one 32-bit store of the four
-            // results per quad); the map words of its next quad are in flight while this one is computed, and those of its first quad were
-            // fetched during the stages of the piece before (a0..a3), so no L2 latency is waited for inside a piece.  The surplus
-            // pixels of a row's last quad are real pixels right of the box (the descriptor's window covers them).
+            // the place of its first tap in the window relative to the pixel's own).  The box is cut into quads of four pixels aligned
+            // to frame columns that are multiples of four, as a flat index; a thread takes every 128th quad (pointer steps with one wrap
+            // test): ONE 128-bit load of the four map words (16-byte aligned: a quarter of the L1 requests of four 32-bit loads, the
+            // kernel is bound by the L1 data pipe), sixteen byte taps from the window, one 32-bit store of the four results.  The pixels
+            // left / right of the box in its first / last quad are real pixels (the descriptor's window and fast-map test cover them).
+            // Measured and dropped: fetching the map words of the next quad (or of the first PF quads) ahead -- more loads in flight made
+            // the kernel slower (0.82 -> 0.88-0.99 ms), the L1 pipe is the limit, not the L2 latency.
             FastIter fi = fast_iter_init(d, tv, tid);
             pd.lead = ux0 & 3;
             const uint8_t* pw = win + (uy0 - wy0 + fi.r) * WIN_W + (ux0 - pd.lead - wx0) + 4 * fi.q;
             uint8_t* pu = S.U + fi.r * UW + 4 * fi.q;
             const int dw = fi.dr * WIN_W + 4 * fi.dq, du = fi.dr * UW + 4 * fi.dq, dm = fi.dr * W + 4 * fi.dq;
             const int dwx = WIN_W - 4 * fi.nq, dux = UW - 4 * fi.nq, dmx = W - 4 * fi.nq;          // the wrap into the next row
-#if PF_BATCH
-            // the map words of the thread's first PF_BATCH quads are all requested before the first one is used: one L2 latency per piece
-            {
-                uint32_t m[PF_BATCH][4];
-                int r2 = fi.r, q2 = fi.q;
-                const int32_t* mp2 = fi.mp;
-#pragma unroll
-                for (int k = 0; k < PF_BATCH; ++k) {
-                    if (r2 < uh) { m[k][0] = (uint32_t)mp2[0]; m[k][1] = (uint32_t)mp2[1]; m[k][2] = (uint32_t)mp2[2]; m[k][3] = (uint32_t)mp2[3]; }
-                    q2 += fi.dq; r2 += fi.dr; mp2 += dm;
-                    if (q2 >= fi.nq) { q2 -= fi.nq; ++r2; mp2 += dmx; }
-                }
-#pragma unroll
-                for (int k = 0; k < PF_BATCH; ++k) {
-                    if (fi.r < uh)
-                        *(uint32_t*)pu = fast_tap(pw, m[k][0]) | (fast_tap(pw + 1, m[k][1]) << 8) | (fast_tap(pw + 2, m[k][2]) << 16) | (fast_tap(pw + 3, m[k][3]) << 24);
-                    fi.q += fi.dq; fi.r += fi.dr; fi.mp += dm; pw += dw; pu += du;
-                    if (fi.q >= fi.nq) { fi.q -= fi.nq; ++fi.r; fi.mp += dmx; pw += dwx; pu += dux; }
-                }
-            }
-#endif
-#if PF_PREFETCH_LOOP
-#if !PF_PREFETCH_PIECE
-            if (fi.r < uh) { a0 = (uint32_t)fi.mp[0]; a1 = (uint32_t)fi.mp[1]; a2 = (uint32_t)fi.mp[2]; a3 = (uint32_t)fi.mp[3]; }
-#endif
-            uint32_t b0, b1, b2, b3;
-            while (fi.r < uh) {
-                const uint8_t* cw_ = pw; uint8_t* cu_ = pu;
-                fi.q += fi.dq; fi.r += fi.dr; fi.mp += dm; pw += dw; pu += du;
-                if (fi.q >= fi.nq) { fi.q -= fi.nq; ++fi.r; fi.mp += dmx; pw += dwx; pu += dux; }
-                if (fi.r < uh) { b0 = (uint32_t)fi.mp[0]; b1 = (uint32_t)fi.mp[1]; b2 = (uint32_t)fi.mp[2]; b3 = (uint32_t)fi.mp[3]; }
-                *(uint32_t*)cu_ = fast_tap(cw_, a0) | (fast_tap(cw_ + 1, a1) << 8) | (fast_tap(cw_ + 2, a2) << 16) | (fast_tap(cw_ + 3, a3) << 24);
-                if (fi.r >= uh) break;
-                cw_ = pw; cu_ = pu;
-                fi.q += fi.dq; fi.r += fi.dr; fi.mp += dm; pw += dw; pu += du;
-                if (fi.q >= fi.nq) { fi.q -= fi.nq; ++fi.r; fi.mp += dmx; pw += dwx; pu += dux; }
-                if (fi.r < uh) { a0 = (uint32_t)fi.mp[0]; a1 = (uint32_t)fi.mp[1]; a2 = (uint32_t)fi.mp[2]; a3 = (uint32_t)fi.mp[3]; }
-                *(uint32_t*)cu_ = fast_tap(cw_, b0) | (fast_tap(cw_ + 1, b1) << 8) | (fast_tap(cw_ + 2, b2) << 16) | (fast_tap(cw_ + 3, b3) << 24);
-            }
-#else
             while (fi.r < uh) {
                 const int4 m = *(const int4*)fi.mp;                             // 16-byte aligned: W, the table and the quad column are
                 *(uint32_t*)pu = fast_tap(pw, (uint32_t)m.x) | (fast_tap(pw + 1, (uint32_t)m.y) << 8) | (fast_tap(pw + 2, (uint32_t)m.z) << 16) |
@@ -757,7 +705,6 @@ __global__ void __launch_bounds__(CL_THREADS, 8) piece_filter_kernel(const uint8
                 fi.q += fi.dq; fi.r += fi.dr; fi.mp += dm; pw += dw; pu += du;
                 if (fi.q >= fi.nq) { fi.q -= fi.nq; ++fi.r; fi.mp += dmx; pw += dwx; pu += dux; }
             }
-#endif
         } else {
             const int n_u = uw * uh;
             const unsigned inv = (1u << 20) / (unsigned)uw + 1u;              // idx / uw == (idx * inv) >> 20 for idx * uw < 2^20
@@ -794,11 +741,7 @@ __global__ void __launch_bounds__(CL_THREADS, 8) piece_filter_kernel(const uint8
         }
         __syncthreads();                                            // U complete; the window is free again
         // post the next piece's window (it lands while the stages below run), fetch the descriptor of the piece after it
-        if (s_next < total && use_win) {
-            PF_ISSUE_WINDOW(s_desc[slot ^ 1]);
-            const FastIter fi = fast_iter_init(s_desc[slot ^ 1], tv, tid);
-            if (PF_PREFETCH_PIECE && fi.on && fi.r < fi.uh) { a0 = (uint32_t)fi.mp[0]; a1 = (uint32_t)fi.mp[1]; a2 = (uint32_t)fi.mp[2]; a3 = (uint32_t)fi.mp[3]; }
-        }
+        if (s_next < total && use_win) PF_ISSUE_WINDOW(s_desc[slot ^ 1]);
         if (wy == 0) {
             nx = __shfl_sync(0xffffffffu, next, 0);
             dn = (lane < 8 && nx < total) ? cw.pieces[8 * (size_t)nx + lane] : 0;

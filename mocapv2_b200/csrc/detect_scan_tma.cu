@@ -134,12 +134,25 @@ __global__ void __launch_bounds__(ST_THREADS, 8) scan_tma_kernel(const __grid_co
         }
         const uint8_t* src = ring + stage * ST_STAGE_BYTES + rpar * ST_BOX_W + chunkl * 16;
         uint32_t a0 = 0, a1 = 0, a2 = 0, a3 = 0, rowbits = 0;
+        // MODE 0 (thresh >= 128): a hot byte has bit 7 set, so four loads (eight rows) are first OR-ed together -- two LOP3 per load --
+        // and the exact per-byte test only runs where some lane of the warp saw such a byte (warp-uniform branch)
 #pragma unroll
-        for (int k = 0; k < ST_BOX_H / 2; ++k) {
-            const uint4 v = *(const uint4*)(src + k * 2 * ST_BOX_W);
-            const uint32_t h0 = hot4<MODE>(v.x, a.add), h1 = hot4<MODE>(v.y, a.add), h2 = hot4<MODE>(v.z, a.add), h3 = hot4<MODE>(v.w, a.add);
-            a0 |= h0; a1 |= h1; a2 |= h2; a3 |= h3;
-            if ((h0 | h1 | h2 | h3) & 0x80808080u) rowbits |= 1u << (2 * k);
+        for (int k4 = 0; k4 < ST_BOX_H / 2; k4 += 4) {
+            uint4 v[4];
+#pragma unroll
+            for (int j = 0; j < 4; ++j) v[j] = *(const uint4*)(src + (k4 + j) * 2 * ST_BOX_W);
+            if (MODE == 0) {
+                uint32_t o = 0;
+#pragma unroll
+                for (int j = 0; j < 4; ++j) o |= v[j].x | v[j].y | v[j].z | v[j].w;
+                if (!__any_sync(0xffffffffu, (o & 0x80808080u) != 0)) continue;
+            }
+#pragma unroll
+            for (int j = 0; j < 4; ++j) {
+                const uint32_t h0 = hot4<MODE>(v[j].x, a.add), h1 = hot4<MODE>(v[j].y, a.add), h2 = hot4<MODE>(v[j].z, a.add), h3 = hot4<MODE>(v[j].w, a.add);
+                a0 |= h0; a1 |= h1; a2 |= h2; a3 |= h3;
+                if ((h0 | h1 | h2 | h3) & 0x80808080u) rowbits |= 1u << (2 * (k4 + j));
+            }
         }
         __syncwarp();
         if (lane == 0) mbar_arrive(&empty[stage]);                           // the box is in registers: the slot can be refilled
