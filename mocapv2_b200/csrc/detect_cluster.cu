@@ -369,10 +369,18 @@ __device__ __forceinline__ void packed_stage_a(PieceSmem& S, const PackedDims& d
         int r = (int)(((unsigned)t * inv_q) >> 20), q = t - r * nq;
         const uint32_t* up = (const uint32_t*)&S.U[r * UW + 4 * q];
         uint32_t w0 = up[0], w1 = up[1];
+#ifdef MOCAP_EMU
         uint32_t s0 = (w0 & 0xff) + ((w0 >> 8) & 0xff) + ((w0 >> 16) & 0xff) + (w0 >> 24) + (w1 & 0xff);
         uint32_t s1 = s0 - (w0 & 0xff) + ((w1 >> 8) & 0xff);
         uint32_t s2 = s1 - ((w0 >> 8) & 0xff) + ((w1 >> 16) & 0xff);
         uint32_t s3 = s2 - ((w0 >> 16) & 0xff) + (w1 >> 24);
+#else
+        // byte sums as dot products with 0/1 weights (IDP.4A): seven instructions for the four sums
+        uint32_t s0 = __dp4a(w0, 0x01010101u, w1 & 0xffu);
+        uint32_t s1 = __dp4a(w0, 0x01010100u, __dp4a(w1, 0x00000101u, 0u));
+        uint32_t s2 = __dp4a(w0, 0x01010000u, __dp4a(w1, 0x00010101u, 0u));
+        uint32_t s3 = __dp4a(w0, 0x01000000u, __dp4a(w1, 0x01010101u, 0u));
+#endif
         uint2 v; v.x = s0 | (s1 << 16); v.y = s2 | (s3 << 16);
         *(uint2*)&S.HS[r * HSW + 4 * q] = v;
     }
@@ -387,19 +395,32 @@ __device__ __forceinline__ void packed_stage_b(PieceSmem& S, const PackedDims& d
     uint8_t* bbits = S.B;
     const int no = (bw + 7) >> 3;
     const uint32_t bias = (0x8000u - (uint32_t)(25 * T)) * 0x00010001u;          // bit 15 of (v + bias) set  <=>  v >= 25 T
-    const unsigned inv_o = (1u << 20) / (unsigned)no + 1u;
-    for (int t = tid; t < bh * no; t += CL_THREADS) {
-        int r = (int)(((unsigned)t * inv_o) >> 20), o = t - r * no;
+    // a thread keeps one column octet and walks down a segment of rows with a sliding 5-row sum: five 128-bit loads for its first
+    // row, two (the row that enters, the row that leaves) for every further one
+    const unsigned inv_o = (1u << 16) / (unsigned)no + 1u;                        // t / no for t <= 128, no <= 9
+    const int seg = (int)(((unsigned)tid * inv_o) >> 16), o = tid - seg * no;
+    const int nseg = (int)(((unsigned)CL_THREADS * inv_o) >> 16);                 // row segments (threads beyond nseg * no idle)
+    const int rps = (bh + nseg - 1) / nseg;                                       // rows per segment
+    const int r0 = seg * rps, r1 = min(bh, r0 + rps);
+    if (seg < nseg && r0 < r1) {
+        const uint16_t* hs = &S.HS[r0 * HSW + 8 * o];
         uint32_t a0 = 0, a1 = 0, a2 = 0, a3 = 0;
 #pragma unroll
         for (int k = 0; k < 5; ++k) {
-            const uint4 h = *(const uint4*)&S.HS[(r + k) * HSW + 8 * o];     // one 128-bit load: eight sums
-            a0 += h.x; a1 += h.y; a2 += h.z; a3 += h.w;                       // packed u16 adds: sums <= 6375, no carry across halves
+            const uint4 h = *(const uint4*)(hs + k * HSW);                        // one 128-bit load: eight sums
+            a0 += h.x; a1 += h.y; a2 += h.z; a3 += h.w;                           // packed u16 adds: sums <= 6375, no carry across halves
         }
-        uint32_t m0 = (a0 + bias) & 0x80008000u, m1 = (a1 + bias) & 0x80008000u;
-        uint32_t m2 = (a2 + bias) & 0x80008000u, m3 = (a3 + bias) & 0x80008000u;
-        uint32_t y = (m0 >> 15) | (m1 >> 13) | (m2 >> 11) | (m3 >> 9);             // even bits 0..6 and 16..22
-        bbits[r * 16 + o] = (uint8_t)((y & 0x55u) | ((y >> 15) & 0xAAu));
+        for (int r = r0;;) {
+            uint32_t m0 = (a0 + bias) & 0x80008000u, m1 = (a1 + bias) & 0x80008000u;
+            uint32_t m2 = (a2 + bias) & 0x80008000u, m3 = (a3 + bias) & 0x80008000u;
+            uint32_t y = (m0 >> 15) | (m1 >> 13) | (m2 >> 11) | (m3 >> 9);         // even bits 0..6 and 16..22
+            bbits[r * 16 + o] = (uint8_t)((y & 0x55u) | ((y >> 15) & 0xAAu));
+            if (++r >= r1) break;
+            const uint4 hin = *(const uint4*)(hs + 5 * HSW), hout = *(const uint4*)hs;
+            a0 += hin.x; a1 += hin.y; a2 += hin.z; a3 += hin.w;                   // the entering row first: no half ever borrows
+            a0 -= hout.x; a1 -= hout.y; a2 -= hout.z; a3 -= hout.w;
+            hs += HSW;
+        }
     }
 }
 
