@@ -18,6 +18,9 @@
 #include "tma.cuh"
 
 #define CL_THREADS 128
+#ifndef PF_WIN_L2_PROMO
+#define PF_WIN_L2_PROMO 128     // bytes a window fetch is widened to in L2 (rows are 96 bytes)
+#endif
 #define HOT_MAX 1024            // hot cells per frame on the cluster path
 #define CELLS_MAX 8192          // TX*TY limit of the dense cell -> slot map held in shared memory
 #define ROOTS_MAX 512
@@ -107,8 +110,8 @@ __device__ __forceinline__ void make_piece_desc(const TableView& tv, int f, int 
     const int ux0 = packed ? px0 - hl - 2 : px0 - 4, uy0 = packed ? py0 - ht - 2 : py0 - 4;
     int ux1 = packed ? px1 + hr + 2 : px1 + 4;
     const int uy1 = packed ? py1 + hb + 2 : py1 + 4;
-    // the fast remap of the piece filter works on quads of four pixels: its box is padded to a multiple of four columns, and the window
-    // and the fast-map test below cover the padding (pixels right of the box: computed, never used)
+    // the fast remap of the piece filter works on quads of four pixels aligned to frame columns that are multiples of four: its box is
+    // padded to such columns on both sides, and the window and the fast-map test below cover the padding (computed, never used)
     const int ux0p = ux0 & ~3, ux1p = ((ux1 + 4) & ~3) - 1;                // quads are aligned to frame columns that are multiples of 4
     const bool padded = packed && ux1p < W;
     const int ux0w = padded ? ux0p : ux0;                                  // the box the window and the fast-map test have to cover
@@ -397,9 +400,13 @@ __device__ __forceinline__ void packed_stage_b(PieceSmem& S, const PackedDims& d
     const uint32_t bias = (0x8000u - (uint32_t)(25 * T)) * 0x00010001u;          // bit 15 of (v + bias) set  <=>  v >= 25 T
     // a thread keeps one column octet and walks down a segment of rows with a sliding 5-row sum: five 128-bit loads for its first
     // row, two (the row that enters, the row that leaves) for every further one
-    const unsigned inv_o = (1u << 16) / (unsigned)no + 1u;                        // t / no for t <= 128, no <= 9
-    const int seg = (int)(((unsigned)tid * inv_o) >> 16), o = tid - seg * no;
-    const int nseg = (int)(((unsigned)CL_THREADS * inv_o) >> 16);                 // row segments (threads beyond nseg * no idle)
+    // up to eight octets per row: a quarter warp per segment, so that the eight lanes whose 128-bit loads are served together read one
+    // row's consecutive bytes (no bank conflict); the ninth octet of the widest boxes falls back to a dense numbering
+    const int per = no <= 8 ? 8 : no;
+    const unsigned inv_o = (1u << 16) / (unsigned)per + 1u;                       // t / per for t <= 128
+    const int seg0 = (int)(((unsigned)tid * inv_o) >> 16), o = tid - seg0 * per;
+    const int nseg = (int)(((unsigned)CL_THREADS * inv_o) >> 16);                 // row segments
+    const int seg = o < no ? seg0 : nseg;                                         // surplus lanes idle
     const int rps = (bh + nseg - 1) / nseg;                                       // rows per segment
     const int r0 = seg * rps, r1 = min(bh, r0 + rps);
     if (seg < nseg && r0 < r1) {
@@ -712,7 +719,9 @@ __global__ void __launch_bounds__(CL_THREADS, 8) piece_filter_kernel(const uint8
             // kernel is bound by the L1 data pipe), sixteen byte taps from the window, one 32-bit store of the four results.  The pixels
             // left / right of the box in its first / last quad are real pixels (the descriptor's window and fast-map test cover them).
             // Measured and dropped: fetching the map words of the next quad (or of the first PF quads) ahead -- more loads in flight made
-            // the kernel slower (0.82 -> 0.88-0.99 ms), the L1 pipe is the limit, not the L2 latency.
+            // the kernel slower (0.82 -> 0.88-0.99 ms), the L1 pipe is the limit, not the L2 latency; four pixels of a COLUMN per thread
+            // (the byte taps of a warp then fall into consecutive bytes: no 2-way bank conflicts, but four 32-bit map loads and four byte
+            // stores): 0.680 against 0.687 ms, and no gain with two calls in flight.
             FastIter fi = fast_iter_init(d, tv, tid);
             pd.lead = ux0 & 3;
             const uint8_t* pw = win + (uy0 - wy0 + fi.r) * WIN_W + (ux0 - pd.lead - wx0) + 4 * fi.q;
@@ -1206,7 +1215,7 @@ int launch_cluster_path(const uint8_t* frames, int n, int H, int W, int64_t fstr
             CUtensorMap tmap;
             memset(&tmap, 0, sizeof(tmap));
             const int T = thresh + 1;
-            const int use_tma = (T >= 0 && T <= 256 && frames_tensor_map(&tmap, frames, n, H, W, fstride, WIN_W, WIN_H)) ? 1 : 0;
+            const int use_tma = (T >= 0 && T <= 256 && frames_tensor_map(&tmap, frames, n, H, W, fstride, WIN_W, WIN_H, PF_WIN_L2_PROMO)) ? 1 : 0;
             LAUNCH(piece_filter_kernel, sms * how.filter_ctas_per_sm, CL_THREADS, 0, sf, frames, fstride, tv, thresh, cw, tmap, use_tma);
         }
 #endif

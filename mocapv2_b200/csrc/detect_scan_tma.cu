@@ -190,7 +190,7 @@ static void* driver_entry(const char* name)
     return fn;
 }
 
-bool frames_tensor_map(CUtensorMap* out, const uint8_t* frames, int n, int H, int W, int64_t fstride, int box_w, int box_h)
+bool frames_tensor_map(CUtensorMap* out, const uint8_t* frames, int n, int H, int W, int64_t fstride, int box_w, int box_h, int l2_promotion)
 {
     static PFN_encodeTiled encode = (PFN_encodeTiled)driver_entry("cuTensorMapEncodeTiled");
     if (!encode || n <= 0 || H <= 0 || W <= 0) return false;
@@ -200,7 +200,10 @@ bool frames_tensor_map(CUtensorMap* out, const uint8_t* frames, int n, int H, in
     const cuuint32_t box[3] = {(cuuint32_t)box_w, (cuuint32_t)box_h, 1};
     const cuuint32_t estr[3] = {1, 1, 1};
     return encode(out, CU_TENSOR_MAP_DATA_TYPE_UINT8, 3, (void*)frames, gdim, gstr, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE,
-                  CU_TENSOR_MAP_SWIZZLE_NONE, CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE) == CUDA_SUCCESS;
+                  CU_TENSOR_MAP_SWIZZLE_NONE,
+                  l2_promotion >= 256 ? CU_TENSOR_MAP_L2_PROMOTION_L2_256B : l2_promotion >= 128 ? CU_TENSOR_MAP_L2_PROMOTION_L2_128B :
+                  l2_promotion >= 64 ? CU_TENSOR_MAP_L2_PROMOTION_L2_64B : CU_TENSOR_MAP_L2_PROMOTION_NONE,
+                  CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE) == CUDA_SUCCESS;
 }
 
 bool scan_tma_supported(const uint8_t* frames, int n, int H, int W, int64_t fstride, int thresh)
@@ -221,7 +224,7 @@ int launch_scan_tma(const uint8_t* frames, int n, int H, int W, int64_t fstride,
                     int* ctrl, int chunks, int chunk_frames, int widx, int item_begin, int item_end, int stages, cudaStream_t s)
 {
     CUtensorMap map;
-    if (!frames_tensor_map(&map, frames, n, H, W, fstride, ST_BOX_W, ST_BOX_H)) return MOCAP_ERR_UNSUPPORTED;
+    if (!frames_tensor_map(&map, frames, n, H, W, fstride, ST_BOX_W, ST_BOX_H, 256)) return MOCAP_ERR_UNSUPPORTED;
     int dev = 0, sms = 148;
     cudaGetDevice(&dev);
     cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);

@@ -35,6 +35,6 @@ __device__ __forceinline__ void tma_load_box(void* dst, const CUtensorMap* map, 
 }
 
 // tensor map of a frame batch viewed as u8 [n][H][W] with boxes of box_w x box_h x 1 (detect_scan_tma.cu); false when the driver entry point
-// is missing or the batch cannot be described (rows / frame stride / base not multiples of 16 bytes)
-bool frames_tensor_map(CUtensorMap* out, const uint8_t* frames, int n, int H, int W, int64_t fstride, int box_w, int box_h);
+// is missing or the batch cannot be described; l2_promotion: bytes (0, 64, 128, 256) a fetch is widened to in L2 (rows / frame stride / base not multiples of 16 bytes)
+bool frames_tensor_map(CUtensorMap* out, const uint8_t* frames, int n, int H, int W, int64_t fstride, int box_w, int box_h, int l2_promotion);
 #endif
