@@ -500,7 +500,11 @@ def run_b200(args):
     detect_rate(2 * flight.depth, True)
     detect_rate(3, False)                   # (the caller's stream gets its own workspace on first use)
     phase["detect_in_flight_ms"] = detect_rate(reps_d, True)
+    lane_pipe = dict(pipe.engine_pipe)
+    pipe.engine_pipe = {"workers": 6, "chunks": 8}          # the single call's own best split (the lanes use fewer, larger chunks)
+    detect_rate(3, False)
     phase["detect_single_call_ms"] = detect_rate(reps_d, False)
+    pipe.engine_pipe = lane_pipe
     phase["steps_in_flight"] = flight.depth
     phase["note"] += ("; with several steps in flight the per-step marks are latencies under overlap -- detect_in_flight_ms is the time per detect "
                       "call of a loop of detect calls alone with the same number in flight, detect_single_call_ms one call after the other")

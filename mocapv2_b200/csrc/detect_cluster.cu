@@ -27,6 +27,7 @@
 #define PIECE 64                // a cluster box is filtered in pieces of at most PIECE x PIECE output pixels
                                 // staged source window of a piece: up to WIN_W (96, common.cuh) x 78 bytes (sized so that 8 CTAs fit one SM)
 #define WIN_H 78
+#define WIN_H_LOW 56            // second TMA box height: most pieces need no more window rows
 #define CAND_PER_FRAME 512      // border-start candidates per frame on the cluster path
 
 // counters[] slots
@@ -547,6 +548,18 @@ __device__ __forceinline__ void piece_threshold_majority(PieceSmem& S, int px0, 
     }
 }
 
+// four fast-map words, kept in L2 (evict last: every piece of every frame reads the map, the frames stream past it)
+#ifdef MOCAP_EMU
+#define ld_map4(p, policy) (*(const int4*)(p))
+#else
+__device__ __forceinline__ int4 ld_map4(const int32_t* p, uint64_t policy)
+{
+    int4 r;
+    asm volatile("ld.global.nc.L2::cache_hint.v4.s32 {%0,%1,%2,%3}, [%4], %5;" : "=r"(r.x), "=r"(r.y), "=r"(r.z), "=r"(r.w) : "l"(p), "l"(policy));
+    return r;
+}
+#endif
+
 // one undistorted pixel from the staged window: m = fast-map word (fx | fy << 8 | tap offset << 16), p = the pixel's own place in the window
 __device__ __forceinline__ uint32_t fast_tap(const uint8_t* p, uint32_t m)
 {
@@ -627,8 +640,9 @@ __device__ __forceinline__ void piece_issue_window(uint8_t* win, const int* d, c
     do {                                                                                                                        \
         if (!PF_USE_TMA) piece_issue_window(win, desc, frames, fstride, W, H);                                                  \
         else if (tid == 0 && (((desc)[2] >> 25) & 1)) {                                                                         \
-            mbar_expect_tx(&wbar, WIN_W * WIN_H);                                                                               \
-            tma_load_box(win, &tmap, (int)(int16_t)((desc)[5] & 0xffff), (desc)[5] >> 16, (desc)[0], &wbar);                     \
+            const bool low_ = (((desc)[4] >> 16) & 0xff) <= WIN_H_LOW;        /* window rows needed */                          \
+            mbar_expect_tx(&wbar, WIN_W * (low_ ? WIN_H_LOW : WIN_H));                                                          \
+            tma_load_box(win, low_ ? &tmap_low : &tmap, (int)(int16_t)((desc)[5] & 0xffff), (desc)[5] >> 16, (desc)[0], &wbar, wpolicy); \
         }                                                                                                                       \
     } while (0)
 #endif
@@ -636,7 +650,7 @@ __device__ __forceinline__ void piece_issue_window(uint8_t* win, const int* d, c
 #define PF_TMA_PARAM
 #define PF_USE_TMA false
 #else
-#define PF_TMA_PARAM , const __grid_constant__ CUtensorMap tmap, int use_tma
+#define PF_TMA_PARAM , const __grid_constant__ CUtensorMap tmap, const __grid_constant__ CUtensorMap tmap_low, int use_tma
 #define PF_USE_TMA (use_tma != 0)
 #endif
 // The source window of a piece comes in as ONE TMA box (cp.async.bulk.tensor.3d of the frame batch viewed as [n][H][W], WIN_W x WIN_H
@@ -650,6 +664,9 @@ __global__ void __launch_bounds__(CL_THREADS, 8) piece_filter_kernel(const uint8
 #ifndef MOCAP_EMU
     __shared__ uint64_t wbar;                                      // "window landed" barrier of the TMA path
     unsigned wphase = 0;
+    uint64_t wpolicy, mpolicy;                                     // L2: the windows are read once (evict first), the fast map by every piece (evict last)
+    asm volatile("createpolicy.fractional.L2::evict_first.b64 %0, 1.0;" : "=l"(wpolicy));
+    asm volatile("createpolicy.fractional.L2::evict_last.b64 %0, 1.0;" : "=l"(mpolicy));
     if (threadIdx.x == 0 && PF_USE_TMA) {
         mbar_init(&wbar, 1);
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
@@ -729,7 +746,7 @@ __global__ void __launch_bounds__(CL_THREADS, 8) piece_filter_kernel(const uint8
             const int dw = fi.dr * WIN_W + 4 * fi.dq, du = fi.dr * UW + 4 * fi.dq, dm = fi.dr * W + 4 * fi.dq;
             const int dwx = WIN_W - 4 * fi.nq, dux = UW - 4 * fi.nq, dmx = W - 4 * fi.nq;          // the wrap into the next row
             while (fi.r < uh) {
-                const int4 m = *(const int4*)fi.mp;                             // 16-byte aligned: W, the table and the quad column are
+                const int4 m = ld_map4(fi.mp, mpolicy);                          // 16-byte aligned: W, the table and the quad column are
                 *(uint32_t*)pu = fast_tap(pw, (uint32_t)m.x) | (fast_tap(pw + 1, (uint32_t)m.y) << 8) | (fast_tap(pw + 2, (uint32_t)m.z) << 16) |
                                  (fast_tap(pw + 3, (uint32_t)m.w) << 24);
                 fi.q += fi.dq; fi.r += fi.dr; fi.mp += dm; pw += dw; pu += du;
@@ -1212,11 +1229,12 @@ int launch_cluster_path(const uint8_t* frames, int n, int H, int W, int64_t fstr
         LAUNCH(piece_filter_kernel, sms * how.filter_ctas_per_sm, CL_THREADS, 0, sf, frames, fstride, tv, thresh, cw);
 #else
         {
-            CUtensorMap tmap;
-            memset(&tmap, 0, sizeof(tmap));
+            CUtensorMap tmap, tmap_low;
+            memset(&tmap, 0, sizeof(tmap)); memset(&tmap_low, 0, sizeof(tmap_low));
             const int T = thresh + 1;
-            const int use_tma = (T >= 0 && T <= 256 && frames_tensor_map(&tmap, frames, n, H, W, fstride, WIN_W, WIN_H, PF_WIN_L2_PROMO)) ? 1 : 0;
-            LAUNCH(piece_filter_kernel, sms * how.filter_ctas_per_sm, CL_THREADS, 0, sf, frames, fstride, tv, thresh, cw, tmap, use_tma);
+            const int use_tma = (T >= 0 && T <= 256 && frames_tensor_map(&tmap, frames, n, H, W, fstride, WIN_W, WIN_H, PF_WIN_L2_PROMO) &&
+                                 frames_tensor_map(&tmap_low, frames, n, H, W, fstride, WIN_W, WIN_H_LOW, PF_WIN_L2_PROMO)) ? 1 : 0;
+            LAUNCH(piece_filter_kernel, sms * how.filter_ctas_per_sm, CL_THREADS, 0, sf, frames, fstride, tv, thresh, cw, tmap, tmap_low, use_tma);
         }
 #endif
         stage_end(timer, 2, sf);

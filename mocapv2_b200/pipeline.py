@@ -201,8 +201,10 @@ class StepsInFlight:
     engine state (detection pipe with its worker streams, workspace), own output / receive buffers, own CUDA stream -- over the
     same rig and the same undistortion tables; submit() runs a step on the next lane's stream, round robin.  While the border
     stages of step t still run (latency-bound, few warps), the streaming scan and the piece filter of step t + 1 have the SMs:
-    1.46 ms per 1024-frame step with two steps in flight against 1.74 ms one after the other (tools/stage_probe.py).
+    1.30 ms per 1024-frame detection with two in flight against 1.63 ms one after the other (tools/stage_probe.py).
     A step's results are valid once its lane's stream has reached the end of the step: join(), or lane_stream.synchronize()."""
+
+    IN_FLIGHT_PIPE = {"workers": 4, "chunks": 4}
 
     def __init__(self, pipe: CapturePipeline, depth: int = 2):
         self.depth = max(1, int(depth))
@@ -212,9 +214,13 @@ class StepsInFlight:
             lane = CapturePipeline(eng, pipe.rig, max_blobs=pipe.max_blobs, obj_count=pipe.obj_count, max_groups=pipe.max_groups,
                                    fp64=pipe.fp64, group=pipe.group)
             lane.pipelined_min_frames = pipe.pipelined_min_frames
-            lane.engine_pipe = dict(pipe.engine_pipe)
             lane.peer_exchange = pipe.peer_exchange
             self.lanes.append(lane)
+        if self.depth > 1:
+            # with several calls in flight fewer, larger chunks per call do better (tools/stage_probe.py: 4 chunks / 4 worker streams
+            # 1.30 ms per call with two calls in flight, 8 / 6 1.36 ms; one call alone: 1.66 against 1.63 ms)
+            for lane in self.lanes:
+                lane.engine_pipe = dict(self.IN_FLIGHT_PIPE)
         dev = pipe.eng.device
         self.streams = [torch.cuda.Stream(dev) for _ in range(self.depth)] if dev.type == "cuda" and self.depth > 1 else [None] * self.depth
         self.turn = 0
