@@ -570,7 +570,8 @@ def run_b200(args):
         bounds = np.linspace(0, FS, chunks + 1).astype(int)
         eng2 = CaptureEngine(device)
         eng2._tables = eng._tables
-        full = pipe._buffers(n_local)
+        full_buf = pipe._buffers(n_local)
+        full = type(det)(full_buf.xy, full_buf.count, full_buf.flags)      # the same tensors, filled chunk by chunk below (one-shot calls)
         cl = pipe.cams_local
         dets = [type(det)(full.xy[bounds[c] * cl:bounds[c + 1] * cl], full.count[bounds[c] * cl:bounds[c + 1] * cl],
                           full.flags[bounds[c] * cl:bounds[c + 1] * cl]) for c in range(chunks)]

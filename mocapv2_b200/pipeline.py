@@ -63,7 +63,6 @@ class CapturePipeline:
         # store-to-peer exchange (symmetric memory): tried once on the first overlapped detection of a multi-rank CUDA pipeline
         self.peer_exchange = True
         self._peer = None                       # {"bufs", "hdls", "tables", "views", "turn", "n", "per"}
-        self._scattered = False
         # overlapped detection (engine.detect_pipelined) for batches large enough to pipeline: 8 chunks on 6 worker streams
         # (tools/pipe_probe.py on the C4 batch: 1.75 ms against 2.03 ms for the one-shot call; 4 chunks / 4 workers 1.78 ms)
         self.pipelined_min_frames = 256
@@ -93,7 +92,8 @@ class CapturePipeline:
         n = FS * cl
         if pipelined is None:
             pipelined = timer is None and n >= self.pipelined_min_frames
-        self._scattered = False
+        buf = self._buffers(n)
+        buf.extras.pop("peer_turn", None)                          # (set below when this call stores its records to the peers)
         if pipelined:
             self.eng.pipe_workers = self.engine_pipe["workers"]
             chunk = -(-n // self.engine_pipe["chunks"])
@@ -102,14 +102,15 @@ class CapturePipeline:
                 peer["turn"] ^= 1
                 self.eng.set_detect_scatter(*peer["tables"][peer["turn"]])
             try:
-                self._det = self.eng.detect_pipelined(flat, self.K0, self.dist0, max_blobs=self.max_blobs, out=self._buffers(n),
+                self._det = self.eng.detect_pipelined(flat, self.K0, self.dist0, max_blobs=self.max_blobs, out=buf,
                                                       chunk_frames=chunk, timeline=timeline)
             finally:
                 if peer is not None:
                     self.eng.set_detect_scatter(None, None)
-            self._scattered = peer is not None
+            if peer is not None:
+                self._det.extras["peer_turn"] = peer["turn"]       # the result knows which receive buffers hold its records
         else:
-            self._det = self.eng.detect(flat, self.K0, self.dist0, max_blobs=self.max_blobs, out=self._buffers(n), timer=timer)
+            self._det = self.eng.detect(flat, self.K0, self.dist0, max_blobs=self.max_blobs, out=buf, timer=timer)
         return self._det
 
     def _peer_setup(self, FS: int):
@@ -157,13 +158,13 @@ class CapturePipeline:
         per = e - b
         if self.world == 1:
             return det.xy.view(FS, cl, mb, 2), det.count.view(FS, cl)
-        if self._scattered and det is self._det and self._peer:
+        turn = det.extras.pop("peer_turn", None) if self._peer else None
+        if turn is not None:
             # the records are already where their consumers read them (store-to-peer epilogue of the detection): wait for the peers
             peer = self._peer
-            peer["hdls"][peer["turn"]].barrier(channel=0)
-            self._scattered = False
+            peer["hdls"][turn].barrier(channel=0)
             self.collectives += 1
-            return peer["views"][peer["turn"]]
+            return peer["views"][turn]
         if self._rx is None or self._rx[0].shape[1] != per:
             self._rx = (torch.empty((self.world, per, cl, mb, 2), dtype=torch.int32, device=self.eng.device),
                         torch.empty((self.world, per, cl), dtype=torch.int32, device=self.eng.device))
