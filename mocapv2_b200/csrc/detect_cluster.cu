@@ -21,6 +21,9 @@
 #ifndef PF_WIN_L2_PROMO
 #define PF_WIN_L2_PROMO 128     // bytes a window fetch is widened to in L2 (rows are 96 bytes)
 #endif
+#ifndef BF_THREADS
+#define BF_THREADS 128          // threads of a border CTA (one frame): with fewer threads a lane follows several borders one after the other
+#endif
 #define HOT_MAX 1024            // hot cells per frame on the cluster path
 #define CELLS_MAX 8192          // TX*TY limit of the dense cell -> slot map held in shared memory
 #define ROOTS_MAX 512
@@ -1064,7 +1067,7 @@ __device__ void frame_finalize(const ClusterWs& cw, int f, uint8_t* keepv /*[max
     const long long* ra = cw.rec_a + (size_t)f * max_contours * 3;
     const double* rper = cw.rec_per + (size_t)f * max_contours;
     const int* info = cw.rec_info + (size_t)f * max_contours * 4;
-    for (int c = tid; c < n; c += CL_THREADS) {
+    for (int c = tid; c < n; c += (int)blockDim.x) {
         long long a00 = ra[3 * c];
         double area = (double)(a00 < 0 ? -a00 : a00) * 0.5, per = rper[c];
         int keep = 0;
@@ -1076,7 +1079,7 @@ __device__ void frame_finalize(const ClusterWs& cw, int f, uint8_t* keepv /*[max
         keepv[c] = (uint8_t)keep;
     }
     __syncthreads();
-    for (int c = tid; c < n; c += CL_THREADS) {
+    for (int c = tid; c < n; c += (int)blockDim.x) {
         long long a00 = ra[3 * c], a10 = ra[3 * c + 1], a01 = ra[3 * c + 2];
         double per = rper[c];
         int keep = keepv[c];
@@ -1249,7 +1252,7 @@ int launch_cluster_path(const uint8_t* frames, int n, int H, int W, int64_t fstr
         LAUNCH(candidates_kernel, sms * how.cand_ctas_per_sm, 128, 0, sb, cw);
         int frame_step = 1;
         for (int pr : {61, 67, 71, 73}) if (n % pr != 0) { frame_step = pr; break; }          // a prime that does not divide n
-        LAUNCH(borders_finalize_kernel, n, CL_THREADS, (size_t)max_contours + 16, sb, cw, W, frame_step, max_contours, max_blobs, min_area, min_circ,
+        LAUNCH(borders_finalize_kernel, n, BF_THREADS, (size_t)max_contours + 16, sb, cw, W, frame_step, max_contours, max_blobs, min_area, min_circ,
                out_xy, out_count, out_flags, out_contours, out_contour_count);
         stage_end(timer, 3, sb);
         if (how.ev_borders) cudaEventRecord(how.ev_borders, sb);

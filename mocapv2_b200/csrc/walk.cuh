@@ -203,9 +203,13 @@ static __device__ int trace_contour64(const uint32_t* __restrict__ rows, int mh,
                 up = load(ny - 1); mid = load(ny); dn = load(ny + 1);
             }
         }
-        if (!slide) {
-            if (ny < wy) { dn = mid; mid = up; up = load(ny - 1); }
-            else if (ny > wy) { up = mid; mid = dn; dn = load(ny + 1); }
+        if (!slide && ny != wy) {
+            // one block for both directions: the lanes of a warp that step up and those that step down share the row load
+            const bool goup = ny < wy;
+            const unsigned long long nr = load(goup ? ny - 1 : ny + 1), om = mid;
+            mid = goup ? up : dn;
+            up = goup ? nr : om;
+            dn = goup ? om : nr;
         }
         wx = nx; wy = ny; s = (d + 4) & 7;
         ++n;
