@@ -45,6 +45,7 @@ def parse():
     ap.add_argument("--e2e-steps", type=int, default=3)
     ap.add_argument("--cpu-sample", type=int, default=1, help="frame-sets timed for cpu_baseline (0 = skip)")
     ap.add_argument("--in-flight", type=int, default=2, help="steps in flight in the timed loop (each on its own lane: stream, detection pipe, buffers)")
+    ap.add_argument("--no-scan-token", action="store_true", help="let the scans of the lanes run side by side (A/B of StepsInFlight.scan_token)")
     ap.add_argument("--no-e2e", action="store_true")
     ap.add_argument("--no-geometry", action="store_true", help="skip the config-5 geometry sweep")
     ap.add_argument("--no-extra", action="store_true", help="skip front step, _find_dot latency and the C1 / C3 configs")
@@ -403,6 +404,8 @@ def run_b200(args):
     n_local = FS * pipe.cams_local
     H, W = rig["H"], rig["W"]
     flight = StepsInFlight(pipe, args.in_flight)
+    if args.no_scan_token:
+        flight.scan_token = False
     corr_outs = {}
 
     def step_on(lane, marks=None):

@@ -132,6 +132,10 @@ int mocap_detect_batch_pipelined(void* pipe, const uint8_t* frames_dev, int n_fr
  * border stage -- to xy_dst[f] (its centroids, int32 pairs) and count_dst[f] (its count): addresses in the receive buffer of the rank that
  * matches the frame's frame-set, mapped into this process (symmetric memory over NVLink).  The exchange step is then a barrier. */
 int mocap_detect_pipe_set_scatter(void* pipe, const uint64_t* xy_dst_dev, const uint64_t* count_dst_dev);
+/* Scan token (several pipes in flight on one GPU, pipeline.StepsInFlight): the following calls of this pipe let their streaming scan wait
+ * for `wait_event` and record `done_event` behind it (cudaEvent_t handles owned by the caller, NULL = none).  Chained from call to call
+ * across the pipes, the HBM-bound scans run one after the other instead of side by side: one ring of TMA boxes per SM instead of two. */
+int mocap_detect_pipe_set_scan_token(void* pipe, void* wait_event, void* done_event);
 /* ms since the fork of the last call with record_timeline: [scan done, join] then per chunk [scan seen, grouped, filtered,
  * borders done]; returns the number of floats written, 0 without a timeline */
 int mocap_detect_pipe_timeline(void* pipe, float* ms_out, int cap);

@@ -50,6 +50,7 @@ SIGNATURES = {
     "mocap_detect_batch_pipelined": (_i, [_p, _p, _i, _i, _i, _i64, _p, _i, _d, _d, _i, _i, _i,
                                           _p, _p, _p, _p, _p, _p, _sz, _p, _p]),
     "mocap_detect_pipe_set_scatter": (_i, [_p, _p, _p]),
+    "mocap_detect_pipe_set_scan_token": (_i, [_p, _p, _p]),
     "mocap_detect_pipe_timeline": (_i, [_p, _p, _i]),
     "mocap_detect_pipe_info": (_i, [_p, _p]),
     "mocap_scan_cells_batch": (_i, [_p, _i, _i, _i, _i64, _p, _i, _i, _p, _p, _sz, _p]),

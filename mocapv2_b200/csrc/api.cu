@@ -287,6 +287,8 @@ static int launch_scatter(const int32_t* xy, const int32_t* count, const unsigne
 struct DetectPipe {
     const unsigned long long* sc_xy = nullptr;      // per-frame destinations of the store-to-peer epilogue (device arrays [n]), or null
     const unsigned long long* sc_count = nullptr;
+    void* tok_wait = nullptr;                       // scan token (mocap_detect_pipe_set_scan_token): cudaEvent_t the scan waits for / records
+    void* tok_done = nullptr;
 #ifndef MOCAP_EMU
     cudaStream_t s_scan = nullptr, s_proc[PIPE_MAX_PROC] = {};
     cudaEvent_t ev_fork = nullptr, ev_scan_done = nullptr, ev_proc_done[PIPE_MAX_PROC] = {}, ev_join = nullptr;
@@ -337,6 +339,15 @@ extern "C" int mocap_detect_pipe_set_scatter(void* pipe, const uint64_t* xy_dst_
     if (!p || ((xy_dst_dev == nullptr) != (count_dst_dev == nullptr))) return MOCAP_ERR_INVALID;
     p->sc_xy = (const unsigned long long*)xy_dst_dev;
     p->sc_count = (const unsigned long long*)count_dst_dev;
+    return MOCAP_OK;
+}
+
+extern "C" int mocap_detect_pipe_set_scan_token(void* pipe, void* wait_event, void* done_event)
+{
+    DetectPipe* p = (DetectPipe*)pipe;
+    if (!p) return MOCAP_ERR_INVALID;
+    p->tok_wait = wait_event;
+    p->tok_done = done_event;
     return MOCAP_OK;
 }
 
@@ -450,6 +461,7 @@ extern "C" int mocap_detect_batch_pipelined(void* pipe, const uint8_t* frames_de
     const bool tl = opts->record_timeline != 0;
     CUDA_TRY(cudaEventRecord(dp->ev_fork, s));
     CUDA_TRY(cudaStreamWaitEvent(dp->s_scan, dp->ev_fork, 0));
+    if (dp->tok_wait) CUDA_TRY(cudaStreamWaitEvent(dp->s_scan, (cudaEvent_t)dp->tok_wait, 0));    // scans of several pipes one after the other
     if (mode == 1) {
         st = launch_scan_tma(frames_dev, n_frames, H, W, frame_stride, tv, thresh, ws.cellbox, ctrl, chunks, cf, 0, 0, -1, opts->scan_stages, dp->s_scan);
         if (st != MOCAP_OK) return st;
@@ -517,6 +529,7 @@ extern "C" int mocap_detect_batch_pipelined(void* pipe, const uint8_t* frames_de
         if (st != MOCAP_OK) return st;
     }
     CUDA_TRY(cudaEventRecord(dp->ev_scan_done, dp->s_scan));
+    if (dp->tok_done) CUDA_TRY(cudaEventRecord((cudaEvent_t)dp->tok_done, dp->s_scan));
     CUDA_TRY(cudaStreamWaitEvent(s, dp->ev_scan_done, 0));
     for (int i = 0; i < dp->n_proc; ++i) {
         CUDA_TRY(cudaEventRecord(dp->ev_proc_done[i], dp->s_proc[i]));

@@ -430,7 +430,9 @@ struct CorrIn {
     }
 };
 
+#ifndef CORR_RPC
 #define CORR_RPC 8        // roots per CTA of the candidate / group kernel
+#endif
 
 // Part 1, grid (S, ceil(max_pts / CORR_RPC)): candidates per (root, camera), candidate groups, triangulation and mean
 // reprojection error of the CTA's roots -> workspace.  Roots are independent until the ranking (Helpers.py:203-273).

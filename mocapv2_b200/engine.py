@@ -333,6 +333,15 @@ class CaptureEngine:
         _cabi.check(self.lib, self.lib.mocap_detect_pipe_set_scatter(self._pipe(), self._ptr(xy_dst), self._ptr(count_dst)),
                     "mocap_detect_pipe_set_scatter")
 
+    def set_scan_token(self, wait_event=None, done_event=None):
+        """The following detect_pipelined calls of the calling thread let their streaming scan wait for `wait_event` and record
+        `done_event` behind it (torch.cuda.Event objects that have been recorded at least once, or None): StepsInFlight chains the
+        scans of its lanes this way (include/mocap_b200.h, mocap_detect_pipe_set_scan_token)."""
+        self._tls.scan_token = (wait_event, done_event)          # keeps the events alive
+        h = lambda e: ctypes.c_void_p(int(e.cuda_event)) if e is not None else ctypes.c_void_p(0)
+        _cabi.check(self.lib, self.lib.mocap_detect_pipe_set_scan_token(self._pipe(), h(wait_event), h(done_event)),
+                    "mocap_detect_pipe_set_scan_token")
+
     def pipe_timeline(self):
         """ms since the fork of the last detect_pipelined(timeline=True): {"scan_done", "join", "chunks": [[seen, grouped, filtered, borders], ...]}"""
         buf = (ctypes.c_float * (2 + 4 * 64))()

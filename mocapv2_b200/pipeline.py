@@ -65,6 +65,7 @@ class CapturePipeline:
         self._peer = None                       # {"bufs", "hdls", "tables", "views", "turn", "n", "per"}
         # overlapped detection (engine.detect_pipelined) for batches large enough to pipeline: 8 chunks on 6 worker streams
         # (tools/pipe_probe.py on the C4 batch: 1.75 ms against 2.03 ms for the one-shot call; 4 chunks / 4 workers 1.78 ms)
+        self.scan_token = None                  # (wait, done) events of the coming overlapped detection, set by StepsInFlight
         self.pipelined_min_frames = 256
         self.engine_pipe = {"workers": 6, "chunks": 8}
 
@@ -96,6 +97,8 @@ class CapturePipeline:
         buf.extras.pop("peer_turn", None)                          # (set below when this call stores its records to the peers)
         if pipelined:
             self.eng.pipe_workers = self.engine_pipe["workers"]
+            if self.scan_token is not None:
+                self.eng.set_scan_token(*self.scan_token)
             chunk = -(-n // self.engine_pipe["chunks"])
             peer = self._peer_setup(FS) if (self.world > 1 and self.peer_exchange) else None
             if peer is not None:
@@ -225,10 +228,23 @@ class StepsInFlight:
         dev = pipe.eng.device
         self.streams = [torch.cuda.Stream(dev) for _ in range(self.depth)] if dev.type == "cuda" and self.depth > 1 else [None] * self.depth
         self.turn = 0
+        # scan token: the HBM-bound scans of the lanes run one after the other (each call's scan waits for the scan of the call
+        # submitted before it), so that never two rings of TMA boxes sit on an SM.  Two events per lane, used in turn.
+        self.scan_token = self.streams[0] is not None
+        self._tok = []
+        if self.scan_token:
+            for _ in range(2 * self.depth):
+                e = torch.cuda.Event()
+                e.record()                                         # creates the CUDA event behind the object
+                self._tok.append(e)
 
     def next_lane(self):
         """(pipeline, stream) of the next step; the stream is None with depth 1 (the caller's stream)."""
         k = self.turn % self.depth
+        if self.scan_token:
+            n = len(self._tok)
+            prev = self._tok[(self.turn - 1) % n] if self.turn > 0 else None
+            self.lanes[k].scan_token = (prev, self._tok[self.turn % n])
         self.turn += 1
         return self.lanes[k], self.streams[k]
 
