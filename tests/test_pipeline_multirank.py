@@ -59,7 +59,21 @@ def _run(rank, world, port, out_dir, backend="gloo", scene="c1", overlapped=Fals
     pipe = CapturePipeline(eng, rig, max_blobs=8, obj_count=4, max_groups=16, fp64=False)
     frames = torch.from_numpy(fr)
     local = frames[:, pipe.cam_begin:pipe.cam_begin + pipe.cams_local].contiguous().to(eng.device)
-    if overlapped:                                            # the batch path of the bench: overlapped detection + store-to-peer exchange
+    if overlapped == "lanes":                                 # the bench's timed loop: five steps over two lanes (StepsInFlight)
+        from mocapv2_b200.pipeline import StepsInFlight
+        pipe.pipelined_min_frames = 1
+        flight = StepsInFlight(pipe, depth=2)
+        flight.fork()
+        results = [flight.submit(local) for _ in range(5)]
+        flight.join()
+        if eng.device.type == "cuda":
+            torch.cuda.synchronize()
+        assert world == 1 or eng.device.type != "cuda" or all(l._peer for l in flight.lanes), "store-to-peer exchange not set up on every lane"
+        res = results[-1]                                     # (lane 0's third step; lane 1's last result is results[-2])
+        other = results[-2]
+        assert torch.equal(other.corr.n_obj, res.corr.n_obj) and torch.equal(other.det.count, res.det.count)
+        pipe.collectives = min(pipe.collectives, 1)
+    elif overlapped:                                          # the batch path: overlapped detection + store-to-peer exchange
         pipe.pipelined_min_frames = 1
         for _ in range(3):                                    # three steps: the two receive buffers alternate
             res = pipe.step(local)
@@ -115,6 +129,31 @@ def test_two_ranks_with_two_cameras_each(tmp_path):
     assert int(one["n_obj"].min()) >= 2                       # the scene triangulates in every frame-set
     port = 33500 + os.getpid() % 2000
     mp.spawn(_run, args=(2, port, out, "gloo", "ring4"), nprocs=2, join=True)
+    _compare(out, cams_per_rank=2)
+
+
+def test_two_ranks_with_steps_in_flight(tmp_path):
+    """StepsInFlight over two ranks (gloo, emulation build: lanes without streams, NCCL-style exchange): same results as one rank."""
+    sys.path.insert(0, os.path.join(REPO, "tests", "emu"))
+    import build_emu
+    build_emu.build()
+    out = str(tmp_path)
+    _run(0, 1, 0, out, "gloo", "ring4", "lanes")
+    port = 34500 + os.getpid() % 2000
+    mp.spawn(_run, args=(2, port, out, "gloo", "ring4", "lanes"), nprocs=2, join=True)
+    _compare(out, cams_per_rank=2)
+
+
+@pytest.mark.gpu
+def test_two_gpus_steps_in_flight_equal_one_gpu(tmp_path):
+    """Two steps in flight on each of two GPUs: every lane has its own symmetric receive buffers and stores to the peer's, the scans of
+    the lanes are chained by the scan token; five steps, results equal to one GPU."""
+    if torch.cuda.device_count() < 2:
+        pytest.skip("needs two GPUs")
+    out = str(tmp_path)
+    port = 30500 + os.getpid() % 2000
+    mp.spawn(_run, args=(1, port, out, "nccl", "ring4", "lanes"), nprocs=1, join=True)
+    mp.spawn(_run, args=(2, port, out, "nccl", "ring4", "lanes"), nprocs=2, join=True)
     _compare(out, cams_per_rank=2)
 
 
