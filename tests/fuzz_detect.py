@@ -1,5 +1,7 @@
-"""Fuzz the detection path on the CUDA-on-CPU build against the oracle: random lenses, frame sizes and scenes
-(development tool; python tests/fuzz_detect.py [iterations] [seed]; it uses the oracle, so it lives under tests/)."""
+"""Fuzz the detection path against the oracle: random lenses, frame sizes and scenes -- on the CUDA-on-CPU build (default) or, with
+--gpu, on the real library (larger frames, row lengths that are multiples of 16 so that the TMA scan / TMA windows run; both the
+one-shot and the overlapped call).  Development tool: python tests/fuzz_detect.py [iterations] [seed] [--gpu]; it uses the oracle, so it
+lives under tests/."""
 import os
 import sys
 
@@ -17,14 +19,22 @@ from util import oracle_contour_table               # noqa: E402
 
 
 def main():
-    iters = int(sys.argv[1]) if len(sys.argv) > 1 else 40
-    rng = np.random.default_rng(int(sys.argv[2]) if len(sys.argv) > 2 else 1)
-    from emu_engine import EmuEngine
-    eng = EmuEngine(build_emu.build())
+    argv = [a for a in sys.argv[1:] if a != "--gpu"]
+    gpu = "--gpu" in sys.argv
+    iters = int(argv[0]) if len(argv) > 0 else 40
+    rng = np.random.default_rng(int(argv[1]) if len(argv) > 1 else 1)
+    if gpu:
+        eng = CaptureEngine("cuda:0")
+    else:
+        from emu_engine import EmuEngine
+        eng = EmuEngine(build_emu.build())
     reasons = {}
     for it in range(iters):
-        H, W = int(rng.integers(40, 300)), int(rng.integers(40, 360))
-        if rng.random() < 0.5:
+        if gpu:
+            H, W = int(rng.integers(64, 900)), int(rng.integers(64, 1200))
+        else:
+            H, W = int(rng.integers(40, 300)), int(rng.integers(40, 360))
+        if gpu or rng.random() < 0.5:
             W = max(48, (W // 16) * 16)
         f = float(rng.uniform(0.45, 6.0)) * max(H, W)
         K = np.array([[f, 0, W * rng.uniform(0.3, 0.7)], [0, f * rng.uniform(0.95, 1.05), H * rng.uniform(0.3, 0.7)], [0, 0, 1]])
@@ -53,7 +63,14 @@ def main():
         min_area = float(rng.choice([0.0, 30.0, 500.0]))
         _, binimg = R.filter_frame(img, K, D)
         _, pts = oracle_contour_table(binimg, min_area)
-        res = eng.detect(torch.from_numpy(img[None].copy()), K, D, min_area=min_area)
+        res = eng.detect(torch.from_numpy(img[None].copy()).to(eng.device), K, D, min_area=min_area)
+        if gpu:                                                  # the overlapped call on the same frame (three copies, two chunks)
+            over = eng.detect_pipelined(torch.from_numpy(np.stack([img] * 3)).to(eng.device), K, D, min_area=min_area, chunk_frames=2)
+            for k in range(3):
+                if over.points(k) != res.points(0) or int(over.flags[k]) != int(res.flags[0]):
+                    np.savez("/tmp/fuzz_fail.npz", img=img, K=K, D=D, min_area=min_area)
+                    print(f"MISMATCH one-shot vs overlapped at iteration {it}, copy {k}")
+                    return 1
         fl = int(res.flags[0])
         reasons[fl >> 8 if fl & 64 else -1] = reasons.get(fl >> 8 if fl & 64 else -1, 0) + 1
         ok = res.points(0) == (pts if pts else [[None, None]]) and (fl & 63 & ~16) == 0
