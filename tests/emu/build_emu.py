@@ -16,6 +16,8 @@ SOURCES = ["api.cu", "detect_filter.cu", "detect_scan_tma.cu", "detect_cluster.c
 
 
 def build(force=False):
+    extra = os.environ.get("MOCAP_EMU_FLAGS", "").split()            # e.g. -DBAYER_NW_MAX=4 (variant checks; forces a rebuild)
+    force = force or bool(extra)
     deps = [os.path.join(CSRC, f) for f in os.listdir(CSRC) if f.endswith((".cu", ".cuh"))] + \
            [os.path.join(HERE, "cuda_emu.h"), os.path.join(HERE, "cuda_emu.cpp"),
             os.path.join(REPO, "include", "mocap_b200.h")]
@@ -26,7 +28,7 @@ def build(force=False):
     for s in SOURCES:
         o = os.path.join(OUT, s + ".o")
         subprocess.check_call(["g++", "-x", "c++", "-std=c++20", "-O1", "-g", "-ffp-contract=off", "-fPIC", "-DMOCAP_EMU",
-                               "-Wno-attributes", "-I", HERE, "-c", os.path.join(CSRC, s), "-o", o])
+                               "-Wno-attributes", "-I", HERE] + extra + ["-c", os.path.join(CSRC, s), "-o", o])
         objs.append(o)
     o = os.path.join(OUT, "cuda_emu.o")
     subprocess.check_call(["g++", "-std=c++20", "-O1", "-g", "-fPIC", "-I", HERE, "-c", os.path.join(HERE, "cuda_emu.cpp"), "-o", o])

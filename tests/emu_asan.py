@@ -15,7 +15,7 @@ def build():
     os.makedirs(OUT, exist_ok=True)
     objs = []
     flags = ["-std=c++20", "-O1", "-g", "-fsanitize=address", "-fno-omit-frame-pointer", "-fPIC", "-I", here]
-    for s in ["api.cu", "detect_filter.cu", "detect_cluster.cu", "detect_blobs.cu", "geometry.cu"]:
+    for s in ["api.cu", "detect_filter.cu", "detect_scan_tma.cu", "detect_cluster.cu", "detect_blobs.cu", "geometry.cu"]:
         o = os.path.join(OUT, s + ".o")
         subprocess.check_call(["g++", "-x", "c++", "-ffp-contract=off", "-DMOCAP_EMU", "-Wno-attributes"] + flags + ["-c", os.path.join(csrc, s), "-o", o])
         objs.append(o)
@@ -56,7 +56,7 @@ def run():
     img[90:120, 0:130] = 255
     assert eng.detect(torch.from_numpy(img[None].copy()), K, D, min_area=0.0).points(0) == \
         eng.detect(torch.from_numpy(img[None].copy()), K, D, min_area=0.0, outputs=("bits", "labels")).points(0)
-    for shape in [(3, 4), (5, 8), (34, 132), (64, 128), (97, 260), (7, 10), (33, 65)]:  # Bayer front step, both kernels
+    for shape in [(3, 4), (5, 8), (34, 132), (64, 128), (97, 260), (7, 10), (33, 65), (3, 8), (12, 1032), (129, 1040), (75, 16)]:  # Bayer front step, both kernels
         eng.bayer_gr2gray(torch.from_numpy(rng.integers(0, 256, (2,) + shape).astype(np.uint8)))
     z = np.load(os.path.join(REPO, "tests", "golden", "c1_frames.npz"))["frames"].reshape(-1, 480, 640)[:2]
     res = eng.detect(torch.from_numpy(z.copy()), K, D)

@@ -60,7 +60,8 @@ def test_stage_undistort_and_blur(engine):
         assert np.array_equal(blur, R.blur5_floor(img))
 
 
-@pytest.mark.parametrize("shape", [(3, 3), (7, 10), (33, 65), (120, 160), (3, 4), (4, 8), (35, 132), (64, 128), (97, 260), (70, 264), (9, 520)])
+@pytest.mark.parametrize("shape", [(3, 3), (7, 10), (33, 65), (120, 160), (3, 4), (4, 8), (35, 132), (64, 128), (97, 260), (70, 264), (9, 520),
+                                   (3, 16), (4, 1032), (10, 16), (11, 8), (12, 2064), (13, 516), (66, 24), (129, 1040), (200, 48), (75, 2048)])
 def test_bayer_front_step(engine, shape):
     """cvtColor(BAYER_GR2BGR) -> cvtColor(BGR2GRAY) in front of _find_dot (RealtimeTracking_FLIR.py:103-104), fused."""
     rng = np.random.default_rng(shape[0])
