@@ -17,6 +17,17 @@
 #define CAM_K 24
 #define CAM_D 33
 
+// One MUFU each: the library's rsqrtf / __fdividef wrap the SFU operation into a denormal test and two predicated rescaling
+// multiplies when the build does not flush denormals (55 of the 296 instructions of a Jacobi sweep); every argument here is a
+// normal number by construction (the tiny terms added below), so the .ftz forms give the same values.
+#ifdef MOCAP_EMU
+static inline float sfu_rsqrt(float x) { return 1.0f / sqrtf(x); }
+static inline float sfu_rcp(float x) { return 1.0f / x; }
+#else
+__device__ __forceinline__ float sfu_rsqrt(float x) { float y; asm("rsqrt.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x)); return y; }
+__device__ __forceinline__ float sfu_rcp(float x) { float y; asm("rcp.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x)); return y; }
+#endif
+
 template <typename T> struct Num;
 template <> struct Num<float> {
     static __device__ __forceinline__ float sqrt_(float x) { return sqrtf(x); }
@@ -58,9 +69,9 @@ __device__ __forceinline__ void jacobi_min_eigvec_f32(float b00, float b01, floa
                 const float apq = A[p][q];
                 const float dl = A[q][q] - A[p][p], two = apq + apq;
                 const float ss = dl * dl + two * two;
-                const float r = ss * rsqrtf(ss + 1e-37f);
-                const float t = __fdividef(two, dl + copysignf(r + 1e-30f, dl));
-                const float c = rsqrtf(t * t + 1.0f), s = t * c;
+                const float r = ss * sfu_rsqrt(ss + 1e-37f);
+                const float t = two * sfu_rcp(dl + copysignf(r + 1e-30f, dl));
+                const float c = sfu_rsqrt(t * t + 1.0f), s = t * c;
                 A[p][p] -= t * apq; A[q][q] += t * apq; A[p][q] = 0.0f; A[q][p] = 0.0f;
 #pragma unroll
                 for (int r2 = 0; r2 < 4; ++r2) {
@@ -253,7 +264,7 @@ __device__ __forceinline__ void project<float>(const float* pose, const float* k
     float Yx = R[0] * X[0] + R[1] * X[1] + R[2] * X[2] + t[0];
     float Yy = R[3] * X[0] + R[4] * X[1] + R[5] * X[2] + t[1];
     float Yz = R[6] * X[0] + R[7] * X[1] + R[8] * X[2] + t[2];
-    float z = Yz != 0.f ? 1.f / Yz : 1.f;
+    float z = Yz != 0.f ? sfu_rcp(Yz) : 1.f;              // SFU reciprocal (1 ulp): the IEEE division's range test and slow path cost more than the projection's matrix product
     float x = Yx * z, y = Yy * z;
     float r2 = x * x + y * y, r4 = r2 * r2, r6 = r4 * r2;
     float a1 = 2.f * x * y, a2 = r2 + 2.f * x * x, a3 = r2 + 2.f * y * y;
@@ -357,6 +368,48 @@ __global__ void __launch_bounds__(128) triangulate_kernel(const T* __restrict__ 
     }
 }
 
+// The bulk case of BASELINE config 5 (every point seen by all CT cameras, FP32, triangulation + reprojection error): the same
+// arithmetic as triangulate_kernel<float, true> with the view loops unrolled -- the camera records sit at constant shared-memory
+// offsets, no validity tests, no per-view address arithmetic (in the generic kernel ~45 of the ~150 instructions per view).
+template <int CT>
+__global__ void __launch_bounds__(128) triangulate_dense_f32_kernel(const float* __restrict__ pts, const double* __restrict__ cams,
+                                                                    long long n, float* __restrict__ xyz_out, float* __restrict__ err_out)
+{
+    DYN_SHARED(smraw);
+    float* sm = (float*)smraw;
+    load_cams<float>(cams, CT, sm);
+    for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (long long)gridDim.x * blockDim.x) {
+        const float* p = pts + (size_t)i * CT * 2;
+        float px[CT], py[CT];
+#pragma unroll
+        for (int c = 0; c < CT; ++c) load_xy(p + 2 * c, px[c], py[c]);
+        Accum<float> acc; acc.clear();
+#pragma unroll
+        for (int c = 0; c < CT; ++c) acc.add_view(sm + c * CAM_T_STRIDE + CAM_P, px[c], py[c]);
+        float X[3];
+        acc.solve(X);
+        if (xyz_out) { xyz_out[(size_t)i * 3] = X[0]; xyz_out[(size_t)i * 3 + 1] = X[1]; xyz_out[(size_t)i * 3 + 2] = X[2]; }
+        if (err_out) {
+            float s = 0.f;
+#pragma unroll
+            for (int c = 0; c < CT; ++c) {
+                float u, v;
+                project<float>(sm + c * CAM_T_STRIDE + CAM_R, sm + c * CAM_T_STRIDE + CAM_K, X, u, v);
+                const float dx = px[c] - u, dy = py[c] - v;
+                s += dx * dx; s += dy * dy;
+            }
+            err_out[i] = s / (float)(2 * CT);
+        }
+    }
+}
+
+template <int CT>
+static void launch_dense(const void* pts, const double* cams, int64_t n, void* xyz_out, void* err_out, unsigned blocks, cudaStream_t s)
+{
+    LAUNCH(triangulate_dense_f32_kernel<CT>, blocks, 128, (size_t)CT * CAM_T_STRIDE * sizeof(float), s, (const float*)pts, cams, (long long)n,
+           (float*)xyz_out, (float*)err_out);
+}
+
 template <typename T>
 static int launch_tri(const void* pts, const uint8_t* valid, const void* xyz_in, const double* cams, int C, int64_t n,
                       void* xyz_out, void* err_out, bool tri, cudaStream_t s, int n_sets = 1)
@@ -372,7 +425,13 @@ static int launch_tri(const void* pts, const uint8_t* valid, const void* xyz_in,
     auto k_rep = triangulate_kernel<T, false>;
     const T* no_in = nullptr;
     T* no_out = nullptr;
-    if (tri) LAUNCH(k_tri, dim3((unsigned)blocks, (unsigned)n_sets), 128, smem, s, (const T*)pts, valid, no_in, cams, C, n, (T*)xyz_out, (T*)err_out);
+    if (tri && sizeof(T) == 4 && !valid && n_sets == 1 && (C == 2 || C == 4 || C == 6 || C == 8 || C == 16)) {
+        if (C == 2) launch_dense<2>(pts, cams, n, xyz_out, err_out, (unsigned)blocks, s);
+        else if (C == 4) launch_dense<4>(pts, cams, n, xyz_out, err_out, (unsigned)blocks, s);
+        else if (C == 6) launch_dense<6>(pts, cams, n, xyz_out, err_out, (unsigned)blocks, s);
+        else if (C == 8) launch_dense<8>(pts, cams, n, xyz_out, err_out, (unsigned)blocks, s);
+        else launch_dense<16>(pts, cams, n, xyz_out, err_out, (unsigned)blocks, s);
+    } else if (tri) LAUNCH(k_tri, dim3((unsigned)blocks, (unsigned)n_sets), 128, smem, s, (const T*)pts, valid, no_in, cams, C, n, (T*)xyz_out, (T*)err_out);
     else LAUNCH(k_rep, (unsigned)blocks, 128, smem, s, (const T*)pts, valid, (const T*)xyz_in, cams, C, n, no_out, (T*)err_out);
     CUDA_TRY(cudaGetLastError());
     return MOCAP_OK;
