@@ -702,6 +702,34 @@ def run_b200(args):
                  "kernel": "bayer_gr2gray_rows_kernel", "ms": fms, "frames_per_s": nb / (fms * 1e-3),
                  "algorithmic_bytes": 2 * nb * H * W, "achieved_gbs": 2 * nb * H * W / (fms * 1e-3) / 1e9}
         del raw, grey
+    # raw sensor frames through front step + detection (what the realtime loop does per frame, RealtimeTracking_FLIR.py:103-105):
+    # the step's resident frames read as Bayer GR mosaics -> grey -> centroid lists, one call after the other on one stream
+    if front is not None and N == 1:                              # (one GPU: the pipeline's detect call is collective-free only there)
+        raw4 = frames                                              # [F0, cams_local, H, W]: any byte image is a valid mosaic
+        grey4 = torch.empty_like(raw4)
+
+        def raw_step():
+            eng.bayer_gr2gray(raw4.view(-1, H, W), out=grey4.view(-1, H, W))
+            return pipe.detect(grey4)
+
+        det_raw = raw_step()
+        rms = _time_loop(raw_step, 10)
+        n_raw = raw4.shape[0] * raw4.shape[1]
+        raw_par = None
+        try:
+            from oracle import cv2_port, restate as R_
+            if cv2_port.available():
+                want = cv2_port.find_dot(R_.bayer_gr_to_gray(raw4[0, 0].cpu().numpy()), rig["camera_params"][0]["intrinsic_matrix"],
+                                         rig["camera_params"][0]["distortion_coef"])
+                got = det_raw.points(0)
+                raw_par = {"frame": 0, "centroid_list_equal": got == want, "n_centroids": 0 if want == [[None, None]] else len(want),
+                           "against": "oracle: bayer_gr_to_gray (== cv2.cvtColor BAYER_GR2BGR -> BGR2GRAY, tests/test_oracle_cv2.py) -> cv2_port.find_dot"}
+        except ImportError:
+            pass
+        front["raw_to_centroids"] = {"frames": n_raw, "ms": rms, "frames_per_s": n_raw / (rms * 1e-3),
+                                     "how": "mocap_bayer_gr2gray_batch then the overlapped detection call on the same stream, CUDA events, no second call in flight",
+                                     "parity_check": raw_par}
+        del grey4, det_raw
 
     # ---- one frame through the drop-in the realtime loop calls: numpy image in, centroid list + undistorted image out ------
     latency = None
