@@ -392,7 +392,12 @@ def run_b200(args):
     local = int(os.environ.get("LOCAL_RANK", "0"))
     torch.cuda.set_device(local)
     device = torch.device(f"cuda:{local}")
+    host_binding = None
     if world > 1:
+        # a rank next to its GPU: CPU affinity + preferred memory node before any pinned buffer exists (N = 1 keeps every host
+        # core for the cpu_baseline leg)
+        from mocapv2_b200 import hostbind
+        host_binding = hostbind.bind_to_gpu(local)
         dist.init_process_group("nccl", device_id=device)
     N = world
     F0 = args.frame_sets
@@ -855,7 +860,7 @@ def run_b200(args):
         "frame_sets_with_group_cap": float(n_pts[1].item()), "centroids_per_frame": float(n_pts[2].item()) / (n_local * N),
         "phase_ms": phase, "output_checksum": checksum, "parity_check": parity,
         "e2e": e2e, "gpu_launches": gpu_launches, "collectives_per_step": 1 if N > 1 else 0,
-        "clocks": clocks, "roofline": roofline, "cpu_baseline": cpu, "geometry": geometry, "front_step": front, "find_dot_latency": latency,
+        "clocks": clocks, "roofline": roofline, "cpu_baseline": cpu, "geometry": geometry, "front_step": front, "find_dot_latency": latency, "host_binding": host_binding,
         "other_configs": others, "bundle_adjustment": ba,
     }
     emit(line)
