@@ -713,11 +713,22 @@ def run_b200(args):
         raw4 = frames                                              # [F0, cams_local, H, W]: any byte image is a valid mosaic
         grey4 = torch.empty_like(raw4)
 
-        def raw_step():
+        cells4 = eng.empty((raw4.shape[0] * raw4.shape[1], (H + 31) // 32, (W + 31) // 32), torch.int32)
+
+        def raw_step_two_passes():                                 # front step, then the detection with its own streaming scan
             eng.bayer_gr2gray(raw4.view(-1, H, W), out=grey4.view(-1, H, W))
             return pipe.detect(grey4)
 
+        def raw_step():                                            # the front step also delivers the detection's hot cell boxes
+            eng.bayer_gr2gray_scan(raw4.view(-1, H, W), out=grey4.view(-1, H, W), cellbox=cells4)
+            return pipe.detect(grey4, cellbox=cells4)
+
+        det2 = raw_step_two_passes()
+        two = (det2.count.clone(), det2.xy.clone())
+        rms2 = _time_loop(raw_step_two_passes, 10)
+        bms = _time_loop(lambda: eng.bayer_gr2gray_scan(raw4.view(-1, H, W), out=grey4.view(-1, H, W), cellbox=cells4), 10)
         det_raw = raw_step()
+        same_as_two = bool(torch.equal(two[0], det_raw.count) and torch.equal(two[1], det_raw.xy))
         rms = _time_loop(raw_step, 10)
         n_raw = raw4.shape[0] * raw4.shape[1]
         raw_par = None
@@ -732,9 +743,13 @@ def run_b200(args):
         except ImportError:
             pass
         front["raw_to_centroids"] = {"frames": n_raw, "ms": rms, "frames_per_s": n_raw / (rms * 1e-3),
-                                     "how": "mocap_bayer_gr2gray_batch then the overlapped detection call on the same stream, CUDA events, no second call in flight",
+                                     "how": "mocap_bayer_gr2gray_scan_batch (grey frames + the hot cell boxes of the detection) then the overlapped detection call "
+                                            "without its streaming scan (mocap_detect_pipe_set_cellbox) on the same stream, CUDA events, no second call in flight",
+                                     "front_step_with_scan_ms": bms,
+                                     "two_passes": {"ms": rms2, "how": "mocap_bayer_gr2gray_batch then the detection call with its own scan",
+                                                    "same_results": same_as_two},
                                      "parity_check": raw_par}
-        del grey4, det_raw
+        del grey4, det_raw, cells4, two
 
     # ---- one frame through the drop-in the realtime loop calls: numpy image in, centroid list + undistorted image out ------
     latency = None

@@ -136,6 +136,10 @@ int mocap_detect_pipe_set_scatter(void* pipe, const uint64_t* xy_dst_dev, const 
  * for `wait_event` and record `done_event` behind it (cudaEvent_t handles owned by the caller, NULL = none).  Chained from call to call
  * across the pipes, the HBM-bound scans run one after the other instead of side by side: one ring of TMA boxes per SM instead of two. */
 int mocap_detect_pipe_set_scan_token(void* pipe, void* wait_event, void* done_event);
+/* Hot cell boxes from the caller: the following mocap_detect_batch_pipelined calls of this pipe skip their streaming scan and take
+ * cellbox_dev [n_frames][ceil(H/32)][ceil(W/32)] (complete on the call's stream before the call; as written by mocap_scan_cells_batch
+ * or mocap_bayer_gr2gray_scan_batch for the same frames and thresh) instead.  NULL switches back. */
+int mocap_detect_pipe_set_cellbox(void* pipe, const uint32_t* cellbox_dev);
 /* ms since the fork of the last call with record_timeline: [scan done, join] then per chunk [scan seen, grouped, filtered,
  * borders done]; returns the number of floats written, 0 without a timeline */
 int mocap_detect_pipe_timeline(void* pipe, float* ms_out, int cap);
@@ -174,6 +178,12 @@ int mocap_median5_threshold_batch(const uint8_t* frames_dev, int n_frames, int H
 /* Bayer front step of the realtime loop: cv2.cvtColor(raw, COLOR_BAYER_GR2BGR) then cv2.cvtColor(., COLOR_BGR2GRAY)
  * (RealtimeTracking_FLIR.py:103-104), fused: raw u8 [n][H][W] -> grey u8 [n][H][W].  H, W >= 3. */
 int mocap_bayer_gr2gray_batch(const uint8_t* raw_dev, int n_frames, int H, int W, uint8_t* out_dev, void* stream);
+/* The same front step, which also delivers what the streaming scan of the detection would compute from the grey frames it writes:
+ * cellbox_out [n][ceil(H/32)][ceil(W/32)] as mocap_scan_cells_batch (the grey bytes are tested while they are in registers).  Handed to
+ * mocap_detect_pipe_set_cellbox, the detection of raw sensor frames (RealtimeTracking_FLIR.py:103-105) reads every frame byte once
+ * less.  workspace >= n * ceil(H/32) * ceil(W/32) * 8 bytes. */
+int mocap_bayer_gr2gray_scan_batch(const uint8_t* raw_dev, int n_frames, int H, int W, uint8_t* out_dev, int thresh,
+                                   uint32_t* cellbox_out, void* workspace, size_t workspace_bytes, void* stream);
 /* cv.undistort alone (lib/ImageOperations.py:38), for stage parity */
 int mocap_undistort_batch(const uint8_t* frames_dev, int n_frames, int H, int W, const void* table_dev,
                           uint8_t* out_dev, void* stream);

@@ -51,6 +51,7 @@ SIGNATURES = {
                                           _p, _p, _p, _p, _p, _p, _sz, _p, _p]),
     "mocap_detect_pipe_set_scatter": (_i, [_p, _p, _p]),
     "mocap_detect_pipe_set_scan_token": (_i, [_p, _p, _p]),
+    "mocap_detect_pipe_set_cellbox": (_i, [_p, _p]),
     "mocap_detect_pipe_timeline": (_i, [_p, _p, _i]),
     "mocap_detect_pipe_info": (_i, [_p, _p]),
     "mocap_scan_cells_batch": (_i, [_p, _i, _i, _i, _i64, _p, _i, _i, _p, _p, _sz, _p]),
@@ -60,6 +61,7 @@ SIGNATURES = {
     "mocap_blur5_batch": (_i, [_p, _i, _i, _i, _p, _p]),
     "mocap_median5_threshold_batch": (_i, [_p, _i, _i, _i, _i, _p, _p]),
     "mocap_bayer_gr2gray_batch": (_i, [_p, _i, _i, _i, _p, _p]),
+    "mocap_bayer_gr2gray_scan_batch": (_i, [_p, _i, _i, _i, _p, _i, _p, _p, _sz, _p]),
     "mocap_undistort_batch": (_i, [_p, _i, _i, _i, _p, _p, _p]),
     "mocap_triangulate_batch": (_i, [_p, _p, _p, _i, _i64, _i, _p, _p, _p]),
     "mocap_ba_residuals_batch": (_i, [_p, _p, _i, _i, _i64, _p, _p]),

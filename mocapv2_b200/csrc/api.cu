@@ -289,6 +289,7 @@ struct DetectPipe {
     const unsigned long long* sc_count = nullptr;
     void* tok_wait = nullptr;                       // scan token (mocap_detect_pipe_set_scan_token): cudaEvent_t the scan waits for / records
     void* tok_done = nullptr;
+    const uint32_t* pre_cellbox = nullptr;          // hot cell boxes of the next calls' frames, computed by the caller (mocap_detect_pipe_set_cellbox)
 #ifndef MOCAP_EMU
     cudaStream_t s_scan = nullptr, s_proc[PIPE_MAX_PROC] = {};
     cudaEvent_t ev_fork = nullptr, ev_scan_done = nullptr, ev_proc_done[PIPE_MAX_PROC] = {}, ev_join = nullptr;
@@ -348,6 +349,14 @@ extern "C" int mocap_detect_pipe_set_scan_token(void* pipe, void* wait_event, vo
     if (!p) return MOCAP_ERR_INVALID;
     p->tok_wait = wait_event;
     p->tok_done = done_event;
+    return MOCAP_OK;
+}
+
+extern "C" int mocap_detect_pipe_set_cellbox(void* pipe, const uint32_t* cellbox_dev)
+{
+    DetectPipe* p = (DetectPipe*)pipe;
+    if (!p) return MOCAP_ERR_INVALID;
+    p->pre_cellbox = cellbox_dev;
     return MOCAP_OK;
 }
 
@@ -423,11 +432,14 @@ extern "C" int mocap_detect_batch_pipelined(void* pipe, const uint8_t* frames_de
     TableView tv; table_view(table_dev, H, W, &tv);
     char* base = (char*)workspace;
     FilterWs ws = filter_ws(base, P.L);
+    // hot cell boxes handed in (the Bayer front step computes them while it writes the grey frames): no streaming scan in this call
+    const bool prescanned = dp->pre_cellbox != nullptr;
+    if (prescanned) ws.cellbox = (uint32_t*)dp->pre_cellbox;
     int* ctrl = (int*)(base + P.off_ctrl);
     int* need_general = (int*)(base + P.off_need);
     const int chunks = P.chunks, cf = P.chunk_frames;
     const int per_frame_items = tv.TY * cdiv(W, 256);
-    const bool tma = opts->scan_variant != 0 && scan_tma_supported(frames_dev, n_frames, H, W, frame_stride, thresh);
+    const bool tma = !prescanned && opts->scan_variant != 0 && scan_tma_supported(frames_dev, n_frames, H, W, frame_stride, thresh);
     int mode = opts->sync_mode;
     if (mode == 1 && !(tma && stream_wait_supported())) mode = 0;
     dp->last_scan = tma ? 1 : 0; dp->last_chunks = chunks; dp->last_mode = mode;
@@ -444,7 +456,7 @@ extern "C" int mocap_detect_batch_pipelined(void* pipe, const uint8_t* frames_de
     for (int c = 0; c < chunks; ++c) {
         const int f0 = c * cf, nc = (n_frames - f0) < cf ? (n_frames - f0) : cf;
         FilterWs wc = ws; wc.cellbox = ws.cellbox + (size_t)f0 * tv.TX * tv.TY;
-        st = launch_scan(frames_dev + (size_t)f0 * frame_stride, nc, H, W, frame_stride, tv, thresh, wc, s, nullptr);
+        st = prescanned ? MOCAP_OK : launch_scan(frames_dev + (size_t)f0 * frame_stride, nc, H, W, frame_stride, tv, thresh, wc, s, nullptr);
         if (st != MOCAP_OK) return st;
         st = launch_cluster_path(frames_dev + (size_t)f0 * frame_stride, nc, H, W, frame_stride, tv, thresh, wc.cellbox,
                                  base + P.off_chunks + (size_t)c * P.chunk_bytes, P.cl_offs, need_general + f0, max_contours, max_blobs, min_area, min_circ,
@@ -502,7 +514,9 @@ extern "C" int mocap_detect_batch_pipelined(void* pipe, const uint8_t* frames_de
         cudaStream_t ps = group_stream(c);
         char* cws = base + P.off_chunks + (size_t)c * P.chunk_bytes;
         CUDA_TRY(cudaMemsetAsync(cws + P.cl_offs[14], 0, P.cl_offs[15], ps));     // the chunk's counters / lists, off the critical path
-        if (mode == 1) {
+        if (prescanned) {
+            // nothing to wait for: the boxes were complete before the fork
+        } else if (mode == 1) {
             st = stream_wait_geq(ps, ctrl + PIPE_CTRL_WORK + chunks + c, 1);
             if (st != MOCAP_OK) return st;
         } else {

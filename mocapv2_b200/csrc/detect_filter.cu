@@ -896,8 +896,13 @@ __device__ __forceinline__ uint32_t bayer_row_grey(const BayerRow& u, const Baye
 
 // interior rows 1 .. H-2 (+ rows 0 and H-1, their copies); NW words (4 NW pixels) per thread and row; the threads of a block
 // lie side by side on one strip of rows (grid: x = spans of 128 threads, y = strips, z = frames)
-template <int NW>
-__global__ void __launch_bounds__(128) bayer_gr2gray_rows_kernel(const uint8_t* __restrict__ in, int H, int W, uint8_t* __restrict__ out)
+// SCAN: the kernel also does the streaming scan of the detection on the grey bytes it holds -- per 32x32 cell of the grey frame the
+// masks of its hot columns and rows (pixel > thresh, the test of scan_hot_*_kernel) are OR-ed into cellmask [n][TY][TX][2];
+// pack_cellmask_kernel turns them into the cell boxes.  A row without a byte >= 128 costs one LOP3 and a branch (thresh >= 128: the
+// detection's threshold is 216); rows with hot pixels are rare (the markers) and issue two RED.OR per thread.
+struct BayerScan { uint32_t* cellmask; uint32_t add; int mode; int TX, TY; };
+template <int NW, bool SCAN>
+__global__ void __launch_bounds__(128) bayer_gr2gray_rows_kernel(const uint8_t* __restrict__ in, int H, int W, uint8_t* __restrict__ out, BayerScan sc)
 {
     const int x0 = (blockIdx.x * 128 + threadIdx.x) * 4 * NW;
     const int ya = max((int)blockIdx.y * BAYER_ROWS, 1), yb = min(((int)blockIdx.y + 1) * BAYER_ROWS, H - 1);   // interior output rows [ya, yb)
@@ -911,6 +916,7 @@ __global__ void __launch_bounds__(128) bayer_gr2gray_rows_kernel(const uint8_t* 
     BayerRows<NW> r[3];
     BayerRaw<NW> fl[BAYER_DEPTH];                                      // the next BAYER_DEPTH input rows are always in flight; fl[0] the oldest
     int yl = ya - 1;                                                   // the last row requested
+    int ysc = ya;                                                      // (SCAN) the next row to be stored
     auto request = [&](BayerRaw<NW>& t) { if (yl + 1 < H) { ++yl; p += W; } bayer_load<NW>(p, eL, eR, t); };
     auto request_fast = [&](BayerRaw<NW>& t) { ++yl; p += W; bayer_load<NW>(p, -4, 4 * NW, t); };     // a row of 1 .. H-2
     auto next_row = [&]() -> BayerRows<NW> {                           // outside the unrolled loop: consume fl[0], request, rotate
@@ -941,6 +947,32 @@ __global__ void __launch_bounds__(128) bayer_gr2gray_rows_kernel(const uint8_t* 
         if (top) store(q - W, g);
         if (bottom) store(q + W, g);
         q += W;
+        if (SCAN) {
+            uint32_t any = g[0];
+#pragma unroll
+            for (int k = 1; k < NW; ++k) any |= g[k];
+            if (((any & 0x80808080u) != 0 && sc.mode != 2) || (sc.mode & 1)) {          // (modes 1 / 3: thresh < 128, every row is tested)
+                uint32_t cm = 0;
+#pragma unroll
+                for (int k = 0; k < NW; ++k) {
+                    const uint32_t t = (g[k] & 0x7f7f7f7fu) + sc.add;
+                    const uint32_t h = sc.mode == 0 ? (g[k] & t) : sc.mode == 1 ? (g[k] | t) : 0x80808080u;
+                    cm |= hot_nibble(h) << (4 * k);
+                }
+                if (cm) {
+                    const int ys = ysc;                                    // the row just stored
+                    auto mark = [&](int row) {
+                        uint32_t* m = sc.cellmask + 2 * (((size_t)blockIdx.z * sc.TY + (row >> 5)) * sc.TX + (x0 >> 5));
+                        atomicOr(m, cm << (x0 & 31));
+                        atomicOr(m + 1, 1u << (row & 31));
+                    };
+                    mark(ys);
+                    if (top) mark(ys - 1);
+                    if (bottom) mark(ys + 1);
+                }
+            }
+            ++ysc;
+        }
     };
     int y = ya;
     if (y & 1) {                                                       // first strip (ya = 1): start the unrolled loop on an even row
@@ -967,22 +999,63 @@ __global__ void __launch_bounds__(128) bayer_gr2gray_rows_kernel(const uint8_t* 
     }
 }
 
-extern "C" int mocap_bayer_gr2gray_batch(const uint8_t* raw_dev, int n, int H, int W, uint8_t* out_dev, void* stream)
+__global__ void pack_cellmask_kernel(const uint32_t* __restrict__ cellmask, long long cells, uint32_t* __restrict__ cellbox)
+{
+    const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i < cells) cellbox[i] = pack_cellbox(cellmask[2 * i], cellmask[2 * i + 1]);
+}
+
+// grey frames (+ with cellbox_out: the hot cell boxes of the grey frames for `thresh`, what the streaming scan of the detection
+// would compute from them; scan_ws >= n * ceil(H/32) * ceil(W/32) * 8 bytes)
+static int bayer_launch(const uint8_t* raw_dev, int n, int H, int W, uint8_t* out_dev, int thresh, uint32_t* cellbox_out, void* scan_ws,
+                        size_t scan_ws_bytes, cudaStream_t st)
 {
     if (!raw_dev || !out_dev || n <= 0 || H < 3 || W < 3 || n > 65535 || (long long)H * W >= (1ll << 31)) return MOCAP_ERR_INVALID;
     const uintptr_t al = (uintptr_t)raw_dev | (uintptr_t)out_dev | (uintptr_t)W;
+    BayerScan sc = {nullptr, 0u, 2, (W + 31) / 32, (H + 31) / 32};
+    const long long cells = (long long)n * sc.TX * sc.TY;
+    const bool scan = cellbox_out != nullptr;
+    if (scan) {
+        if (!scan_ws || scan_ws_bytes < (size_t)cells * 8) return MOCAP_ERR_WORKSPACE;
+        HotTest ht = make_hot_test(thresh);
+        sc.cellmask = (uint32_t*)scan_ws; sc.add = ht.add; sc.mode = ht.mode;
+    }
     if (al % 4 == 0) {
-        const cudaStream_t st = (cudaStream_t)stream;
         const int ny = cdiv(H, BAYER_ROWS);
+        if (scan) CUDA_TRY(cudaMemsetAsync(scan_ws, 0, (size_t)cells * 8, st));
         // (four words per thread -- 128-bit loads, 88-96 registers -- measured slower: 0.44-0.47 ms against 0.436 per 256 frames)
-        if (al % 8 == 0) LAUNCH(bayer_gr2gray_rows_kernel<2>, dim3(cdiv(W, 1024), ny, n), 128, 0, st, raw_dev, H, W, out_dev);
-        else LAUNCH(bayer_gr2gray_rows_kernel<1>, dim3(cdiv(W, 512), ny, n), 128, 0, st, raw_dev, H, W, out_dev);
+        if (al % 8 == 0) {
+            if (scan) LAUNCH((bayer_gr2gray_rows_kernel<2, true>), dim3(cdiv(W, 1024), ny, n), 128, 0, st, raw_dev, H, W, out_dev, sc);
+            else LAUNCH((bayer_gr2gray_rows_kernel<2, false>), dim3(cdiv(W, 1024), ny, n), 128, 0, st, raw_dev, H, W, out_dev, sc);
+        } else {
+            if (scan) LAUNCH((bayer_gr2gray_rows_kernel<1, true>), dim3(cdiv(W, 512), ny, n), 128, 0, st, raw_dev, H, W, out_dev, sc);
+            else LAUNCH((bayer_gr2gray_rows_kernel<1, false>), dim3(cdiv(W, 512), ny, n), 128, 0, st, raw_dev, H, W, out_dev, sc);
+        }
+        if (scan) LAUNCH(pack_cellmask_kernel, (unsigned)((cells + 255) / 256), 256, 0, st, (const uint32_t*)scan_ws, cells, cellbox_out);
         CUDA_TRY(cudaGetLastError());
         return MOCAP_OK;
     }
-    LAUNCH(bayer_gr2gray_kernel, dim3(cdiv(W, 64), cdiv(H, 4), n), dim3(64, 4), 0, (cudaStream_t)stream, raw_dev, n, H, W, out_dev);
+    LAUNCH(bayer_gr2gray_kernel, dim3(cdiv(W, 64), cdiv(H, 4), n), dim3(64, 4), 0, st, raw_dev, n, H, W, out_dev);
     CUDA_TRY(cudaGetLastError());
+    if (scan) {                                                            // rows that are not a multiple of 4 bytes: the generic scan on the grey frames
+        TableView tv = {};
+        tv.H = H; tv.W = W; tv.TX = sc.TX; tv.TY = sc.TY;                  // (the scalar scan reads the frame geometry only)
+        LAUNCH(scan_hot_scalar_kernel, 148 * 8, 256, 0, st, (const uint8_t*)out_dev, n, (int64_t)H * W, tv, thresh, cellbox_out);
+        CUDA_TRY(cudaGetLastError());
+    }
     return MOCAP_OK;
+}
+
+extern "C" int mocap_bayer_gr2gray_batch(const uint8_t* raw_dev, int n, int H, int W, uint8_t* out_dev, void* stream)
+{
+    return bayer_launch(raw_dev, n, H, W, out_dev, 0, nullptr, nullptr, 0, (cudaStream_t)stream);
+}
+
+extern "C" int mocap_bayer_gr2gray_scan_batch(const uint8_t* raw_dev, int n, int H, int W, uint8_t* out_dev, int thresh,
+                                              uint32_t* cellbox_out, void* workspace, size_t workspace_bytes, void* stream)
+{
+    if (!cellbox_out) return MOCAP_ERR_INVALID;
+    return bayer_launch(raw_dev, n, H, W, out_dev, thresh, cellbox_out, workspace, workspace_bytes, (cudaStream_t)stream);
 }
 
 __global__ void undistort_kernel(const uint8_t* __restrict__ in, int n, int H, int W, const int32_t* __restrict__ map,

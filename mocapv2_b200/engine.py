@@ -282,9 +282,10 @@ class CaptureEngine:
     def detect_pipelined(self, frames: torch.Tensor, K, dist, *, thresh=THRESH_U8, min_area=MIN_AREA, min_circ=MIN_CIRC,
                          max_blobs=None, max_contours=None, max_runs=None, outputs=(), out: DetectResult | None = None,
                          chunk_frames=128, sync_mode=1, scan_variant=1, filter_ctas_per_sm=0, cand_ctas_per_sm=0,
-                         stream_plan=0, scan_stages=6, timeline=False) -> DetectResult:
+                         stream_plan=0, scan_stages=6, timeline=False, cellbox: torch.Tensor | None = None) -> DetectResult:
         """Same results as detect() (centroid lists, optionally the contour table), computed chunk by chunk with the streaming
-        scan overlapped with the other stages (mocap_detect_batch_pipelined)."""
+        scan overlapped with the other stages (mocap_detect_batch_pipelined).  cellbox: the frames' hot cell boxes from
+        bayer_gr2gray_scan (same thresh) -- the call then has no streaming scan."""
         if frames.dim() != 3:
             raise ValueError("frames must be [n, H, W]")
         if frames.device != self.device or frames.dtype != torch.uint8:
@@ -310,11 +311,20 @@ class CaptureEngine:
         opts = _cabi.PipeOpts(int(chunk_frames), int(sync_mode), int(scan_variant), int(filter_ctas_per_sm), int(cand_ctas_per_sm),
                               1 if timeline else 0, int(stream_plan), int(scan_stages))
         ws = self._workspace(nbytes)
-        st = self.lib.mocap_detect_batch_pipelined(
-            self._pipe(), self._ptr(frames), n, H, W, stride, self._ptr(tab), int(thresh), float(min_area), float(min_circ),
-            max_blobs, max_contours, max_runs, self._ptr(out.xy), self._ptr(out.count), self._ptr(out.flags),
-            self._ptr(ex.get("contours")), self._ptr(ex.get("contour_count")), self._ptr(ws), nbytes, self._stream(),
-            ctypes.byref(opts))
+        if cellbox is not None:
+            if tuple(cellbox.shape) != (n, (H + 31) // 32, (W + 31) // 32):
+                raise ValueError("cellbox must be [n, ceil(H/32), ceil(W/32)]")
+            self._check_dev(cellbox, torch.int32, "cellbox")
+            _cabi.check(self.lib, self.lib.mocap_detect_pipe_set_cellbox(self._pipe(), self._ptr(cellbox)), "mocap_detect_pipe_set_cellbox")
+        try:
+            st = self.lib.mocap_detect_batch_pipelined(
+                self._pipe(), self._ptr(frames), n, H, W, stride, self._ptr(tab), int(thresh), float(min_area), float(min_circ),
+                max_blobs, max_contours, max_runs, self._ptr(out.xy), self._ptr(out.count), self._ptr(out.flags),
+                self._ptr(ex.get("contours")), self._ptr(ex.get("contour_count")), self._ptr(ws), nbytes, self._stream(),
+                ctypes.byref(opts))
+        finally:
+            if cellbox is not None:
+                self.lib.mocap_detect_pipe_set_cellbox(self._pipe(), None)
         _cabi.check(self.lib, st, "mocap_detect_batch_pipelined")
         info = (ctypes.c_int * 3)()
         self.lib.mocap_detect_pipe_info(self._pipe(), info)
@@ -449,6 +459,35 @@ class CaptureEngine:
         _cabi.check(self.lib, self.lib.mocap_bayer_gr2gray_batch(self._ptr(raw), n, H, W, self._ptr(out), self._stream()),
                     "mocap_bayer_gr2gray_batch")
         return out
+
+    def bayer_gr2gray_scan(self, raw: torch.Tensor, out: torch.Tensor | None = None, *, thresh=THRESH_U8,
+                           cellbox: torch.Tensor | None = None):
+        """bayer_gr2gray that also returns the hot cell boxes of the grey frames ([n, ceil(H/32), ceil(W/32)] int32, what scan_cells
+        computes from them): detect_pipelined(grey, ..., cellbox=...) then skips its streaming scan (mocap_bayer_gr2gray_scan_batch)."""
+        raw = self._check_dev(raw.contiguous(), torch.uint8, "raw")
+        n, H, W = raw.shape
+        if out is None:
+            out = torch.empty_like(raw)
+        elif out.shape != raw.shape:
+            raise ValueError("out must have the shape of raw")
+        else:
+            self._check_dev(out, torch.uint8, "out")
+        cells = (n, (H + 31) // 32, (W + 31) // 32)
+        if cellbox is None:
+            cellbox = self.empty(cells, torch.int32)
+        elif tuple(cellbox.shape) != cells:
+            raise ValueError("cellbox must be [n, ceil(H/32), ceil(W/32)]")
+        else:
+            self._check_dev(cellbox, torch.int32, "cellbox")
+        nbytes = cells[0] * cells[1] * cells[2] * 8
+        tls = self._tls
+        mask = getattr(tls, "bayer_mask", None)                   # its own scratch: the detection workspace is in use by calls in flight
+        if mask is None or mask.numel() < nbytes:
+            mask = tls.bayer_mask = self.empty((nbytes,), torch.uint8)
+        _cabi.check(self.lib, self.lib.mocap_bayer_gr2gray_scan_batch(self._ptr(raw), n, H, W, self._ptr(out), int(thresh), self._ptr(cellbox),
+                                                                      self._ptr(mask), nbytes, self._stream()),
+                    "mocap_bayer_gr2gray_scan_batch")
+        return out, cellbox
 
     def undistort(self, frames: torch.Tensor, K, dist) -> torch.Tensor:
         """cv.undistort(img, K, dist) (lib/ImageOperations.py:38) for a batch [n, H, W] uint8."""

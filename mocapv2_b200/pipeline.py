@@ -85,14 +85,17 @@ class CapturePipeline:
             self._rx = None
         return self._det
 
-    def detect(self, frames: torch.Tensor, timer=None, pipelined=None, timeline=False) -> DetectResult:
-        """frames [FS, cams_local, H, W] uint8 on the device -> centroid lists of this rank's cameras."""
+    def detect(self, frames: torch.Tensor, timer=None, pipelined=None, timeline=False, cellbox=None) -> DetectResult:
+        """frames [FS, cams_local, H, W] uint8 on the device -> centroid lists of this rank's cameras.  cellbox: the frames' hot cell
+        boxes from CaptureEngine.bayer_gr2gray_scan (raw sensor input): the overlapped call then runs without its streaming scan."""
         FS, cl, H, W = frames.shape
         assert cl == self.cams_local and (H, W) == (self.H, self.W)
         flat = frames.view(FS * cl, H, W)
         n = FS * cl
         if pipelined is None:
-            pipelined = timer is None and n >= self.pipelined_min_frames
+            pipelined = cellbox is not None or (timer is None and n >= self.pipelined_min_frames)
+        if cellbox is not None and not pipelined:
+            raise ValueError("cellbox is taken by the overlapped detection call only")
         buf = self._buffers(n)
         buf.extras.pop("peer_turn", None)                          # (set below when this call stores its records to the peers)
         if pipelined:
@@ -106,7 +109,7 @@ class CapturePipeline:
                 self.eng.set_detect_scatter(*peer["tables"][peer["turn"]])
             try:
                 self._det = self.eng.detect_pipelined(flat, self.K0, self.dist0, max_blobs=self.max_blobs, out=buf,
-                                                      chunk_frames=chunk, timeline=timeline)
+                                                      chunk_frames=chunk, timeline=timeline, cellbox=cellbox)
             finally:
                 if peer is not None:
                     self.eng.set_detect_scatter(None, None)
