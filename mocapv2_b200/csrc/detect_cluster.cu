@@ -18,6 +18,9 @@
 #include "tma.cuh"
 
 #define CL_THREADS 128
+#ifndef BORDERS_MIN_CTAS
+#define BORDERS_MIN_CTAS 1                                        // (8 caps borders_finalize_kernel at 64 registers: build-time A/B)
+#endif
 #ifndef PF_WIN_L2_PROMO
 #define PF_WIN_L2_PROMO 64      // bytes a window fetch is widened to in L2 (rows are 96 bytes; 64: 0.99 GB of DRAM reads per 1024 frames, 128 or none: 1.30 GB)
 #endif
@@ -1131,7 +1134,7 @@ __device__ void frame_finalize(const ClusterWs& cw, int f, uint8_t* keepv /*[max
 
 // One CTA per frame: the traces of the frame's border-start candidates, the nesting check and -- unless the frame was
 // handed to the general path on the way -- the reference's filter / centroid / output order.
-__global__ void __launch_bounds__(CL_THREADS) borders_finalize_kernel(ClusterWs cw, int W, int frame_step, int max_contours, int max_blobs, double min_area, double min_circ,
+__global__ void __launch_bounds__(CL_THREADS, BORDERS_MIN_CTAS) borders_finalize_kernel(ClusterWs cw, int W, int frame_step, int max_contours, int max_blobs, double min_area, double min_circ,
                                                                       int32_t* __restrict__ out_xy, int32_t* __restrict__ out_count, int32_t* __restrict__ out_flags,
                                                                       double* __restrict__ out_contours, int32_t* __restrict__ out_contour_count)
 {
