@@ -859,6 +859,8 @@ def run_b200(args):
                              "lib/ImageOperations.py:33-65 (numba blur -> its integer restatement) + lib/Helpers.py:178-280 in NumPy "
                              f"with the same candidate cap; frames over a {threads}-thread pool", "points_per_s": npts / dt}
         try:
+            det, corr = step()                                   # the pipeline's result buffers were reused by the sections above
+            torch.cuda.synchronize()
             parity = _parity_check(rig, frames, det, corr, pipe.cams_local)
         except Exception as ex:                                  # the check must never cost the bench line
             parity = {"checked": False, "why": repr(ex)}
