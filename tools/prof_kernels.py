@@ -64,6 +64,7 @@ def main():
 
     def bayer():
         eng.bayer_gr2gray(raw, out=grey)
+        eng.bayer_gr2gray_scan(raw, out=grey)                      # the front step that also delivers the detection's hot cell boxes
 
     for _ in range(3):
         step(); geometry(); bayer(); overlapped()
