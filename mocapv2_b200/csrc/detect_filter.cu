@@ -824,6 +824,9 @@ __global__ void bayer_gr2gray_kernel(const uint8_t* __restrict__ in, int n, int 
 // 32768 <= 2^24 - 32768) put the result into byte 2 of the sum, i.e. three IDP.2A per pixel (FMA pipe) and no shift; three PRMT
 // assemble the four bytes of a word, the last one with a per-lane selector that also copies column 1 to column 0 and column
 // W-2 to column W-1.  Rows 0 and H-1 (copies of rows 1 and H-2) are stored by the warps that produce rows 1 and H-2.
+#ifndef BAYER_MIN_CTAS
+#define BAYER_MIN_CTAS 1                                      // (9 / 10 cap the registers at 56 / 48: 0.46 / 0.45 ms against 0.436 per 256 frames)
+#endif
 #ifndef BAYER_ROWS
 #define BAYER_ROWS 64
 #endif
@@ -902,7 +905,7 @@ __device__ __forceinline__ uint32_t bayer_row_grey(const BayerRow& u, const Baye
 // detection's threshold is 216); rows with hot pixels are rare (the markers) and issue two RED.OR per thread.
 struct BayerScan { uint32_t* cellmask; uint32_t add; int mode; int TX, TY; };
 template <int NW, bool SCAN>
-__global__ void __launch_bounds__(128) bayer_gr2gray_rows_kernel(const uint8_t* __restrict__ in, int H, int W, uint8_t* __restrict__ out, BayerScan sc)
+__global__ void __launch_bounds__(128, BAYER_MIN_CTAS) bayer_gr2gray_rows_kernel(const uint8_t* __restrict__ in, int H, int W, uint8_t* __restrict__ out, BayerScan sc)
 {
     const int x0 = (blockIdx.x * 128 + threadIdx.x) * 4 * NW;
     const int ya = max((int)blockIdx.y * BAYER_ROWS, 1), yb = min(((int)blockIdx.y + 1) * BAYER_ROWS, H - 1);   // interior output rows [ya, yb)
