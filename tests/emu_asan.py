@@ -58,6 +58,7 @@ def run():
         eng.detect(torch.from_numpy(img[None].copy()), K, D, min_area=0.0, outputs=("bits", "labels")).points(0)
     for shape in [(3, 4), (5, 8), (34, 132), (64, 128), (97, 260), (7, 10), (33, 65), (3, 8), (12, 1032), (129, 1040), (75, 16)]:  # Bayer front step, both kernels
         eng.bayer_gr2gray(torch.from_numpy(rng.integers(0, 256, (2,) + shape).astype(np.uint8)))
+        eng.bayer_gr2gray_scan(torch.from_numpy(rng.integers(0, 256, (2,) + shape).astype(np.uint8)), thresh=int(rng.integers(0, 256)))
     z = np.load(os.path.join(REPO, "tests", "golden", "c1_frames.npz"))["frames"].reshape(-1, 480, 640)[:2]
     res = eng.detect(torch.from_numpy(z.copy()), K, D)
     rig = S.config_rig("c1")
